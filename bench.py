@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Throughput of the LTM consolidation path (BASELINE.json metric) on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (libinfltm, sm_100a)
+  python bench.py --impl reference ...                     # the reference algorithm on the host cores
+
+Workload (config.workload): the NExT-QA shape of BASELINE.json configs[1] -- chunks of L=256 frames x 32
+Q-former tokens x 768, num_basis=256, tau=0.75, sticky re-sampling, 32 queries -- for `--videos` independent
+videos per GPU (weak scaling; cfg5 shards 1024 videos over 8 GPUs = 128 per GPU), C=8 sequential chunks each.
+One "step" = consolidating all chunks of all videos of the batch once = videos*C module calls per GPU.
+`value` = calls/s with inputs resident in HBM; `e2e` = the same through `step_host` with pinned HOST buffers
+(H2D of k,q,u and D2H of the context inside the timed region).  Inputs (videos*C*25 MB) are far larger than
+the 126 MB L2, so no L2 flush is needed between iterations.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "video chunks consolidated/sec (LTM update+continuous attn) at 1/2/4/8 B200; % roofline"
+L, T, E, Q, NB, TAU, S, H, DH = 256, 32, 768, 32, 256, 0.75, 512, 12, 64
+D = H * DH
+
+
+def algorithmic_bytes_per_call(Lf=L, Tt=T, e=E, q=Q, n=NB):
+    """4*(L*T*e + 2*Q*D + 2*N*e) + 8*S  [read k, read q, write ctx, read B_past, write B, read u]."""
+    return 4 * (Lf * Tt * e + 2 * q * D + 2 * n * e) + 8 * S
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+            except Exception:
+                continue
+            for name, idx in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > idx and r[idx].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def make_cpu_inputs(chunks, seed=1234):
+    g = torch.Generator().manual_seed(seed)
+    ks = [torch.randn(1, L * T, E, generator=g) for _ in range(chunks)]
+    qs = [torch.randn(1, Q, D, generator=g) for _ in range(chunks)]
+    us = [torch.rand(1, S, dtype=torch.float64, generator=g) for _ in range(chunks)]
+    return ks, qs, us
+
+
+def cpu_reference_video(orc, ks, qs, us):
+    """One video through the reference algorithm (oracle port: dense ridge inverse, 1000-point quadrature,
+    tables rebuilt on every call like long_term_attention_gibbs.py:298)."""
+    with torch.no_grad():
+        for c in range(len(ks)):
+            out = orc.forward(ks[c], qs[c], c == 0, us[c])
+    return out
+
+
+def cpu_arm(chunks, budget_s, max_videos):
+    from oracle import ltm_oracle as O   # bench.py's cpu_baseline / --impl reference legs only
+    torch.manual_seed(0)
+    key, val = torch.nn.Linear(E, D), torch.nn.Linear(E, D)
+    orc = O.RectLTM(NB, TAU, key.weight.detach(), key.bias.detach(), val.weight.detach(), val.bias.detach(),
+                    tokens_per_frame=T, sticky=True, faithful_quadrature=True, rebuild_tables=True)
+    ks, qs, us = make_cpu_inputs(chunks)
+    return orc, ks, qs, us
+
+
+def run_reference_impl(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    torch.set_num_threads(os.cpu_count() or 1)
+    chunks = args.chunks
+    orc, ks, qs, us = cpu_arm(chunks, 0, 0)
+    for _ in range(args.warmup):
+        cpu_reference_video(orc, ks[:2], qs[:2], us[:2])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_video(orc, ks, qs, us)
+    dt = time.perf_counter() - t0
+    calls = args.steps * chunks
+    val = calls / dt
+    sample = f"{args.steps} video(s) x {chunks} chunks, batch 1, sequential (the reference module is batch-1)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "chunks/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(1, chunks, "gibbs"),
+        "cpu_baseline": {"value": val, "unit": "chunks/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": val, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(videos, chunks, variant):
+    return {"workload": "cfg2 NExT-QA shape (BASELINE.json configs[1]): LongTermAttention.forward per chunk",
+            "variant": variant, "frames_per_chunk_L": L, "tokens_per_frame_T": T, "encoder_width_e": E,
+            "queries_Q": Q, "num_basis": NB, "tau": TAU, "sticky": True, "nb_samples": S,
+            "chunks_per_video": chunks, "videos_per_gpu": videos,
+            "l2_policy": "inputs larger than L2 (videos*chunks*25.2 MB resident in HBM); no flush"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_b200(args):
+    from infinite_video_b200 import _capi, dist as D_
+    from infinite_video_b200.batched import BatchedRectLTM
+
+    rank, local, world = D_.init_from_env()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    lib = _capi.lib()
+    _capi.check(lib.ltm_device_check(), "device_check")
+    Bv, C = args.videos, args.chunks
+    torch.manual_seed(0)
+    key, val = torch.nn.Linear(E, D), torch.nn.Linear(E, D)
+    eng = BatchedRectLTM(NB, TAU, key.weight.detach(), key.bias.detach(), val.weight.detach(), val.bias.detach(),
+                         tokens_per_frame=T, sticky=True, precision=args.precision, device=dev)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    ks = [torch.randn(Bv, L * T, E, device=dev, generator=g) for _ in range(C)]
+    qs = [torch.randn(Bv, Q, D, device=dev, generator=g) for _ in range(C)]
+    us = [torch.rand(Bv, S, device=dev, dtype=torch.float64, generator=g) for _ in range(C)]
+    stream = torch.cuda.current_stream(dev)
+
+    def one_step():
+        out = None
+        for c in range(C):
+            out = eng.step(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0))
+        if world > 1:
+            out = D_.gather_videos(out, Bv * world)       # one NCCL all_gather of per-video outputs, outside the loop
+        return out
+
+    # stage events (pool = dominant kernel) recorded inside the timed region on the launching stream
+    import ctypes as Ct
+    n_sets = args.steps * C
+    ev_sets = []
+    for _ in range(n_sets):
+        evs = []
+        for _i in range(10):
+            h = Ct.c_void_p()
+            _capi.check(lib.ltm_event_create(Ct.byref(h)), "event_create")
+            evs.append(h)
+        ev_sets.append(evs)
+
+    for _ in range(args.warmup):
+        one_step()
+    torch.cuda.synchronize(dev)
+    D_.barrier(dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record(stream)
+    i = 0
+    for _ in range(args.steps):
+        out = None
+        for c in range(C):
+            eng.prof_events = ev_sets[i]
+            i += 1
+            out = eng.step(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0))
+        if world > 1:
+            out = D_.gather_videos(out, Bv * world)
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    eng.prof_events = None
+    D_.barrier(dev)
+    clocks = sampler.stop() if rank == 0 else None
+    ms = D_.max_over_ranks(e0.elapsed_time(e1), dev)
+    calls_total = Bv * C * args.steps * world
+    value = calls_total / (ms * 1e-3)
+
+    # per-stage device times (this rank)
+    names = ["pool", "resample", "consolidate", "project_kv", "attention"]
+    stage_ms = {n: [] for n in names}
+    f = Ct.c_float()
+    for si, evs in enumerate(ev_sets):
+        first = (si % C) == 0
+        for j, n in enumerate(names):
+            if n == "resample" and first:
+                continue
+            _capi.check(lib.ltm_event_elapsed_ms(evs[2 * j], evs[2 * j + 1], Ct.byref(f)), "event_elapsed")
+            stage_ms[n].append(f.value)
+    stage_avg = {n: (sum(v) / len(v) if v else 0.0) for n, v in stage_ms.items()}
+    for evs in ev_sets:
+        for h in evs:
+            lib.ltm_event_destroy(h)
+
+    peak, peak_src = measured_peaks()
+    pool_bytes = 4.0 * Bv * L * T * E                       # algorithmic bytes of the dominant kernel per launch
+    pool_gbs = pool_bytes / (stage_avg["pool"] * 1e-3) / 1e9 if stage_avg["pool"] > 0 else 0.0
+    step_bytes = algorithmic_bytes_per_call() * Bv * C + 4 * 2 * (E * D + D)   # + weights once per launch
+    ms_per_step = ms / args.steps
+    step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9
+
+    # ---------------- end to end through the host entry point (pinned host buffers, ring of 2 chunk slots)
+    e2e = None
+    if not args.no_e2e:
+        hk = [torch.randn(Bv, L * T, E).pin_memory() for _ in range(2)]
+        hq = [torch.randn(Bv, Q, D).pin_memory() for _ in range(2)]
+        hu = [torch.rand(Bv, S, dtype=torch.float64).pin_memory() for _ in range(2)]
+        hout = [torch.empty(Bv, Q, D).pin_memory() for _ in range(2)]
+
+        def host_step():
+            for c in range(C):
+                eng.step_host(hk[c & 1], hq[c & 1], hu[c & 1], new_doc=(c == 0), out=hout[c & 1])
+            torch.cuda.synchronize(dev)
+            return float(hout[(C - 1) & 1][0, 0, 0])        # the result is read on the host
+
+        host_step()
+        D_.barrier(dev)
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            host_step()
+        dt = D_.max_over_ranks(time.perf_counter() - t0, dev)
+        h2d = C * (hk[0].numel() * 4 + hq[0].numel() * 4) + (C - 1) * hu[0].numel() * 8
+        d2h = C * hout[0].numel() * 4
+        e2e = {"value": Bv * C * args.e2e_steps * world / dt, "unit": "chunks/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+               "note": "BatchedRectLTM.step_host -> ltm_rect_step_host (C-ABI): pinned host k,q,u -> device, "
+                       "kernels, ctx -> pinned host, per chunk; PCIe-bound"}
+
+    # ---------------- CPU baseline beside it (rank 0, N=1 only): the reference algorithm on the host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        orc, cks, cqs, cus = cpu_arm(C, 0, 0)
+        cpu_reference_video(orc, cks[:2], cqs[:2], cus[:2])
+        t0 = time.perf_counter()
+        n_calls = 0
+        while time.perf_counter() - t0 < 12.0 and n_calls < 4 * C:
+            cpu_reference_video(orc, cks, cqs, cus)
+            n_calls += C
+        dt = time.perf_counter() - t0
+        cpu = {"value": n_calls / dt, "unit": "chunks/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{n_calls // C} video(s) x {C} chunks of the same shape, batch 1 sequential, "
+                         f"oracle port of long_term_attention_gibbs.py (tables rebuilt per call, 1000-pt quadrature)"}
+
+    if rank == 0:
+        launches = args.steps * (C * 5 - 1)
+        line = {
+            "metric": METRIC, "value": value, "unit": "chunks/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (tf32 tensor-core products for the K/V projection, fp32 accumulate)"
+            if args.precision == "tf32" else "f32 (split-tf32 x3 tensor-core products, fp32 accumulate)",
+            "data": "synthetic", "config": workload_config(Bv, C, "gibbs"),
+            "frame_blocks_per_s": value * L,
+            "roofline": {"bound": "hbm", "kernel": "pool_mean_kernel", "achieved": pool_gbs, "peak": peak,
+                         "unit": "GB/s", "frac": pool_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": pool_bytes, "avg_launch_ms": stage_avg["pool"]},
+            "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s",
+                              "frac": step_gbs / peak, "algorithmic_bytes_per_step": step_bytes},
+            "stage_ms_per_chunk_step": stage_avg,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--videos", type=int, default=128, help="videos per GPU")
+    ap.add_argument("--chunks", type=int, default=8, help="sequential chunks per video")
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32x3"])
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference_impl(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,173 @@
+/*
+ * infltm.h -- C ABI of the B200-native infinity-Video LTM consolidation path (libinfltm.so).
+ *
+ * The reference (deep-spin/Infinite-Video) is pure Python; the interface this library sits under
+ * is `LongTermAttention.forward(k, q, new_doc, layer_n)`
+ * (infty-Video-LLaMA/InfVideoLLaMA/models/long_term_attention_gibbs.py:288-346, live "gibbs"
+ * variant; .../long_term_attention.py:259-392, Gaussian variant).  The Python mirror of that class
+ * (infinite_video_b200/ltm.py) binds these entry points with ctypes; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to caller-owned memory unless the name ends in `_host`;
+ *     tensors are contiguous row-major; fp32 unless stated; indices int32; uniforms fp64.
+ *   - `stream` is a cudaStream_t passed as void*; nothing here synchronises or allocates device
+ *     memory (exception: the *_host entry points enqueue cudaMemcpyAsync on `stream`).
+ *   - return 0 on success, <0 on error; ltm_last_error() gives the thread-local message.
+ *   - symbols: Bv videos, L frames per chunk, T tokens per frame, e encoder width, N basis
+ *     functions, S=512 re-samples, H heads, d head size, D=H*d, Q queries.
+ */
+#ifndef INFLTM_H
+#define INFLTM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LTM_STICKY_EDGES 129
+
+int         ltm_version(void);
+const char* ltm_last_error(void);
+/* 0 when the loaded binary carries sm_100a code and a tcgen05-capable device is current */
+int         ltm_device_check(void);
+
+/* ---- R4: frame pooling.  gibbs:304  `k.reshape(B,L,T,e).mean(dim=2)`
+ * k[Bv,L,T,e] -> xpart[Bv,L,splits,e]; the mean of frame l is sum_s xpart[.,l,s,:]. */
+int ltm_pool_mean(const float* k, float* xpart, int Bv, int L, int T, int e, int splits, void* stream);
+
+/* ---- R6: sticky histogram of the previous call's density.  gibbs:196-203 (+score :224-230,
+ * compute_probability :232-249).  scores[Bv,H,Q,N] -> hist_part[Bv,H,127] (sum over q; the sum
+ * over heads happens in ltm_resample).  Normally fused into ltm_cont_attn_rect. */
+int ltm_sticky_hist_rect(const float* scores, const int32_t* jb, const float* tb, float* hist_part,
+                         int Bv, int H, int Q, int N, void* stream);
+
+/* ---- G3: sticky histogram from the previous (mu, sigma).  long_term_attention.py:220-229.
+ * mu,sd[Bv,R] -> hist[Bv,128] (un-normalised). */
+int ltm_sticky_hist_gauss(const float* mu, const float* sd, const float* tb, float* hist,
+                          int Bv, int R, void* stream);
+
+/* ---- R7/G3: inverse-CDF re-sampling == Categorical(p).sample((S,)) with explicit uniforms.
+ * gibbs:204-208, gauss:230-238.  hist_part[Bv,parts,ncat] is summed over `parts` in a fixed
+ * order; normalize!=0 applies the reference's two p/sum(p) passes first.  CDF = sequential fp32
+ * running sum / total, last entry forced to 1, draw -> first category with cdf >= u (fp64).
+ * Outputs (any may be NULL): p_out[Bv,ncat] the probabilities used; b_draw[Bv,S] bins in draw
+ * order; b_used[Bv,S] bins as consumed (sorted ascending when sort!=0, the Gaussian variant);
+ * ts[Bv,S]=bins[b_used]; idx[Bv,S]=bin2basis[b_used] (bin2basis may be NULL -> idx=b_used). */
+int ltm_resample(const float* hist_part, int parts, int ncat, int normalize, const double* u,
+                 const float* bins, const int32_t* bin2basis, int sort,
+                 float* p_out, int32_t* b_draw, int32_t* b_used, float* ts, int32_t* idx,
+                 int Bv, int S, void* stream);
+
+/* ---- R3/R5/R8: memory contraction + regression for rectangular bases.  gibbs:184-222.
+ * The ridge operator has <=1 non-zero per row, so B = G^T [xm ; x] is a segmented mean:
+ *   B_new[v,j,:] = g[j] * sum_{p in seg(j)} row(p),  row(p) = B_past[v, idx[v,p], :] for p < S
+ *   (zero row when idx < 0), else the pooled frame p-S.  Table set 0 (first chunk, members are
+ *   frame indices) is used where new_doc[v] != 0 (or B_past == NULL), table set 1 otherwise. */
+int ltm_consolidate_rect(const float* B_past, const float* xpart, const int32_t* idx,
+                         const uint8_t* new_doc,
+                         const int32_t* seg_ptr0, const int32_t* seg_mem0, const float* g0,
+                         const int32_t* seg_ptr1, const int32_t* seg_mem1, const float* g1,
+                         float* B_new, int Bv, int N, int e, int L, int splits, int S, void* stream);
+
+/* ---- batched GEMM on tcgen05 tensor cores (kind::tf32, fp32 operands fed by TMA, fp32
+ * accumulate in TMEM).  C[b] (M x Nc, ldc) = A[b] (M x K) * B[b] (K x Nc) (+ bias[Nc]).
+ *   a_kmajor: A[b] stored [M][K] (K contiguous, lda = row pitch) else [K][M] (lda = pitch of a K row)
+ *   b_kmajor: B[b] stored [Nc][K] (K contiguous)              else [K][Nc]
+ *   B may be split along K: rows [0,K1) come from B, rows [K1,K) from B2 (same layout rules);
+ *   pass B2 = NULL, K1 = K for a single segment.
+ *   batch strides in elements (0 = operand shared by all batches).
+ *   precision: 1 = single-pass TF32; 3 = split hi/lo 3-pass (fp32-grade accuracy).
+ *   impl: 0 = tcgen05 (product path), 1 = fp32 SIMT check kernel (tests/debug only). */
+typedef struct {
+  const float* A;  int64_t lda;  int64_t strideA;  int a_kmajor;
+  const float* B;  int64_t ldb;  int64_t strideB;  int b_kmajor;
+  const float* B2; int64_t ldb2; int64_t strideB2; int K1;
+  const float* bias;
+  float* C;        int64_t ldc;  int64_t strideC;
+  int M, Nc, K, batch;
+  int precision;
+  int impl;
+} ltm_gemm_args;
+int ltm_gemm(const ltm_gemm_args* args, void* stream);
+
+/* ---- R9: K/V projection.  gibbs:312-313  keys=proj_key(B), values=proj_value(B).
+ * KV[M, 2D] = Bcoef[M, e] * Wkv[2D, e]^T + bkv   (M = Bv*N; Wkv = [W_key ; W_value]). */
+int ltm_project_kv(const float* Bcoef, const float* Wkv, const float* bkv, float* KV,
+                   int M, int e, int D2, int precision, int impl, void* stream);
+
+/* ---- R10/R11 (+R6 fused): continuous attention over rectangular bases.  gibbs:224-286,:346.
+ * r_j = W_j e^{S_j} / (sum_i W_i e^{S_i} + W_out),  S = (q_h/sqrt(d)) K_h^T,  ctx = r V.
+ * q[Bv,Q,D], KV[Bv,N,2D] -> ctx[Bv,Q,D]; optional scores_out[Bv,H,Q,N];
+ * optional hist_part[Bv, H*ceil(Q/32), 127] (next call's sticky histogram partials). */
+int ltm_cont_attn_rect(const float* q, const float* KV, const float* W, float W_out,
+                       const int32_t* jb, const float* tb,
+                       float* ctx, float* scores_out, float* hist_part,
+                       int Bv, int Q, int N, int H, int d, void* stream);
+
+/* ---- G4: continuous attention, Gaussian closed form.  long_term_attention.py:286-325.
+ * a = softmax(20 S); mu = a.mu_b; var = a.(mu_b^2+sigma_b^2) - mu^2;
+ * r_j = N(mu; mu_j, sigma_j^2 + var); ctx = r V.  Also writes mu_out, sd_out [Bv, H*Q]. */
+int ltm_cont_attn_gauss(const float* q, const float* KV, const float* basis_mu, const float* basis_sigma,
+                        float* ctx, float* scores_out, float* mu_out, float* sd_out,
+                        int Bv, int Q, int N, int H, int d, void* stream);
+
+/* ---- G1: Gaussian RBF evaluation.  basis_functions.py:158-164.
+ * out[p, j] (ld) = N(t_p; mu_j, sigma_j^2); t may be gathered: t_p = tvals[tidx[p]] when tidx != NULL. */
+int ltm_rbf_eval(const float* tvals, const int32_t* tidx, const float* basis_mu, const float* basis_sigma,
+                 float* out, int64_t ld, int P, int N, void* stream);
+
+/* ---- G2: ridge operator  G = F^T (F F^T + ridge I)^-1 for the Gaussian design matrix, solved in
+ * fp64 on the device.  long_term_attention.py:70-86.  positions[P] (padded), rows [trim, trim+rows)
+ * are kept.  Outputs (either may be NULL): G[rows, N] and GT[N, rows] (row pitch ldgt >= rows) in fp32.
+ * workspace: fp64, ltm_ridge_workspace_doubles(P, N) elements. */
+int64_t ltm_ridge_workspace_doubles(int P, int N);
+int ltm_ridge_solve(const float* positions, int P, int trim, int rows,
+                    const float* basis_mu, const float* basis_sigma, int N, double ridge,
+                    float* G, float* GT, int64_t ldgt, double* workspace, void* stream);
+
+/* ---- gather rows: out[v, s, :] = src[v, idx[v,s], :]  (zero row when idx < 0) */
+int ltm_gather_rows(const float* src, const int32_t* idx, float* out, int Bv, int rows_src, int S, int e,
+                    void* stream);
+
+/* ---- whole per-chunk step of variant R for Bv videos (device buffers), and the same through
+ * host buffers (H2D of k,q,u,new_doc and D2H of ctx enqueued on `stream`; caller synchronises). */
+typedef struct {
+  int Bv, L, T, e, N, Q, H, d, S, splits, sticky, precision, gemm_impl;
+  /* constant tables (device) */
+  const int32_t *seg_ptr0, *seg_mem0; const float* g0;
+  const int32_t *seg_ptr1, *seg_mem1; const float* g1;
+  const int32_t* jb; const float* tb; const float* bins; const int32_t* bin2basis;
+  const int32_t* idx_uniform;           /* [S] used when sticky == 0 */
+  const float* W; float W_out;
+  const float *Wkv, *bkv;               /* [2D,e], [2D] */
+  /* per-video state (device) */
+  const float* B_past; float* B_new;    /* [Bv,N,e] ping-pong, caller swaps after the call */
+  float* hist_part;                     /* [Bv, H*ceil(Q/32), 127] previous call's partials (in) and new (out) */
+  /* workspace (device) */
+  float* xpart;                         /* [Bv,L,splits,e] */
+  float* KV;                            /* [Bv,N,2D] */
+  int32_t *b_draw, *idx; float* ts;     /* [Bv,S] */
+  float* p;                             /* [Bv,127] */
+  float* scores;                        /* optional [Bv,H,Q,N] */
+  /* device staging for the *_host entry point */
+  float* k_dev; float* q_dev; double* u_dev; uint8_t* new_doc_dev; float* ctx_dev;
+  /* optional cudaEvent_t pairs recorded on `stream` around each stage (NULL = skip):
+   * [0,1] pool  [2,3] re-sample  [4,5] consolidate  [6,7] K/V projection  [8,9] attention */
+  void* prof_events[10];
+} ltm_rect_step_args;
+int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const float* q, const double* u,
+                  const uint8_t* new_doc, float* ctx, void* stream);
+int ltm_rect_step_host(const ltm_rect_step_args* a, const float* k_host, const float* q_host,
+                       const double* u_host, const uint8_t* new_doc_host, float* ctx_host, void* stream);
+
+/* ---- CUDA-event helpers so a ctypes host can time stages on the launching stream */
+int ltm_event_create(void** ev);
+int ltm_event_record(void* ev, void* stream);
+int ltm_event_elapsed_ms(void* start, void* stop, float* ms);   /* synchronises on `stop` */
+int ltm_event_destroy(void* ev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INFLTM_H */

@@ -1,0 +1,119 @@
+"""ctypes binding of libinfltm.so (include/infltm.h).  No CPU fallback: if the library is missing or
+a call fails, this raises."""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libinfltm.so")
+_lib = None
+
+c_f32p = C.c_void_p
+c_i32p = C.c_void_p
+c_f64p = C.c_void_p
+c_u8p = C.c_void_p
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("lda", C.c_int64), ("strideA", C.c_int64), ("a_kmajor", C.c_int),
+        ("B", C.c_void_p), ("ldb", C.c_int64), ("strideB", C.c_int64), ("b_kmajor", C.c_int),
+        ("B2", C.c_void_p), ("ldb2", C.c_int64), ("strideB2", C.c_int64), ("K1", C.c_int),
+        ("bias", C.c_void_p),
+        ("C", C.c_void_p), ("ldc", C.c_int64), ("strideC", C.c_int64),
+        ("M", C.c_int), ("Nc", C.c_int), ("K", C.c_int), ("batch", C.c_int),
+        ("precision", C.c_int), ("impl", C.c_int),
+    ]
+
+
+class RectStepArgs(C.Structure):
+    _fields_ = [
+        ("Bv", C.c_int), ("L", C.c_int), ("T", C.c_int), ("e", C.c_int), ("N", C.c_int), ("Q", C.c_int),
+        ("H", C.c_int), ("d", C.c_int), ("S", C.c_int), ("splits", C.c_int), ("sticky", C.c_int),
+        ("precision", C.c_int), ("gemm_impl", C.c_int),
+        ("seg_ptr0", C.c_void_p), ("seg_mem0", C.c_void_p), ("g0", C.c_void_p),
+        ("seg_ptr1", C.c_void_p), ("seg_mem1", C.c_void_p), ("g1", C.c_void_p),
+        ("jb", C.c_void_p), ("tb", C.c_void_p), ("bins", C.c_void_p), ("bin2basis", C.c_void_p),
+        ("idx_uniform", C.c_void_p),
+        ("W", C.c_void_p), ("W_out", C.c_float),
+        ("Wkv", C.c_void_p), ("bkv", C.c_void_p),
+        ("B_past", C.c_void_p), ("B_new", C.c_void_p),
+        ("hist_part", C.c_void_p),
+        ("xpart", C.c_void_p), ("KV", C.c_void_p),
+        ("b_draw", C.c_void_p), ("idx", C.c_void_p), ("ts", C.c_void_p),
+        ("p", C.c_void_p), ("scores", C.c_void_p),
+        ("k_dev", C.c_void_p), ("q_dev", C.c_void_p), ("u_dev", C.c_void_p), ("new_doc_dev", C.c_void_p),
+        ("ctx_dev", C.c_void_p),
+        ("prof_events", C.c_void_p * 10),
+    ]
+
+
+_I, _F, _P, _L = C.c_int, C.c_float, C.c_void_p, C.c_int64
+_SIGS = {
+    "ltm_version": (C.c_int, []),
+    "ltm_last_error": (C.c_char_p, []),
+    "ltm_device_check": (C.c_int, []),
+    "ltm_pool_mean": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "ltm_sticky_hist_rect": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "ltm_sticky_hist_gauss": (C.c_int, [_P, _P, _P, _P, _I, _I, _P]),
+    "ltm_resample": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "ltm_consolidate_rect": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "ltm_gemm": (C.c_int, [C.POINTER(GemmArgs), _P]),
+    "ltm_project_kv": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "ltm_cont_attn_rect": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "ltm_cont_attn_gauss": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "ltm_rbf_eval": (C.c_int, [_P, _P, _P, _P, _P, _L, _I, _I, _P]),
+    "ltm_ridge_workspace_doubles": (C.c_int64, [_I, _I]),
+    "ltm_ridge_solve": (C.c_int, [_P, _I, _I, _I, _P, _P, _I, C.c_double, _P, _P, _L, _P, _P]),
+    "ltm_gather_rows": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "ltm_event_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "ltm_event_record": (C.c_int, [_P, _P]),
+    "ltm_event_elapsed_ms": (C.c_int, [_P, _P, C.POINTER(C.c_float)]),
+    "ltm_event_destroy": (C.c_int, [_P]),
+    "ltm_rect_step": (C.c_int, [C.POINTER(RectStepArgs), _P, _P, _P, _P, _P, _P]),
+    "ltm_rect_step_host": (C.c_int, [C.POINTER(RectStepArgs), _P, _P, _P, _P, _P, _P]),
+}
+EXPORTED = tuple(_SIGS)
+
+
+def lib():
+    """The loaded library.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m infinite_video_b200.build` "
+                "(nvcc, sm_100a).  There is no CPU fallback for the LTM consolidation path.")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().ltm_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libinfltm {what} failed (rc={rc}): {msg}")
+
+
+def ptr(t):
+    """Device (or pinned host) pointer of a contiguous tensor; None -> NULL."""
+    if t is None:
+        return None
+    if not t.is_contiguous():
+        raise ValueError("libinfltm needs contiguous tensors")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise ValueError("libinfltm operates on CUDA tensors only (no CPU fallback)")

@@ -1,0 +1,341 @@
+"""LTM consolidation for Bv independent videos with explicit per-video state and explicit uniforms.
+
+This is the layer the reference does not have: its module is batch-1 and sequential
+(long_term_attention_gibbs.py:346 `reshape(1, qlen, -1)`, :208 `ts[0]`).  Chunks of one video stay strictly
+sequential (B_past and the sticky density depend on the previous call), videos are independent, so the
+batch dimension is the only free axis and every kernel carries it.
+
+State per video
+  variant R: B_past[N,e]; sticky histogram partials of the previous call's density [H*ceil(Q/32),127]
+  variant G: B_past[N,e]; (mu, sigma)[H*Q] of the previous call
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import ops, tables
+from ._capi import RectStepArgs, check, lib, ptr, require_cuda, stream_ptr
+
+SM_COUNT = 148
+
+
+def _as_flags(new_doc, Bv, device):
+    """bool | sequence | tensor -> (all_new: bool|None, uint8 device tensor|None)."""
+    if isinstance(new_doc, (bool, int)):
+        return bool(new_doc), None
+    t = torch.as_tensor(new_doc)
+    if t.numel() != Bv:
+        raise ValueError("new_doc must be a bool or one flag per video")
+    t = t.to(device=device, dtype=torch.uint8).contiguous()
+    return None, t
+
+
+def _pad_rows(m):
+    """Copy a 2-D matrix into storage whose row pitch is a multiple of 4 floats (TMA: 16-byte pitches)."""
+    r, c = m.shape
+    buf = torch.zeros(r, (c + 3) // 4 * 4, device=m.device, dtype=torch.float32)
+    buf[:, :c] = m
+    return buf[:, :c]
+
+
+class _BatchedBase:
+    def __init__(self, num_basis, tau, w_key, b_key, w_value, b_value, n_heads, head_size, sticky, nb_samples,
+                 precision, gemm_impl, device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("the LTM consolidation path runs on CUDA devices only (no CPU fallback)")
+        self.N = int(num_basis)
+        self.tau = float(tau)
+        self.H, self.d = int(n_heads), int(head_size)
+        self.D = self.H * self.d
+        self.sticky = bool(sticky)
+        self.S = int(nb_samples)
+        self.precision = precision
+        self.gemm_impl = gemm_impl
+        self.set_projections(w_key, b_key, w_value, b_value)
+        self.Bv = None
+        self.has_state = False
+
+    def set_projections(self, w_key, b_key, w_value, b_value):
+        """[W_key ; W_value] -> one [2D,e] operand so K and V come out of a single GEMM (gibbs:312-313)."""
+        dev = self.device
+        wk = w_key.detach().to(dev, torch.float32)
+        wv = w_value.detach().to(dev, torch.float32)
+        self.e = wk.shape[1]
+        if wk.shape[0] != self.D or wv.shape != wk.shape:
+            raise ValueError(f"projection weights must be [{self.D}, e]")
+        bk = torch.zeros(self.D, device=dev) if b_key is None else b_key.detach().to(dev, torch.float32)
+        bv = torch.zeros(self.D, device=dev) if b_value is None else b_value.detach().to(dev, torch.float32)
+        self.Wkv = torch.cat([wk, wv], 0).contiguous()
+        self.bkv = torch.cat([bk, bv], 0).contiguous()
+
+    def reset(self):
+        """Forget every video (new_doc for all)."""
+        self.has_state = False
+
+
+class BatchedRectLTM(_BatchedBase):
+    """Variant R ("gibbs", the live module): rectangular bases, Gibbs density.
+    One `step` == one `LongTermAttention.forward` per video (gibbs:288-346)."""
+
+    def __init__(self, num_basis, tau, w_key, b_key, w_value, b_value, *, n_heads=12, head_size=64,
+                 tokens_per_frame=32, sticky=True, nb_samples=tables.NB_SAMPLES, precision="tf32",
+                 gemm_impl="tcgen05", device="cuda", keep_scores=False):
+        super().__init__(num_basis, tau, w_key, b_key, w_value, b_value, n_heads, head_size, sticky, nb_samples,
+                         precision, gemm_impl, device)
+        self.T = int(tokens_per_frame)
+        self.keep_scores = keep_scores
+        self.prof_events = None       # optional list of 10 cudaEvent_t handles (bench.py stage timing)
+        self._ws = {}
+        self._B = None
+        self._cur = 0
+        self.last = {}
+
+    # ------------------------------------------------------------------ buffers
+    def _workspace(self, Bv, L, Q):
+        key = (Bv, L, Q)
+        ws = self._ws.get(key)
+        if ws is None:
+            dev = self.device
+            units = Bv * L
+            splits = max(1, min(self.T, -(-SM_COUNT * 8 // units)))
+            f32 = dict(device=dev, dtype=torch.float32)
+            i32 = dict(device=dev, dtype=torch.int32)
+            ws = dict(
+                splits=splits,
+                xpart=torch.empty(Bv, L, splits, self.e, **f32),
+                KV=torch.empty(Bv, self.N, 2 * self.D, **f32),
+                b_draw=torch.empty(Bv, self.S, **i32), idx=torch.empty(Bv, self.S, **i32),
+                ts=torch.empty(Bv, self.S, **f32), p=torch.empty(Bv, 127, **f32),
+                scores=torch.empty(Bv, self.H, Q, self.N, **f32) if self.keep_scores else None,
+                k_dev=None, q_dev=None, u_dev=None, nd_dev=None, ctx_dev=None,
+            )
+            self._ws = {key: ws}          # one live shape at a time
+        return ws
+
+    def _state(self, Bv, Q):
+        qt = (Q + 31) // 32
+        if self._B is None or self.Bv != Bv or self._hist.shape[1] != self.H * qt:
+            f32 = dict(device=self.device, dtype=torch.float32)
+            self._B = [torch.zeros(Bv, self.N, self.e, **f32), torch.zeros(Bv, self.N, self.e, **f32)]
+            self._hist = torch.ones(Bv, self.H * qt, 127, **f32)
+            self._cur = 0
+            self.Bv = Bv
+            self.has_state = False
+
+    @property
+    def B_past(self):
+        return self._B[self._cur] if (self._B is not None and self.has_state) else None
+
+    # ------------------------------------------------------------------ one chunk
+    def _args(self, Bv, L, Q, ws, tab, tdev):
+        a = RectStepArgs()
+        a.Bv, a.L, a.T, a.e, a.N, a.Q, a.H, a.d, a.S = Bv, L, self.T, self.e, self.N, Q, self.H, self.d, self.S
+        a.splits, a.sticky = ws["splits"], int(self.sticky)
+        a.precision, a.gemm_impl = ops.PRECISION[self.precision], ops.GEMM_IMPL[self.gemm_impl]
+        for name in ("seg_ptr0", "seg_mem0", "g0", "seg_ptr1", "seg_mem1", "g1", "jb", "tb", "bins", "bin2basis",
+                     "idx_uniform", "W"):
+            setattr(a, name, tdev[name].data_ptr())
+        a.W_out = tab.W_out
+        a.Wkv, a.bkv = self.Wkv.data_ptr(), self.bkv.data_ptr()
+        a.B_past = self._B[self._cur].data_ptr() if self.has_state else None
+        a.B_new = self._B[1 - self._cur].data_ptr()
+        a.hist_part = self._hist.data_ptr()
+        a.xpart, a.KV = ws["xpart"].data_ptr(), ws["KV"].data_ptr()
+        a.b_draw, a.idx, a.ts, a.p = (ws["b_draw"].data_ptr(), ws["idx"].data_ptr(), ws["ts"].data_ptr(),
+                                      ws["p"].data_ptr())
+        a.scores = ws["scores"].data_ptr() if ws["scores"] is not None else None
+        for f, n in (("k_dev", "k_dev"), ("q_dev", "q_dev"), ("u_dev", "u_dev"), ("new_doc_dev", "nd_dev"),
+                     ("ctx_dev", "ctx_dev")):
+            setattr(a, f, ws[n].data_ptr() if ws[n] is not None else None)
+        if self.prof_events is not None:
+            for i, ev in enumerate(self.prof_events):
+                a.prof_events[i] = ev
+        return a
+
+    def _prepare(self, kshape, qshape, new_doc):
+        Bv, LT, e = kshape
+        if e != self.e:
+            raise ValueError(f"k has width {e}, projections expect {self.e}")
+        if LT % self.T:
+            raise ValueError(f"k has {LT} tokens, not a multiple of tokens_per_frame={self.T}")
+        L = LT // self.T
+        Q = qshape[1]
+        if qshape[0] != Bv or qshape[2] != self.D:
+            raise ValueError(f"q must be [{Bv}, Q, {self.D}]")
+        self._state(Bv, Q)
+        all_new, flags = _as_flags(new_doc, Bv, self.device)
+        if all_new:
+            self.has_state = False
+        elif flags is not None and not self.has_state:
+            flags = None                     # nothing to keep anyway: everything is a first chunk
+        tab = tables.rect_tables(L, self.N, self.tau, self.S)
+        return Bv, L, Q, tab, tab.to(self.device), flags
+
+    def _finish(self, ws):
+        self._cur = 1 - self._cur
+        self.has_state = True
+        self.last = dict(b=ws["b_draw"], ts=ws["ts"], idx=ws["idx"], p=ws["p"], scores=ws["scores"], KV=ws["KV"])
+
+    def step(self, k, q, u=None, new_doc=False):
+        """k[Bv, L*T, e], q[Bv,Q,D] fp32 CUDA; u[Bv,S] fp64 uniforms (needed from the second chunk on when
+        sticky); new_doc: bool or per-video flags.  Returns ctx[Bv,Q,D]."""
+        require_cuda(k, q, u)
+        if k.dtype != torch.float32 or q.dtype != torch.float32:
+            raise ValueError("k and q must be float32")
+        k, q = k.contiguous(), q.contiguous()
+        Bv, L, Q, tab, tdev, flags = self._prepare(k.shape, q.shape, new_doc)
+        ws = self._workspace(Bv, L, Q)
+        if self.has_state and self.sticky:
+            if u is None or u.dtype != torch.float64 or tuple(u.shape) != (Bv, self.S):
+                raise ValueError(f"sticky re-sampling needs u: float64 [{Bv},{self.S}]")
+            u = u.contiguous()
+        ctx = torch.empty(Bv, Q, self.D, device=self.device, dtype=torch.float32)
+        a = self._args(Bv, L, Q, ws, tab, tdev)
+        check(lib().ltm_rect_step(C.byref(a), ptr(k), ptr(q), ptr(u), ptr(flags), ptr(ctx),
+                                  stream_ptr(self.device)), "rect_step")
+        self._finish(ws)
+        return ctx
+
+    def step_host(self, k_host, q_host, u_host=None, new_doc=False, out=None):
+        """Same as `step` but through HOST buffers (ideally pinned): the C entry point enqueues the H2D copies,
+        the kernels and the D2H copy of ctx on the current stream.  Returns the host ctx tensor; the caller
+        synchronises the stream before reading it."""
+        if k_host.is_cuda or q_host.is_cuda:
+            raise ValueError("step_host takes host tensors")
+        Bv, L, Q, tab, tdev, flags = self._prepare(k_host.shape, q_host.shape, new_doc)
+        ws = self._workspace(Bv, L, Q)
+        dev = self.device
+        if ws["k_dev"] is None:
+            ws["k_dev"] = torch.empty(Bv, L * self.T, self.e, device=dev, dtype=torch.float32)
+            ws["q_dev"] = torch.empty(Bv, Q, self.D, device=dev, dtype=torch.float32)
+            ws["u_dev"] = torch.empty(Bv, self.S, device=dev, dtype=torch.float64)
+            ws["nd_dev"] = torch.empty(Bv, device=dev, dtype=torch.uint8)
+            ws["ctx_dev"] = torch.empty(Bv, Q, self.D, device=dev, dtype=torch.float32)
+        if out is None:
+            out = torch.empty(Bv, Q, self.D, dtype=torch.float32, pin_memory=True)
+        need_u = self.has_state and self.sticky
+        if need_u and (u_host is None or u_host.dtype != torch.float64):
+            raise ValueError("sticky re-sampling needs u_host: float64 [Bv,S]")
+        a = self._args(Bv, L, Q, ws, tab, tdev)
+        nd_host = None
+        if flags is not None:
+            nd_host = torch.as_tensor(new_doc).to(torch.uint8).contiguous()
+        check(lib().ltm_rect_step_host(C.byref(a), ptr(k_host.contiguous()), ptr(q_host.contiguous()),
+                                       ptr(u_host.contiguous()) if need_u else None,
+                                       ptr(nd_host), ptr(out), stream_ptr(dev)), "rect_step_host")
+        self._keep = (k_host, q_host, u_host, nd_host)      # keep host buffers alive until the stream drains
+        self._finish(ws)
+        return out
+
+
+class BatchedGaussLTM(_BatchedBase):
+    """Variant G: Gaussian RBF bases, dense ridge regression, closed-form continuous softmax
+    (long_term_attention.py:259-325).  `k` is consumed un-pooled: [Bv, Lk, e]."""
+
+    def __init__(self, num_basis, tau, w_key, b_key, w_value, b_value, *, sigmas=(0.005, 0.01), n_heads=12,
+                 head_size=64, sticky=True, nb_samples=tables.NB_SAMPLES, precision="tf32x3",
+                 proj_precision=None, gemm_impl="tcgen05", device="cuda", ridge=tables.RIDGE_PENALTY):
+        ns = len(sigmas)
+        n = int(num_basis)
+        if n % ns:
+            n += ns - n % ns
+        super().__init__(n, tau, w_key, b_key, w_value, b_value, n_heads, head_size, sticky, nb_samples,
+                         precision, gemm_impl, device)
+        self.sigmas = tuple(float(s) for s in sigmas)
+        self.proj_precision = proj_precision or precision
+        self.ridge = float(ridge)
+        self._ops = {}
+        self._B = None
+        self.last = {}
+
+    # ------------------------------------------------------------------ constant operators
+    def operators(self, L):
+        """Device tables + ridge operators for chunk length L (solved once, fp64, on the device)."""
+        op = self._ops.get(L)
+        if op is None:
+            t = tables.gauss_tables(L, self.N, self.tau, self.sigmas, self.S)
+            dev = self.device
+            f = lambda a: torch.from_numpy(a).to(dev)
+            op = dict(t=t, mu=f(t.basis_mu), sigma=f(t.basis_sigma), tb=f(t.tb), bins=f(t.bins))
+            _, op["G0T"] = ops.ridge_solve(f(t.pos0), t.trim0, L, op["mu"], op["sigma"], self.ridge,
+                                           want_G=False, want_GT=True)                       # [N, L]
+            _, op["GinfT"] = ops.ridge_solve(f(t.pos1), t.trim1, self.S + L, op["mu"], op["sigma"], self.ridge,
+                                             want_G=False, want_GT=True)                     # [N, S+L]
+            # design of the 128 possible sticky sample positions (bins[b], b=0..127): rows of Psi
+            op["Psi_tab"] = ops.rbf_eval(op["bins"][:128].contiguous(), op["mu"], op["sigma"])   # [128, N]
+            op["Psi_uniform"] = ops.rbf_eval(f(t.old_over_tau), op["mu"], op["sigma"])           # [S, N]
+            self._ops[L] = op
+        return op
+
+    def set_operators(self, L, G0=None, G_inf=None):
+        """Inject ridge operators ([L,N] / [S+L,N]) computed elsewhere (used by the parity tests to share
+        the reference's fp32 `.inverse()` result)."""
+        op = self.operators(L)
+        if G0 is not None:
+            op["G0T"] = _pad_rows(G0.to(self.device, torch.float32).t())
+        if G_inf is not None:
+            op["GinfT"] = _pad_rows(G_inf.to(self.device, torch.float32).t())
+
+    @property
+    def B_past(self):
+        return self._B if self.has_state else None
+
+    def step(self, k, q, u=None, new_doc=False):
+        """k[Bv,Lk,e], q[Bv,Q,D], u[Bv,S] fp64.  Returns ctx[Bv,Q,D]."""
+        require_cuda(k, q, u)
+        if k.dtype != torch.float32 or q.dtype != torch.float32:
+            raise ValueError("k and q must be float32")
+        k, q = k.contiguous(), q.contiguous()
+        Bv, L, e = k.shape
+        if e != self.e:
+            raise ValueError(f"k has width {e}, projections expect {self.e}")
+        if isinstance(new_doc, (bool, int)):
+            if new_doc:
+                self.has_state = False
+        else:
+            raise ValueError("variant G takes one new_doc flag for the whole batch")
+        if self.Bv != Bv:
+            self.Bv, self.has_state = Bv, False
+        op = self.operators(L)
+        info = {}
+        if not self.has_state:
+            # B = G0^T k      (A = G0T [N,L] K-major, shared;  B = k[v] [L,e] MN-major)
+            B = ops.gemm(op["G0T"], k, a_kmajor=True, b_kmajor=False, precision=self.precision, impl=self.gemm_impl)
+        else:
+            if self.sticky:
+                if u is None or u.dtype != torch.float64 or tuple(u.shape) != (Bv, self.S):
+                    raise ValueError(f"sticky re-sampling needs u: float64 [{Bv},{self.S}]")
+                hist = ops.sticky_hist_gauss(self._mu, self._sd, op["tb"])
+                rs = ops.resample(hist, u.contiguous(), op["bins"], None, normalize=True, sort=True)
+                info.update(p=rs["p"], b=rs["b_draw"], b_sorted=rs["b_used"], ts=rs["ts"])
+                # reconstruct the old signal at the 128 candidate positions, then gather the 512 drawn rows:
+                # xm[s] = Psi(ts_s) B_past  ==  (Psi_tab B_past)[b_s]
+                R = ops.gemm(op["Psi_tab"], self._B, a_kmajor=True, b_kmajor=False, precision=self.precision,
+                             impl=self.gemm_impl)                                          # [Bv,128,e]
+                xm = ops.gather_rows(R, rs["b_used"])                                       # [Bv,S,e]
+            else:
+                xm = ops.gemm(op["Psi_uniform"], self._B, a_kmajor=True, b_kmajor=False, precision=self.precision,
+                              impl=self.gemm_impl)
+            # B = G_inf^T [xm ; k]  without materialising the concatenation
+            B = ops.gemm(op["GinfT"], xm, B2=k, a_kmajor=True, b_kmajor=False, precision=self.precision,
+                         impl=self.gemm_impl)
+        self._B = B
+        KV = ops.project_kv(B, self.Wkv, self.bkv, precision=self.proj_precision, impl=self.gemm_impl)
+        KV = KV.view(Bv, self.N, 2 * self.D)
+        ctx, scores, mu, sd = ops.cont_attn_gauss(q, KV, op["mu"], op["sigma"], n_heads=self.H)
+        self._mu, self._sd = mu, sd
+        self.has_state = True
+        info.update(mu=mu, sd=sd, KV=KV)
+        self.last = info
+        return ctx
+
+
+def BatchedLTM(variant="gibbs", **kw):
+    """Factory: variant in {"gibbs", "gaussian"}."""
+    if variant in ("gibbs", "rect", "R"):
+        return BatchedRectLTM(**kw)
+    if variant in ("gaussian", "gauss", "G"):
+        return BatchedGaussLTM(**kw)
+    raise ValueError(f"unknown LTM variant {variant!r}")

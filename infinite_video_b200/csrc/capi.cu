@@ -1,0 +1,147 @@
+// C-ABI glue: error reporting, device check, and the fused per-chunk step of variant R.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace ltm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+__global__ void arch_probe_kernel(int* out) {
+#if defined(__CUDA_ARCH_FEAT_SM100_ALL) || defined(__CUDA_ARCH_SPECIFIC__) || (__CUDA_ARCH__ >= 1000)
+  *out = __CUDA_ARCH__;
+#else
+  *out = -1;
+#endif
+}
+
+}  // namespace ltm
+
+extern "C" int ltm_version(void) { return 100; }   // 0.1.0
+
+extern "C" const char* ltm_last_error(void) { return ltm::g_err; }
+
+extern "C" int ltm_device_check(void) {
+  using namespace ltm;
+  int dev = 0;
+  LTM_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  LTM_CUDA(cudaGetDeviceProperties(&prop, dev));
+  LTM_REQUIRE(prop.major == 10, "device %s is sm_%d%d; libinfltm carries sm_100a code only", prop.name, prop.major,
+              prop.minor);
+  cudaFuncAttributes fa;
+  LTM_CUDA(cudaFuncGetAttributes(&fa, arch_probe_kernel));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One chunk of variant R for Bv videos:  pool -> (re-sample) -> consolidate -> project K,V ->
+// continuous attention (+ next call's sticky histogram).  long_term_attention_gibbs.py:288-346.
+// ------------------------------------------------------------------------------------------------
+extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const float* q, const double* u,
+                             const uint8_t* new_doc, float* ctx, void* stream) {
+  using namespace ltm;
+  LTM_REQUIRE(a && k && q && ctx, "rect_step: null pointer");
+  const int D = a->H * a->d;
+  const int qtiles = (a->Q + 31) / 32;
+  cudaStream_t st_ = (cudaStream_t)stream;
+#define LTM_PROF(i) do { if (a->prof_events[i]) cudaEventRecord((cudaEvent_t)a->prof_events[i], st_); } while (0)
+  LTM_PROF(0);
+  int rc = ltm_pool_mean(k, a->xpart, a->Bv, a->L, a->T, a->e, a->splits, stream);
+  if (rc) return rc;
+  LTM_PROF(1);
+  const float* B_past = a->B_past;
+  const int32_t* idx = a->idx_uniform;     // non-sticky: fixed table shared by all videos
+  if (B_past != nullptr && a->sticky) {
+    LTM_REQUIRE(u != nullptr, "rect_step: sticky re-sampling needs the uniform draws");
+    LTM_PROF(2);
+    rc = ltm_resample(a->hist_part, a->H * qtiles, LTM_STICKY_EDGES - 2, 1, u, a->bins, a->bin2basis, 0, a->p,
+                      a->b_draw, nullptr, a->ts, a->idx, a->Bv, a->S, stream);
+    if (rc) return rc;
+    LTM_PROF(3);
+    idx = a->idx;
+  } else if (B_past != nullptr) {
+    // broadcast the uniform table: consolidate reads idx[v*S + p]; give every video the same row
+    LTM_REQUIRE(a->idx != nullptr, "rect_step: idx workspace missing");
+    for (int v = 0; v < a->Bv; ++v)
+      LTM_CUDA(cudaMemcpyAsync(a->idx + (size_t)v * a->S, a->idx_uniform, sizeof(int32_t) * a->S,
+                               cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    idx = a->idx;
+  }
+  LTM_PROF(4);
+  rc = ltm_consolidate_rect(B_past, a->xpart, idx, new_doc, a->seg_ptr0, a->seg_mem0, a->g0, a->seg_ptr1,
+                            a->seg_mem1, a->g1, a->B_new, a->Bv, a->N, a->e, a->L, a->splits, a->S, stream);
+  if (rc) return rc;
+  LTM_PROF(5);
+  LTM_PROF(6);
+  rc = ltm_project_kv(a->B_new, a->Wkv, a->bkv, a->KV, a->Bv * a->N, a->e, 2 * D, a->precision, a->gemm_impl, stream);
+  if (rc) return rc;
+  LTM_PROF(7);
+  LTM_PROF(8);
+  rc = ltm_cont_attn_rect(q, a->KV, a->W, a->W_out, a->jb, a->tb, ctx, a->scores, a->sticky ? a->hist_part : nullptr,
+                          a->Bv, a->Q, a->N, a->H, a->d, stream);
+  LTM_PROF(9);
+#undef LTM_PROF
+  return rc;
+}
+
+extern "C" int ltm_event_create(void** ev) {
+  using namespace ltm;
+  LTM_REQUIRE(ev != nullptr, "event_create: null pointer");
+  cudaEvent_t e;
+  LTM_CUDA(cudaEventCreate(&e));
+  *ev = (void*)e;
+  return 0;
+}
+extern "C" int ltm_event_record(void* ev, void* stream) {
+  using namespace ltm;
+  LTM_CUDA(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)stream));
+  return 0;
+}
+extern "C" int ltm_event_elapsed_ms(void* start, void* stop, float* ms) {
+  using namespace ltm;
+  LTM_REQUIRE(ms != nullptr, "event_elapsed_ms: null pointer");
+  LTM_CUDA(cudaEventSynchronize((cudaEvent_t)stop));
+  LTM_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+  return 0;
+}
+extern "C" int ltm_event_destroy(void* ev) {
+  using namespace ltm;
+  LTM_CUDA(cudaEventDestroy((cudaEvent_t)ev));
+  return 0;
+}
+
+extern "C" int ltm_rect_step_host(const ltm_rect_step_args* a, const float* k_host, const float* q_host,
+                                  const double* u_host, const uint8_t* new_doc_host, float* ctx_host, void* stream) {
+  using namespace ltm;
+  LTM_REQUIRE(a && k_host && q_host && ctx_host, "rect_step_host: null pointer");
+  LTM_REQUIRE(a->k_dev && a->q_dev && a->ctx_dev, "rect_step_host: device staging buffers missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t D = (size_t)a->H * a->d;
+  LTM_CUDA(cudaMemcpyAsync(a->k_dev, k_host, sizeof(float) * (size_t)a->Bv * a->L * a->T * a->e,
+                           cudaMemcpyHostToDevice, st));
+  LTM_CUDA(cudaMemcpyAsync(a->q_dev, q_host, sizeof(float) * (size_t)a->Bv * a->Q * D, cudaMemcpyHostToDevice, st));
+  const double* u_dev = nullptr;
+  if (u_host) {
+    LTM_REQUIRE(a->u_dev, "rect_step_host: u staging buffer missing");
+    LTM_CUDA(cudaMemcpyAsync(a->u_dev, u_host, sizeof(double) * (size_t)a->Bv * a->S, cudaMemcpyHostToDevice, st));
+    u_dev = a->u_dev;
+  }
+  const uint8_t* nd_dev = nullptr;
+  if (new_doc_host) {
+    LTM_REQUIRE(a->new_doc_dev, "rect_step_host: new_doc staging buffer missing");
+    LTM_CUDA(cudaMemcpyAsync(a->new_doc_dev, new_doc_host, (size_t)a->Bv, cudaMemcpyHostToDevice, st));
+    nd_dev = a->new_doc_dev;
+  }
+  int rc = ltm_rect_step(a, a->k_dev, a->q_dev, u_dev, nd_dev, a->ctx_dev, stream);
+  if (rc) return rc;
+  LTM_CUDA(cudaMemcpyAsync(ctx_host, a->ctx_dev, sizeof(float) * (size_t)a->Bv * a->Q * D, cudaMemcpyDeviceToHost, st));
+  return 0;
+}

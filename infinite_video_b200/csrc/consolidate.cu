@@ -1,0 +1,101 @@
+// R3/R5/R8 -- memory contraction + ridge regression for rectangular bases
+// (long_term_attention_gibbs.py:184-222, compute_G :68-84).
+//
+// With indicator bases F F^T is diagonal, so G = F^T (F F^T + 0.5 I)^-1 has one non-zero per row,
+// 1/(cnt_j + 0.5), and  B = G^T [xm ; x]  is a segmented mean over the (contiguous) positions that
+// fall into bin j: contracted re-samples of the old memory -- rows of B_past gathered through the
+// sticky sample indices, i.e. the one-hot product B_past^T Psi^T of :208-210 -- followed by the
+// new pooled frames.  One CTA produces one coefficient row; one thread one 128-bit column group.
+#include "common.cuh"
+
+namespace ltm {
+
+__global__ void __launch_bounds__(256)
+consolidate_rect_kernel(const float4* __restrict__ B_past, const float4* __restrict__ xpart,
+                        const int32_t* __restrict__ idx, const uint8_t* __restrict__ new_doc,
+                        const int32_t* __restrict__ seg_ptr0, const int32_t* __restrict__ seg_mem0,
+                        const float* __restrict__ g0,
+                        const int32_t* __restrict__ seg_ptr1, const int32_t* __restrict__ seg_mem1,
+                        const float* __restrict__ g1,
+                        float4* __restrict__ B_new, int N, int e4, int L, int splits, int S) {
+  const int j = blockIdx.x;
+  const int v = blockIdx.y;
+  const bool first = (B_past == nullptr) || (new_doc != nullptr && new_doc[v] != 0);
+  const int32_t* seg_ptr = first ? seg_ptr0 : seg_ptr1;
+  const int32_t* seg_mem = first ? seg_mem0 : seg_mem1;
+  const float g = first ? g0[j] : g1[j];
+  const int m0 = seg_ptr[j], m1 = seg_ptr[j + 1];
+  const int frame_base = first ? 0 : S;       // member ids >= frame_base are frames
+  const float4* xv = xpart + (size_t)v * L * splits * e4;
+  const float4* bv = first ? nullptr : B_past + (size_t)v * N * e4;
+  const int32_t* iv = first ? nullptr : idx + (size_t)v * S;
+  for (int c = threadIdx.x; c < e4; c += blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int m = m0; m < m1; ++m) {
+      const int p = seg_mem[m];
+      if (p >= frame_base) {
+        const float4* src = xv + (size_t)(p - frame_base) * splits * e4 + c;
+        for (int s = 0; s < splits; ++s) f4_add(acc, src[(size_t)s * e4]);
+      } else {
+        const int row = iv[p];
+        if (row >= 0) f4_add(acc, bv[(size_t)row * e4 + c]);
+      }
+    }
+    acc.x *= g; acc.y *= g; acc.z *= g; acc.w *= g;
+    B_new[((size_t)v * N + j) * e4 + c] = acc;
+  }
+}
+
+// out[v,s,:] = src[v, idx[v,s], :]
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float4* __restrict__ src, const int32_t* __restrict__ idx, float4* __restrict__ out,
+                   int rows_src, int S, int e4) {
+  const int s = blockIdx.x, v = blockIdx.y;
+  const int row = idx[(size_t)v * S + s];
+  for (int c = threadIdx.x; c < e4; c += blockDim.x) {
+    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row >= 0 && row < rows_src) val = src[((size_t)v * rows_src + row) * e4 + c];
+    out[((size_t)v * S + s) * e4 + c] = val;
+  }
+}
+
+}  // namespace ltm
+
+extern "C" int ltm_consolidate_rect(const float* B_past, const float* xpart, const int32_t* idx,
+                                    const uint8_t* new_doc,
+                                    const int32_t* seg_ptr0, const int32_t* seg_mem0, const float* g0,
+                                    const int32_t* seg_ptr1, const int32_t* seg_mem1, const float* g1,
+                                    float* B_new, int Bv, int N, int e, int L, int splits, int S, void* stream) {
+  using namespace ltm;
+  LTM_REQUIRE(xpart && B_new && seg_ptr0 && seg_mem0 && g0, "consolidate_rect: null pointer");
+  LTM_REQUIRE(B_past == nullptr || (idx && seg_ptr1 && seg_mem1 && g1),
+              "consolidate_rect: update tables / sample indices missing");
+  LTM_REQUIRE(B_past != B_new, "consolidate_rect: B_past and B_new must not alias (rows are gathered)");
+  LTM_REQUIRE(Bv > 0 && N > 0 && L > 0 && splits > 0 && S > 0 && e > 0 && e % 4 == 0,
+              "consolidate_rect: bad shape Bv=%d N=%d e=%d L=%d splits=%d", Bv, N, e, L, splits);
+  LTM_REQUIRE(Bv <= 65535, "consolidate_rect: Bv=%d exceeds grid.y", Bv);
+  LTM_REQUIRE(aligned16(B_past) && aligned16(xpart) && aligned16(B_new), "consolidate_rect: 16-byte alignment");
+  const int e4 = e / 4;
+  const int threads = e4 >= 256 ? 256 : ((e4 + 31) / 32) * 32;
+  dim3 grid(N, Bv);
+  consolidate_rect_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(B_past), reinterpret_cast<const float4*>(xpart), idx, new_doc,
+      seg_ptr0, seg_mem0, g0, seg_ptr1, seg_mem1, g1, reinterpret_cast<float4*>(B_new), N, e4, L, splits, S);
+  LTM_CHECK_LAUNCH("consolidate_rect");
+  return 0;
+}
+
+extern "C" int ltm_gather_rows(const float* src, const int32_t* idx, float* out, int Bv, int rows_src, int S,
+                               int e, void* stream) {
+  using namespace ltm;
+  LTM_REQUIRE(src && idx && out, "gather_rows: null pointer");
+  LTM_REQUIRE(Bv > 0 && Bv <= 65535 && S > 0 && e > 0 && e % 4 == 0, "gather_rows: bad shape");
+  LTM_REQUIRE(aligned16(src) && aligned16(out), "gather_rows: 16-byte alignment");
+  const int e4 = e / 4;
+  const int threads = e4 >= 256 ? 256 : ((e4 + 31) / 32) * 32;
+  dim3 grid(S, Bv);
+  gather_rows_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(src), idx, reinterpret_cast<float4*>(out), rows_src, S, e4);
+  LTM_CHECK_LAUNCH("gather_rows");
+  return 0;
+}

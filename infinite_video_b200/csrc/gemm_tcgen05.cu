@@ -1,0 +1,424 @@
+// Batched fp32-in / fp32-out GEMM on the 5th-generation tensor cores of sm_100a.
+//
+//   C[b] (M x Nc) = A[b] (M x K) * B[b] (K x Nc) (+ bias)         tcgen05.mma kind::tf32
+//
+// * operands stay fp32 in HBM; TMA (cp.async.bulk.tensor, SWIZZLE_128B) drops 128x32 / BNx32 tiles
+//   into shared memory, the tensor core reads them as TF32, the accumulator lives in TMEM (fp32) and
+//   comes back through tcgen05.ld for the bias/store epilogue.
+// * both operand major-nesses are supported (K-major rows of 32 floats, or MN-major slabs of
+//   [32 k][32 mn]); B may be the row-concatenation of two tensors (the Gaussian variant regresses
+//   [re-sampled memory ; new chunk] without materialising the concatenation,
+//   long_term_attention.py:249-250).
+// * precision 3 = split-TF32: every tile is split in shared memory into hi = tf32(x) and lo = x - hi
+//   and three MMAs (hi*hi + lo*hi + hi*lo) reproduce fp32-grade products.  Needed for the Gaussian
+//   variant whose RBF design values reach 80 with heavy cancellation (single-pass TF32 -> 1e-2 error).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2-5 = operand splitter (precision 3) and epilogue (TMEM lane quarter = warp_id % 4).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+
+namespace ltm {
+
+int gemm_simt_launch(const ltm_gemm_args& g, cudaStream_t stream);
+
+constexpr int BM = 128;
+constexpr int BK = 32;                       // 32 fp32 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 8;                    // 32 B of K per tcgen05.mma for tf32
+constexpr int GEMM_THREADS = 192;
+constexpr int A_BYTES = BM * BK * 4;         // 16 KB
+constexpr int SLAB_BYTES = 32 * BK * 4;      // MN-major slab: 32 k-rows x 128 B
+
+struct GemmDev {
+  float* C;
+  const float* bias;
+  long long ldc, strideC;
+  int M, Nc, K, K1;
+  int a_kmajor, b_kmajor;
+  int a_batched, b_batched, b2_batched, has_b2;
+};
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
+// Bounded wait: a broken pipeline traps (launch error) after ~2 s instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3fffu) == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 2000000000ull) {
+        printf("libinfltm gemm: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y,
+               blockIdx.z, threadIdx.x);
+        asm volatile("trap;");
+      }
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// UMMA shared-memory matrix descriptor (sm_100): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
+// version=1 [46,48) | layout SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+// K-major tile [rows][32 fp32]: 8-row groups 1024 B apart (SBO); K advances 32 B inside the swizzle row.
+// MN-major tile [mn/32 slabs][32 k][32 fp32]: slabs LBO = 4096 B apart, 8-k groups SBO = 1024 B apart;
+// K advances one 8-k group (1024 B) per MMA.
+__device__ __forceinline__ uint64_t operand_desc(uint32_t tile, int kmajor, int k) {
+  return kmajor ? umma_desc(tile + k * (UMMA_K * 4), 16, 1024) : umma_desc(tile + k * 1024, SLAB_BYTES, 1024);
+}
+
+template <int BN, int STAGES, bool SPLIT>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (SPLIT ? 2 : 1);
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + slack for 1024 B alignment
+  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+};
+
+template <int BN, int STAGES, bool SPLIT>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                 const __grid_constant__ CUtensorMap mapB2, const GemmDev g) {
+  using C_ = Cfg<BN, STAGES, SPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B wants 1024 B alignment
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bars = smem_base + STAGES * C_::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto split_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (3 * STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_al + STAGES * C_::STAGE_BYTES + 8 * (3 * STAGES + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, bz = blockIdx.z;
+  const int num_kb = (g.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+    if (g.has_b2) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB2)) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(split_bar(s), 128);      // every splitter thread arrives after its proxy fence
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)C_::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const int za = g.a_batched ? bz : 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_arrive_expect_tx(full_bar(s), A_BYTES + C_::B_BYTES);
+        const uint32_t sa = smem_base + s * C_::STAGE_BYTES;
+        const uint32_t sb = sa + A_BYTES;
+        const int k0 = kb * BK;
+        if (g.a_kmajor) {
+          tma_load_3d(&mapA, sa, full_bar(s), k0, m0, za);
+        } else {
+#pragma unroll
+          for (int i = 0; i < BM / 32; ++i) tma_load_3d(&mapA, sa + i * SLAB_BYTES, full_bar(s), m0 + 32 * i, k0, za);
+        }
+        const bool seg2 = g.has_b2 && (k0 >= g.K1);
+        const CUtensorMap* mb = seg2 ? &mapB2 : &mapB;
+        const int kk = seg2 ? k0 - g.K1 : k0;
+        const int zb = seg2 ? (g.b2_batched ? bz : 0) : (g.b_batched ? bz : 0);
+        if (g.b_kmajor) {
+          tma_load_3d(mb, sb, full_bar(s), kk, n0, zb);
+        } else {
+#pragma unroll
+          for (int i = 0; i < BN / 32; ++i) tma_load_3d(mb, sb + i * SLAB_BYTES, full_bar(s), n0 + 32 * i, kk, zb);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      // instruction descriptor: D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2, a_major bit15,
+      // b_major bit16 (1 = MN-major), N>>3 [17,23), M>>4 [24,29)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((g.a_kmajor ? 0u : 1u) << 15) |
+                             ((g.b_kmajor ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(BM >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(SPLIT ? split_bar(s) : full_bar(s), ph);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_base + s * C_::STAGE_BYTES;
+        const uint32_t sb = sa + A_BYTES;
+        const uint32_t sa_lo = sb + C_::B_BYTES;
+        const uint32_t sb_lo = sa_lo + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t da = operand_desc(sa, g.a_kmajor, k);
+          const uint64_t db = operand_desc(sb, g.b_kmajor, k);
+          tcgen05_mma_tf32(tmem_acc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          if (SPLIT) {
+            tcgen05_mma_tf32(tmem_acc, operand_desc(sa_lo, g.a_kmajor, k), db, idesc, 1u);
+            tcgen05_mma_tf32(tmem_acc, da, operand_desc(sb_lo, g.b_kmajor, k), idesc, 1u);
+          }
+        }
+        tcgen05_commit(empty_bar(s));          // frees the stage once these MMAs have read it
+      }
+      tcgen05_commit(tmem_full_bar);           // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ splitter + epilogue warps
+    const int et = threadIdx.x - 64;           // 0..127
+    if (SPLIT) {
+      constexpr int NV = (A_BYTES + C_::B_BYTES) / 16;      // float4 count of [A | B]
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(full_bar(s), ph);
+        float4* hi = reinterpret_cast<float4*>(smem_al + s * C_::STAGE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(smem_al + s * C_::STAGE_BYTES + A_BYTES + C_::B_BYTES);
+#pragma unroll 4
+        for (int f = et; f < NV; f += 128) {
+          const float4 x = hi[f];
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+          h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+          h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+          h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+          l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
+          hi[f] = h;
+          lo[f] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA)
+        mbar_arrive(split_bar(s));
+      }
+    }
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const int quarter = warp & 3;              // TMEM lanes [32*quarter, 32*quarter+32)
+    const int row = m0 + quarter * 32 + lane;
+    float* crow = g.C + (size_t)bz * g.strideC + (size_t)row * g.ldc;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= g.Nc) break;              // warp-uniform
+      uint32_t r[32];
+      const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < g.M) {
+        const int cbase = n0 + c0;
+        if (cbase + 32 <= g.Nc && ((g.ldc & 3) == 0)) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 o;
+            o.x = __uint_as_float(r[4 * i + 0]); o.y = __uint_as_float(r[4 * i + 1]);
+            o.z = __uint_as_float(r[4 * i + 2]); o.w = __uint_as_float(r[4 * i + 3]);
+            if (g.bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + cbase) + i);
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            reinterpret_cast<float4*>(crow + cbase)[i] = o;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (cbase + i < g.Nc) crow[cbase + i] = __uint_as_float(r[i]) + (g.bias ? g.bias[cbase + i] : 0.f);
+          }
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)C_::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+static int resolve_encode() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  LTM_REQUIRE(e == cudaSuccess && fn != nullptr && qres == cudaDriverEntryPointSuccess,
+              "gemm: cuTensorMapEncodeTiled unavailable (%s)", cudaGetErrorString(e));
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  return 0;
+}
+
+// rows x K operand.  kmajor: memory [rows][K] -> dims {K, rows, batch}, box {32, box_rows, 1};
+// otherwise memory [K][rows] -> dims {rows, K, batch}, box {32, 32, 1}.
+static int encode_operand(CUtensorMap* map, const float* base, int rows, int K, long long ld, long long bstride,
+                          int batch, int kmajor, int box_rows, const char* what) {
+  LTM_REQUIRE(aligned16(base), "gemm: %s base pointer must be 16-byte aligned", what);
+  LTM_REQUIRE(ld % 4 == 0 && ld > 0, "gemm: %s leading dimension %lld must be a positive multiple of 4", what, ld);
+  LTM_REQUIRE(bstride % 4 == 0, "gemm: %s batch stride %lld must be a multiple of 4", what, bstride);
+  const int nb = (bstride == 0) ? 1 : batch;
+  const long long inner = kmajor ? K : rows, outer = kmajor ? rows : K;
+  LTM_REQUIRE(ld >= inner, "gemm: %s leading dimension %lld < inner extent %lld", what, ld, inner);
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)nb};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4ull, (cuuint64_t)((bstride == 0 ? ld * outer : bstride) * 4ll)};
+  cuuint32_t box[3] = {32u, (cuuint32_t)(kmajor ? box_rows : 32), 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LTM_REQUIRE(r == CUDA_SUCCESS, "gemm: cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+  return 0;
+}
+
+template <int BN, int STAGES, bool SPLIT>
+static int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mB2, const GemmDev& d,
+                      int batch, cudaStream_t stream) {
+  using C_ = Cfg<BN, STAGES, SPLIT>;
+  static bool configured = false;
+  if (!configured) {
+    LTM_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C_::SMEM_BYTES));
+    configured = true;
+  }
+  dim3 grid((d.Nc + BN - 1) / BN, (d.M + BM - 1) / BM, batch);
+  LTM_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm: grid too large (M tiles %u, batch %u)", grid.y, grid.z);
+  gemm_tf32_kernel<BN, STAGES, SPLIT><<<grid, GEMM_THREADS, C_::SMEM_BYTES, stream>>>(mA, mB, mB2, d);
+  LTM_CHECK_LAUNCH("gemm(tcgen05)");
+  return 0;
+}
+
+static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
+  if (resolve_encode()) return -1;
+  const bool two = a.B2 != nullptr && a.K1 < a.K;
+  LTM_REQUIRE(!two || (a.K1 > 0 && a.K1 % BK == 0), "gemm: K1=%d must be a positive multiple of %d", a.K1, BK);
+  LTM_REQUIRE(a.precision == 1 || a.precision == 3, "gemm: precision must be 1 (tf32) or 3 (split tf32)");
+  const bool split = a.precision == 3;
+  const int bn = (!split && a.Nc > 128) ? 256 : 128;
+  const int K1 = two ? a.K1 : a.K;
+  CUtensorMap mA, mB, mB2;
+  if (encode_operand(&mA, a.A, a.M, a.K, a.lda, a.strideA, a.batch, a.a_kmajor, BM, "A")) return -1;
+  if (encode_operand(&mB, a.B, a.Nc, K1, a.ldb, a.strideB, a.batch, a.b_kmajor, bn, "B")) return -1;
+  if (two) {
+    if (encode_operand(&mB2, a.B2, a.Nc, a.K - K1, a.ldb2, a.strideB2, a.batch, a.b_kmajor, bn, "B2")) return -1;
+  } else {
+    mB2 = mB;
+  }
+  GemmDev d{};
+  d.C = a.C; d.bias = a.bias; d.ldc = a.ldc; d.strideC = a.strideC;
+  d.M = a.M; d.Nc = a.Nc; d.K = a.K; d.K1 = K1;
+  d.a_kmajor = a.a_kmajor ? 1 : 0; d.b_kmajor = a.b_kmajor ? 1 : 0;
+  d.a_batched = a.strideA != 0; d.b_batched = a.strideB != 0; d.b2_batched = a.strideB2 != 0; d.has_b2 = two ? 1 : 0;
+  if (split) return launch_cfg<128, 3, true>(mA, mB, mB2, d, a.batch, stream);
+  if (bn == 256) return launch_cfg<256, 4, false>(mA, mB, mB2, d, a.batch, stream);
+  return launch_cfg<128, 6, false>(mA, mB, mB2, d, a.batch, stream);
+}
+
+}  // namespace ltm
+
+extern "C" int ltm_gemm(const ltm_gemm_args* args, void* stream) {
+  using namespace ltm;
+  LTM_REQUIRE(args != nullptr, "gemm: null argument block");
+  const ltm_gemm_args& a = *args;
+  LTM_REQUIRE(a.A && a.B && a.C, "gemm: null operand");
+  LTM_REQUIRE(ltm::aligned16(a.C) && a.strideC % 4 == 0, "gemm: C must be 16-byte aligned with a batch stride multiple of 4");
+  LTM_REQUIRE(a.bias == nullptr || ltm::aligned16(a.bias), "gemm: bias must be 16-byte aligned");
+  LTM_REQUIRE(a.M > 0 && a.Nc > 0 && a.K > 0 && a.batch > 0, "gemm: bad shape M=%d N=%d K=%d batch=%d", a.M, a.Nc,
+              a.K, a.batch);
+  if (a.impl == 1) return gemm_simt_launch(a, (cudaStream_t)stream);
+  LTM_REQUIRE(a.impl == 0, "gemm: unknown impl %d", a.impl);
+  return gemm_tcgen05_launch(a, (cudaStream_t)stream);
+}
+
+extern "C" int ltm_project_kv(const float* Bcoef, const float* Wkv, const float* bkv, float* KV, int M, int e,
+                              int D2, int precision, int impl, void* stream) {
+  ltm_gemm_args a;
+  memset(&a, 0, sizeof(a));
+  a.A = Bcoef; a.lda = e; a.strideA = 0; a.a_kmajor = 1;
+  a.B = Wkv; a.ldb = e; a.strideB = 0; a.b_kmajor = 1;
+  a.B2 = nullptr; a.K1 = e;
+  a.bias = bkv;
+  a.C = KV; a.ldc = D2; a.strideC = 0;
+  a.M = M; a.Nc = D2; a.K = e; a.batch = 1;
+  a.precision = precision; a.impl = impl;
+  return ltm_gemm(&a, stream);
+}

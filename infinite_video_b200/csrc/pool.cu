@@ -1,0 +1,68 @@
+// R4 -- frame pooling: x[v,l,:] = mean_t k[v,l,t,:]   (long_term_attention_gibbs.py:304; the
+// VideoChat2 copy pools 14x14 tokens of width 1024, VCB/long_term_attention_gibbs.py:304).
+//
+// This kernel moves >90 % of the algorithmic bytes of a variant-R call (L*T*e*4 of the
+// 4*(L*T*e + 2*Q*D + 2*N*e) + 8*S bytes), so it is a pure HBM streamer: one CTA per
+// (frame, token-split), one thread per 128-bit column group, 8 independent 128-bit loads in
+// flight per thread through the read-only path with no L1 allocation and an L2 evict-first
+// policy (the chunk is read exactly once).  Partial sums over `splits` token ranges are kept
+// separate (deterministic, no atomics) and added by the consolidation kernel; splits > 1 only
+// exists to fill the 148 SMs when Bv*L is small.
+#include "common.cuh"
+
+namespace ltm {
+
+constexpr int POOL_UNROLL = 8;
+
+__global__ void __launch_bounds__(256)
+pool_mean_kernel(const float4* __restrict__ k, float4* __restrict__ xpart,
+                 int T, int e4, int splits, float Tf) {
+  const int unit = blockIdx.x / splits;          // (v*L + l)
+  const int sp = blockIdx.x - unit * splits;
+  const int r0 = (int)(((long long)T * sp) / splits);
+  const int r1 = (int)(((long long)T * (sp + 1)) / splits);
+  const uint64_t pol = policy_evict_first();
+  const float4* base = k + (size_t)unit * T * e4;
+  for (int c = threadIdx.x; c < e4; c += blockDim.x) {
+    float4 acc[POOL_UNROLL];
+#pragma unroll
+    for (int i = 0; i < POOL_UNROLL; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int r = r0;
+    for (; r + POOL_UNROLL <= r1; r += POOL_UNROLL) {
+      float4 v[POOL_UNROLL];
+#pragma unroll
+      for (int i = 0; i < POOL_UNROLL; ++i) v[i] = ldg_stream(base + (size_t)(r + i) * e4 + c, pol);
+#pragma unroll
+      for (int i = 0; i < POOL_UNROLL; ++i) f4_add(acc[i], v[i]);
+    }
+    for (; r < r1; ++r) f4_add(acc[0], ldg_stream(base + (size_t)r * e4 + c, pol));
+#pragma unroll
+    for (int s = POOL_UNROLL / 2; s > 0; s >>= 1)
+#pragma unroll
+      for (int i = 0; i < s; ++i) f4_add(acc[i], acc[i + s]);
+    float4 o = acc[0];
+    // torch.mean == sum / T (true division, so T = 196 rounds like the reference)
+    o.x = __fdiv_rn(o.x, Tf); o.y = __fdiv_rn(o.y, Tf); o.z = __fdiv_rn(o.z, Tf); o.w = __fdiv_rn(o.w, Tf);
+    xpart[((size_t)unit * splits + sp) * e4 + c] = o;
+  }
+}
+
+}  // namespace ltm
+
+extern "C" int ltm_pool_mean(const float* k, float* xpart, int Bv, int L, int T, int e, int splits,
+                             void* stream) {
+  using namespace ltm;
+  LTM_REQUIRE(k && xpart, "pool_mean: null pointer");
+  LTM_REQUIRE(Bv > 0 && L > 0 && T > 0 && e > 0, "pool_mean: bad shape Bv=%d L=%d T=%d e=%d", Bv, L, T, e);
+  LTM_REQUIRE(e % 4 == 0, "pool_mean: e=%d must be a multiple of 4 (128-bit access)", e);
+  LTM_REQUIRE(splits >= 1 && splits <= T, "pool_mean: splits=%d out of range [1,%d]", splits, T);
+  LTM_REQUIRE(aligned16(k) && aligned16(xpart), "pool_mean: pointers must be 16-byte aligned");
+  const long long units = (long long)Bv * L * splits;
+  LTM_REQUIRE(units < (1ll << 31), "pool_mean: too many frames");
+  const int e4 = e / 4;
+  const int threads = e4 >= 256 ? 256 : ((e4 + 31) / 32) * 32;
+  pool_mean_kernel<<<(unsigned)units, threads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(k), reinterpret_cast<float4*>(xpart), T, e4, splits, (float)T);
+  LTM_CHECK_LAUNCH("pool_mean");
+  return 0;
+}

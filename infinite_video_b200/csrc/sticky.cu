@@ -1,0 +1,217 @@
+// R6 / G3 / R7 -- sticky memories: density histogram over the 128 sticky bins and inverse-CDF
+// re-sampling (long_term_attention_gibbs.py:196-208, long_term_attention.py:220-238).
+#include "common.cuh"
+#include "rect_hist.cuh"
+
+namespace ltm {
+
+// Standalone op: scores[Bv,H,Q,N] -> hist_part[Bv,H,127]; one CTA per (head, video).
+__global__ void __launch_bounds__(256)
+sticky_hist_rect_kernel(const float* __restrict__ scores, const int32_t* __restrict__ jb,
+                        const float* __restrict__ tb, float* __restrict__ hist_part, int H, int Q, int N) {
+  extern __shared__ float smem[];
+  const int h = blockIdx.x, v = blockIdx.y;
+  const float* S = scores + ((size_t)(v * H + h) * Q) * N;
+  constexpr int RT = 32;
+  float* Eb = smem;                       // [RT][130]
+  float* Zb = Eb + RT * (EDGES + 1);      // [RT]
+  float* mr = Zb + RT;                    // [RT]
+  float* part = mr + RT;                  // [128]
+  float* accum = part + 128;              // [128]
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) accum[i] = 0.f;
+  for (int q0 = 0; q0 < Q; q0 += RT) {
+    const int rows = min(RT, Q - q0);
+    __syncthreads();
+    // per-row shift m = max(0, max_i z_i) keeps exp() finite; it cancels in E/Z
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int r = warp; r < rows; r += nw) {
+      float m = 0.f;
+      for (int i = lane; i < EDGES; i += 32) {
+        const int j = jb[i];
+        if (j >= 0) m = fmaxf(m, S[(size_t)(q0 + r) * N + j]);
+      }
+      m = warp_max(m);
+      if (lane == 0) mr[r] = m;
+    }
+    __syncthreads();
+    rect_hist_tile([&](int r, int j) { return S[(size_t)(q0 + r) * N + j]; }, mr, rows, jb, tb, Eb, Zb, part);
+    __syncthreads();
+    for (int i = threadIdx.x; i < EDGES - 2; i += blockDim.x) accum[i] += part[i];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < EDGES - 2; i += blockDim.x)
+    hist_part[((size_t)v * H + h) * (EDGES - 2) + i] = accum[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gaussian variant histogram: p_i = sum_r Phi((tb_{i+1}-mu_r)/sd_r) - Phi((tb_i-mu_r)/sd_r), i<128
+// (Normal.cdf of torch: 0.5*(1+erf((x-loc)*(1/scale)/sqrt(2)))).  One CTA per video.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+sticky_hist_gauss_kernel(const float* __restrict__ mu, const float* __restrict__ sd,
+                         const float* __restrict__ tb, float* __restrict__ hist, int R) {
+  const int v = blockIdx.x;
+  const int i = threadIdx.x;               // interval 0..127
+  const float lo = tb[i], hi = tb[i + 1];
+  const float* m = mu + (size_t)v * R;
+  const float* s = sd + (size_t)v * R;
+  float acc = 0.f;
+  for (int r = 0; r < R; ++r) {
+    const float inv = __frcp_rn(s[r]);
+    const float chi = 0.5f * (1.f + erff(__fdiv_rn((hi - m[r]) * inv, 1.4142135623730951f)));
+    const float clo = 0.5f * (1.f + erff(__fdiv_rn((lo - m[r]) * inv, 1.4142135623730951f)));
+    acc += chi - clo;
+  }
+  hist[(size_t)v * (EDGES - 1) + i] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Re-sampling.  One warp per video.
+//   1. p = sum of `parts` partial histograms (fixed order), optionally normalised twice like the
+//      reference (p/p.sum() at gibbs:203, then again inside Categorical.__init__).
+//   2. CDF exactly as torch's CPU multinomial-with-replacement: sequential fp32 running sum (lane 0),
+//      divided by the total, last entry forced to 1.
+//   3. each lane binary-searches its share of the S fp64 uniforms: first category with cdf >= u.
+//   4. optional ascending order of the drawn bins (Gaussian variant sorts ts, gauss:238): counting
+//      sort -- bin counts via shared atomics, exclusive warp-shuffle prefix scan, run fill.
+// ------------------------------------------------------------------------------------------------
+constexpr int MAX_CAT = 128;
+
+__global__ void __launch_bounds__(128)
+resample_kernel(const float* __restrict__ hist_part, int parts, int ncat, int normalize,
+                const double* __restrict__ u, const float* __restrict__ bins,
+                const int32_t* __restrict__ bin2basis, int sort,
+                float* __restrict__ p_out, int32_t* __restrict__ b_draw, int32_t* __restrict__ b_used,
+                float* __restrict__ ts, int32_t* __restrict__ idx, int Bv, int S) {
+  __shared__ float cdf_s[4][MAX_CAT];
+  __shared__ int cnt_s[4][MAX_CAT];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int v = blockIdx.x * 4 + wib;
+  if (v >= Bv) return;                       // warp-uniform; no block-level barrier below
+  float* cdf = cdf_s[wib];
+  int* cnt = cnt_s[wib];
+
+  // 1. assemble p
+  float tot = 0.f;
+  for (int i = lane; i < ncat; i += 32) {
+    float a = 0.f;
+    for (int pt = 0; pt < parts; ++pt) a += hist_part[((size_t)v * parts + pt) * ncat + i];
+    cdf[i] = a;
+    tot += a;
+  }
+  if (normalize) {
+    tot = warp_sum(tot);
+    float tot2 = 0.f;
+    for (int i = lane; i < ncat; i += 32) { cdf[i] = __fdiv_rn(cdf[i], tot); tot2 += cdf[i]; }
+    tot2 = warp_sum(tot2);
+    for (int i = lane; i < ncat; i += 32) cdf[i] = __fdiv_rn(cdf[i], tot2);
+  }
+  __syncwarp();
+  if (p_out) for (int i = lane; i < ncat; i += 32) p_out[(size_t)v * ncat + i] = cdf[i];
+  __syncwarp();
+
+  // 2. sequential fp32 cumulative sum, then normalise by the total (must not be re-associated)
+  float total = 0.f;
+  if (lane == 0) {
+    float s = 0.f;
+    for (int i = 0; i < ncat; ++i) { s = __fadd_rn(s, cdf[i]); cdf[i] = s; }
+    total = s;
+  }
+  total = __shfl_sync(0xffffffffu, total, 0);
+  __syncwarp();
+  for (int i = lane; i < ncat; i += 32) cdf[i] = __fdiv_rn(cdf[i], total);
+  __syncwarp();
+  if (lane == 0) cdf[ncat - 1] = 1.0f;
+  for (int i = lane; i < ncat; i += 32) cnt[i] = 0;
+  __syncwarp();
+
+  // 3. inverse-CDF search
+  for (int s = lane; s < S; s += 32) {
+    const double us = u[(size_t)v * S + s];
+    int left = 0, right = ncat;
+    while (right - left > 0) {
+      const int mid = left + (right - left) / 2;
+      if ((double)cdf[mid] < us) left = mid + 1; else right = mid;
+    }
+    const int b = min(left, ncat - 1);       // only reachable with NaN/garbage histograms
+    if (b_draw) b_draw[(size_t)v * S + s] = b;
+    if (sort) {
+      atomicAdd(&cnt[b], 1);
+    } else {
+      if (b_used) b_used[(size_t)v * S + s] = b;
+      if (ts) ts[(size_t)v * S + s] = bins[b];
+      if (idx) idx[(size_t)v * S + s] = bin2basis ? bin2basis[b] : b;
+    }
+  }
+  if (!sort) return;
+  __syncwarp();
+
+  // 4. counting sort: exclusive scan of the bin counts (4 bins per lane + warp shuffle scan)
+  const int per = (ncat + 31) / 32;          // <= 4
+  int local[4] = {0, 0, 0, 0};
+  int run = 0;
+  for (int t = 0; t < per; ++t) {
+    const int i = lane * per + t;
+    local[t] = (i < ncat) ? cnt[i] : 0;
+    run += local[t];
+  }
+  int incl = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  int start = incl - run;
+  for (int t = 0; t < per; ++t) {
+    const int i = lane * per + t;
+    if (i < ncat) {
+      const float tv = bins[i];
+      const int ix = bin2basis ? bin2basis[i] : i;
+      for (int s = start; s < start + local[t]; ++s) {
+        if (b_used) b_used[(size_t)v * S + s] = i;
+        if (ts) ts[(size_t)v * S + s] = tv;
+        if (idx) idx[(size_t)v * S + s] = ix;
+      }
+      start += local[t];
+    }
+  }
+}
+
+}  // namespace ltm
+
+extern "C" int ltm_sticky_hist_rect(const float* scores, const int32_t* jb, const float* tb, float* hist_part,
+                                    int Bv, int H, int Q, int N, void* stream) {
+  using namespace ltm;
+  LTM_REQUIRE(scores && jb && tb && hist_part, "sticky_hist_rect: null pointer");
+  LTM_REQUIRE(Bv > 0 && Bv <= 65535 && H > 0 && Q > 0 && N > 0, "sticky_hist_rect: bad shape");
+  const size_t smem = sizeof(float) * (32 * (EDGES + 1) + 32 + 32 + 128 + 128);
+  dim3 grid(H, Bv);
+  sticky_hist_rect_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(scores, jb, tb, hist_part, H, Q, N);
+  LTM_CHECK_LAUNCH("sticky_hist_rect");
+  return 0;
+}
+
+extern "C" int ltm_sticky_hist_gauss(const float* mu, const float* sd, const float* tb, float* hist,
+                                     int Bv, int R, void* stream) {
+  using namespace ltm;
+  LTM_REQUIRE(mu && sd && tb && hist, "sticky_hist_gauss: null pointer");
+  LTM_REQUIRE(Bv > 0 && R > 0, "sticky_hist_gauss: bad shape");
+  sticky_hist_gauss_kernel<<<Bv, EDGES - 1, 0, (cudaStream_t)stream>>>(mu, sd, tb, hist, R);
+  LTM_CHECK_LAUNCH("sticky_hist_gauss");
+  return 0;
+}
+
+extern "C" int ltm_resample(const float* hist_part, int parts, int ncat, int normalize, const double* u,
+                            const float* bins, const int32_t* bin2basis, int sort,
+                            float* p_out, int32_t* b_draw, int32_t* b_used, float* ts, int32_t* idx,
+                            int Bv, int S, void* stream) {
+  using namespace ltm;
+  LTM_REQUIRE(hist_part && u && bins, "resample: null pointer");
+  LTM_REQUIRE(ncat >= 1 && ncat <= MAX_CAT, "resample: ncat=%d out of range [1,%d]", ncat, MAX_CAT);
+  LTM_REQUIRE(parts >= 1 && Bv > 0 && S > 0, "resample: bad shape");
+  resample_kernel<<<(Bv + 3) / 4, 128, 0, (cudaStream_t)stream>>>(hist_part, parts, ncat, normalize, u, bins,
+                                                               bin2basis, sort, p_out, b_draw, b_used, ts, idx,
+                                                               Bv, S);
+  LTM_CHECK_LAUNCH("resample");
+  return 0;
+}

@@ -1,0 +1,150 @@
+"""Drop-in `LongTermAttention` for the infinity-Video Q-formers, executing on libinfltm (sm_100a).
+
+Mirrors the constructor and `forward(k, q, new_doc, layer_n)` of the reference module
+(infty-Video-LLaMA/InfVideoLLaMA/models/long_term_attention_gibbs.py:25-65,288-346 -- the live
+"gibbs" variant imported by Qformer.py:50 -- and .../long_term_attention.py:25-67,259-392 for the
+Gaussian variant).  The caller (`BertSelfAttention`, Qformer.py:135-158,216-223) constructs it through a
+keyword `partial`, writes `.length` / `.target_len` before each call, passes its own `key` / `value`
+`nn.Linear` modules as `proj_key` / `proj_value`, and `.detach()`es the result.
+
+Install by swapping one import (Qformer.py:50):
+    from infinite_video_b200 import LongTermAttention
+
+Differences that are deliberate (DESIGN.md section "boundary"):
+  * constant tables are cached per (L, N, tau) instead of being rebuilt on the CPU every call;
+  * the uniform draws of the sticky re-sampling are explicit: `u=` (float64 [B,512]) or a
+    `torch.Generator`; by default they are taken from torch's global CPU generator in the same
+    amount and order as the reference running on CPU (512 used + 512 discarded fp64 draws per call);
+  * a batch of B > 1 independent videos is accepted (the reference hard-wires B = 1);
+  * the Video-LLaMA copy's per-call pickle of the attention density to ./alphas_uniform
+    (gibbs:320-345) is not written.
+"""
+import torch
+import torch.nn as nn
+
+from . import tables
+from .batched import BatchedGaussLTM, BatchedRectLTM
+
+
+class LongTermAttention(nn.Module):
+    def __init__(self, head_size: int, length: int, target_len: int, attn_func: str, attn_num_basis: int,
+                 continuous: bool, attn_drop: float, infinite_memory: bool, n_layers: int, n_heads: int,
+                 affines: bool, mask: bool, mask_type: str, kl_regularizer: bool, proj_key, proj_value,
+                 sigma_0, mu_0, sticky_memories, sigmas, tau, variant: str = "gibbs",
+                 tokens_per_frame: int = 32, precision: str = None, gemm_impl: str = "tcgen05", **kwargs):
+        super().__init__()
+        if not continuous:
+            raise NotImplementedError("only the continuous-attention memory is on the LTM path (continuous=True)")
+        if not infinite_memory:
+            raise NotImplementedError("infinite_memory=False is never used by the Q-formers (Qformer.py:141)")
+        if attn_func != "softmax":
+            raise NotImplementedError("attn_func must be 'softmax' (Qformer.py:140)")
+        if kl_regularizer:
+            raise NotImplementedError("kl_regularizer is never enabled by the callers (Qformer.py:149)")
+        if variant not in ("gibbs", "gaussian"):
+            raise ValueError("variant must be 'gibbs' (live module) or 'gaussian'")
+        # same attribute surface as the reference (gibbs:32-65)
+        self.device = "cuda"
+        self.length = length
+        self.target_len = target_len
+        self.head_size = head_size
+        self.attn_num_basis = attn_num_basis
+        self.continuous = continuous
+        self.attn_func = attn_func
+        self.n_head = n_heads
+        self.sigmas = sigmas
+        self.kl_regularizer = kl_regularizer
+        self.sigma_0 = sigma_0
+        self.mu_0 = mu_0
+        # the caller's nn.Linear modules; not registered as sub-modules twice on purpose: the reference
+        # stores them as plain attributes of an nn.Module as well (which registers them) -> keep parity
+        self.proj_key = proj_key
+        self.proj_value = proj_value
+        self.affines = affines
+        self.sticky_memories = sticky_memories
+        self.mem_threshold = 2048
+        self.infinite_memory = infinite_memory
+        self.nb_samples = tables.NB_SAMPLES
+        self.tau = tau
+        self.count = 0
+        self.x_past = None
+        self.ridge_penalty = tables.RIDGE_PENALTY
+        self.padding = True
+        self.spacing = "linear"
+        self.variant = variant
+        self.tokens_per_frame = tokens_per_frame
+        self.precision = precision
+        self.gemm_impl = gemm_impl
+        self._engine = None
+        self._wver = None
+
+    # ------------------------------------------------------------------ engine / weights
+    def _weights_version(self):
+        ps = [self.proj_key.weight, self.proj_key.bias, self.proj_value.weight, self.proj_value.bias]
+        return tuple((p.data_ptr(), p._version) if p is not None else None for p in ps)
+
+    def _get_engine(self, device):
+        ver = self._weights_version()
+        if self._engine is None or self._engine.device != device:
+            common = dict(num_basis=self.attn_num_basis, tau=self.tau, w_key=self.proj_key.weight,
+                          b_key=self.proj_key.bias, w_value=self.proj_value.weight, b_value=self.proj_value.bias,
+                          n_heads=self.n_head, head_size=self.head_size, sticky=bool(self.sticky_memories),
+                          nb_samples=self.nb_samples, gemm_impl=self.gemm_impl, device=device)
+            if self.variant == "gibbs":
+                self._engine = BatchedRectLTM(tokens_per_frame=self.tokens_per_frame,
+                                              precision=self.precision or "tf32", **common)
+            else:
+                sig = self.sigmas if self.sigmas is not None else (0.005, 0.01)
+                self._engine = BatchedGaussLTM(sigmas=tuple(sig), precision=self.precision or "tf32x3", **common)
+            self._wver = ver
+        elif ver != self._wver:
+            self._engine.set_projections(self.proj_key.weight, self.proj_key.bias, self.proj_value.weight,
+                                         self.proj_value.bias)
+            self._wver = ver
+        return self._engine
+
+    @property
+    def B_past(self):
+        return None if self._engine is None else self._engine.B_past
+
+    @B_past.setter
+    def B_past(self, value):
+        if value is not None:
+            raise AttributeError("B_past can only be cleared (set to None)")
+        if self._engine is not None:
+            self._engine.reset()
+
+    # ------------------------------------------------------------------ forward
+    def _draw_uniforms(self, bsz, generator):
+        # Categorical(p).sample((512,)) consumes bsz*512 fp64 draws, the dummy bins_cat.sample((512, 1))
+        # another 512 that are thrown away (gibbs:205-206).
+        u = torch.rand(bsz, self.nb_samples, dtype=torch.float64, generator=generator)
+        torch.rand(self.nb_samples, dtype=torch.float64, generator=generator)
+        return u
+
+    @torch.no_grad()
+    def forward(self, k, q, new_doc, layer_n=None, u=None, generator=None):
+        if not k.is_cuda:
+            raise RuntimeError("infinite_video_b200.LongTermAttention runs on CUDA tensors only (no CPU fallback)")
+        self.device = k.device
+        eng = self._get_engine(k.device)
+        out_dtype = q.dtype
+        k32 = k.float().contiguous()
+        q32 = q.float().contiguous()
+        bsz = k32.size(0)
+        if self.variant == "gibbs":
+            self.length = k32.size(1) // self.tokens_per_frame            # gibbs:291-292
+        if new_doc:
+            eng.reset()                                                    # gibbs:300-302
+        if eng.has_state and eng.sticky:
+            if u is None:
+                u = self._draw_uniforms(bsz, generator)
+            u = u.to(k.device, torch.float64)
+        else:
+            u = None
+        ctx = eng.step(k32, q32, u=u, new_doc=False)
+        return ctx.to(out_dtype)
+
+    def extra_repr(self):
+        return (f"variant={self.variant}, num_basis={self.attn_num_basis}, tau={self.tau}, "
+                f"sticky={self.sticky_memories}, nb_samples={self.nb_samples}")

@@ -1,0 +1,236 @@
+"""Python wrappers of the individual libinfltm kernels (one per row of include/infltm.h).
+
+Every function takes/returns CUDA tensors, launches on torch's current stream and never synchronises.
+torch is used for device memory and streams only; all arithmetic happens in libinfltm.so."""
+import ctypes as C
+
+import torch
+
+from . import _capi
+from ._capi import GemmArgs, check, lib, ptr, require_cuda, stream_ptr
+
+STICKY_EDGES = 129
+PRECISION = {"tf32": 1, "tf32x3": 3, 1: 1, 3: 3}
+GEMM_IMPL = {"tcgen05": 0, "simt": 1, 0: 0, 1: 1}
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise ValueError(f"expected float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _rowmajor(t):
+    """float32 2-D/3-D operand whose rows are dense (row pitch may exceed the row length)."""
+    if t.dtype != torch.float32:
+        raise ValueError(f"expected float32, got {t.dtype}")
+    if t.stride(-1) != 1 or (t.dim() == 3 and t.shape[0] > 1 and t.stride(0) < t.stride(1)):
+        t = t.contiguous()
+    return t
+
+
+def pool_mean(k, splits=1):
+    """k[Bv,L,T,e] -> xpart[Bv,L,splits,e] (frame means as `splits` partial sums).  gibbs:304."""
+    require_cuda(k)
+    k = _f32c(k)
+    Bv, L, T, e = k.shape
+    out = torch.empty(Bv, L, splits, e, device=k.device, dtype=torch.float32)
+    check(lib().ltm_pool_mean(ptr(k), ptr(out), Bv, L, T, e, splits, stream_ptr(k.device)), "pool_mean")
+    return out
+
+
+def sticky_hist_rect(scores, jb, tb):
+    """scores[Bv,H,Q,N] -> hist_part[Bv,H,127].  gibbs:196-203."""
+    require_cuda(scores, jb, tb)
+    scores = _f32c(scores)
+    Bv, H, Q, N = scores.shape
+    out = torch.empty(Bv, H, STICKY_EDGES - 2, device=scores.device, dtype=torch.float32)
+    check(lib().ltm_sticky_hist_rect(ptr(scores), ptr(jb), ptr(tb), ptr(out), Bv, H, Q, N,
+                                     stream_ptr(scores.device)), "sticky_hist_rect")
+    return out
+
+
+def sticky_hist_gauss(mu, sd, tb):
+    """mu,sd[Bv,R] -> hist[Bv,128].  long_term_attention.py:220-229."""
+    require_cuda(mu, sd, tb)
+    mu, sd = _f32c(mu), _f32c(sd)
+    Bv, R = mu.shape
+    out = torch.empty(Bv, STICKY_EDGES - 1, device=mu.device, dtype=torch.float32)
+    check(lib().ltm_sticky_hist_gauss(ptr(mu), ptr(sd), ptr(tb), ptr(out), Bv, R, stream_ptr(mu.device)),
+          "sticky_hist_gauss")
+    return out
+
+
+def resample(hist_part, u, bins, bin2basis=None, normalize=True, sort=False, out=None):
+    """Inverse-CDF sampling with explicit fp64 uniforms.  hist_part[Bv,parts,ncat] (or [Bv,ncat]),
+    u[Bv,S] -> dict(p, b_draw, b_used, ts, idx).  gibbs:204-208 / gauss:230-238."""
+    require_cuda(hist_part, u, bins, bin2basis)
+    hist_part = _f32c(hist_part)
+    if hist_part.dim() == 2:
+        hist_part = hist_part.unsqueeze(1)
+    Bv, parts, ncat = hist_part.shape
+    if u.dtype != torch.float64 or u.shape[0] != Bv:
+        raise ValueError("u must be float64 [Bv,S]")
+    u = u.contiguous()
+    S = u.shape[1]
+    dev = hist_part.device
+    o = out or {}
+    o.setdefault("p", torch.empty(Bv, ncat, device=dev, dtype=torch.float32))
+    for name in ("b_draw", "b_used", "idx"):
+        o.setdefault(name, torch.empty(Bv, S, device=dev, dtype=torch.int32))
+    o.setdefault("ts", torch.empty(Bv, S, device=dev, dtype=torch.float32))
+    check(lib().ltm_resample(ptr(hist_part), parts, ncat, int(bool(normalize)), ptr(u), ptr(bins), ptr(bin2basis),
+                             int(bool(sort)), ptr(o["p"]), ptr(o["b_draw"]), ptr(o["b_used"]), ptr(o["ts"]),
+                             ptr(o["idx"]), Bv, S, stream_ptr(dev)), "resample")
+    return o
+
+
+def consolidate_rect(B_past, xpart, idx, new_doc, tab, S, out=None):
+    """Segmented-mean regression of variant R.  `tab` = RectTables.to(device).  gibbs:184-222."""
+    require_cuda(B_past, xpart, idx, new_doc)
+    Bv, L, splits, e = xpart.shape
+    N = tab["g0"].numel()
+    if out is None:
+        out = torch.empty(Bv, N, e, device=xpart.device, dtype=torch.float32)
+    check(lib().ltm_consolidate_rect(ptr(B_past), ptr(xpart), ptr(idx), ptr(new_doc),
+                                     ptr(tab["seg_ptr0"]), ptr(tab["seg_mem0"]), ptr(tab["g0"]),
+                                     ptr(tab["seg_ptr1"]), ptr(tab["seg_mem1"]), ptr(tab["g1"]),
+                                     ptr(out), Bv, N, e, L, splits, S, stream_ptr(xpart.device)),
+          "consolidate_rect")
+    return out
+
+
+def gemm(A, B, *, a_kmajor=True, b_kmajor=True, B2=None, bias=None, out=None, precision="tf32x3",
+         impl="tcgen05", M=None, Nc=None, K=None):
+    """Batched C[b] = A[b] @ B[b] (+bias) on tcgen05 (kind::tf32).
+
+    A: [batch?, M, K] if a_kmajor else [batch?, K, M];  B: [batch?, Nc, K] if b_kmajor else [batch?, K, Nc].
+    A 2-D operand is shared by every batch.  B2 (same layout as B) continues B along K."""
+    require_cuda(A, B, B2, bias, out)
+    A, B = _rowmajor(A), _rowmajor(B)
+    batch = max(A.shape[0] if A.dim() == 3 else 1, B.shape[0] if B.dim() == 3 else 1)
+
+    def desc(t, kmajor):
+        m = t if t.dim() == 3 else t.unsqueeze(0)
+        stride = m.stride(0) if (t.dim() == 3 and t.shape[0] > 1) else 0
+        rows, k = (m.shape[1], m.shape[2]) if kmajor else (m.shape[2], m.shape[1])
+        return rows, k, m.stride(1), stride
+
+    Ma, Ka, lda, sA = desc(A, a_kmajor)
+    Nb, Kb, ldb, sB = desc(B, b_kmajor)
+    if A.dim() == 3 and A.shape[0] == batch and batch > 1:
+        sA = A.stride(0)
+    if B.dim() == 3 and B.shape[0] == batch and batch > 1:
+        sB = B.stride(0)
+    K1 = Kb
+    ldb2 = sB2 = 0
+    if B2 is not None:
+        B2 = _rowmajor(B2)
+        Nb2, Kb2, ldb2, sB2 = desc(B2, b_kmajor)
+        if B2.dim() == 3 and B2.shape[0] == batch and batch > 1:
+            sB2 = B2.stride(0)
+        if Nb2 != Nb:
+            raise ValueError("B and B2 disagree on N")
+        Kb = Kb + Kb2
+    if Ka != Kb:
+        raise ValueError(f"inner dimensions disagree: A has K={Ka}, B has K={Kb}")
+    M = Ma if M is None else M
+    Nc = Nb if Nc is None else Nc
+    if out is None:
+        out = torch.empty(batch, M, Nc, device=A.device, dtype=torch.float32)
+    o3 = out if out.dim() == 3 else out.unsqueeze(0)
+    g = GemmArgs()
+    g.A, g.lda, g.strideA, g.a_kmajor = A.data_ptr(), lda, sA, int(a_kmajor)
+    g.B, g.ldb, g.strideB, g.b_kmajor = B.data_ptr(), ldb, sB, int(b_kmajor)
+    g.B2 = B2.data_ptr() if B2 is not None else None
+    g.ldb2, g.strideB2, g.K1 = ldb2, sB2, K1
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.C, g.ldc, g.strideC = o3.data_ptr(), o3.stride(1), (o3.stride(0) if batch > 1 else 0)
+    g.M, g.Nc, g.K, g.batch = M, Nc, Ka, batch
+    g.precision, g.impl = PRECISION[precision], GEMM_IMPL[impl]
+    check(lib().ltm_gemm(C.byref(g), stream_ptr(A.device)), "gemm")
+    return out
+
+
+def project_kv(Bcoef, Wkv, bkv, precision="tf32", impl="tcgen05", out=None):
+    """KV[M,2D] = Bcoef[M,e] @ Wkv[2D,e]^T + bkv.  gibbs:312-313."""
+    require_cuda(Bcoef, Wkv, bkv)
+    Bc = _f32c(Bcoef).reshape(-1, Bcoef.shape[-1])
+    M, e = Bc.shape
+    D2 = Wkv.shape[0]
+    if out is None:
+        out = torch.empty(M, D2, device=Bc.device, dtype=torch.float32)
+    check(lib().ltm_project_kv(ptr(Bc), ptr(Wkv), ptr(bkv), ptr(out), M, e, D2, PRECISION[precision],
+                               GEMM_IMPL[impl], stream_ptr(Bc.device)), "project_kv")
+    return out
+
+
+def cont_attn_rect(q, KV, W, W_out, jb=None, tb=None, n_heads=12, want_scores=False, want_hist=True):
+    """q[Bv,Q,D], KV[Bv,N,2D] -> (ctx[Bv,Q,D], scores|None, hist_part|None).  gibbs:224-286."""
+    require_cuda(q, KV, W, jb, tb)
+    q, KV = _f32c(q), _f32c(KV)
+    Bv, Q, D = q.shape
+    N = KV.shape[1]
+    H = n_heads
+    d = D // H
+    ctx = torch.empty(Bv, Q, D, device=q.device, dtype=torch.float32)
+    scores = torch.empty(Bv, H, Q, N, device=q.device, dtype=torch.float32) if want_scores else None
+    hist = (torch.empty(Bv, H * ((Q + 31) // 32), STICKY_EDGES - 2, device=q.device, dtype=torch.float32)
+            if want_hist else None)
+    check(lib().ltm_cont_attn_rect(ptr(q), ptr(KV), ptr(W), float(W_out), ptr(jb), ptr(tb), ptr(ctx), ptr(scores),
+                                   ptr(hist), Bv, Q, N, H, d, stream_ptr(q.device)), "cont_attn_rect")
+    return ctx, scores, hist
+
+
+def cont_attn_gauss(q, KV, basis_mu, basis_sigma, n_heads=12, want_scores=False):
+    """-> (ctx[Bv,Q,D], scores|None, mu[Bv,H*Q], sd[Bv,H*Q]).  long_term_attention.py:286-325."""
+    require_cuda(q, KV, basis_mu, basis_sigma)
+    q, KV = _f32c(q), _f32c(KV)
+    Bv, Q, D = q.shape
+    N = KV.shape[1]
+    H = n_heads
+    d = D // H
+    ctx = torch.empty(Bv, Q, D, device=q.device, dtype=torch.float32)
+    scores = torch.empty(Bv, H, Q, N, device=q.device, dtype=torch.float32) if want_scores else None
+    mu = torch.empty(Bv, H * Q, device=q.device, dtype=torch.float32)
+    sd = torch.empty(Bv, H * Q, device=q.device, dtype=torch.float32)
+    check(lib().ltm_cont_attn_gauss(ptr(q), ptr(KV), ptr(basis_mu), ptr(basis_sigma), ptr(ctx), ptr(scores), ptr(mu),
+                                    ptr(sd), Bv, Q, N, H, d, stream_ptr(q.device)), "cont_attn_gauss")
+    return ctx, scores, mu, sd
+
+
+def rbf_eval(tvals, basis_mu, basis_sigma, tidx=None, out=None):
+    """out[p,j] = N(t_p; mu_j, sigma_j^2), t_p = tvals[tidx[p]] if tidx is given.  basis_functions.py:158-164."""
+    require_cuda(tvals, basis_mu, basis_sigma, tidx)
+    P = tidx.numel() if tidx is not None else tvals.numel()
+    N = basis_mu.numel()
+    if out is None:
+        out = torch.empty(P, N, device=tvals.device, dtype=torch.float32)
+    check(lib().ltm_rbf_eval(ptr(tvals), ptr(tidx), ptr(basis_mu), ptr(basis_sigma), ptr(out), out.stride(0), P, N,
+                             stream_ptr(tvals.device)), "rbf_eval")
+    return out
+
+
+def ridge_solve(positions, trim, rows, basis_mu, basis_sigma, ridge=0.5, want_G=True, want_GT=True):
+    """Ridge operator of the Gaussian design, fp64 solve on device.  -> (G[rows,N]|None, GT[N,rows]|None)."""
+    require_cuda(positions, basis_mu, basis_sigma)
+    P, N = positions.numel(), basis_mu.numel()
+    dev = positions.device
+    ws = torch.empty(int(lib().ltm_ridge_workspace_doubles(P, N)), device=dev, dtype=torch.float64)
+    G = torch.empty(rows, N, device=dev, dtype=torch.float32) if want_G else None
+    ld = (rows + 3) // 4 * 4                      # TMA wants 16-byte row pitches
+    GTp = torch.zeros(N, ld, device=dev, dtype=torch.float32) if want_GT else None
+    check(lib().ltm_ridge_solve(ptr(positions), P, trim, rows, ptr(basis_mu), ptr(basis_sigma), N, float(ridge),
+                                ptr(G), ptr(GTp), ld, ptr(ws), stream_ptr(dev)), "ridge_solve")
+    return G, (GTp[:, :rows] if want_GT else None)
+
+
+def gather_rows(src, idx, out=None):
+    """out[v,s,:] = src[v, idx[v,s], :]."""
+    require_cuda(src, idx)
+    Bv, R, e = src.shape
+    S = idx.shape[1]
+    if out is None:
+        out = torch.empty(Bv, S, e, device=src.device, dtype=torch.float32)
+    check(lib().ltm_gather_rows(ptr(src), ptr(idx), ptr(out), Bv, R, S, e, stream_ptr(src.device)), "gather_rows")
+    return out

@@ -1,0 +1,240 @@
+"""Host-side constant tables of the LTM consolidation path.
+
+Everything here depends only on ``(L, N, tau)`` (and the sigma set for the Gaussian variant) --
+never on data -- so it is built once per shape on the host, cached, uploaded once, and reused
+by every call / video.  The reference rebuilds the same information inside ``get_basis`` on
+*every* forward (long_term_attention_gibbs.py:67-165, :298).
+
+Why the host, and why torch CPU ops: membership of a position in a rectangular basis function is
+decided by fp32 rounding of ``linspace``/``(edges[:-1]+edges[1:])/2``/``mu -+ width/2`` and the
+half-open compare ``lo <= t < hi`` (basis_functions.py:227-266).  For non power-of-two ``N`` some
+positions fall in *no* bin, so the integer tables must come from the very
+same fp32 expressions, never from ``floor(t*N)``.  These are small integer/plan tables; no
+per-call arithmetic happens here.
+
+Variant R ("gibbs"): ``F F^T`` is diagonal (each position activates at most one indicator), hence
+``G = F^T (F F^T + ridge I)^-1`` has at most one non-zero per row, ``1/(cnt_j + ridge)``.  The dense
+ridge solve of the reference collapses to a segmented mean described by a CSR membership list.
+"""
+from dataclasses import dataclass, field
+from functools import lru_cache
+
+import numpy as np
+import torch
+
+NB_SAMPLES = 512          # long_term_attention_gibbs.py:55
+RIDGE_PENALTY = 0.5       # :62
+NB_STICKY_EDGES = 129     # :163
+NUM_QUAD_POINTS = 1000    # :251 (expected_value default)
+
+
+def _rect_bounds(n):
+    """fp32 lower/upper bounds of the N indicator functions (gibbs:176-182, basis:248-249)."""
+    edges = torch.linspace(0, 1, n + 1)
+    mu = (edges[:-1] + edges[1:]) / 2
+    width = torch.ones(n) / n
+    return mu - width / 2, mu + width / 2
+
+
+def rect_bin_of(t, n):
+    """Index of the indicator active at each fp32 position (-1: none).  Raises if a position
+    activates two indicators (then F F^T is not diagonal and the segmented-mean form is invalid)."""
+    lo, hi = _rect_bounds(n)
+    t = torch.as_tensor(t, dtype=torch.float32).reshape(-1, 1)
+    hit = (t >= lo.unsqueeze(0)) & (t < hi.unsqueeze(0))
+    nhit = hit.sum(1)
+    if int(nhit.max()) > 1:
+        raise NotImplementedError(
+            f"num_basis={n}: a position activates two rectangular basis functions; the ridge system is "
+            "not diagonal for this N")
+    idx = hit.float().argmax(1)
+    return torch.where(nhit > 0, idx, torch.full_like(idx, -1)).to(torch.int32)
+
+
+def first_chunk_positions(l):
+    """Padded frame positions of a first chunk (gibbs:103-110)."""
+    if l % 2:
+        s = 1 / float(l)
+        return torch.linspace(-.5 + s, 1.5 - s, 2 * l - 1), (l - 1) // 2
+    s = 1 / float(2 * l)
+    return torch.linspace(-.5 + s, 1.5 - s, 2 * l), l // 2
+
+
+def update_positions(l, tau, nb_samples=NB_SAMPLES):
+    """Padded positions of [S contracted samples | L new frames] (gibbs:134-150).
+    Returns (all positions, number of left pads, sample positions)."""
+    old = torch.arange(1, nb_samples + 1).float() * tau / nb_samples
+    new = torch.arange(nb_samples + 1, l + nb_samples + 1).float()
+    new = tau + (1 - tau) * (new - nb_samples) / l
+    if l % 2:
+        s = 1 / float(l + nb_samples)
+        pad = torch.linspace(-.5 + s, 1.5 - s, 2 * (l + nb_samples) - 1)
+    else:
+        s = 1 / float(2 * l + nb_samples)
+        pad = torch.linspace(-.5 + s, 1.5 - s, 2 * (l + nb_samples))
+    left, right = pad[pad < 0], pad[pad > 1]
+    tot = nb_samples + l
+    trim = (tot - 1) // 2 if tot % 2 else tot // 2
+    allpos = torch.cat([left, old, new, right], 0)
+    if left.numel() != trim or allpos.numel() - 2 * trim != tot:
+        raise NotImplementedError(f"pad/trim misalignment for L={l}: the reference would regress shifted rows")
+    return allpos, trim, old
+
+
+def sticky_edges():
+    bins = torch.linspace(0, 1, NB_STICKY_EDGES)
+    nudged = bins.clone()
+    nudged[0] = -.000001       # gibbs:198
+    nudged[-1] = 1.000001      # gibbs:199
+    return bins, nudged
+
+
+def _csr(member_bin, n):
+    """member_bin[p] in [-1,n) -> (ptr[n+1], members) listing positions per bin in ascending order."""
+    mb = np.asarray(member_bin)
+    order = np.argsort(mb, kind="stable")
+    order = order[mb[order] >= 0]
+    counts = np.bincount(mb[mb >= 0], minlength=n)
+    ptr = np.zeros(n + 1, dtype=np.int32)
+    ptr[1:] = np.cumsum(counts)
+    return ptr, order.astype(np.int32)
+
+
+@dataclass
+class RectTables:
+    """Constant tables of variant R for one (L, N, tau).  All arrays are host numpy; ``.to(device)``
+    uploads them once as torch tensors."""
+    L: int
+    N: int
+    tau: float
+    S: int
+    # first chunk: B = G0^T x
+    seg_ptr0: np.ndarray = None      # int32 [N+1]
+    seg_mem0: np.ndarray = None      # int32 [nnz0]  frame indices
+    g0: np.ndarray = None            # fp32  [N]     1/(cnt+ridge)
+    # update: B = G_inf^T [xm ; x]
+    seg_ptr1: np.ndarray = None      # int32 [N+1]
+    seg_mem1: np.ndarray = None      # int32 [nnz1]  p < S: sample p ; p >= S: frame p-S
+    g1: np.ndarray = None            # fp32  [N]
+    # sticky histogram (129 nudged edges) and sampling
+    tb: np.ndarray = None            # fp32 [129] evaluation edges
+    jb: np.ndarray = None            # int32 [129] basis index at each edge (-1 none)
+    bins: np.ndarray = None          # fp32 [129] un-nudged edges (sample positions are bins[b])
+    bin2basis: np.ndarray = None     # int32 [128] basis index of position bins[b]
+    # quadrature of expected_value: r_j = W_j e^{S_j} / (sum_i W_i e^{S_i} + W_out)
+    W: np.ndarray = None             # fp32 [N]
+    W_out: float = 0.0
+    # uniform (non-sticky) resampling table: basis index of sample s (-1 none)  (gibbs:152-157,:212)
+    idx_uniform: np.ndarray = None   # int32 [S]
+    _dev: dict = field(default_factory=dict, repr=False)
+
+    def to(self, device):
+        key = str(device)
+        if key not in self._dev:
+            d = {}
+            for name in ("seg_ptr0", "seg_mem0", "g0", "seg_ptr1", "seg_mem1", "g1", "tb", "jb", "bins",
+                         "bin2basis", "W", "idx_uniform"):
+                d[name] = torch.from_numpy(getattr(self, name)).to(device)
+            self._dev[key] = d
+        return self._dev[key]
+
+    def dense_G0(self):
+        """Dense [L,N] operator (for tests): G0[p,j] = g0[j] if frame p is in bin j."""
+        G = np.zeros((self.L, self.N), np.float32)
+        for j in range(self.N):
+            G[self.seg_mem0[self.seg_ptr0[j]:self.seg_ptr0[j + 1]], j] = self.g0[j]
+        return G
+
+    def dense_Ginf(self):
+        G = np.zeros((self.S + self.L, self.N), np.float32)
+        for j in range(self.N):
+            G[self.seg_mem1[self.seg_ptr1[j]:self.seg_ptr1[j + 1]], j] = self.g1[j]
+        return G
+
+
+@lru_cache(maxsize=64)
+def rect_tables(L: int, N: int, tau: float, S: int = NB_SAMPLES, num_quad: int = NUM_QUAD_POINTS) -> RectTables:
+    if L < 2:
+        raise ValueError("chunks of a single frame are not supported (the reference fails on L=1)")
+    t = RectTables(L=L, N=N, tau=float(tau), S=S)
+    ridge = torch.tensor(RIDGE_PENALTY)
+
+    # --- first chunk (gibbs:99-131 + compute_G :68-84)
+    pos0, trim0 = first_chunk_positions(L)
+    b0 = rect_bin_of(pos0, N).numpy()
+    cnt0 = np.bincount(b0[b0 >= 0], minlength=N)                      # counts include pad positions
+    frames0 = b0[trim0:trim0 + L]
+    assert frames0.shape[0] == L
+    t.seg_ptr0, t.seg_mem0 = _csr(frames0, N)
+    t.g0 = (1.0 / (torch.from_numpy(cnt0).float() + ridge)).numpy()
+
+    # --- update (gibbs:134-160)
+    pos1, trim1, old = update_positions(L, tau, S)
+    b1 = rect_bin_of(pos1, N).numpy()
+    cnt1 = np.bincount(b1[b1 >= 0], minlength=N)
+    core1 = b1[trim1:trim1 + S + L]
+    t.seg_ptr1, t.seg_mem1 = _csr(core1, N)
+    t.g1 = (1.0 / (torch.from_numpy(cnt1).float() + ridge)).numpy()
+
+    # --- sticky edges (gibbs:163,:197-199,:207-208)
+    bins, nudged = sticky_edges()
+    t.tb = nudged.numpy().copy()
+    t.bins = bins.numpy().copy()
+    t.jb = rect_bin_of(nudged, N).numpy()
+    t.bin2basis = rect_bin_of(bins[:-1], N).numpy()
+
+    # --- quadrature weights of the 1000-point trapezoid rule folded per basis (gibbs:251-286)
+    tq = torch.linspace(0, 1, num_quad)
+    jq = rect_bin_of(tq, N).numpy()
+    dt = (tq[1:] - tq[:-1]).double().numpy()
+    wt = np.zeros(num_quad)
+    wt[:-1] += dt / 2
+    wt[1:] += dt / 2
+    W = np.zeros(N)
+    np.add.at(W, jq[jq >= 0], wt[jq >= 0])
+    t.W = W.astype(np.float32)
+    t.W_out = float(wt[jq < 0].sum())
+
+    # --- uniform re-sampling table (gibbs:152-157): psi.evaluate(t/tau) for each contracted position
+    t.idx_uniform = rect_bin_of(old / tau, N).numpy()
+    return t
+
+
+# ----------------------------------------------------------------------------------------------
+# Variant G (Gaussian RBF): host side only provides positions / basis parameters; the design matrix
+# and the ridge solve run on the device (csrc/ridge.cu).
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class GaussTables:
+    L: int
+    N: int
+    tau: float
+    S: int
+    sigmas: tuple
+    basis_mu: np.ndarray = None      # fp32 [N]   (long_term_attention.py:191-198, mu-major meshgrid)
+    basis_sigma: np.ndarray = None   # fp32 [N]
+    pos0: np.ndarray = None          # fp32 [P0]  padded first-chunk positions
+    trim0: int = 0
+    pos1: np.ndarray = None          # fp32 [P1]  padded update positions
+    trim1: int = 0
+    tb: np.ndarray = None            # fp32 [129] nudged edges
+    bins: np.ndarray = None          # fp32 [129]
+    old_over_tau: np.ndarray = None  # fp32 [S]   uniform re-sampling positions
+
+
+@lru_cache(maxsize=64)
+def gauss_tables(L: int, N: int, tau: float, sigmas=(0.005, 0.01), S: int = NB_SAMPLES) -> GaussTables:
+    if L % 2:
+        raise ValueError("variant G: odd chunk lengths are broken upstream (long_term_attention.py:162-168)")
+    ns = len(sigmas)
+    if N % ns:
+        N += ns - N % ns                                              # (:107-108)
+    mu, sg = torch.meshgrid(torch.linspace(0, 1, N // ns), torch.Tensor(list(sigmas)), indexing="ij")
+    pos0, trim0 = first_chunk_positions(L)
+    pos1, trim1, old = update_positions(L, tau, S)
+    bins, nudged = sticky_edges()
+    return GaussTables(L=L, N=N, tau=float(tau), S=S, sigmas=tuple(sigmas),
+                       basis_mu=mu.flatten().numpy().copy(), basis_sigma=sg.flatten().numpy().copy(),
+                       pos0=pos0.numpy().copy(), trim0=trim0, pos1=pos1.numpy().copy(), trim1=trim1,
+                       tb=nudged.numpy().copy(), bins=bins.numpy().copy(),
+                       old_over_tau=(old / tau).numpy().copy())

@@ -1,0 +1,103 @@
+"""TEST INFRASTRUCTURE ONLY -- loader for the *real* reference LTM modules.
+
+Imports the unmodified reference files from ``/root/reference`` (read-only, only
+present in the dev container) so that the clean-room oracle (``ltm_oracle.py``)
+and the golden fixtures under ``tests/golden/`` can be pinned against them.
+Nothing in the product package may import this module.
+
+Scaffolding needed to import the files in isolation:
+  * ``matplotlib`` is imported at module top of both LTM files
+    (long_term_attention_gibbs.py:21, long_term_attention.py:21) but never used on
+    the path and is not installed -> a stub is placed in ``sys.modules``.
+  * both files use the relative import ``.basis_functions`` -> they are loaded
+    under a synthetic package so that ``InfVideoLLaMA/__init__`` (which pulls
+    omegaconf/decord/...) is never executed.
+  * the Gaussian file references the undefined name ``ContinuousSoftmax``
+    (long_term_attention.py:99,332; it lives in the un-vendored
+    deep-spin/infinite-former repo).  A shim with the published forward
+    (theta -> (mu, sigma^2) -> psi.integrate_psi_gaussian) is injected.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+REF_ROOT = os.environ.get("INFLTM_REFERENCE_ROOT", "/root/reference")
+_VL = os.path.join(REF_ROOT, "infty-Video-LLaMA", "InfVideoLLaMA", "models")
+_VC = os.path.join(REF_ROOT, "infty-VideoChat2", "models", "blip2")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(_VL, "long_term_attention_gibbs.py"))
+
+
+def _stub_matplotlib():
+    if "matplotlib" not in sys.modules:
+        m = types.ModuleType("matplotlib")
+        p = types.ModuleType("matplotlib.pyplot")
+        m.pyplot = p
+        sys.modules["matplotlib"] = m
+        sys.modules["matplotlib.pyplot"] = p
+
+
+def _load_pkg(pkg_name: str, directory: str, files):
+    _stub_matplotlib()
+    if pkg_name not in sys.modules:
+        pkg = types.ModuleType(pkg_name)
+        pkg.__path__ = [directory]
+        sys.modules[pkg_name] = pkg
+    mods = {}
+    for f in files:
+        full = f"{pkg_name}.{f}"
+        if full in sys.modules:
+            mods[f] = sys.modules[full]
+            continue
+        spec = importlib.util.spec_from_file_location(full, os.path.join(directory, f + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[full] = mod
+        spec.loader.exec_module(mod)
+        mods[f] = mod
+    return mods
+
+
+class _ContinuousSoftmaxShim:
+    """Forward of deep-spin/infinite-former ``continuous_softmax.py`` (un-vendored):
+    canonical parameters theta=[mu/sigma^2, -1/(2 sigma^2)] -> E_{N(mu,sigma^2)}[psi_j]."""
+
+    def __init__(self, psi=None):
+        self.psi = psi
+
+    def __call__(self, theta):
+        sigma_sq = -0.5 / theta[:, 1]
+        mu = theta[:, 0] * sigma_sq
+        return self.psi[0].integrate_psi_gaussian(mu.unsqueeze(1), sigma_sq.unsqueeze(1))
+
+
+def load_gibbs_vl():
+    """Reference live variant, Video-LLaMA flavour (T=32, e=768 hard-coded)."""
+    m = _load_pkg("_ref_vl", _VL, ["basis_functions", "long_term_attention_gibbs"])
+    return m["long_term_attention_gibbs"]
+
+
+def load_gibbs_vc():
+    """Reference live variant, VideoChat2 flavour (14x14 tokens, e=1024 hard-coded)."""
+    m = _load_pkg("_ref_vc", _VC, ["basis_functions", "long_term_attention_gibbs"])
+    return m["long_term_attention_gibbs"]
+
+
+def load_gaussian_vl():
+    """Reference Gaussian/closed-form variant (dead code upstream; needs the shim)."""
+    m = _load_pkg("_ref_vl", _VL, ["basis_functions", "long_term_attention"])
+    mod = m["long_term_attention"]
+    mod.ContinuousSoftmax = _ContinuousSoftmaxShim
+    return mod
+
+
+def caller_kwargs(num_basis, tau, sticky, proj_key, proj_value, sigmas=None, n_heads=12, head_size=64):
+    """Keyword set the reference caller passes (Qformer.py:135-158)."""
+    return dict(attn_num_basis=num_basis, head_size=head_size, length=768, target_len=768,
+                attn_func="softmax", infinite_memory=True, n_layers=2, attn_drop=0.1,
+                n_heads=n_heads, d_model=n_heads * head_size, affines=True, mask=True,
+                mask_type="cnn", kl_regularizer=False, sigma_0=None, mu_0=None,
+                sticky_memories=sticky, continuous=True, sigmas=sigmas, tau=tau,
+                proj_key=proj_key, proj_value=proj_value)

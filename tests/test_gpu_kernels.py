@@ -1,0 +1,276 @@
+"""Per-kernel parity: every libinfltm entry point (through the C-ABI / ctypes) against the CPU oracle on the
+same seeded inputs.  Integer / index outputs bit-exact; floating point within the stated tolerance."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ltm_oracle as O
+from tests.helpers import make_inputs, make_proj, proj_tensors, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev(cuda_device):
+    return cuda_device
+
+
+def _ops():
+    from infinite_video_b200 import ops
+    return ops
+
+
+def _tables():
+    from infinite_video_b200 import tables
+    return tables
+
+
+# ---------------------------------------------------------------------------------------- R4
+@pytest.mark.parametrize("Bv,L,T,e,splits", [(2, 8, 32, 768, 1), (2, 8, 32, 768, 4), (1, 16, 196, 1024, 1),
+                                             (1, 16, 196, 1024, 7), (3, 5, 9, 772, 2)])
+def test_pool_mean(dev, Bv, L, T, e, splits):
+    g = torch.Generator().manual_seed(1)
+    k = torch.randn(Bv, L, T, e, generator=g)
+    want = k.mean(dim=2)                                    # gibbs:304
+    got = _ops().pool_mean(k.to(dev), splits).sum(2).cpu()
+    assert relerr(got, want) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------- R7
+@pytest.mark.parametrize("ncat,Bv,zeros,sort", [(127, 1, False, False), (127, 37, True, False),
+                                                (128, 5, False, True), (128, 4, True, True)])
+def test_resample_is_bit_exact(dev, ncat, Bv, zeros, sort):
+    """Given identical (p, u): bins, positions and basis indices bit-exact (north_star)."""
+    ops, T = _ops(), _tables()
+    g = torch.Generator().manual_seed(ncat + Bv)
+    p = torch.rand(Bv, ncat, generator=g) ** 3
+    if zeros:
+        p[:, ::5] = 0
+    u = torch.rand(Bv, 512, dtype=torch.float64, generator=g)
+    # a few uniforms exactly on CDF edges (ties must resolve like torch: first category with cdf >= u)
+    cum = torch.cumsum(p[0], 0)
+    cdf0 = (cum / cum[-1]).double()
+    u[0, :8] = cdf0[[3, 10, 20, 50, 70, 90, 100, ncat - 1]]
+    tab = T.rect_tables(8, 256, .75)
+    bins = torch.from_numpy(tab.bins).to(dev)
+    b2b = torch.from_numpy(tab.bin2basis).to(dev)
+    want_b = O.inverse_cdf_sample(p, u)
+    out = ops.resample(p.to(dev), u.to(dev), bins, b2b, normalize=False, sort=sort)
+    assert torch.equal(out["b_draw"].cpu().long(), want_b)
+    used = torch.sort(want_b, -1)[0] if sort else want_b
+    assert torch.equal(out["b_used"].cpu().long(), used)
+    assert torch.equal(out["ts"].cpu(), torch.from_numpy(tab.bins)[used])          # exact bin left edges
+    assert torch.equal(out["idx"].cpu().long(), torch.from_numpy(tab.bin2basis).long()[used])
+    assert torch.equal(out["p"].cpu(), p)
+
+
+def test_resample_normalised_partials(dev):
+    """parts > 1 + the reference's two p/sum(p) passes; draws must be consistent with the p it reports."""
+    ops, T = _ops(), _tables()
+    g = torch.Generator().manual_seed(3)
+    part = torch.rand(6, 12, 127, generator=g)
+    u = torch.rand(6, 512, dtype=torch.float64, generator=g)
+    tab = T.rect_tables(8, 64, .75)
+    out = ops.resample(part.to(dev), u.to(dev), torch.from_numpy(tab.bins).to(dev),
+                       torch.from_numpy(tab.bin2basis).to(dev), normalize=True, sort=False)
+    p = part.sum(1)
+    p = p / p.sum(-1, keepdim=True)
+    p = p / p.sum(-1, keepdim=True)
+    assert relerr(out["p"], p) < 1e-6
+    assert torch.equal(out["b_draw"].cpu().long(), O.inverse_cdf_sample(out["p"].cpu(), u))
+
+
+# ---------------------------------------------------------------------------------------- R6 / R10 / R11
+def _rect_case(N, L, Q, seed, q_scale):
+    key, val = make_proj(seed, 768)
+    orc = O.RectLTM(N, .75, *proj_tensors(key, val), rebuild_tables=False)
+    ks, qs, us = make_inputs(seed + 1, 1, 2, L * 32, 768, Q, q_scale)
+    with torch.no_grad():
+        outs = []
+        for v in range(2):
+            o = O.RectLTM(N, .75, *proj_tensors(key, val), rebuild_tables=False)
+            ctx = o.forward(ks[0][v:v + 1], qs[0][v:v + 1], True)
+            outs.append((o, ctx))
+    return key, val, ks[0], qs[0], outs
+
+
+@pytest.mark.parametrize("N,L,Q,q_scale", [(64, 8, 32, 1.0), (256, 16, 32, 8.0), (512, 16, 32, 4.0),
+                                           (64, 8, 96, 2.0), (100, 30, 40, 2.0)])
+def test_cont_attn_rect_and_fused_histogram(dev, N, L, Q, q_scale):
+    ops, T = _ops(), _tables()
+    key, val, k, q, outs = _rect_case(N, L, Q, 7, q_scale)
+    tab = T.rect_tables(L, N, .75)
+    td = tab.to(dev)
+    Wkv = torch.cat([key.weight, val.weight]).detach()
+    bkv = torch.cat([key.bias, val.bias]).detach()
+    B = torch.cat([o.B_past for o, _ in outs])                                   # [2,N,e]
+    KV = torch.nn.functional.linear(B, Wkv, bkv)                                 # fp32 CPU projection
+    ctx, scores, hist = ops.cont_attn_rect(q.to(dev), KV.to(dev), td["W"], tab.W_out, td["jb"], td["tb"],
+                                           want_scores=True, want_hist=True)
+    want_ctx = torch.cat([c for _, c in outs])
+    want_S = torch.cat([o.last["scores"] for o, _ in outs])
+    assert relerr(scores, want_S) < 1e-5
+    assert relerr(ctx, want_ctx) < 1e-4
+    # fused sticky histogram == what the oracle would compute at the *next* call (gibbs:196-203)
+    want_p = torch.cat([o.sticky_hist(o.tables(L)) for o, _ in outs])
+    bins = td["bins"]
+    u = torch.rand(2, 512, dtype=torch.float64).to(dev)
+    got = ops.resample(hist, u, bins, td["bin2basis"], normalize=True)
+    assert relerr(got["p"], want_p) < 2e-5
+    # the standalone histogram op agrees with the fused one
+    hp = ops.sticky_hist_rect(scores, td["jb"], td["tb"])
+    got2 = ops.resample(hp, u, bins, td["bin2basis"], normalize=True)
+    assert relerr(got2["p"], got["p"]) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------- R3/R5/R8
+@pytest.mark.parametrize("N,L,tau,splits", [(64, 8, .75, 1), (256, 32, .75, 2), (100, 30, .5, 1), (64, 7, .75, 3)])
+def test_consolidate_rect(dev, N, L, tau, splits):
+    ops, T = _ops(), _tables()
+    g = torch.Generator().manual_seed(N + L)
+    Bv, e = 3, 768
+    x = torch.randn(Bv, L, e, generator=g)
+    B_past = torch.randn(Bv, N, e, generator=g)
+    tab = T.rect_tables(L, N, tau)
+    td = tab.to(dev)
+    b = torch.randint(0, 127, (Bv, 512), generator=g)
+    idx = torch.from_numpy(tab.bin2basis).long()[b]
+    # split x into partial sums
+    w = torch.rand(splits, generator=g)
+    w = w / w.sum()
+    xpart = torch.stack([x * w[s] for s in range(splits)], 2).contiguous()
+    # first chunk: B = G0^T x
+    want0 = torch.matmul(x.transpose(1, 2), torch.from_numpy(tab.dense_G0())).permute(0, 2, 1)
+    got0 = ops.consolidate_rect(None, xpart.to(dev), None, None, td, 512)
+    assert relerr(got0, want0) < 2e-6
+    # update: B = G_inf^T [B_past[idx] ; x]
+    xm = torch.stack([torch.where((idx[v] >= 0).unsqueeze(1), B_past[v][idx[v].clamp(min=0)],
+                                  torch.zeros(1)) for v in range(Bv)])
+    xcat = torch.cat([xm, x], 1)
+    want1 = torch.matmul(xcat.transpose(1, 2), torch.from_numpy(tab.dense_Ginf())).permute(0, 2, 1)
+    got1 = ops.consolidate_rect(B_past.to(dev), xpart.to(dev), idx.int().to(dev), None, td, 512)
+    assert relerr(got1, want1) < 2e-6
+    # per-video new_doc flags select the table set
+    flags = torch.tensor([0, 1, 0], dtype=torch.uint8)
+    got2 = ops.consolidate_rect(B_past.to(dev), xpart.to(dev), idx.int().to(dev), flags.to(dev), td, 512).cpu()
+    assert torch.equal(got2[1], got0[1].cpu()) and torch.equal(got2[0], got1[0].cpu())
+
+
+# ---------------------------------------------------------------------------------------- GEMM (tcgen05)
+GEMM_CASES = [
+    # M, N, K, batch, a_kmajor, b_kmajor, two_segment, bias
+    (128, 128, 32, 1, True, True, False, False),       # one tile, one k-block
+    (128, 128, 256, 1, True, True, False, True),
+    (256, 1536, 768, 1, True, True, False, True),      # K/V projection shape (per 256 coefficient rows)
+    (100, 72, 40, 1, True, True, False, False),        # ragged tails everywhere
+    (128, 768, 256, 3, True, False, False, False),     # Psi_tab @ B_past[v]   (B MN-major, batched)
+    (256, 768, 544, 2, True, False, True, False),      # G_inf^T [xm ; k]      (two K segments)
+    (64, 768, 8, 2, True, False, False, False),        # G0^T k with Lk = 8
+    (128, 256, 96, 2, False, True, False, False),      # A MN-major
+    (96, 160, 64, 2, False, False, False, True),
+]
+
+
+@pytest.mark.parametrize("M,N,K,batch,akm,bkm,two,bias", GEMM_CASES)
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
+def test_gemm_tcgen05(dev, M, N, K, batch, akm, bkm, two, bias, precision):
+    ops = _ops()
+    g = torch.Generator().manual_seed(M * 7 + N + K)
+    A = torch.randn(*((M, K) if akm else (K, M)), generator=g)                  # shared across the batch
+    K1 = 32 * ((K // 2) // 32) if two else K
+    Bfull = torch.randn(batch, *((N, K) if bkm else (K, N)), generator=g)
+    bias_t = torch.randn(N, generator=g) if bias else None
+    Am = A if akm else A.t()
+    Bm = Bfull.transpose(1, 2) if bkm else Bfull                                  # [batch,K,N]
+    want = torch.matmul(Am.double(), Bm.double())
+    if bias:
+        want = want + bias_t.double()
+    if two:
+        B1 = (Bfull[:, :, :K1] if bkm else Bfull[:, :K1]).contiguous()
+        B2 = (Bfull[:, :, K1:] if bkm else Bfull[:, K1:]).contiguous()
+    else:
+        B1, B2 = Bfull, None
+    got = ops.gemm(A.to(dev), B1.to(dev), B2=None if B2 is None else B2.to(dev), a_kmajor=akm, b_kmajor=bkm,
+                   bias=None if bias_t is None else bias_t.to(dev), precision=precision, impl="tcgen05")
+    tol = 3e-3 if precision == "tf32" else 2e-5
+    assert relerr(got, want) < tol
+    chk = ops.gemm(A.to(dev), B1.to(dev), B2=None if B2 is None else B2.to(dev), a_kmajor=akm, b_kmajor=bkm,
+                   bias=None if bias_t is None else bias_t.to(dev), precision=precision, impl="simt")
+    assert relerr(chk, want) < 1e-5
+
+
+def test_project_kv(dev):
+    ops = _ops()
+    key, val = make_proj(2, 768)
+    g = torch.Generator().manual_seed(5)
+    B = torch.randn(512, 768, generator=g) * 0.02
+    Wkv = torch.cat([key.weight, val.weight]).detach()
+    bkv = torch.cat([key.bias, val.bias]).detach()
+    want = torch.nn.functional.linear(B.double(), Wkv.double(), bkv.double())
+    assert relerr(ops.project_kv(B.to(dev), Wkv.to(dev), bkv.to(dev), "tf32"), want) < 1e-3
+    assert relerr(ops.project_kv(B.to(dev), Wkv.to(dev), bkv.to(dev), "tf32x3"), want) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------- variant G kernels
+def test_rbf_eval_and_sticky_hist_gauss(dev):
+    ops = _ops()
+    psi = O.GaussBasis(256, [0.005, 0.01])
+    t = torch.linspace(0, 1, 129)[:128]
+    want = psi.at(t)
+    got = ops.rbf_eval(t.to(dev), psi.mu[0].to(dev), psi.sigma[0].to(dev))
+    assert relerr(got, want) < 1e-5
+    g = torch.Generator().manual_seed(9)
+    mu = torch.rand(3, 384, generator=g)
+    sd = torch.rand(3, 384, generator=g) * 0.05 + 0.004
+    key, val = make_proj(1, 768)
+    orc = O.GaussLTM(256, .75, *proj_tensors(key, val))
+    orc.attn_past = [mu, sd]
+    bins, nudged = O.sticky_edges()
+    want_p = orc.sticky_hist(dict(nudged=nudged))
+    hist = ops.sticky_hist_gauss(mu.to(dev), sd.to(dev), nudged.to(dev))
+    u = torch.rand(3, 512, dtype=torch.float64).to(dev)
+    got = ops.resample(hist, u, bins.to(dev), None, normalize=True, sort=True)
+    assert relerr(got["p"], want_p) < 1e-5
+
+
+@pytest.mark.parametrize("N,L", [(64, 8), (256, 256)])
+def test_ridge_solve_against_fp64(dev, N, L):
+    """The device solver is checked against exact (fp64) arithmetic, not against the reference's fp32
+    `.inverse()`, which is itself off by 1e-2 at this conditioning."""
+    ops, T = _ops(), _tables()
+    t = T.gauss_tables(L, N, .75)
+    mu, sg = torch.from_numpy(t.basis_mu), torch.from_numpy(t.basis_sigma)
+    for pos, trim, rows in ((t.pos0, t.trim0, L), (t.pos1, t.trim1, 512 + L)):
+        p = torch.from_numpy(pos).double()
+        z = (p.unsqueeze(0) - mu.double().unsqueeze(1)) / sg.double().unsqueeze(1)
+        F = torch.exp(-0.5 * z * z) / math.sqrt(2 * math.pi) / sg.double().unsqueeze(1)       # [N,P]
+        A = F @ F.t() + 0.5 * torch.eye(N, dtype=torch.float64)
+        G_true = torch.linalg.solve(A, F).t()[trim:trim + rows]                                # [rows,N]
+        G, GT = ops.ridge_solve(torch.from_numpy(pos).to(dev), trim, rows, mu.to(dev), sg.to(dev), 0.5)
+        assert relerr(G, G_true) < 1e-5
+        assert torch.equal(GT.cpu(), G.cpu().t())
+        # residual of the normal equations in fp64:  G (F F^T + ridge I) == F^T
+        res = G.cpu().double() @ A - F.t()[trim:trim + rows]
+        assert float(res.abs().max() / F.abs().max()) < 1e-5
+
+
+def test_cont_attn_gauss(dev):
+    ops = _ops()
+    key, val = make_proj(4, 768)
+    N, L, Bv = 256, 16, 2
+    orc = O.GaussLTM(N, .75, *proj_tensors(key, val), rebuild_tables=False)
+    ks, qs, _ = make_inputs(8, 1, Bv, L, 768, 32)
+    with torch.no_grad():
+        want = orc.forward(ks[0], qs[0], True)
+    Wkv = torch.cat([key.weight, val.weight]).detach()
+    bkv = torch.cat([key.bias, val.bias]).detach()
+    KV = torch.nn.functional.linear(orc.B_past, Wkv, bkv)
+    psi = orc.tables(L)["psi"]
+    ctx, scores, mu, sd = ops.cont_attn_gauss(qs[0].to(dev), KV.to(dev), psi.mu[0].to(dev), psi.sigma[0].to(dev),
+                                              want_scores=True)
+    assert relerr(scores, orc.last["scores"]) < 1e-5
+    assert relerr(mu, orc.attn_past[0]) < 1e-5
+    assert relerr(sd, orc.attn_past[1]) < 1e-3       # var = E[t^2] - mu^2 cancels; see DESIGN.md
+    assert relerr(ctx, want) < 1e-3

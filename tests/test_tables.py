@@ -1,0 +1,75 @@
+"""Host constant tables (product code) against the oracle's dense reference operators."""
+import numpy as np
+import pytest
+import torch
+
+from infinite_video_b200 import tables as T
+from oracle import ltm_oracle as O
+from tests.helpers import make_inputs, make_proj, proj_tensors
+
+SHAPES = [(64, 8, .75), (256, 256, .75), (512, 256, .75), (64, 16, .75), (256, 256, .9), (100, 30, .5),
+          (64, 7, .75), (64, 2, .75), (128, 1024, .75), (64, 3, .6)]
+
+
+@pytest.mark.parametrize("N,L,tau", SHAPES)
+def test_segmented_mean_tables_equal_dense_ridge_operators(N, L, tau):
+    t = T.rect_tables(L, N, tau)
+    psi = O.RectBasis(N)
+    G0 = O.ridge_operator(psi, O.first_chunk_positions(L), L).numpy()
+    pos, _ = O.update_positions(L, tau)
+    Gi = O.ridge_operator(psi, pos, 512 + L).numpy()
+    assert np.array_equal(t.dense_G0(), G0)           # bitwise: 1/(cnt+0.5) in fp32
+    assert np.array_equal(t.dense_Ginf(), Gi)
+    assert (Gi[-1] == 0).all()                        # the last new frame (position 1.0) is dropped
+    assert t.idx_uniform[-1] == -1                    # uniform table: t/tau == 1.0 hits no basis
+    assert t.jb[0] == -1 and t.jb[-1] == -1           # nudged end edges hit no basis
+
+
+@pytest.mark.parametrize("N", [64, 128, 256, 512])
+def test_sticky_positions_map_to_floor_bins_for_pow2(N):
+    t = T.rect_tables(8, N, .75)
+    want = np.floor(np.arange(128) / 128.0 * N).astype(np.int32)
+    assert np.array_equal(t.bin2basis, want)
+
+
+@pytest.mark.parametrize("N,L", [(64, 8), (256, 32), (512, 16), (100, 30)])
+def test_closed_form_quadrature_and_histogram(N, L):
+    """r_j = W_j e^{S_j}/(sum W e^S + W_out) == the reference's 1000-point trapezoid integral; the closed-form
+    sticky histogram == cumulative_trapezoid/diff of the reference."""
+    key, val = make_proj(1, 768)
+    orc = O.RectLTM(N, .75, *proj_tensors(key, val))
+    ks, qs, us = make_inputs(2, 2, 1, L * 32, 768, 32, q_scale=4.0)
+    t = T.rect_tables(L, N, .75)
+    with torch.no_grad():
+        orc.forward(ks[0], qs[0], True)
+        S = orc.last["scores"].double()
+        W = torch.from_numpy(t.W).double()
+        num = W * torch.exp(S)
+        r = num / (num.sum(-1, keepdim=True) + t.W_out)
+        err = float((r - orc.last["r"].double()).abs().max() / orc.last["r"].abs().max())
+        assert err < 2e-5, err
+        # histogram
+        p_ref = orc.sticky_hist(orc.tables(L))[0].double()
+        jb = torch.from_numpy(t.jb).long()
+        tb = torch.from_numpy(t.tb).double()
+        z = torch.where(jb >= 0, S[..., jb.clamp(min=0)], torch.zeros((), dtype=torch.float64))
+        E = torch.exp(z)
+        dt = tb[1:] - tb[:-1]
+        Z = (dt * (E[..., 1:] + E[..., :-1]) / 2).sum(-1, keepdim=True)
+        inc = dt * (E[..., 1:] + E[..., :-1]) / 2 / Z
+        p = inc[..., 1:].sum((1, 2))[0]
+        p = p / p.sum()
+        assert float((p - p_ref).abs().max() / p_ref.max()) < 2e-5
+
+
+def test_single_frame_chunks_are_rejected():
+    with pytest.raises(ValueError):
+        T.rect_tables(1, 64, .75)
+
+
+def test_gauss_tables_shapes():
+    t = T.gauss_tables(8, 63, .75)
+    assert t.N == 64 and t.pos0.shape[0] == 16 and t.pos1.shape[0] == 2 * (512 + 8)
+    assert t.trim1 == 260 and t.trim0 == 4
+    with pytest.raises(ValueError):
+        T.gauss_tables(7, 64, .75)
