@@ -99,7 +99,9 @@ class BatchedRectLTM(_BatchedBase):
         if ws is None:
             dev = self.device
             units = Bv * L
-            splits = max(1, min(self.T, -(-SM_COUNT * 8 // units)))
+            # split the token range of a frame over several CTAs only when there are too few frames to fill the
+            # 148 SMs (small batches); otherwise one CTA per frame, one pass, no partial sums
+            splits = 1 if units >= 2 * SM_COUNT else max(1, min(self.T, -(-SM_COUNT * 8 // units)))
             f32 = dict(device=dev, dtype=torch.float32)
             i32 = dict(device=dev, dtype=torch.int32)
             ws = dict(

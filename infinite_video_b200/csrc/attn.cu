@@ -13,9 +13,11 @@
 // var = a.(mu_b^2 + sigma_b^2) - mu^2; r_j = N(mu; mu_j, sigma_j^2 + var)  (closed-form Gaussian x RBF
 // integral, basis_functions.py:154-156,209-211); ctx = r V; (mu, sqrt(var)) saved for the next call.
 //
-// One CTA per (32-query tile, head, video); K_h / V_h tiles of 64 basis rows stream through shared
-// memory (coalesced 128-bit loads of 256-byte row segments); each lane owns one query row for
-// S = q K^T (K rows are warp-broadcast from shared memory) and each thread 8 output columns for r V.
+// One CTA per (32-query tile, head, video).  K_h / V_h tiles of 64 basis rows stream through a two-slot
+// cp.async ring (coalesced 16-byte copies of 256-byte row segments, the next tile in flight while the
+// current one is consumed).  Each lane owns one query row: S = q K^T with the query row in registers and
+// 4 K rows warp-broadcast per step; ctx = r V with all 64 output columns in registers and the basis
+// dimension split across the 8 warps, reduced once through shared memory.
 #include "common.cuh"
 #include "rect_hist.cuh"
 
@@ -42,20 +44,34 @@ struct AttnParams {
   int Q, N, H;
 };
 
-__host__ __device__ inline int attn_tile_floats() {
-  const int a = JT * DH, b = QT * (EDGES + 1);
-  return a > b ? a : b;
+static_assert(2 * JT * DH >= QT * (EDGES + 1), "histogram scratch must fit the (idle) tile ring");
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+// Shared-memory carve-up (floats).  The [8 warps][16][32] float4 reduction scratch of phase 3 aliases the
+// score tile + the K/V tile ring once both are dead.
+__host__ __device__ inline int attn_front_floats(int N) {
+  const int ss = (QT * (N + 1) + 3) & ~3;
+  const int need = ss + 2 * JT * DH;
+  const int red = 8 * QT * DH;
+  return need > red ? need : red;
 }
 
 template <int MODE>  // 0 = rect, 1 = gauss
-__global__ void __launch_bounds__(ATTN_THREADS)
+__global__ void __launch_bounds__(ATTN_THREADS, 2)
 cont_attn_kernel(const AttnParams p) {
   extern __shared__ __align__(16) float smem[];
   const int N = p.N, Q = p.Q, H = p.H, D = H * DH;
   const int SS = N + 1;                                  // padded row stride of the score tile
   float* Ss = smem;                                      // [QT][N+1]
-  float* tile = Ss + ((QT * SS + 3) & ~3);               // [JT][DH]  (aliased by the histogram scratch)
-  float* qs = tile + attn_tile_floats();                 // [QT][DH+1]
+  float* tiles = Ss + ((QT * SS + 3) & ~3);              // [2][JT][DH] cp.async ring (buffer 0 doubles as hist scratch)
+  float* qs = smem + attn_front_floats(N);               // [QT][DH+1]
   float* tabA = qs + QT * (DH + 1);                      // [N]
   float* tabB = tabA + N;                                // [N]
   float* mrow = tabB + N;                                // [QT]
@@ -67,6 +83,22 @@ cont_attn_kernel(const AttnParams p) {
   const int rows = min(QT, Q - q0);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* KVv = p.KV + (size_t)v * N * 2 * D;
+  const int ntile = (N + JT - 1) / JT;
+
+  // tile t in [0, 2*ntile): first the K_h tiles, then the V_h tiles; rows beyond N are zero-filled
+  auto issue_tile = [&](int t) {
+    const int isv = t >= ntile;
+    const int j0 = (isv ? t - ntile : t) * JT;
+    float* dst = tiles + (t & 1) * (JT * DH);
+    const float* src = KVv + (isv ? D : 0) + h * DH;
+    for (int f = tid; f < JT * (DH / 4); f += ATTN_THREADS) {
+      const int r = f / (DH / 4), c4 = f - r * (DH / 4);
+      if (j0 + r < N) cp_async16(dst + r * DH + 4 * c4, src + (size_t)(j0 + r) * 2 * D + 4 * c4);
+      else reinterpret_cast<float4*>(dst + r * DH)[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    cp_async_commit();
+  };
+  issue_tile(0);
 
   // ---- stage the query tile (scaled by 1/sqrt(d), gibbs:226) and the per-basis tables
   const float inv_sqrt_d = 1.0f / sqrtf((float)DH);      // d = 64 -> exactly 1/8
@@ -78,43 +110,48 @@ cont_attn_kernel(const AttnParams p) {
   }
   for (int j = tid; j < N; j += ATTN_THREADS) {
     tabA[j] = p.tabA[j];
-    if (MODE == 1) {
-      const float m = p.tabA[j], s = p.tabB[j];
-      tabB[j] = s;
-      (void)m;
-    }
+    if (MODE == 1) tabB[j] = p.tabB[j];
   }
   __syncthreads();
-  float qreg[DH];
-#pragma unroll
-  for (int c = 0; c < DH; ++c) qreg[c] = qs[lane * (DH + 1) + c];
 
-  // ---- phase 1: S[q, j] = q_h . K_h[j]
-  for (int j0 = 0; j0 < N; j0 += JT) {
-    const int jn = min(JT, N - j0);
-    __syncthreads();
-    for (int f = tid; f < JT * (DH / 4); f += ATTN_THREADS) {
-      const int r = f / (DH / 4), c4 = f - r * (DH / 4);
-      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < jn) val = ldg_nc(reinterpret_cast<const float4*>(KVv + (size_t)(j0 + r) * 2 * D + h * DH) + c4);
-      reinterpret_cast<float4*>(tile)[f] = val;
-    }
-    __syncthreads();
-    for (int jj = warp; jj < jn; jj += ATTN_THREADS / 32) {
-      const float4* kr = reinterpret_cast<const float4*>(tile + jj * DH);
-      float acc = 0.f;
+  // ---- phase 1: S[q, j] = q_h . K_h[j]; lane = query row (held in registers), each warp owns 8 of the 64
+  //      tile rows as two groups of 4, K rows are warp-broadcast from shared memory
+  {
+    float qreg[DH];
 #pragma unroll
-      for (int c4 = 0; c4 < DH / 4; ++c4) {
-        const float4 kk = kr[c4];
-        acc = fmaf(qreg[4 * c4 + 0], kk.x, acc);
-        acc = fmaf(qreg[4 * c4 + 1], kk.y, acc);
-        acc = fmaf(qreg[4 * c4 + 2], kk.z, acc);
-        acc = fmaf(qreg[4 * c4 + 3], kk.w, acc);
+    for (int c = 0; c < DH; ++c) qreg[c] = qs[lane * (DH + 1) + c];
+    for (int t = 0; t < ntile; ++t) {
+      if (t + 1 < ntile) { issue_tile(t + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+      __syncthreads();
+      const float* tile = tiles + (t & 1) * (JT * DH);
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int jj = warp * 8 + g * 4;
+        const float4* k0 = reinterpret_cast<const float4*>(tile + (jj + 0) * DH);
+        const float4* k1 = reinterpret_cast<const float4*>(tile + (jj + 1) * DH);
+        const float4* k2 = reinterpret_cast<const float4*>(tile + (jj + 2) * DH);
+        const float4* k3 = reinterpret_cast<const float4*>(tile + (jj + 3) * DH);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int c4 = 0; c4 < DH / 4; ++c4) {
+          const float4 x0 = k0[c4], x1 = k1[c4], x2 = k2[c4], x3 = k3[c4];
+          const float qa = qreg[4 * c4], qb = qreg[4 * c4 + 1], qc = qreg[4 * c4 + 2], qd = qreg[4 * c4 + 3];
+          a0 = fmaf(qa, x0.x, a0); a1 = fmaf(qa, x1.x, a1); a2 = fmaf(qa, x2.x, a2); a3 = fmaf(qa, x3.x, a3);
+          a0 = fmaf(qb, x0.y, a0); a1 = fmaf(qb, x1.y, a1); a2 = fmaf(qb, x2.y, a2); a3 = fmaf(qb, x3.y, a3);
+          a0 = fmaf(qc, x0.z, a0); a1 = fmaf(qc, x1.z, a1); a2 = fmaf(qc, x2.z, a2); a3 = fmaf(qc, x3.z, a3);
+          a0 = fmaf(qd, x0.w, a0); a1 = fmaf(qd, x1.w, a1); a2 = fmaf(qd, x2.w, a2); a3 = fmaf(qd, x3.w, a3);
+        }
+        const int j = t * JT + jj;
+        float* dst = Ss + lane * SS + j;
+        if (j + 0 < N) dst[0] = a0;
+        if (j + 1 < N) dst[1] = a1;
+        if (j + 2 < N) dst[2] = a2;
+        if (j + 3 < N) dst[3] = a3;
       }
-      Ss[lane * SS + j0 + jj] = acc;
+      __syncthreads();                                   // tile (t&1) may be overwritten by the next prefetch
     }
   }
-  __syncthreads();
+  // here: all scores are in Ss and the tile ring is idle (it serves as histogram scratch below)
 
   if (p.scores_out) {
     for (int f = tid; f < rows * N; f += ATTN_THREADS) {
@@ -135,12 +172,17 @@ cont_attn_kernel(const AttnParams p) {
     }
     __syncthreads();
     if (p.hist_part) {
-      rect_hist_tile([&](int r, int j) { return Ss[r * SS + j]; }, mrow, rows, p.jb, p.tb, tile, zrow, part);
+      rect_hist_tile([&](int r, int j) { return Ss[r * SS + j]; }, mrow, rows, p.jb, p.tb, tiles, zrow, part);
       __syncthreads();
       float* dst = p.hist_part + ((size_t)v * (H * gridDim.x) + h * gridDim.x + qt) * (EDGES - 2);
       for (int i = tid; i < EDGES - 2; i += ATTN_THREADS) dst[i] = part[i];
     }
-    for (int r = warp; r < rows; r += ATTN_THREADS / 32) {
+    issue_tile(ntile);                                   // first V tile loads while the weights are formed
+    for (int r = warp; r < QT; r += ATTN_THREADS / 32) {
+      if (r >= rows) {                                   // unused query rows contribute nothing in phase 3
+        for (int j = lane; j < N; j += 32) Ss[r * SS + j] = 0.f;
+        continue;
+      }
       const float m = mrow[r];
       float z = 0.f;
       for (int j = lane; j < N; j += 32) {
@@ -152,7 +194,12 @@ cont_attn_kernel(const AttnParams p) {
       for (int j = lane; j < N; j += 32) Ss[r * SS + j] = Ss[r * SS + j] / z;
     }
   } else {
-    for (int r = warp; r < rows; r += ATTN_THREADS / 32) {
+    issue_tile(ntile);
+    for (int r = warp; r < QT; r += ATTN_THREADS / 32) {
+      if (r >= rows) {
+        for (int j = lane; j < N; j += 32) Ss[r * SS + j] = 0.f;
+        continue;
+      }
       // a = softmax(20 S)  (gauss:289)
       float m = -INFINITY;
       for (int j = lane; j < N; j += 32) m = fmaxf(m, 20.f * Ss[r * SS + j]);
@@ -200,44 +247,49 @@ cont_attn_kernel(const AttnParams p) {
   }
   __syncthreads();
 
-  // ---- phase 3: ctx[q, :] = sum_j r[q, j] V_h[j, :]
-  const int qr = tid >> 3;            // 0..31
-  const int dg = tid & 7;             // 8 columns each
-  float acc[8];
+  // ---- phase 3: ctx[q, :] = sum_j r[q, j] V_h[j, :]; lane = query row with all 64 output columns in
+  //      registers, each warp owns 8 rows of every V tile (split-j), partial sums are reduced at the end
+  float acc[DH];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  for (int j0 = 0; j0 < N; j0 += JT) {
-    const int jn = min(JT, N - j0);
+  for (int c = 0; c < DH; ++c) acc[c] = 0.f;
+  for (int t = ntile; t < 2 * ntile; ++t) {
+    if (t + 1 < 2 * ntile) { issue_tile(t + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
-    for (int f = tid; f < JT * (DH / 4); f += ATTN_THREADS) {
-      const int r = f / (DH / 4), c4 = f - r * (DH / 4);
-      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < jn)
-        val = ldg_nc(reinterpret_cast<const float4*>(KVv + (size_t)(j0 + r) * 2 * D + D + h * DH) + c4);
-      reinterpret_cast<float4*>(tile)[f] = val;
+    const float* tile = tiles + (t & 1) * (JT * DH);
+    const int jb0 = (t - ntile) * JT + warp * 8;
+#pragma unroll 2
+    for (int jj = 0; jj < 8; ++jj) {
+      const int j = jb0 + jj;
+      const float w = (j < N) ? Ss[lane * SS + j] : 0.f;
+      const float4* vr = reinterpret_cast<const float4*>(tile + (warp * 8 + jj) * DH);
+#pragma unroll
+      for (int c4 = 0; c4 < DH / 4; ++c4) {
+        const float4 x = vr[c4];
+        acc[4 * c4 + 0] = fmaf(w, x.x, acc[4 * c4 + 0]);
+        acc[4 * c4 + 1] = fmaf(w, x.y, acc[4 * c4 + 1]);
+        acc[4 * c4 + 2] = fmaf(w, x.z, acc[4 * c4 + 2]);
+        acc[4 * c4 + 3] = fmaf(w, x.w, acc[4 * c4 + 3]);
+      }
     }
     __syncthreads();
-    const float* rr = Ss + qr * SS + j0;
-    for (int jj = 0; jj < jn; ++jj) {
-      const float w = rr[jj];
-      const float4 v0 = reinterpret_cast<const float4*>(tile + jj * DH + dg * 8)[0];
-      const float4 v1 = reinterpret_cast<const float4*>(tile + jj * DH + dg * 8)[1];
-      acc[0] = fmaf(w, v0.x, acc[0]); acc[1] = fmaf(w, v0.y, acc[1]);
-      acc[2] = fmaf(w, v0.z, acc[2]); acc[3] = fmaf(w, v0.w, acc[3]);
-      acc[4] = fmaf(w, v1.x, acc[4]); acc[5] = fmaf(w, v1.y, acc[5]);
-      acc[6] = fmaf(w, v1.z, acc[6]); acc[7] = fmaf(w, v1.w, acc[7]);
-    }
   }
-  if (qr < rows) {
-    float4* dst = reinterpret_cast<float4*>(p.ctx + ((size_t)v * Q + q0 + qr) * D + h * DH + dg * 8);
-    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  // cross-warp reduction through shared memory: red[warp][c4][q] as float4 (conflict-free both ways)
+  float4* red = reinterpret_cast<float4*>(smem);
+#pragma unroll
+  for (int c4 = 0; c4 < DH / 4; ++c4)
+    red[(warp * (DH / 4) + c4) * QT + lane] = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
+  __syncthreads();
+  for (int f = tid; f < (DH / 4) * QT; f += ATTN_THREADS) {
+    const int c4 = f / QT, qr = f - c4 * QT;
+    float4 s = red[c4 * QT + qr];
+#pragma unroll
+    for (int w = 1; w < ATTN_THREADS / 32; ++w) f4_add(s, red[(w * (DH / 4) + c4) * QT + qr]);
+    if (qr < rows) *reinterpret_cast<float4*>(p.ctx + ((size_t)v * Q + q0 + qr) * D + h * DH + 4 * c4) = s;
   }
 }
 
 static size_t attn_smem_bytes(int N) {
-  size_t f = ((size_t)(QT * (N + 1) + 3) & ~(size_t)3) + attn_tile_floats() + QT * (DH + 1) + 2 * (size_t)N +
-             2 * QT + 128;
+  size_t f = (size_t)attn_front_floats(N) + QT * (DH + 1) + 2 * (size_t)N + 2 * QT + 128;
   return f * sizeof(float);
 }
 

@@ -38,6 +38,7 @@ struct GemmDev {
   int M, Nc, K, K1;
   int a_kmajor, b_kmajor;
   int a_batched, b_batched, b2_batched, has_b2;
+  unsigned mn_layout, mn_lbo, mn_sbo, mn_kadv;
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -104,21 +105,27 @@ __device__ __forceinline__ void tcgen05_mma_tf32(uint32_t tmem_d, uint64_t adesc
 }
 
 // UMMA shared-memory matrix descriptor (sm_100): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
-// version=1 [46,48) | layout SWIZZLE_128B=2 [61,64).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// version=1 [46,48) | layout type [61,64): SWIZZLE_128B = 2, SWIZZLE_128B_BASE32B = 1.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= 1ull << 46;
-  d |= 2ull << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
-// K-major tile [rows][32 fp32]: 8-row groups 1024 B apart (SBO); K advances 32 B inside the swizzle row.
-// MN-major tile [mn/32 slabs][32 k][32 fp32]: slabs LBO = 4096 B apart, 8-k groups SBO = 1024 B apart;
-// K advances one 8-k group (1024 B) per MMA.
-__device__ __forceinline__ uint64_t operand_desc(uint32_t tile, int kmajor, int k) {
-  return kmajor ? umma_desc(tile + k * (UMMA_K * 4), 16, 1024) : umma_desc(tile + k * 1024, SLAB_BYTES, 1024);
+// MN-major descriptor parameters.  For 32-bit (tf32) MN-major operands the only legal canonical layout is
+// the 128-byte swizzle with 32-byte atoms (TMA: SWIZZLE_128B_ATOM_32B): atoms of [4 k][32 mn], i.e. the
+// K groups are 4 rows = 512 B apart (SBO), the 32-wide MN atoms one slab = 4096 B apart (LBO), and one
+// MMA (K = 8) advances two K groups = 1024 B.  Kept in a struct so a bring-up harness can override them.
+struct MnDesc { uint32_t layout, lbo, sbo, kadv; };
+// K-major tile [rows][32 fp32], SWIZZLE_128B: 8-row groups 1024 B apart (SBO); K advances 32 B inside the
+// swizzle row.  MN-major tile [mn/32 slabs][32 k][32 fp32]: see MnDesc.
+__device__ __forceinline__ uint64_t operand_desc(uint32_t tile, int kmajor, int k, const MnDesc& mn) {
+  return kmajor ? umma_desc(tile + k * (UMMA_K * 4), 16, 1024, 2u)
+                : umma_desc(tile + k * mn.kadv, mn.lbo, mn.sbo, mn.layout);
 }
 
 template <int BN, int STAGES, bool SPLIT>
@@ -211,6 +218,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((g.a_kmajor ? 0u : 1u) << 15) |
                              ((g.b_kmajor ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
+      const MnDesc mn{g.mn_layout, g.mn_lbo, g.mn_sbo, g.mn_kadv};
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
@@ -222,12 +230,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const uint32_t sb_lo = sa_lo + A_BYTES;
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t da = operand_desc(sa, g.a_kmajor, k);
-          const uint64_t db = operand_desc(sb, g.b_kmajor, k);
+          const uint64_t da = operand_desc(sa, g.a_kmajor, k, mn);
+          const uint64_t db = operand_desc(sb, g.b_kmajor, k, mn);
           tcgen05_mma_tf32(tmem_acc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           if (SPLIT) {
-            tcgen05_mma_tf32(tmem_acc, operand_desc(sa_lo, g.a_kmajor, k), db, idesc, 1u);
-            tcgen05_mma_tf32(tmem_acc, da, operand_desc(sb_lo, g.b_kmajor, k), idesc, 1u);
+            tcgen05_mma_tf32(tmem_acc, operand_desc(sa_lo, g.a_kmajor, k, mn), db, idesc, 1u);
+            tcgen05_mma_tf32(tmem_acc, da, operand_desc(sb_lo, g.b_kmajor, k, mn), idesc, 1u);
           }
         }
         tcgen05_commit(empty_bar(s));          // frees the stage once these MMAs have read it
@@ -317,6 +325,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
 // ------------------------------------------------------------------------------------------ host
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+// bring-up override of the MN-major layout parameters: {layout, lbo, sbo, kadv, tma swizzle enum}
+static unsigned g_mn_desc[5] = {1u, (unsigned)SLAB_BYTES, 512u, 1024u, (unsigned)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B};
 
 static int resolve_encode() {
   if (g_encode) return 0;
@@ -344,7 +354,9 @@ static int encode_operand(CUtensorMap* map, const float* base, int rows, int K, 
   cuuint32_t box[3] = {32u, (cuuint32_t)(kmajor ? box_rows : 32), 1u};
   cuuint32_t estr[3] = {1u, 1u, 1u};
   CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        kmajor ? CU_TENSOR_MAP_SWIZZLE_128B : (CUtensorMapSwizzle)g_mn_desc[4],
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   LTM_REQUIRE(r == CUDA_SUCCESS, "gemm: cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
   return 0;
@@ -387,6 +399,7 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   d.C = a.C; d.bias = a.bias; d.ldc = a.ldc; d.strideC = a.strideC;
   d.M = a.M; d.Nc = a.Nc; d.K = a.K; d.K1 = K1;
   d.a_kmajor = a.a_kmajor ? 1 : 0; d.b_kmajor = a.b_kmajor ? 1 : 0;
+  d.mn_layout = g_mn_desc[0]; d.mn_lbo = g_mn_desc[1]; d.mn_sbo = g_mn_desc[2]; d.mn_kadv = g_mn_desc[3];
   d.a_batched = a.strideA != 0; d.b_batched = a.strideB != 0; d.b2_batched = a.strideB2 != 0; d.has_b2 = two ? 1 : 0;
   if (split) return launch_cfg<128, 3, true>(mA, mB, mB2, d, a.batch, stream);
   if (bn == 256) return launch_cfg<256, 4, false>(mA, mB, mB2, d, a.batch, stream);
@@ -394,6 +407,12 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
 }
 
 }  // namespace ltm
+
+// Bring-up hook (not part of include/infltm.h): override the MN-major descriptor parameters.
+extern "C" void ltm_debug_set_mn_desc(unsigned layout, unsigned lbo, unsigned sbo, unsigned kadv, unsigned swz) {
+  ltm::g_mn_desc[0] = layout; ltm::g_mn_desc[1] = lbo; ltm::g_mn_desc[2] = sbo; ltm::g_mn_desc[3] = kadv;
+  ltm::g_mn_desc[4] = swz;
+}
 
 extern "C" int ltm_gemm(const ltm_gemm_args* args, void* stream) {
   using namespace ltm;

@@ -15,7 +15,11 @@ def dev(cuda_device):
 
 
 def _run_rect(dev, N, L, C, Bv, T=32, e=768, Q=32, tau=.75, sticky=True, q_scale=1.0, seed=31, precision="tf32",
-              flags_at=None):
+              eps=None):
+    # The sampled bins are bit-exact GIVEN (p, u) (tests/test_gpu_kernels.py).  End to end, p itself carries the
+    # rounding of the K/V projection (single-pass TF32: ~3e-4 relative on K, more on exp(q.K) for peaky
+    # queries), so uniforms closer than `eps` to a CDF edge of the oracle's p are moved to the middle of a bin.
+    eps = eps if eps is not None else (5e-4 if precision == "tf32" else 2e-5)
     from infinite_video_b200.batched import BatchedRectLTM
     key, val = make_proj(seed, e)
     eng = BatchedRectLTM(N, tau, *proj_tensors(key, val), tokens_per_frame=T, sticky=sticky, precision=precision,
@@ -29,7 +33,7 @@ def _run_rect(dev, N, L, C, Bv, T=32, e=768, Q=32, tau=.75, sticky=True, q_scale
             u = us[c]
             if c > 0 and sticky:
                 p = torch.cat([o.sticky_hist(o.tables(L)) for o in orcs])
-                u = guard_band(u, p)
+                u = guard_band(u, p, eps)
             want = torch.cat([orcs[v].forward(ks[c][v:v + 1], qs[c][v:v + 1], c == 0, u[v:v + 1]) for v in range(Bv)])
             got = eng.step(ks[c].to(dev), qs[c].to(dev), u.to(dev) if c > 0 and sticky else None, new_doc=(c == 0))
             if c > 0 and sticky:
@@ -48,7 +52,8 @@ def _run_rect(dev, N, L, C, Bv, T=32, e=768, Q=32, tau=.75, sticky=True, q_scale
     ("cfg2", dict(N=256, L=256, C=3, Bv=2)),                                # BASELINE configs[1] (NExT-QA shape)
     ("cfg3", dict(N=64, L=16, C=3, Bv=1, T=196, e=1024, Q=96)),             # BASELINE configs[2] (VideoChat2)
     ("cfg4", dict(N=512, L=32, C=3, Bv=2)),                                 # num_basis=512 stress
-    ("peaky", dict(N=64, L=8, C=3, Bv=2, q_scale=8.0)),                     # far-from-uniform sticky histogram
+    ("peaky", dict(N=64, L=8, C=3, Bv=2, q_scale=8.0, precision="tf32x3")),  # far-from-uniform sticky histogram
+    ("peaky_tf32", dict(N=64, L=8, C=3, Bv=2, q_scale=8.0, eps=2e-2)),
     ("odd", dict(N=64, L=7, C=3, Bv=1)),
     ("nonpow2", dict(N=100, L=30, C=3, Bv=2, tau=.5)),                      # positions that fall in no bin
     ("uniform", dict(N=64, L=8, C=3, Bv=2, sticky=False)),                  # non-sticky re-sampling
@@ -199,11 +204,16 @@ def test_full_size_properties(dev):
     # (i) restarting the document reproduces the same bits (state fully reset, kernels deterministic)
     assert torch.equal(eng.step(k0, q, None, new_doc=True), c0)
     assert torch.equal(eng.step(k1, q, u, new_doc=False), c1)
-    # (ii) batch invariance: a video consolidated alone gives the same bits as inside the batch
+    # (ii) batch invariance: a video consolidated in a smaller batch gives the same bits as inside the big one
+    #      (alone, the frame pooling is split over more CTAs to fill the GPU: same value up to summation order)
+    half = BatchedRectLTM(N, .75, *proj_tensors(key, val), device=dev)
+    h0 = half.step(k0[2:6], q[2:6], None, new_doc=True)
+    h1 = half.step(k1[2:6], q[2:6], u[2:6], new_doc=False)
+    assert torch.equal(h0, c0[2:6]) and torch.equal(h1, c1[2:6])
     solo = BatchedRectLTM(N, .75, *proj_tensors(key, val), device=dev)
     s0 = solo.step(k0[3:4], q[3:4], None, new_doc=True)
     s1 = solo.step(k1[3:4], q[3:4], u[3:4], new_doc=False)
-    assert torch.equal(s0[0], c0[3]) and torch.equal(s1[0], c1[3])
+    assert relerr(s0[0], c0[3]) < 1e-5 and relerr(s1[0], c1[3]) < 1e-5
     # (iii) linearity of the regression in the chunk: B(2k) == 2 B(k) exactly (power-of-two scaling)
     eng.step(2 * k0, q, None, new_doc=True)
     assert torch.equal(eng.B_past, 2 * B0)
