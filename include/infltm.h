@@ -131,7 +131,10 @@ int ltm_gather_rows(const float* src, const int32_t* idx, float* out, int Bv, in
                     void* stream);
 
 /* ---- whole per-chunk step of variant R for Bv videos (device buffers), and the same through
- * host buffers (H2D of k,q,u,new_doc and D2H of ctx enqueued on `stream`; caller synchronises). */
+ * host buffers (H2D of k,q,u,new_doc and D2H of ctx enqueued on `stream`; caller synchronises).
+ * ltm_rect_step with k == NULL skips the frame pooling and consumes a->xpart as already filled by an
+ * earlier ltm_pool_mean (pooling does not depend on the memory state, so a host may issue it for the
+ * next chunk on a second stream while this chunk's regression / projection / attention run). */
 typedef struct {
   int Bv, L, T, e, N, Q, H, d, S, splits, sticky, precision, gemm_impl;
   /* constant tables (device) */

@@ -87,6 +87,8 @@ class BatchedRectLTM(_BatchedBase):
         self.T = int(tokens_per_frame)
         self.keep_scores = keep_scores
         self.prof_events = None       # optional list of 10 cudaEvent_t handles (bench.py stage timing)
+        self._side = None             # side stream for pooling the next chunk ahead of time
+        self._pref = None             # (data_ptr, shape, done_event) of a pending prefetch
         self._ws = {}
         self._B = None
         self._cur = 0
@@ -106,7 +108,8 @@ class BatchedRectLTM(_BatchedBase):
             i32 = dict(device=dev, dtype=torch.int32)
             ws = dict(
                 splits=splits,
-                xpart=torch.empty(Bv, L, splits, self.e, **f32),
+                xparts=[torch.empty(Bv, L, splits, self.e, **f32), torch.empty(Bv, L, splits, self.e, **f32)],
+                xi=0,
                 KV=torch.empty(Bv, self.N, 2 * self.D, **f32),
                 b_draw=torch.empty(Bv, self.S, **i32), idx=torch.empty(Bv, self.S, **i32),
                 ts=torch.empty(Bv, self.S, **f32), p=torch.empty(Bv, 127, **f32),
@@ -144,7 +147,7 @@ class BatchedRectLTM(_BatchedBase):
         a.B_past = self._B[self._cur].data_ptr() if self.has_state else None
         a.B_new = self._B[1 - self._cur].data_ptr()
         a.hist_part = self._hist.data_ptr()
-        a.xpart, a.KV = ws["xpart"].data_ptr(), ws["KV"].data_ptr()
+        a.xpart, a.KV = ws["xparts"][ws["xi"]].data_ptr(), ws["KV"].data_ptr()
         a.b_draw, a.idx, a.ts, a.p = (ws["b_draw"].data_ptr(), ws["idx"].data_ptr(), ws["ts"].data_ptr(),
                                       ws["p"].data_ptr())
         a.scores = ws["scores"].data_ptr() if ws["scores"] is not None else None
@@ -180,6 +183,33 @@ class BatchedRectLTM(_BatchedBase):
         self.has_state = True
         self.last = dict(b=ws["b_draw"], ts=ws["ts"], idx=ws["idx"], p=ws["p"], scores=ws["scores"], KV=ws["KV"])
 
+    def prefetch(self, k_next, Q, events=None):
+        """Pool the frames of the NEXT chunk now, on a side stream, into the alternate buffer.
+
+        Frame pooling (gibbs:304) does not depend on the memory state, and it is the HBM-bound 93 % of a
+        call's bytes, while regression / projection / attention of the current chunk are compute-bound; issuing
+        it one chunk ahead lets the two overlap.  The following `step(k_next, ...)` must pass the same tensor."""
+        require_cuda(k_next)
+        k_next = k_next.contiguous()
+        Bv, LT, e = k_next.shape
+        L = LT // self.T
+        ws = self._workspace(Bv, L, Q)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream(self.device)
+        self._side.wait_stream(main)          # the alternate buffer was last read by work already queued on `main`
+        k_next.record_stream(self._side)
+        dst = ws["xparts"][1 - ws["xi"]]
+        sp = C.c_void_p(self._side.cuda_stream)
+        if events is not None:
+            check(lib().ltm_event_record(events[0], sp), "event_record")
+        check(lib().ltm_pool_mean(ptr(k_next), ptr(dst), Bv, L, self.T, self.e, ws["splits"], sp), "pool_mean")
+        if events is not None:
+            check(lib().ltm_event_record(events[1], sp), "event_record")
+        done = torch.cuda.Event()
+        done.record(self._side)
+        self._pref = (k_next.data_ptr(), tuple(k_next.shape), done)
+
     def step(self, k, q, u=None, new_doc=False):
         """k[Bv, L*T, e], q[Bv,Q,D] fp32 CUDA; u[Bv,S] fp64 uniforms (needed from the second chunk on when
         sticky); new_doc: bool or per-video flags.  Returns ctx[Bv,Q,D]."""
@@ -194,8 +224,16 @@ class BatchedRectLTM(_BatchedBase):
                 raise ValueError(f"sticky re-sampling needs u: float64 [{Bv},{self.S}]")
             u = u.contiguous()
         ctx = torch.empty(Bv, Q, self.D, device=self.device, dtype=torch.float32)
+        pooled = False
+        if self._pref is not None:
+            pptr, pshape, done = self._pref
+            self._pref = None
+            if pptr == k.data_ptr() and pshape == tuple(k.shape):
+                torch.cuda.current_stream(self.device).wait_event(done)
+                ws["xi"] = 1 - ws["xi"]
+                pooled = True
         a = self._args(Bv, L, Q, ws, tab, tdev)
-        check(lib().ltm_rect_step(C.byref(a), ptr(k), ptr(q), ptr(u), ptr(flags), ptr(ctx),
+        check(lib().ltm_rect_step(C.byref(a), None if pooled else ptr(k), ptr(q), ptr(u), ptr(flags), ptr(ctx),
                                   stream_ptr(self.device)), "rect_step")
         self._finish(ws)
         return ctx

@@ -48,15 +48,18 @@ extern "C" int ltm_device_check(void) {
 extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const float* q, const double* u,
                              const uint8_t* new_doc, float* ctx, void* stream) {
   using namespace ltm;
-  LTM_REQUIRE(a && k && q && ctx, "rect_step: null pointer");
+  LTM_REQUIRE(a && q && ctx, "rect_step: null pointer");
   const int D = a->H * a->d;
   const int qtiles = (a->Q + 31) / 32;
   cudaStream_t st_ = (cudaStream_t)stream;
 #define LTM_PROF(i) do { if (a->prof_events[i]) cudaEventRecord((cudaEvent_t)a->prof_events[i], st_); } while (0)
-  LTM_PROF(0);
-  int rc = ltm_pool_mean(k, a->xpart, a->Bv, a->L, a->T, a->e, a->splits, stream);
-  if (rc) return rc;
-  LTM_PROF(1);
+  int rc = 0;
+  if (k != nullptr) {          // k == NULL: a->xpart was already filled (frame pooling is stateless and may be
+    LTM_PROF(0);               // issued ahead of time on another stream, see BatchedRectLTM.prefetch)
+    rc = ltm_pool_mean(k, a->xpart, a->Bv, a->L, a->T, a->e, a->splits, stream);
+    if (rc) return rc;
+    LTM_PROF(1);
+  }
   const float* B_past = a->B_past;
   const int32_t* idx = a->idx_uniform;     // non-sticky: fixed table shared by all videos
   if (B_past != nullptr && a->sticky) {

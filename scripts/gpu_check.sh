@@ -12,7 +12,6 @@ mkdir -p $OUT
 python __graft_entry__.py > $OUT/build.log 2>&1
 run() { name=$1; shift; timeout 900 python -m pytest -q -m gpu -p no:cacheprovider "$@" > $OUT/test_$name.log 2>&1; echo "$name rc=$?" >> $OUT/summary.txt; tail -3 $OUT/test_$name.log >> $OUT/summary.txt; }
 : > $OUT/summary.txt
-timeout 300 python scripts/gemm_mn_sweep.py > $OUT/mn_sweep.log 2>&1
 run gemm tests/test_gpu_kernels.py -k "gemm or project_kv"
 run kernels tests/test_gpu_kernels.py -k "not gemm and not project_kv"
 run e2e_rect tests/test_gpu_e2e.py -k "rect or host or drop_in or properties"
@@ -20,7 +19,7 @@ run e2e_gauss tests/test_gpu_e2e.py -k "gauss"
 timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; echo "smoke rc=$?" >> $OUT/summary.txt
 if [ "$MODE" = "full" ]; then
   timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" >> $OUT/summary.txt
-  timeout 900 python bench.py --steps 5 --warmup 3 --precision tf32x3 --no-e2e --no-cpu-baseline > $OUT/bench_x3.json 2> $OUT/bench_x3.err
+  timeout 900 python bench.py --steps 5 --warmup 3 --no-overlap --no-e2e --no-cpu-baseline > $OUT/bench_noov.json 2> $OUT/bench_noov.err
   timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
       python bench.py --steps 1 --warmup 3 --videos 32 --no-e2e --no-cpu-baseline > $OUT/ncu_launch.log 2>&1
