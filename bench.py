@@ -179,6 +179,7 @@ def run_b200(args):
     stream = torch.cuda.current_stream(dev)
 
     overlap = not args.no_overlap
+    eng.pool_ctas = args.pool_ctas_per_sm * 148
 
     def one_step():
         out = None
@@ -333,11 +334,16 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="do not pool chunk c+1 under chunk c's compute")
+    ap.add_argument("--pool-ctas-per-sm", type=int, default=0, help="grid bound of the prefetch pooling kernel")
+    ap.add_argument("--hi-prio", action="store_true", help="run the main stream at high priority")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference_impl(args)
+    if args.hi_prio:
+        with torch.cuda.stream(torch.cuda.Stream(priority=-1)):
+            return run_b200(args)
     return run_b200(args)
 
 

@@ -35,6 +35,10 @@ int         ltm_device_check(void);
 /* ---- R4: frame pooling.  gibbs:304  `k.reshape(B,L,T,e).mean(dim=2)`
  * k[Bv,L,T,e] -> xpart[Bv,L,splits,e]; the mean of frame l is sum_s xpart[.,l,s,:]. */
 int ltm_pool_mean(const float* k, float* xpart, int Bv, int L, int T, int e, int splits, void* stream);
+/* same with a bounded (persistent) grid of max_ctas CTAs (0 = one CTA per frame-split): used when the pooling
+ * of the next chunk runs on a side stream under the compute-bound kernels of the current chunk. */
+int ltm_pool_mean_grid(const float* k, float* xpart, int Bv, int L, int T, int e, int splits, int max_ctas,
+                       void* stream);
 
 /* ---- R6: sticky histogram of the previous call's density.  gibbs:196-203 (+score :224-230,
  * compute_probability :232-249).  scores[Bv,H,Q,N] -> hist_part[Bv,H,127] (sum over q; the sum

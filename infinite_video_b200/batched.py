@@ -88,7 +88,8 @@ class BatchedRectLTM(_BatchedBase):
         self.keep_scores = keep_scores
         self.prof_events = None       # optional list of 10 cudaEvent_t handles (bench.py stage timing)
         self._side = None             # side stream for pooling the next chunk ahead of time
-        self._pref = None             # (data_ptr, shape, done_event) of a pending prefetch
+        self._pref = {}               # pending prefetches: (data_ptr, shape) -> (buffer index, done event)
+        self.pool_ctas = 0            # grid bound of the side-stream pooling kernel (0 = one CTA per frame)
         self._ws = {}
         self._B = None
         self._cur = 0
@@ -109,7 +110,7 @@ class BatchedRectLTM(_BatchedBase):
             ws = dict(
                 splits=splits,
                 xparts=[torch.empty(Bv, L, splits, self.e, **f32), torch.empty(Bv, L, splits, self.e, **f32)],
-                xi=0,
+                xi=0, xnext=0,
                 KV=torch.empty(Bv, self.N, 2 * self.D, **f32),
                 b_draw=torch.empty(Bv, self.S, **i32), idx=torch.empty(Bv, self.S, **i32),
                 ts=torch.empty(Bv, self.S, **f32), p=torch.empty(Bv, 127, **f32),
@@ -196,19 +197,23 @@ class BatchedRectLTM(_BatchedBase):
         ws = self._workspace(Bv, L, Q)
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device)
+        if len(self._pref) >= 2:
+            raise RuntimeError("at most two chunks may be in flight (the pooled frames are double-buffered)")
         main = torch.cuda.current_stream(self.device)
-        self._side.wait_stream(main)          # the alternate buffer was last read by work already queued on `main`
+        self._side.wait_stream(main)          # the target buffer was last read by work already queued on `main`
         k_next.record_stream(self._side)
-        dst = ws["xparts"][1 - ws["xi"]]
+        b = ws["xnext"]
+        ws["xnext"] = 1 - b
         sp = C.c_void_p(self._side.cuda_stream)
         if events is not None:
             check(lib().ltm_event_record(events[0], sp), "event_record")
-        check(lib().ltm_pool_mean(ptr(k_next), ptr(dst), Bv, L, self.T, self.e, ws["splits"], sp), "pool_mean")
+        check(lib().ltm_pool_mean_grid(ptr(k_next), ptr(ws["xparts"][b]), Bv, L, self.T, self.e, ws["splits"],
+                                       int(self.pool_ctas), sp), "pool_mean")
         if events is not None:
             check(lib().ltm_event_record(events[1], sp), "event_record")
         done = torch.cuda.Event()
         done.record(self._side)
-        self._pref = (k_next.data_ptr(), tuple(k_next.shape), done)
+        self._pref[(k_next.data_ptr(), tuple(k_next.shape))] = (b, done)
 
     def step(self, k, q, u=None, new_doc=False):
         """k[Bv, L*T, e], q[Bv,Q,D] fp32 CUDA; u[Bv,S] fp64 uniforms (needed from the second chunk on when
@@ -224,14 +229,14 @@ class BatchedRectLTM(_BatchedBase):
                 raise ValueError(f"sticky re-sampling needs u: float64 [{Bv},{self.S}]")
             u = u.contiguous()
         ctx = torch.empty(Bv, Q, self.D, device=self.device, dtype=torch.float32)
-        pooled = False
-        if self._pref is not None:
-            pptr, pshape, done = self._pref
-            self._pref = None
-            if pptr == k.data_ptr() and pshape == tuple(k.shape):
-                torch.cuda.current_stream(self.device).wait_event(done)
-                ws["xi"] = 1 - ws["xi"]
-                pooled = True
+        hit = self._pref.pop((k.data_ptr(), tuple(k.shape)), None)
+        pooled = hit is not None
+        if pooled:
+            ws["xi"] = hit[0]
+            torch.cuda.current_stream(self.device).wait_event(hit[1])
+        else:
+            ws["xi"] = ws["xnext"]
+            ws["xnext"] = 1 - ws["xnext"]
         a = self._args(Bv, L, Q, ws, tab, tdev)
         check(lib().ltm_rect_step(C.byref(a), None if pooled else ptr(k), ptr(q), ptr(u), ptr(flags), ptr(ctx),
                                   stream_ptr(self.device)), "rect_step")

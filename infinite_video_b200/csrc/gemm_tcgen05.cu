@@ -13,8 +13,9 @@
 //   and three MMAs (hi*hi + lo*hi + hi*lo) reproduce fp32-grade products.  Needed for the Gaussian
 //   variant whose RBF design values reach 80 with heavy cancellation (single-pass TF32 -> 1e-2 error).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2-5 = operand splitter (precision 3) and epilogue (TMEM lane quarter = warp_id % 4).
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 =
+// epilogue (TMEM lane quarter = warp_id % 4), warps 6-9 = operand splitter (precision 3 only); two TMEM
+// accumulators so the epilogue of one tile overlaps the MMAs of the next.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -27,7 +28,6 @@ int gemm_simt_launch(const ltm_gemm_args& g, cudaStream_t stream);
 constexpr int BM = 128;
 constexpr int BK = 32;                       // 32 fp32 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 8;                    // 32 B of K per tcgen05.mma for tf32
-constexpr int GEMM_THREADS = 192;
 constexpr int A_BYTES = BM * BK * 4;         // 16 KB
 constexpr int SLAB_BYTES = 32 * BK * 4;      // MN-major slab: 32 k-rows x 128 B
 
@@ -35,7 +35,7 @@ struct GemmDev {
   float* C;
   const float* bias;
   long long ldc, strideC;
-  int M, Nc, K, K1;
+  int M, Nc, K, K1, batch;
   int a_kmajor, b_kmajor;
   int a_batched, b_batched, b2_batched, has_b2;
   unsigned mn_layout, mn_lbo, mn_sbo, mn_kadv;
@@ -128,33 +128,50 @@ __device__ __forceinline__ uint64_t operand_desc(uint32_t tile, int kmajor, int 
                 : umma_desc(tile + k * mn.kadv, mn.lbo, mn.sbo, mn.layout);
 }
 
+constexpr int STG_LD = 33;                                    // padded row of the epilogue staging tile
+constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;                 // one 32x32 fp32 tile per epilogue warp
+
 template <int BN, int STAGES, bool SPLIT>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (SPLIT ? 2 : 1);
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + slack for 1024 B alignment
-  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;   // + 1024 B alignment slack
+  static constexpr int TMEM_COLS = 2 * BN;                     // two accumulator buffers (256 or 512 columns)
+  static constexpr int THREADS = SPLIT ? 320 : 192;
+  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two <= 512");
 };
 
+// Persistent kernel: grid = min(#tiles, #SMs); every role walks the same static tile sequence
+// t = blockIdx.x, blockIdx.x + gridDim.x, ...  (tile -> (batch, m, n), n fastest so that CTAs running at the
+// same time share the A rows).  The smem ring and its phases run continuously across tiles; the accumulator is
+// double-buffered in TMEM so the epilogue of tile i drains while the MMAs of tile i+1 run.
+//   warp 0      TMA producer (one lane)
+//   warp 1      TMEM owner + tcgen05.mma issuer (one lane)
+//   warps 2-5   epilogue: tcgen05.ld -> registers -> (+bias) -> per-warp smem transpose -> 128-byte coalesced stores
+//   warps 6-9   (precision 3 only) operand splitter hi/lo
 template <int BN, int STAGES, bool SPLIT>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(Cfg<BN, STAGES, SPLIT>::THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ CUtensorMap mapB2, const GemmDev g) {
   using C_ = Cfg<BN, STAGES, SPLIT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B wants 1024 B alignment
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bars = smem_base + STAGES * C_::STAGE_BYTES;
+  float* staging = reinterpret_cast<float*>(smem_al + STAGES * C_::STAGE_BYTES);
+  const uint32_t bars = smem_base + STAGES * C_::STAGE_BYTES + STG_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto split_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
-  const uint32_t tmem_full_bar = bars + 8u * (3 * STAGES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_al + STAGES * C_::STAGE_BYTES + 8 * (3 * STAGES + 1));
+  auto tfull_bar = [&](int b) { return bars + 8u * (3 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bars + 8u * (3 * STAGES + 2 + b); };
+  uint32_t* tmem_slot =
+      reinterpret_cast<uint32_t*>(smem_al + STAGES * C_::STAGE_BYTES + STG_BYTES + 8 * (3 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, bz = blockIdx.z;
   const int num_kb = (g.K + BK - 1) / BK;
+  const int tiles_n = (g.Nc + BN - 1) / BN, tiles_m = (g.M + BM - 1) / BM;
+  const int num_tiles = tiles_n * tiles_m * g.batch;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
@@ -165,7 +182,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       mbar_init(empty_bar(s), 1);
       mbar_init(split_bar(s), 128);      // every splitter thread arrives after its proxy fence
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);        // tcgen05.commit of the last MMA of a tile
+      mbar_init(tempty_bar(b), 128);     // every epilogue thread after its last tcgen05.ld of the tile
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -177,35 +197,41 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_acc = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      const int za = g.a_batched ? bz : 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_arrive_expect_tx(full_bar(s), A_BYTES + C_::B_BYTES);
-        const uint32_t sa = smem_base + s * C_::STAGE_BYTES;
-        const uint32_t sb = sa + A_BYTES;
-        const int k0 = kb * BK;
-        if (g.a_kmajor) {
-          tma_load_3d(&mapA, sa, full_bar(s), k0, m0, za);
-        } else {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int n0 = (t % tiles_n) * BN, m0 = ((t / tiles_n) % tiles_m) * BM, bz = t / (tiles_n * tiles_m);
+        const int za = g.a_batched ? bz : 0;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_arrive_expect_tx(full_bar(s), A_BYTES + C_::B_BYTES);
+          const uint32_t sa = smem_base + s * C_::STAGE_BYTES;
+          const uint32_t sb = sa + A_BYTES;
+          const int k0 = kb * BK;
+          if (g.a_kmajor) {
+            tma_load_3d(&mapA, sa, full_bar(s), k0, m0, za);
+          } else {
 #pragma unroll
-          for (int i = 0; i < BM / 32; ++i) tma_load_3d(&mapA, sa + i * SLAB_BYTES, full_bar(s), m0 + 32 * i, k0, za);
-        }
-        const bool seg2 = g.has_b2 && (k0 >= g.K1);
-        const CUtensorMap* mb = seg2 ? &mapB2 : &mapB;
-        const int kk = seg2 ? k0 - g.K1 : k0;
-        const int zb = seg2 ? (g.b2_batched ? bz : 0) : (g.b_batched ? bz : 0);
-        if (g.b_kmajor) {
-          tma_load_3d(mb, sb, full_bar(s), kk, n0, zb);
-        } else {
+            for (int i = 0; i < BM / 32; ++i)
+              tma_load_3d(&mapA, sa + i * SLAB_BYTES, full_bar(s), m0 + 32 * i, k0, za);
+          }
+          const bool seg2 = g.has_b2 && (k0 >= g.K1);
+          const CUtensorMap* mb = seg2 ? &mapB2 : &mapB;
+          const int kk = seg2 ? k0 - g.K1 : k0;
+          const int zb = seg2 ? (g.b2_batched ? bz : 0) : (g.b_batched ? bz : 0);
+          if (g.b_kmajor) {
+            tma_load_3d(mb, sb, full_bar(s), kk, n0, zb);
+          } else {
 #pragma unroll
-          for (int i = 0; i < BN / 32; ++i) tma_load_3d(mb, sb + i * SLAB_BYTES, full_bar(s), n0 + 32 * i, kk, zb);
+            for (int i = 0; i < BN / 32; ++i)
+              tma_load_3d(mb, sb + i * SLAB_BYTES, full_bar(s), n0 + 32 * i, kk, zb);
+          }
         }
       }
     }
@@ -219,97 +245,109 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                              ((g.b_kmajor ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
       const MnDesc mn{g.mn_layout, g.mn_lbo, g.mn_sbo, g.mn_kadv};
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(SPLIT ? split_bar(s) : full_bar(s), ph);
+      uint32_t it = 0, tc = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tc) {
+        const uint32_t buf = tc & 1u, tph = (tc >> 1) & 1u;
+        mbar_wait(tempty_bar(buf), tph ^ 1u);                 // epilogue has drained this accumulator
         tcgen05_fence_after();
-        const uint32_t sa = smem_base + s * C_::STAGE_BYTES;
-        const uint32_t sb = sa + A_BYTES;
-        const uint32_t sa_lo = sb + C_::B_BYTES;
-        const uint32_t sb_lo = sa_lo + A_BYTES;
+        const uint32_t tmem_acc = tmem_base + buf * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(SPLIT ? split_bar(s) : full_bar(s), ph);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_base + s * C_::STAGE_BYTES;
+          const uint32_t sb = sa + A_BYTES;
+          const uint32_t sa_lo = sb + C_::B_BYTES;
+          const uint32_t sb_lo = sa_lo + A_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t da = operand_desc(sa, g.a_kmajor, k, mn);
-          const uint64_t db = operand_desc(sb, g.b_kmajor, k, mn);
-          tcgen05_mma_tf32(tmem_acc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-          if (SPLIT) {
-            tcgen05_mma_tf32(tmem_acc, operand_desc(sa_lo, g.a_kmajor, k, mn), db, idesc, 1u);
-            tcgen05_mma_tf32(tmem_acc, da, operand_desc(sb_lo, g.b_kmajor, k, mn), idesc, 1u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = operand_desc(sa, g.a_kmajor, k, mn);
+            const uint64_t db = operand_desc(sb, g.b_kmajor, k, mn);
+            tcgen05_mma_tf32(tmem_acc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (SPLIT) {
+              tcgen05_mma_tf32(tmem_acc, operand_desc(sa_lo, g.a_kmajor, k, mn), db, idesc, 1u);
+              tcgen05_mma_tf32(tmem_acc, da, operand_desc(sb_lo, g.b_kmajor, k, mn), idesc, 1u);
+            }
           }
+          tcgen05_commit(empty_bar(s));          // frees the stage once these MMAs have read it
         }
-        tcgen05_commit(empty_bar(s));          // frees the stage once these MMAs have read it
+        tcgen05_commit(tfull_bar(buf));          // accumulator of this tile complete
       }
-      tcgen05_commit(tmem_full_bar);           // accumulator complete
     }
     __syncwarp();
-  } else {
-    // ------------------------------------------------------------------ splitter + epilogue warps
-    const int et = threadIdx.x - 64;           // 0..127
-    if (SPLIT) {
-      constexpr int NV = (A_BYTES + C_::B_BYTES) / 16;      // float4 count of [A | B]
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(full_bar(s), ph);
-        float4* hi = reinterpret_cast<float4*>(smem_al + s * C_::STAGE_BYTES);
-        float4* lo = reinterpret_cast<float4*>(smem_al + s * C_::STAGE_BYTES + A_BYTES + C_::B_BYTES);
-#pragma unroll 4
-        for (int f = et; f < NV; f += 128) {
-          const float4 x = hi[f];
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-          h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-          h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-          h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-          l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
-          hi[f] = h;
-          lo[f] = l;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA)
-        mbar_arrive(split_bar(s));
-      }
-    }
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
-    const int quarter = warp & 3;              // TMEM lanes [32*quarter, 32*quarter+32)
-    const int row = m0 + quarter * 32 + lane;
-    float* crow = g.C + (size_t)bz * g.strideC + (size_t)row * g.ldc;
+  } else if (warp < 6) {
+    // ------------------------------------------------------------------ epilogue warps
+    const int quarter = warp & 3;                // TMEM lanes [32*quarter, 32*quarter+32)
+    float* stg = staging + quarter * (32 * STG_LD);
+    uint32_t tc = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tc) {
+      const int n0 = (t % tiles_n) * BN, m0 = ((t / tiles_n) % tiles_m) * BM, bz = t / (tiles_n * tiles_m);
+      const uint32_t buf = tc & 1u, tph = (tc >> 1) & 1u;
+      mbar_wait(tfull_bar(buf), tph);
+      tcgen05_fence_after();
+      const int row0 = m0 + quarter * 32;
+      float* cbase_ptr = g.C + (size_t)bz * g.strideC;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= g.Nc) break;              // warp-uniform
-      uint32_t r[32];
-      const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr)
-          : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < g.M) {
-        const int cbase = n0 + c0;
-        if (cbase + 32 <= g.Nc && ((g.ldc & 3) == 0)) {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= g.Nc) break;              // warp-uniform
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // thread `lane` holds row (row0 + lane), columns c0..c0+31 -> transpose through the warp's staging tile
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 o;
-            o.x = __uint_as_float(r[4 * i + 0]); o.y = __uint_as_float(r[4 * i + 1]);
-            o.z = __uint_as_float(r[4 * i + 2]); o.w = __uint_as_float(r[4 * i + 3]);
-            if (g.bias) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + cbase) + i);
-              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-            }
-            reinterpret_cast<float4*>(crow + cbase)[i] = o;
+        for (int i = 0; i < 32; ++i) stg[lane * STG_LD + i] = __uint_as_float(r[i]);
+        __syncwarp();
+        const int col = n0 + c0 + lane;          // now lane = column
+        const bool col_ok = col < g.Nc;
+        const float bv = (g.bias != nullptr && col_ok) ? __ldg(g.bias + col) : 0.f;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+          const int row = row0 + i;
+          if (row < g.M && col_ok) cbase_ptr[(size_t)row * g.ldc + col] = stg[i * STG_LD + lane] + bv;
+        }
+        __syncwarp();
+      }
+      tcgen05_fence_before();
+      mbar_arrive(tempty_bar(buf));              // 128 arrivals hand the accumulator back to the MMA warp
+    }
+  } else {
+    // ------------------------------------------------------------------ operand splitter (precision 3)
+    if (SPLIT) {
+      const int et = threadIdx.x - 192;          // 0..127
+      constexpr int NV = (A_BYTES + C_::B_BYTES) / 16;      // float4 count of [A | B]
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(full_bar(s), ph);
+          float4* hi = reinterpret_cast<float4*>(smem_al + s * C_::STAGE_BYTES);
+          float4* lo = reinterpret_cast<float4*>(smem_al + s * C_::STAGE_BYTES + A_BYTES + C_::B_BYTES);
+#pragma unroll 4
+          for (int f = et; f < NV; f += 128) {
+            const float4 x = hi[f];
+            float4 h, l;
+            h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+            h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+            h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+            h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+            l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
+            hi[f] = h;
+            lo[f] = l;
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (cbase + i < g.Nc) crow[cbase + i] = __uint_as_float(r[i]) + (g.bias ? g.bias[cbase + i] : 0.f);
-          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA)
+          mbar_arrive(split_bar(s));
         }
       }
     }
@@ -318,7 +356,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)C_::TMEM_COLS)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C_::TMEM_COLS)
                  : "memory");
   }
 }
@@ -372,9 +410,16 @@ static int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const CUtens
                                   C_::SMEM_BYTES));
     configured = true;
   }
-  dim3 grid((d.Nc + BN - 1) / BN, (d.M + BM - 1) / BM, batch);
-  LTM_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm: grid too large (M tiles %u, batch %u)", grid.y, grid.z);
-  gemm_tf32_kernel<BN, STAGES, SPLIT><<<grid, GEMM_THREADS, C_::SMEM_BYTES, stream>>>(mA, mB, mB2, d);
+  const long long tiles = (long long)((d.Nc + BN - 1) / BN) * ((d.M + BM - 1) / BM) * batch;
+  LTM_REQUIRE(tiles < (1ll << 31), "gemm: too many tiles");
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    LTM_CUDA(cudaGetDevice(&dev));
+    LTM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);     // persistent: one CTA per SM
+  gemm_tf32_kernel<BN, STAGES, SPLIT><<<grid, C_::THREADS, C_::SMEM_BYTES, stream>>>(mA, mB, mB2, d);
   LTM_CHECK_LAUNCH("gemm(tcgen05)");
   return 0;
 }
@@ -397,7 +442,7 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   }
   GemmDev d{};
   d.C = a.C; d.bias = a.bias; d.ldc = a.ldc; d.strideC = a.strideC;
-  d.M = a.M; d.Nc = a.Nc; d.K = a.K; d.K1 = K1;
+  d.M = a.M; d.Nc = a.Nc; d.K = a.K; d.K1 = K1; d.batch = a.batch;
   d.a_kmajor = a.a_kmajor ? 1 : 0; d.b_kmajor = a.b_kmajor ? 1 : 0;
   d.mn_layout = g_mn_desc[0]; d.mn_lbo = g_mn_desc[1]; d.mn_sbo = g_mn_desc[2]; d.mn_kadv = g_mn_desc[3];
   d.a_batched = a.strideA != 0; d.b_batched = a.strideB != 0; d.b2_batched = a.strideB2 != 0; d.has_b2 = two ? 1 : 0;

@@ -16,12 +16,15 @@ constexpr int POOL_UNROLL = 8;
 
 __global__ void __launch_bounds__(256)
 pool_mean_kernel(const float4* __restrict__ k, float4* __restrict__ xpart,
-                 int T, int e4, int splits, float Tf) {
-  const int unit = blockIdx.x / splits;          // (v*L + l)
-  const int sp = blockIdx.x - unit * splits;
+                 int T, int e4, int splits, float Tf, unsigned total) {
+  const uint64_t pol = policy_evict_first();
+  // grid == total: one CTA per (frame, split).  A smaller (persistent) grid leaves SM resources to kernels
+  // of other streams while this one keeps HBM busy.
+  for (unsigned work = blockIdx.x; work < total; work += gridDim.x) {
+  const int unit = work / splits;                // (v*L + l)
+  const int sp = work - unit * splits;
   const int r0 = (int)(((long long)T * sp) / splits);
   const int r1 = (int)(((long long)T * (sp + 1)) / splits);
-  const uint64_t pol = policy_evict_first();
   const float4* base = k + (size_t)unit * T * e4;
   for (int c = threadIdx.x; c < e4; c += blockDim.x) {
     float4 acc[POOL_UNROLL];
@@ -45,12 +48,18 @@ pool_mean_kernel(const float4* __restrict__ k, float4* __restrict__ xpart,
     o.x = __fdiv_rn(o.x, Tf); o.y = __fdiv_rn(o.y, Tf); o.z = __fdiv_rn(o.z, Tf); o.w = __fdiv_rn(o.w, Tf);
     xpart[((size_t)unit * splits + sp) * e4 + c] = o;
   }
+  }
 }
 
 }  // namespace ltm
 
 extern "C" int ltm_pool_mean(const float* k, float* xpart, int Bv, int L, int T, int e, int splits,
                              void* stream) {
+  return ltm_pool_mean_grid(k, xpart, Bv, L, T, e, splits, 0, stream);
+}
+
+extern "C" int ltm_pool_mean_grid(const float* k, float* xpart, int Bv, int L, int T, int e, int splits,
+                                  int max_ctas, void* stream) {
   using namespace ltm;
   LTM_REQUIRE(k && xpart, "pool_mean: null pointer");
   LTM_REQUIRE(Bv > 0 && L > 0 && T > 0 && e > 0, "pool_mean: bad shape Bv=%d L=%d T=%d e=%d", Bv, L, T, e);
@@ -61,8 +70,9 @@ extern "C" int ltm_pool_mean(const float* k, float* xpart, int Bv, int L, int T,
   LTM_REQUIRE(units < (1ll << 31), "pool_mean: too many frames");
   const int e4 = e / 4;
   const int threads = e4 >= 256 ? 256 : ((e4 + 31) / 32) * 32;
-  pool_mean_kernel<<<(unsigned)units, threads, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float4*>(k), reinterpret_cast<float4*>(xpart), T, e4, splits, (float)T);
+  const unsigned grid = (max_ctas > 0 && max_ctas < units) ? (unsigned)max_ctas : (unsigned)units;
+  pool_mean_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(k), reinterpret_cast<float4*>(xpart), T, e4, splits, (float)T, (unsigned)units);
   LTM_CHECK_LAUNCH("pool_mean");
   return 0;
 }

@@ -260,24 +260,23 @@ def test_full_size_properties(dev):
 
 
 def test_prefetched_pooling_is_bit_identical(dev):
-    """Pooling chunk c+1 ahead of time on the side stream must not change a single bit."""
+    """Pooling chunk c+1 ahead of time on the side stream (full or bounded grid) must not change a single bit."""
     from infinite_video_b200.batched import BatchedRectLTM
     key, val = make_proj(61, 768)
     a = BatchedRectLTM(256, .75, *proj_tensors(key, val), device=dev)
     b = BatchedRectLTM(256, .75, *proj_tensors(key, val), device=dev)
+    b.pool_ctas = 148 * 2
     ks, qs, us = make_inputs(62, 4, 4, 64 * 32, 768, 32)
     ks = [k.to(dev) for k in ks]
     qs = [q.to(dev) for q in qs]
     us = [u.to(dev) for u in us]
+    b.prefetch(ks[0], 32)
     for c in range(4):
         x = a.step(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0))
         if c + 1 < 4:
-            b.prefetch(ks[c + 1], 32) if c else None
-        if c == 0:
-            b.prefetch(ks[0], 32)
-            y = b.step(ks[0], qs[0], None, new_doc=True)
-            b.prefetch(ks[1], 32)
-        else:
-            y = b.step(ks[c], qs[c], us[c], new_doc=False)
+            b.prefetch(ks[c + 1], 32)             # next chunk is pooled while this one is consolidated
+        y = b.step(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0))
         assert torch.equal(x, y), f"chunk {c}"
         assert torch.equal(a.B_past, b.B_past)
+    with pytest.raises(RuntimeError):
+        b.prefetch(ks[0], 32); b.prefetch(ks[1], 32); b.prefetch(ks[2], 32)
