@@ -231,15 +231,21 @@ class BatchedRectLTM(_BatchedBase):
         ctx = torch.empty(Bv, Q, self.D, device=self.device, dtype=torch.float32)
         hit = self._pref.pop((k.data_ptr(), tuple(k.shape)), None)
         pooled = hit is not None
+        main = torch.cuda.current_stream(self.device)
+        run = main
         if pooled:
             ws["xi"] = hit[0]
-            torch.cuda.current_stream(self.device).wait_event(hit[1])
+            run = self._compute                      # fork: high-priority compute stream, joined below
+            run.wait_stream(main)
+            run.wait_event(hit[1])
         else:
             ws["xi"] = ws["xnext"]
             ws["xnext"] = 1 - ws["xnext"]
         a = self._args(Bv, L, Q, ws, tab, tdev)
         check(lib().ltm_rect_step(C.byref(a), None if pooled else ptr(k), ptr(q), ptr(u), ptr(flags), ptr(ctx),
-                                  stream_ptr(self.device)), "rect_step")
+                                  C.c_void_p(run.cuda_stream)), "rect_step")
+        if pooled:
+            main.wait_stream(run)
         self._finish(ws)
         return ctx
 

@@ -111,8 +111,13 @@ extern "C" int ltm_event_record(void* ev, void* stream) {
 extern "C" int ltm_event_elapsed_ms(void* start, void* stop, float* ms) {
   using namespace ltm;
   LTM_REQUIRE(ms != nullptr, "event_elapsed_ms: null pointer");
-  LTM_CUDA(cudaEventSynchronize((cudaEvent_t)stop));
-  LTM_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+  cudaError_t e = cudaEventSynchronize((cudaEvent_t)stop);
+  if (e == cudaSuccess) e = cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();            // e.g. an event that was never recorded: do not leave a stale error behind
+    set_error("event_elapsed_ms: %s", cudaGetErrorString(e));
+    return -3;
+  }
   return 0;
 }
 extern "C" int ltm_event_destroy(void* ev) {

@@ -14,13 +14,14 @@ namespace ltm {
 
 constexpr int POOL_UNROLL = 8;
 
+// PERSISTENT = false: one CTA per (frame, split).  PERSISTENT = true: a bounded grid walks the work list, which
+// leaves SM resources to kernels of other streams while this one keeps HBM busy.
+template <bool PERSISTENT>
 __global__ void __launch_bounds__(256)
 pool_mean_kernel(const float4* __restrict__ k, float4* __restrict__ xpart,
                  int T, int e4, int splits, float Tf, unsigned total) {
   const uint64_t pol = policy_evict_first();
-  // grid == total: one CTA per (frame, split).  A smaller (persistent) grid leaves SM resources to kernels
-  // of other streams while this one keeps HBM busy.
-  for (unsigned work = blockIdx.x; work < total; work += gridDim.x) {
+  for (unsigned work = blockIdx.x; work < (PERSISTENT ? total : blockIdx.x + 1); work += gridDim.x) {
   const int unit = work / splits;                // (v*L + l)
   const int sp = work - unit * splits;
   const int r0 = (int)(((long long)T * sp) / splits);
@@ -70,9 +71,13 @@ extern "C" int ltm_pool_mean_grid(const float* k, float* xpart, int Bv, int L, i
   LTM_REQUIRE(units < (1ll << 31), "pool_mean: too many frames");
   const int e4 = e / 4;
   const int threads = e4 >= 256 ? 256 : ((e4 + 31) / 32) * 32;
-  const unsigned grid = (max_ctas > 0 && max_ctas < units) ? (unsigned)max_ctas : (unsigned)units;
-  pool_mean_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float4*>(k), reinterpret_cast<float4*>(xpart), T, e4, splits, (float)T, (unsigned)units);
+  if (max_ctas > 0 && max_ctas < units) {
+    pool_mean_kernel<true><<<(unsigned)max_ctas, threads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(k), reinterpret_cast<float4*>(xpart), T, e4, splits, (float)T, (unsigned)units);
+  } else {
+    pool_mean_kernel<false><<<(unsigned)units, threads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(k), reinterpret_cast<float4*>(xpart), T, e4, splits, (float)T, (unsigned)units);
+  }
   LTM_CHECK_LAUNCH("pool_mean");
   return 0;
 }

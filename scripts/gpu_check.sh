@@ -21,10 +21,8 @@ if [ "$MODE" = "full" ]; then
   timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" >> $OUT/summary.txt
   B="timeout 600 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline"
   $B --no-overlap > $OUT/bench_noov.json 2> $OUT/bench_noov.err
-  $B --pool-ctas-per-sm 2 > $OUT/bench_p2.json 2> $OUT/bench_p2.err
+  $B --pool-ctas-per-sm 6 > $OUT/bench_p6.json 2> $OUT/bench_p6.err
   $B --pool-ctas-per-sm 4 > $OUT/bench_p4.json 2> $OUT/bench_p4.err
-  $B --pool-ctas-per-sm 2 --hi-prio > $OUT/bench_p2hi.json 2> $OUT/bench_p2hi.err
-  $B --hi-prio > $OUT/bench_hi.json 2> $OUT/bench_hi.err
   $B --precision tf32x3 --no-overlap > $OUT/bench_x3.json 2> $OUT/bench_x3.err
   timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
