@@ -196,7 +196,11 @@ class BatchedRectLTM(_BatchedBase):
         L = LT // self.T
         ws = self._workspace(Bv, L, Q)
         if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device)
+            # pooling runs at the lowest priority, the compute-bound kernels of `step` on a high-priority stream:
+            # the block scheduler then places regression / projection / attention CTAs as soon as resources free
+            # up and the streaming kernel fills whatever is left
+            self._side = torch.cuda.Stream(device=self.device, priority=0)
+            self._compute = torch.cuda.Stream(device=self.device, priority=-1)
         if len(self._pref) >= 2:
             raise RuntimeError("at most two chunks may be in flight (the pooled frames are double-buffered)")
         main = torch.cuda.current_stream(self.device)

@@ -14,14 +14,9 @@ namespace ltm {
 
 constexpr int POOL_UNROLL = 8;
 
-// PERSISTENT = false: one CTA per (frame, split).  PERSISTENT = true: a bounded grid walks the work list, which
-// leaves SM resources to kernels of other streams while this one keeps HBM busy.
-template <bool PERSISTENT>
-__global__ void __launch_bounds__(256)
-pool_mean_kernel(const float4* __restrict__ k, float4* __restrict__ xpart,
-                 int T, int e4, int splits, float Tf, unsigned total) {
-  const uint64_t pol = policy_evict_first();
-  for (unsigned work = blockIdx.x; work < (PERSISTENT ? total : blockIdx.x + 1); work += gridDim.x) {
+// One (frame, token-split) work item: the threads of the CTA each own 128-bit column groups.
+__device__ __forceinline__ void pool_unit(const float4* __restrict__ k, float4* __restrict__ xpart, int T, int e4,
+                                          int splits, float Tf, unsigned work, uint64_t pol) {
   const int unit = work / splits;                // (v*L + l)
   const int sp = work - unit * splits;
   const int r0 = (int)(((long long)T * sp) / splits);
@@ -49,7 +44,21 @@ pool_mean_kernel(const float4* __restrict__ k, float4* __restrict__ xpart,
     o.x = __fdiv_rn(o.x, Tf); o.y = __fdiv_rn(o.y, Tf); o.z = __fdiv_rn(o.z, Tf); o.w = __fdiv_rn(o.w, Tf);
     xpart[((size_t)unit * splits + sp) * e4 + c] = o;
   }
-  }
+}
+
+// one CTA per (frame, split)
+__global__ void __launch_bounds__(256)
+pool_mean_kernel(const float4* __restrict__ k, float4* __restrict__ xpart, int T, int e4, int splits, float Tf) {
+  pool_unit(k, xpart, T, e4, splits, Tf, blockIdx.x, policy_evict_first());
+}
+
+// bounded (persistent) grid walking the work list: leaves SM resources to kernels of other streams while this
+// one keeps HBM busy
+__global__ void __launch_bounds__(256)
+pool_mean_persistent_kernel(const float4* __restrict__ k, float4* __restrict__ xpart, int T, int e4, int splits,
+                            float Tf, unsigned total) {
+  const uint64_t pol = policy_evict_first();
+  for (unsigned work = blockIdx.x; work < total; work += gridDim.x) pool_unit(k, xpart, T, e4, splits, Tf, work, pol);
 }
 
 }  // namespace ltm
@@ -72,11 +81,11 @@ extern "C" int ltm_pool_mean_grid(const float* k, float* xpart, int Bv, int L, i
   const int e4 = e / 4;
   const int threads = e4 >= 256 ? 256 : ((e4 + 31) / 32) * 32;
   if (max_ctas > 0 && max_ctas < units) {
-    pool_mean_kernel<true><<<(unsigned)max_ctas, threads, 0, (cudaStream_t)stream>>>(
+    pool_mean_persistent_kernel<<<(unsigned)max_ctas, threads, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(k), reinterpret_cast<float4*>(xpart), T, e4, splits, (float)T, (unsigned)units);
   } else {
-    pool_mean_kernel<false><<<(unsigned)units, threads, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(k), reinterpret_cast<float4*>(xpart), T, e4, splits, (float)T, (unsigned)units);
+    pool_mean_kernel<<<(unsigned)units, threads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(k), reinterpret_cast<float4*>(xpart), T, e4, splits, (float)T);
   }
   LTM_CHECK_LAUNCH("pool_mean");
   return 0;
