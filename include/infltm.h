@@ -92,6 +92,10 @@ typedef struct {
   int M, Nc, K, batch;
   int precision;
   int impl;
+  /* optional transposed store: columns [0, ct_cols) of the product go to CT instead of C, transposed inside
+   * groups of ct_group consecutive rows: CT[(m / ct_group) * ct_cols + c][m % ct_group]; the remaining columns
+   * c >= ct_cols go to C[m * ldc + (c - ct_cols)].  ct_cols % 32 == 0, ct_group % 32 == 0.  CT = NULL: off. */
+  float* CT; int ct_cols; int ct_group;
 } ltm_gemm_args;
 int ltm_gemm(const ltm_gemm_args* args, void* stream);
 
@@ -99,6 +103,11 @@ int ltm_gemm(const ltm_gemm_args* args, void* stream);
  * KV[M, 2D] = Bcoef[M, e] * Wkv[2D, e]^T + bkv   (M = Bv*N; Wkv = [W_key ; W_value]). */
 int ltm_project_kv(const float* Bcoef, const float* Wkv, const float* bkv, float* KV,
                    int M, int e, int D2, int precision, int impl, void* stream);
+
+/* same projection, keys stored transposed per head for the fast attention path:
+ * Kt[Bv, H, 64, N] (= [M/N][D][N]) and V[M, D]. */
+int ltm_project_kv_t(const float* Bcoef, const float* Wkv, const float* bkv, float* Kt, float* V,
+                     int M, int e, int D, int N, int precision, int impl, void* stream);
 
 /* ---- R10/R11 (+R6 fused): continuous attention over rectangular bases.  gibbs:224-286,:346.
  * r_j = W_j e^{S_j} / (sum_i W_i e^{S_i} + W_out),  S = (q_h/sqrt(d)) K_h^T,  ctx = r V.
@@ -115,6 +124,16 @@ int ltm_cont_attn_rect(const float* q, const float* KV, const float* W, float W_
 int ltm_cont_attn_gauss(const float* q, const float* KV, const float* basis_mu, const float* basis_sigma,
                         float* ctx, float* scores_out, float* mu_out, float* sd_out,
                         int Bv, int Q, int N, int H, int d, void* stream);
+
+/* ---- fast path of both attention variants for num_basis in {64,128,256}, head_size 64: keys transposed
+ * (Kt[Bv,H,64,N], from ltm_project_kv_t), values V[Bv,N,ldv].  Same outputs as the two functions above. */
+int ltm_attn_fast_supported(int N, int d);
+int ltm_cont_attn_rect_t(const float* q, const float* Kt, const float* V, int64_t ldv, const float* W, float W_out,
+                         const int32_t* jb, const float* tb, float* ctx, float* scores_out, float* hist_part,
+                         int Bv, int Q, int N, int H, int d, void* stream);
+int ltm_cont_attn_gauss_t(const float* q, const float* Kt, const float* V, int64_t ldv, const float* basis_mu,
+                          const float* basis_sigma, float* ctx, float* scores_out, float* mu_out, float* sd_out,
+                          int Bv, int Q, int N, int H, int d, void* stream);
 
 /* ---- G1: Gaussian RBF evaluation.  basis_functions.py:158-164.
  * out[p, j] (ld) = N(t_p; mu_j, sigma_j^2); t may be gathered: t_p = tvals[tidx[p]] when tidx != NULL. */
@@ -153,7 +172,8 @@ typedef struct {
   float* hist_part;                     /* [Bv, H*ceil(Q/32), 127] previous call's partials (in) and new (out) */
   /* workspace (device) */
   float* xpart;                         /* [Bv,L,splits,e] */
-  float* KV;                            /* [Bv,N,2D] */
+  float* KV;                            /* [Bv,N,2D] (generic attention path) */
+  float* Kt; float* V;                  /* [Bv,H,64,N], [Bv,N,D]: fast path when N in {64,128,256} (else NULL) */
   int32_t *b_draw, *idx; float* ts;     /* [Bv,S] */
   float* p;                             /* [Bv,127] */
   float* scores;                        /* optional [Bv,H,Q,N] */

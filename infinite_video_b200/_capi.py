@@ -24,6 +24,7 @@ class GemmArgs(C.Structure):
         ("C", C.c_void_p), ("ldc", C.c_int64), ("strideC", C.c_int64),
         ("M", C.c_int), ("Nc", C.c_int), ("K", C.c_int), ("batch", C.c_int),
         ("precision", C.c_int), ("impl", C.c_int),
+        ("CT", C.c_void_p), ("ct_cols", C.c_int), ("ct_group", C.c_int),
     ]
 
 
@@ -40,7 +41,7 @@ class RectStepArgs(C.Structure):
         ("Wkv", C.c_void_p), ("bkv", C.c_void_p),
         ("B_past", C.c_void_p), ("B_new", C.c_void_p),
         ("hist_part", C.c_void_p),
-        ("xpart", C.c_void_p), ("KV", C.c_void_p),
+        ("xpart", C.c_void_p), ("KV", C.c_void_p), ("Kt", C.c_void_p), ("V", C.c_void_p),
         ("b_draw", C.c_void_p), ("idx", C.c_void_p), ("ts", C.c_void_p),
         ("p", C.c_void_p), ("scores", C.c_void_p),
         ("k_dev", C.c_void_p), ("q_dev", C.c_void_p), ("u_dev", C.c_void_p), ("new_doc_dev", C.c_void_p),
@@ -62,6 +63,10 @@ _SIGS = {
     "ltm_consolidate_rect": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ltm_gemm": (C.c_int, [C.POINTER(GemmArgs), _P]),
     "ltm_project_kv": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "ltm_project_kv_t": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "ltm_attn_fast_supported": (C.c_int, [_I, _I]),
+    "ltm_cont_attn_rect_t": (C.c_int, [_P, _P, _P, _L, _P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "ltm_cont_attn_gauss_t": (C.c_int, [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_cont_attn_rect": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_cont_attn_gauss": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_rbf_eval": (C.c_int, [_P, _P, _P, _P, _P, _L, _I, _I, _P]),

@@ -84,12 +84,22 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
   if (rc) return rc;
   LTM_PROF(5);
   LTM_PROF(6);
-  rc = ltm_project_kv(a->B_new, a->Wkv, a->bkv, a->KV, a->Bv * a->N, a->e, 2 * D, a->precision, a->gemm_impl, stream);
+  const bool fast = a->Kt != nullptr && a->V != nullptr && ltm_attn_fast_supported(a->N, a->d);
+  if (fast)
+    rc = ltm_project_kv_t(a->B_new, a->Wkv, a->bkv, a->Kt, a->V, a->Bv * a->N, a->e, D, a->N, a->precision,
+                          a->gemm_impl, stream);
+  else
+    rc = ltm_project_kv(a->B_new, a->Wkv, a->bkv, a->KV, a->Bv * a->N, a->e, 2 * D, a->precision, a->gemm_impl,
+                        stream);
   if (rc) return rc;
   LTM_PROF(7);
   LTM_PROF(8);
-  rc = ltm_cont_attn_rect(q, a->KV, a->W, a->W_out, a->jb, a->tb, ctx, a->scores, a->sticky ? a->hist_part : nullptr,
-                          a->Bv, a->Q, a->N, a->H, a->d, stream);
+  if (fast)
+    rc = ltm_cont_attn_rect_t(q, a->Kt, a->V, D, a->W, a->W_out, a->jb, a->tb, ctx, a->scores,
+                              a->sticky ? a->hist_part : nullptr, a->Bv, a->Q, a->N, a->H, a->d, stream);
+  else
+    rc = ltm_cont_attn_rect(q, a->KV, a->W, a->W_out, a->jb, a->tb, ctx, a->scores,
+                            a->sticky ? a->hist_part : nullptr, a->Bv, a->Q, a->N, a->H, a->d, stream);
   LTM_PROF(9);
 #undef LTM_PROF
   return rc;

@@ -70,7 +70,13 @@ gemm_simt_kernel(const ltm_gemm_args g) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
-      if (n < g.Nc) C[(size_t)m * g.ldc + n] = acc[i][j] + (g.bias ? g.bias[n] : 0.f);
+      if (n < g.Nc) {
+        const float val = acc[i][j] + (g.bias ? g.bias[n] : 0.f);
+        if (g.CT != nullptr && n < g.ct_cols)
+          (g.CT + (size_t)b * g.strideC)[((size_t)(m / g.ct_group) * g.ct_cols + n) * g.ct_group + (m % g.ct_group)] = val;
+        else
+          C[(size_t)m * g.ldc + n - (g.CT != nullptr ? g.ct_cols : 0)] = val;
+      }
     }
   }
 }

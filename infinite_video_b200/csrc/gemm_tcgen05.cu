@@ -39,6 +39,8 @@ struct GemmDev {
   int a_kmajor, b_kmajor;
   int a_batched, b_batched, b2_batched, has_b2;
   unsigned mn_layout, mn_lbo, mn_sbo, mn_kadv;
+  float* CT;
+  int ct_cols, ct_group;
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -304,17 +306,31 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             : "r"(taddr)
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        // thread `lane` holds row (row0 + lane), columns c0..c0+31 -> transpose through the warp's staging tile
+        // thread `lane` holds row (row0 + lane), columns c0..c0+31
+        if (g.CT != nullptr && n0 + c0 < g.ct_cols) {
+          // transposed store (keys per head): lanes are consecutive rows of one group -> 128-byte coalesced
+          const int row = row0 + lane;
+          if (row < g.M) {
+            float* dst = g.CT + (size_t)bz * g.strideC +
+                         ((size_t)(row / g.ct_group) * g.ct_cols + n0 + c0) * g.ct_group + (row % g.ct_group);
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              dst[(size_t)i * g.ct_group] = __uint_as_float(r[i]) + (g.bias ? __ldg(g.bias + n0 + c0 + i) : 0.f);
+          }
+          continue;
+        }
+        // row-major store: transpose through the warp's staging tile so that lanes become columns
 #pragma unroll
         for (int i = 0; i < 32; ++i) stg[lane * STG_LD + i] = __uint_as_float(r[i]);
         __syncwarp();
-        const int col = n0 + c0 + lane;          // now lane = column
+        const int col = n0 + c0 + lane;
         const bool col_ok = col < g.Nc;
         const float bv = (g.bias != nullptr && col_ok) ? __ldg(g.bias + col) : 0.f;
+        const int ccol = col - (g.CT != nullptr ? g.ct_cols : 0);
 #pragma unroll 8
         for (int i = 0; i < 32; ++i) {
           const int row = row0 + i;
-          if (row < g.M && col_ok) cbase_ptr[(size_t)row * g.ldc + col] = stg[i * STG_LD + lane] + bv;
+          if (row < g.M && col_ok) cbase_ptr[(size_t)row * g.ldc + ccol] = stg[i * STG_LD + lane] + bv;
         }
         __syncwarp();
       }
@@ -444,6 +460,7 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   d.C = a.C; d.bias = a.bias; d.ldc = a.ldc; d.strideC = a.strideC;
   d.M = a.M; d.Nc = a.Nc; d.K = a.K; d.K1 = K1; d.batch = a.batch;
   d.a_kmajor = a.a_kmajor ? 1 : 0; d.b_kmajor = a.b_kmajor ? 1 : 0;
+  d.CT = a.CT; d.ct_cols = a.ct_cols; d.ct_group = a.ct_group;
   d.mn_layout = g_mn_desc[0]; d.mn_lbo = g_mn_desc[1]; d.mn_sbo = g_mn_desc[2]; d.mn_kadv = g_mn_desc[3];
   d.a_batched = a.strideA != 0; d.b_batched = a.strideB != 0; d.b2_batched = a.strideB2 != 0; d.has_b2 = two ? 1 : 0;
   if (split) return launch_cfg<128, 3, true>(mA, mB, mB2, d, a.batch, stream);
@@ -468,9 +485,27 @@ extern "C" int ltm_gemm(const ltm_gemm_args* args, void* stream) {
   LTM_REQUIRE(a.bias == nullptr || ltm::aligned16(a.bias), "gemm: bias must be 16-byte aligned");
   LTM_REQUIRE(a.M > 0 && a.Nc > 0 && a.K > 0 && a.batch > 0, "gemm: bad shape M=%d N=%d K=%d batch=%d", a.M, a.Nc,
               a.K, a.batch);
+  LTM_REQUIRE(a.CT == nullptr || (a.ct_cols > 0 && a.ct_cols % 32 == 0 && a.ct_cols <= a.Nc && a.ct_group > 0 &&
+                                  a.ct_group % 32 == 0 && a.M % a.ct_group == 0),
+              "gemm: transposed store needs ct_cols %% 32 == 0, ct_group %% 32 == 0 and M %% ct_group == 0");
   if (a.impl == 1) return gemm_simt_launch(a, (cudaStream_t)stream);
   LTM_REQUIRE(a.impl == 0, "gemm: unknown impl %d", a.impl);
   return gemm_tcgen05_launch(a, (cudaStream_t)stream);
+}
+
+extern "C" int ltm_project_kv_t(const float* Bcoef, const float* Wkv, const float* bkv, float* Kt, float* V, int M,
+                                int e, int D, int N, int precision, int impl, void* stream) {
+  ltm_gemm_args a;
+  memset(&a, 0, sizeof(a));
+  a.A = Bcoef; a.lda = e; a.strideA = 0; a.a_kmajor = 1;
+  a.B = Wkv; a.ldb = e; a.strideB = 0; a.b_kmajor = 1;
+  a.B2 = nullptr; a.K1 = e;
+  a.bias = bkv;
+  a.C = V; a.ldc = D; a.strideC = 0;
+  a.CT = Kt; a.ct_cols = D; a.ct_group = N;
+  a.M = M; a.Nc = 2 * D; a.K = e; a.batch = 1;
+  a.precision = precision; a.impl = impl;
+  return ltm_gemm(&a, stream);
 }
 
 extern "C" int ltm_project_kv(const float* Bcoef, const float* Wkv, const float* bkv, float* KV, int M, int e,

@@ -8,7 +8,12 @@ rows = list(csv.reader(sys.stdin))
 top = int(sys.argv[1]) if len(sys.argv) > 1 else 25
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 h = rows[hi]
-body = [r for r in rows[hi + 1:] if len(r) == len(h)]
+body = []
+for r in rows[hi + 1:]:
+    if r and r[0] in ("Kernel Name", "Address"):
+        break                                  # a second captured launch follows: summarise the first only
+    if len(r) == len(h):
+        body.append(r)
 c = {n: i for i, n in enumerate(h)}
 S = "Warp Stall Sampling (All Samples)"
 tot = sum(float(r[c[S]] or 0) for r in body) or 1.0
