@@ -81,11 +81,13 @@ class BatchedRectLTM(_BatchedBase):
 
     def __init__(self, num_basis, tau, w_key, b_key, w_value, b_value, *, n_heads=12, head_size=64,
                  tokens_per_frame=32, sticky=True, nb_samples=tables.NB_SAMPLES, precision="tf32",
-                 gemm_impl="tcgen05", device="cuda", keep_scores=False):
+                 gemm_impl="tcgen05", device="cuda", keep_scores=False, fast_attn=True):
         super().__init__(num_basis, tau, w_key, b_key, w_value, b_value, n_heads, head_size, sticky, nb_samples,
                          precision, gemm_impl, device)
         self.T = int(tokens_per_frame)
         self.keep_scores = keep_scores
+        # transposed-key attention path (num_basis 64/128/256, head size 64); `fast_attn=False` forces the generic one
+        self.fast_attn = bool(fast_attn) and ops.attn_fast_supported(self.N, self.d)
         self.prof_events = None       # optional list of 10 cudaEvent_t handles (bench.py stage timing)
         self._side = None             # side stream for pooling the next chunk ahead of time
         self._pref = {}               # pending prefetches: (data_ptr, shape) -> (buffer index, done event)
@@ -111,7 +113,9 @@ class BatchedRectLTM(_BatchedBase):
                 splits=splits,
                 xparts=[torch.empty(Bv, L, splits, self.e, **f32), torch.empty(Bv, L, splits, self.e, **f32)],
                 xi=0, xnext=0,
-                KV=torch.empty(Bv, self.N, 2 * self.D, **f32),
+                KV=None if self.fast_attn else torch.empty(Bv, self.N, 2 * self.D, **f32),
+                Kt=torch.empty(Bv, self.H, self.d, self.N, **f32) if self.fast_attn else None,
+                V=torch.empty(Bv, self.N, self.D, **f32) if self.fast_attn else None,
                 b_draw=torch.empty(Bv, self.S, **i32), idx=torch.empty(Bv, self.S, **i32),
                 ts=torch.empty(Bv, self.S, **f32), p=torch.empty(Bv, 127, **f32),
                 scores=torch.empty(Bv, self.H, Q, self.N, **f32) if self.keep_scores else None,
@@ -148,7 +152,10 @@ class BatchedRectLTM(_BatchedBase):
         a.B_past = self._B[self._cur].data_ptr() if self.has_state else None
         a.B_new = self._B[1 - self._cur].data_ptr()
         a.hist_part = self._hist.data_ptr()
-        a.xpart, a.KV = ws["xparts"][ws["xi"]].data_ptr(), ws["KV"].data_ptr()
+        a.xpart = ws["xparts"][ws["xi"]].data_ptr()
+        a.KV = ws["KV"].data_ptr() if ws["KV"] is not None else None
+        a.Kt = ws["Kt"].data_ptr() if ws["Kt"] is not None else None
+        a.V = ws["V"].data_ptr() if ws["V"] is not None else None
         a.b_draw, a.idx, a.ts, a.p = (ws["b_draw"].data_ptr(), ws["idx"].data_ptr(), ws["ts"].data_ptr(),
                                       ws["p"].data_ptr())
         a.scores = ws["scores"].data_ptr() if ws["scores"] is not None else None
@@ -182,7 +189,8 @@ class BatchedRectLTM(_BatchedBase):
     def _finish(self, ws):
         self._cur = 1 - self._cur
         self.has_state = True
-        self.last = dict(b=ws["b_draw"], ts=ws["ts"], idx=ws["idx"], p=ws["p"], scores=ws["scores"], KV=ws["KV"])
+        V = ws["V"] if ws["V"] is not None else ws["KV"][:, :, self.D:]
+        self.last = dict(b=ws["b_draw"], ts=ws["ts"], idx=ws["idx"], p=ws["p"], scores=ws["scores"], V=V)
 
     def prefetch(self, k_next, Q, events=None):
         """Pool the frames of the NEXT chunk now, on a side stream, into the alternate buffer.
@@ -377,12 +385,17 @@ class BatchedGaussLTM(_BatchedBase):
             B = ops.gemm(op["GinfT"], xm, B2=k, a_kmajor=True, b_kmajor=False, precision=self.precision,
                          impl=self.gemm_impl)
         self._B = B
-        KV = ops.project_kv(B, self.Wkv, self.bkv, precision=self.proj_precision, impl=self.gemm_impl)
-        KV = KV.view(Bv, self.N, 2 * self.D)
-        ctx, scores, mu, sd = ops.cont_attn_gauss(q, KV, op["mu"], op["sigma"], n_heads=self.H)
+        if ops.attn_fast_supported(self.N, self.d):
+            Kt, V = ops.project_kv_t(B, self.Wkv, self.bkv, self.N, precision=self.proj_precision,
+                                     impl=self.gemm_impl)
+            ctx, scores, mu, sd = ops.cont_attn_gauss_t(q, Kt, V, op["mu"], op["sigma"])
+        else:
+            KV = ops.project_kv(B, self.Wkv, self.bkv, precision=self.proj_precision, impl=self.gemm_impl)
+            KV = KV.view(Bv, self.N, 2 * self.D)
+            ctx, scores, mu, sd = ops.cont_attn_gauss(q, KV, op["mu"], op["sigma"], n_heads=self.H)
         self._mu, self._sd = mu, sd
         self.has_state = True
-        info.update(mu=mu, sd=sd, KV=KV)
+        info.update(mu=mu, sd=sd)
         self.last = info
         return ctx
 

@@ -488,6 +488,7 @@ extern "C" int ltm_gemm(const ltm_gemm_args* args, void* stream) {
   LTM_REQUIRE(a.CT == nullptr || (a.ct_cols > 0 && a.ct_cols % 32 == 0 && a.ct_cols <= a.Nc && a.ct_group > 0 &&
                                   a.ct_group % 32 == 0 && a.M % a.ct_group == 0),
               "gemm: transposed store needs ct_cols %% 32 == 0, ct_group %% 32 == 0 and M %% ct_group == 0");
+  LTM_REQUIRE(a.CT == nullptr || a.batch == 1, "gemm: transposed store is defined for batch == 1");
   if (a.impl == 1) return gemm_simt_launch(a, (cudaStream_t)stream);
   LTM_REQUIRE(a.impl == 0, "gemm: unknown impl %d", a.impl);
   return gemm_tcgen05_launch(a, (cudaStream_t)stream);

@@ -148,6 +148,7 @@ def gemm(A, B, *, a_kmajor=True, b_kmajor=True, B2=None, bias=None, out=None, pr
     g.C, g.ldc, g.strideC = o3.data_ptr(), o3.stride(1), (o3.stride(0) if batch > 1 else 0)
     g.M, g.Nc, g.K, g.batch = M, Nc, Ka, batch
     g.precision, g.impl = PRECISION[precision], GEMM_IMPL[impl]
+    g.CT, g.ct_cols, g.ct_group = None, 0, 0
     check(lib().ltm_gemm(C.byref(g), stream_ptr(A.device)), "gemm")
     return out
 
@@ -163,6 +164,56 @@ def project_kv(Bcoef, Wkv, bkv, precision="tf32", impl="tcgen05", out=None):
     check(lib().ltm_project_kv(ptr(Bc), ptr(Wkv), ptr(bkv), ptr(out), M, e, D2, PRECISION[precision],
                                GEMM_IMPL[impl], stream_ptr(Bc.device)), "project_kv")
     return out
+
+
+def attn_fast_supported(N, d=64):
+    return bool(lib().ltm_attn_fast_supported(int(N), int(d)))
+
+
+def project_kv_t(Bcoef, Wkv, bkv, N, precision="tf32", impl="tcgen05"):
+    """Same projection with the keys stored transposed per head: -> (Kt[Bv,H,64,N], V[Bv,N,D])."""
+    require_cuda(Bcoef, Wkv, bkv)
+    Bc = _f32c(Bcoef).reshape(-1, Bcoef.shape[-1])
+    M, e = Bc.shape
+    D = Wkv.shape[0] // 2
+    Bv = M // N
+    Kt = torch.empty(Bv, D // 64, 64, N, device=Bc.device, dtype=torch.float32)
+    V = torch.empty(Bv, N, D, device=Bc.device, dtype=torch.float32)
+    check(lib().ltm_project_kv_t(ptr(Bc), ptr(Wkv), ptr(bkv), ptr(Kt), ptr(V), M, e, D, N, PRECISION[precision],
+                                 GEMM_IMPL[impl], stream_ptr(Bc.device)), "project_kv_t")
+    return Kt, V
+
+
+def cont_attn_rect_t(q, Kt, V, W, W_out, jb=None, tb=None, want_scores=False, want_hist=True):
+    """Fast path (num_basis 64/128/256): q[Bv,Q,D], Kt[Bv,H,64,N], V[Bv,N,D] -> (ctx, scores|None, hist_part|None)."""
+    require_cuda(q, Kt, V, W, jb, tb)
+    q = _f32c(q)
+    Bv, Q, D = q.shape
+    H, d, N = Kt.shape[1], Kt.shape[2], Kt.shape[3]
+    ctx = torch.empty(Bv, Q, D, device=q.device, dtype=torch.float32)
+    scores = torch.empty(Bv, H, Q, N, device=q.device, dtype=torch.float32) if want_scores else None
+    hist = (torch.empty(Bv, H * ((Q + 31) // 32), STICKY_EDGES - 2, device=q.device, dtype=torch.float32)
+            if want_hist else None)
+    check(lib().ltm_cont_attn_rect_t(ptr(q), ptr(Kt), ptr(V), V.stride(1), ptr(W), float(W_out), ptr(jb), ptr(tb),
+                                     ptr(ctx), ptr(scores), ptr(hist), Bv, Q, N, H, d, stream_ptr(q.device)),
+          "cont_attn_rect_t")
+    return ctx, scores, hist
+
+
+def cont_attn_gauss_t(q, Kt, V, basis_mu, basis_sigma, want_scores=False):
+    """Fast path of the Gaussian closed form -> (ctx, scores|None, mu[Bv,H*Q], sd[Bv,H*Q])."""
+    require_cuda(q, Kt, V, basis_mu, basis_sigma)
+    q = _f32c(q)
+    Bv, Q, D = q.shape
+    H, d, N = Kt.shape[1], Kt.shape[2], Kt.shape[3]
+    ctx = torch.empty(Bv, Q, D, device=q.device, dtype=torch.float32)
+    scores = torch.empty(Bv, H, Q, N, device=q.device, dtype=torch.float32) if want_scores else None
+    mu = torch.empty(Bv, H * Q, device=q.device, dtype=torch.float32)
+    sd = torch.empty(Bv, H * Q, device=q.device, dtype=torch.float32)
+    check(lib().ltm_cont_attn_gauss_t(ptr(q), ptr(Kt), ptr(V), V.stride(1), ptr(basis_mu), ptr(basis_sigma), ptr(ctx),
+                                      ptr(scores), ptr(mu), ptr(sd), Bv, Q, N, H, d, stream_ptr(q.device)),
+          "cont_attn_gauss_t")
+    return ctx, scores, mu, sd
 
 
 def cont_attn_rect(q, KV, W, W_out, jb=None, tb=None, n_heads=12, want_scores=False, want_hist=True):

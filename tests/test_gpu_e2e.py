@@ -15,7 +15,7 @@ def dev(cuda_device):
 
 
 def _run_rect(dev, N, L, C, Bv, T=32, e=768, Q=32, tau=.75, sticky=True, q_scale=1.0, seed=31, precision="tf32",
-              eps=None):
+              eps=None, fast_attn=True):
     # The sampled bins are bit-exact GIVEN (p, u) (tests/test_gpu_kernels.py).  End to end, p itself carries the
     # rounding of the K/V projection (single-pass TF32: ~3e-4 relative on K, more on exp(q.K) for peaky
     # queries), so uniforms closer than `eps` to a CDF edge of the oracle's p are moved to the middle of a bin.
@@ -23,7 +23,7 @@ def _run_rect(dev, N, L, C, Bv, T=32, e=768, Q=32, tau=.75, sticky=True, q_scale
     from infinite_video_b200.batched import BatchedRectLTM
     key, val = make_proj(seed, e)
     eng = BatchedRectLTM(N, tau, *proj_tensors(key, val), tokens_per_frame=T, sticky=sticky, precision=precision,
-                         device=dev, keep_scores=True)
+                         device=dev, keep_scores=True, fast_attn=fast_attn)
     orcs = [O.RectLTM(N, tau, *proj_tensors(key, val), tokens_per_frame=T, sticky=sticky, rebuild_tables=False)
             for _ in range(Bv)]
     ks, qs, us = make_inputs(seed + 1, C, Bv, L * T, e, Q, q_scale)
@@ -49,6 +49,7 @@ def _run_rect(dev, N, L, C, Bv, T=32, e=768, Q=32, tau=.75, sticky=True, q_scale
 
 @pytest.mark.parametrize("name,kw", [
     ("cfg1", dict(N=64, L=8, C=4, Bv=3)),                                   # BASELINE configs[0]
+    ("n128", dict(N=128, L=16, C=3, Bv=2, Q=40)),
     ("cfg2", dict(N=256, L=256, C=3, Bv=2)),                                # BASELINE configs[1] (NExT-QA shape)
     ("cfg3", dict(N=64, L=16, C=3, Bv=1, T=196, e=1024, Q=96)),             # BASELINE configs[2] (VideoChat2)
     ("cfg4", dict(N=512, L=32, C=3, Bv=2)),                                 # num_basis=512 stress
@@ -62,6 +63,14 @@ def test_rect_matches_oracle_over_chunks(dev, name, kw):
     w = _run_rect(dev, **kw)
     assert w["B"] < 1e-5, w            # the segmented mean is fp32 exact up to summation order
     assert w["ctx"] < TOL_CTX, w       # single-pass TF32 projection, fp32 accumulate
+
+
+@pytest.mark.parametrize("kw", [dict(N=256, L=32, C=3, Bv=2), dict(N=64, L=8, C=3, Bv=2, Q=96),
+                                dict(N=128, L=16, C=3, Bv=3, q_scale=4.0, precision="tf32x3")])
+def test_generic_attention_path_still_matches(dev, kw):
+    """num_basis 64/128/256 normally take the transposed-key kernels; the generic kernels must agree too."""
+    w = _run_rect(dev, fast_attn=False, **kw)
+    assert w["B"] < 1e-5 and w["ctx"] < TOL_CTX, w
 
 
 def test_rect_split_tf32_is_fp32_grade(dev):
@@ -252,9 +261,9 @@ def test_full_size_properties(dev):
     assert torch.equal(eng.B_past, B1)
     # (vi) zero queries: S == 0 so r_j == W_j exactly and ctx == sum_j W_j V_j  (W sums to 1 - W_out)
     eng.step(k0, torch.zeros_like(q), None, new_doc=True)
-    KV = eng.last["KV"].view(Bv, N, 2 * 768)
+    V = eng.last["V"]
     W = tables.rect_tables(L, N, .75).to(dev)["W"]
-    want = torch.einsum("j,vjd->vd", W / (W.sum() + tables.rect_tables(L, N, .75).W_out), KV[:, :, 768:])
+    want = torch.einsum("j,vjd->vd", W / (W.sum() + tables.rect_tables(L, N, .75).W_out), V)
     got = eng.step(k0, torch.zeros_like(q), None, new_doc=True)
     assert relerr(got[:, 0], want) < 1e-5 and relerr(got[:, 31], want) < 1e-5
 

@@ -123,6 +123,18 @@ def test_cont_attn_rect_and_fused_histogram(dev, N, L, Q, q_scale):
     hp = ops.sticky_hist_rect(scores, td["jb"], td["tb"])
     got2 = ops.resample(hp, u, bins, td["bin2basis"], normalize=True)
     assert relerr(got2["p"], got["p"]) < 1e-5
+    # transposed-key fast path (same inputs, K handed over as Kt[v][h][d][j])
+    if ops.attn_fast_supported(N):
+        Kt = KV[:, :, :768].reshape(2, N, 12, 64).permute(0, 2, 3, 1).contiguous()
+        Vv = KV[:, :, 768:].contiguous()
+        ctx3, scores3, hist3 = ops.cont_attn_rect_t(q.to(dev), Kt.to(dev), Vv.to(dev), td["W"], tab.W_out, td["jb"],
+                                                     td["tb"], want_scores=True, want_hist=True)
+        assert relerr(scores3, want_S) < 1e-5
+        assert relerr(ctx3, want_ctx) < 1e-4
+        got3 = ops.resample(hist3, u, bins, td["bin2basis"], normalize=True)
+        assert relerr(got3["p"], want_p) < 2e-5
+        ctx4, _, _ = ops.cont_attn_rect_t(q.to(dev), Kt.to(dev), Vv.to(dev), td["W"], tab.W_out, want_hist=False)
+        assert torch.equal(ctx4, ctx3)
 
 
 # ---------------------------------------------------------------------------------------- R3/R5/R8
@@ -211,6 +223,12 @@ def test_project_kv(dev):
     want = torch.nn.functional.linear(B.double(), Wkv.double(), bkv.double())
     assert relerr(ops.project_kv(B.to(dev), Wkv.to(dev), bkv.to(dev), "tf32"), want) < 1e-3
     assert relerr(ops.project_kv(B.to(dev), Wkv.to(dev), bkv.to(dev), "tf32x3"), want) < 1e-5
+    # keys transposed per head / values compact (fast attention path): same numbers, different layout
+    for N in (64, 256):
+        for impl in ("tcgen05", "simt"):
+            Kt, V = ops.project_kv_t(B.to(dev), Wkv.to(dev), bkv.to(dev), N, "tf32x3", impl)
+            wk = want[:, :768].reshape(512 // N, N, 12, 64).permute(0, 2, 3, 1)
+            assert relerr(Kt, wk) < 1e-5 and relerr(V.reshape(512, 768), want[:, 768:]) < 1e-5
 
 
 # ---------------------------------------------------------------------------------------- variant G kernels
@@ -274,3 +292,8 @@ def test_cont_attn_gauss(dev):
     assert relerr(mu, orc.attn_past[0]) < 1e-5
     assert relerr(sd, orc.attn_past[1]) < 1e-3       # var = E[t^2] - mu^2 cancels; see DESIGN.md
     assert relerr(ctx, want) < 1e-3
+    Kt = KV[:, :, :768].reshape(Bv, N, 12, 64).permute(0, 2, 3, 1).contiguous()
+    ctx2, scores2, mu2, sd2 = ops.cont_attn_gauss_t(qs[0].to(dev), Kt.to(dev), KV[:, :, 768:].contiguous().to(dev),
+                                                    psi.mu[0].to(dev), psi.sigma[0].to(dev), want_scores=True)
+    assert relerr(scores2, orc.last["scores"]) < 1e-5 and relerr(mu2, orc.attn_past[0]) < 1e-5
+    assert relerr(sd2, orc.attn_past[1]) < 1e-3 and relerr(ctx2, want) < 1e-3
