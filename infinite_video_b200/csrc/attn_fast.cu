@@ -274,22 +274,28 @@ cont_attn_fast_kernel(const Params p) {
     const int slot = (st + 1) & 1;
     if (st + 1 < NST3) { issue_v(st + 1, slot ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();                            // also orders the Rt writes before the first reads
-    const float* vst = ring + slot * RING + dh * 32 + 4 * dg;
-#pragma unroll 4
-    for (int jl = 0; jl < 16; ++jl) {
-      const int jloc = jw * 16 + jl;
-      const int j = st * 64 + jloc;
-      const int sw = (j >> 3) & 7;
-      const float4 r0 = *reinterpret_cast<const float4*>(Rt + j * QT + 4 * ((2 * qg) ^ sw));
-      const float4 r1 = *reinterpret_cast<const float4*>(Rt + j * QT + 4 * ((2 * qg + 1) ^ sw));
-      const float4 vv = *reinterpret_cast<const float4*>(vst + jloc * DH);
-      const float rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    const float* vst = ring + slot * RING + dh * 32 + 4 * dg + (jw * 16) * DH;
+    // the warp's 16 basis rows of this stage are two runs of 8 with a constant swizzle term each
 #pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        o[a][0] = fmaf(rr[a], vv.x, o[a][0]);
-        o[a][1] = fmaf(rr[a], vv.y, o[a][1]);
-        o[a][2] = fmaf(rr[a], vv.z, o[a][2]);
-        o[a][3] = fmaf(rr[a], vv.w, o[a][3]);
+    for (int half = 0; half < 2; ++half) {
+      const int jbase = st * 64 + jw * 16 + half * 8;
+      const int sw = (jbase >> 3) & 7;
+      const float* rp0 = Rt + jbase * QT + 4 * ((2 * qg) ^ sw);
+      const float* rp1 = Rt + jbase * QT + 4 * ((2 * qg + 1) ^ sw);
+      const float* vp = vst + (half * 8) * DH;
+#pragma unroll
+      for (int jl = 0; jl < 8; ++jl) {
+        const float4 r0 = *reinterpret_cast<const float4*>(rp0 + jl * QT);
+        const float4 r1 = *reinterpret_cast<const float4*>(rp1 + jl * QT);
+        const float4 vv = *reinterpret_cast<const float4*>(vp + jl * DH);
+        const float rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          o[a][0] = fmaf(rr[a], vv.x, o[a][0]);
+          o[a][1] = fmaf(rr[a], vv.y, o[a][1]);
+          o[a][2] = fmaf(rr[a], vv.z, o[a][2]);
+          o[a][3] = fmaf(rr[a], vv.w, o[a][3]);
+        }
       }
     }
     __syncthreads();

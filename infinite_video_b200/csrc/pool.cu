@@ -13,6 +13,7 @@
 namespace ltm {
 
 constexpr int POOL_UNROLL = 8;
+constexpr int POOL_ACC = 2;
 
 // One (frame, token-split) work item: the threads of the CTA each own 128-bit column groups.
 __device__ __forceinline__ void pool_unit(const float4* __restrict__ k, float4* __restrict__ xpart, int T, int e4,
@@ -23,22 +24,22 @@ __device__ __forceinline__ void pool_unit(const float4* __restrict__ k, float4* 
   const int r1 = (int)(((long long)T * (sp + 1)) / splits);
   const float4* base = k + (size_t)unit * T * e4;
   for (int c = threadIdx.x; c < e4; c += blockDim.x) {
-    float4 acc[POOL_UNROLL];
+    // 8 independent 128-bit loads in flight, folded into two accumulators: the register file is what limits how
+    // many of these CTAs fit next to the compute-bound kernels of the other stream (44 registers -> 7 per SM)
+    float4 acc[POOL_ACC];
 #pragma unroll
-    for (int i = 0; i < POOL_UNROLL; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < POOL_ACC; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     int r = r0;
     for (; r + POOL_UNROLL <= r1; r += POOL_UNROLL) {
       float4 v[POOL_UNROLL];
 #pragma unroll
       for (int i = 0; i < POOL_UNROLL; ++i) v[i] = ldg_stream(base + (size_t)(r + i) * e4 + c, pol);
 #pragma unroll
-      for (int i = 0; i < POOL_UNROLL; ++i) f4_add(acc[i], v[i]);
+      for (int i = 0; i < POOL_UNROLL; ++i) f4_add(acc[i % POOL_ACC], v[i]);
     }
     for (; r < r1; ++r) f4_add(acc[0], ldg_stream(base + (size_t)r * e4 + c, pol));
 #pragma unroll
-    for (int s = POOL_UNROLL / 2; s > 0; s >>= 1)
-#pragma unroll
-      for (int i = 0; i < s; ++i) f4_add(acc[i], acc[i + s]);
+    for (int i = 1; i < POOL_ACC; ++i) f4_add(acc[0], acc[i]);
     float4 o = acc[0];
     // torch.mean == sum / T (true division, so T = 196 rounds like the reference)
     o.x = __fdiv_rn(o.x, Tf); o.y = __fdiv_rn(o.y, Tf); o.z = __fdiv_rn(o.z, Tf); o.w = __fdiv_rn(o.w, Tf);
