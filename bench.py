@@ -57,7 +57,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.gpu), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -258,6 +258,11 @@ def run_b200(args):
     ms_per_step = ms / args.steps
     step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9
 
+    # ---------------- secondary arm: the Gaussian variant (north_star wording) on the same chunk shape
+    gauss = None
+    if rank == 0 and world == 1 and not args.no_gauss:
+        gauss = run_gauss_arm(dev, args.gauss_videos, 3, args.gauss_frames)
+
     # ---------------- end to end through the host entry point (pinned host buffers, ring of 2 chunk slots)
     e2e = None
     if not args.no_e2e:
@@ -317,11 +322,61 @@ def run_b200(args):
                               "frac": step_gbs / peak, "algorithmic_bytes_per_step": step_bytes},
             "stage_ms_per_chunk_step": stage_avg,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "variant_gaussian": gauss,
         }
         print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0
+
+
+def run_gauss_arm(dev, Bv, C, Lk, steps=3):
+    """Variant G (long_term_attention.py): k[Bv,Lk,e] consumed un-pooled, ridge operators solved on the device
+    (fp64), every contraction on tcgen05 in split-TF32.  Reported against the tensor roofline (TF32 = 1/2 bf16)."""
+    from infinite_video_b200.batched import BatchedGaussLTM
+    torch.manual_seed(0)
+    key, val = torch.nn.Linear(E, D), torch.nn.Linear(E, D)
+    eng = BatchedGaussLTM(NB, TAU, key.weight.detach(), key.bias.detach(), val.weight.detach(), val.bias.detach(),
+                          device=dev)
+    g = torch.Generator(device=dev).manual_seed(99)
+    ks = [torch.randn(Bv, Lk, E, device=dev, generator=g) for _ in range(C)]
+    qs = [torch.randn(Bv, Q, D, device=dev, generator=g) for _ in range(C)]
+    us = [torch.rand(Bv, S, device=dev, dtype=torch.float64, generator=g) for _ in range(C)]
+
+    def one():
+        for c in range(C):
+            out = eng.step(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0))
+        return out
+    t0 = time.perf_counter()
+    eng.operators(Lk)
+    torch.cuda.synchronize(dev)
+    t_ridge = time.perf_counter() - t0
+    for _ in range(2):
+        one()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(steps):
+        out = one()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    finite = bool(torch.isfinite(out).all())
+    # algorithmic flops of an update call: reconstruct (128 candidate rows) + regress + project + attention
+    fl = 2 * E * NB * 128 + 2 * E * (S + Lk) * NB + 4 * NB * E * D + 4 * Q * NB * D
+    calls = Bv * C
+    peak_tf32 = 0.5 * 1655.1
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak_tf32 = 0.5 * float(json.load(f)["bf16_tflops"])
+    except Exception:
+        pass
+    tfl = fl * calls / (ms * 1e-3) / 1e12
+    return {"value": calls / (ms * 1e-3), "unit": "chunks/s", "videos": Bv, "chunks": C, "frames_per_chunk": Lk,
+            "ms_per_step": ms, "precision": "tf32x3", "finite": finite, "ridge_setup_s": t_ridge,
+            "roofline": {"bound": "tensor", "achieved": tfl, "peak": peak_tf32, "unit": "TFLOP/s",
+                         "frac": tfl / peak_tf32, "note": "algorithmic (single-product) flops; the split-TF32 path "
+                         "issues 3 MMAs per product; peak = 1/2 of the measured bf16 GEMM"}}
 
 
 def main():
@@ -339,6 +394,9 @@ def main():
     ap.add_argument("--pool-ctas-per-sm", type=int, default=0, help="grid bound of the prefetch pooling kernel")
     ap.add_argument("--hi-prio", action="store_true", help="run the main stream at high priority")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gauss", action="store_true", help="skip the secondary Gaussian-variant measurement")
+    ap.add_argument("--gauss-videos", type=int, default=32)
+    ap.add_argument("--gauss-frames", type=int, default=256, help="Lk of the Gaussian arm (k is consumed un-pooled)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -19,18 +19,19 @@ run e2e_gauss tests/test_gpu_e2e.py -k "gauss"
 timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; echo "smoke rc=$?" >> $OUT/summary.txt
 if [ "$MODE" = "full" ]; then
   timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" >> $OUT/summary.txt
-  B="timeout 600 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline"
+  B="timeout 600 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-gauss"
   $B --no-overlap > $OUT/bench_noov.json 2> $OUT/bench_noov.err
   $B --precision tf32x3 --no-overlap > $OUT/bench_x3.json 2> $OUT/bench_x3.err
+  timeout 600 python bench.py --steps 2 --warmup 3 --videos 8 --no-e2e --no-cpu-baseline --gauss-videos 8 --gauss-frames 8192 > $OUT/bench_gauss_raw.json 2> $OUT/bench_gauss_raw.err
   timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
-      python bench.py --steps 1 --warmup 3 --videos 32 --no-e2e --no-cpu-baseline > $OUT/ncu_launch.log 2>&1
+      python bench.py --steps 1 --warmup 3 --videos 32 --no-e2e --no-cpu-baseline --no-gauss > $OUT/ncu_launch.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:pool_mean -s 8 -c 2 -f -o $OUT/prof_pool \
-      python bench.py --steps 1 --warmup 3 --videos 32 --no-e2e --no-cpu-baseline > $OUT/ncu_pool.log 2>&1
+      python bench.py --steps 1 --warmup 3 --videos 32 --no-e2e --no-cpu-baseline --no-gauss > $OUT/ncu_pool.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32 -s 8 -c 1 -f -o $OUT/prof_gemm \
-      python bench.py --steps 1 --warmup 3 --videos 32 --no-e2e --no-cpu-baseline > $OUT/ncu_gemm.log 2>&1
+      python bench.py --steps 1 --warmup 3 --videos 32 --no-e2e --no-cpu-baseline --no-gauss > $OUT/ncu_gemm.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:cont_attn -s 8 -c 1 -f -o $OUT/prof_attn \
-      python bench.py --steps 1 --warmup 3 --videos 32 --no-e2e --no-cpu-baseline > $OUT/ncu_attn.log 2>&1
+      python bench.py --steps 1 --warmup 3 --videos 32 --no-e2e --no-cpu-baseline --no-gauss > $OUT/ncu_attn.log 2>&1
 fi
 cat $OUT/summary.txt
 [ -f $OUT/bench.json ] && cat $OUT/bench.json
