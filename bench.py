@@ -162,6 +162,8 @@ def run_b200(args):
     from infinite_video_b200 import _capi, dist as D_
     from infinite_video_b200.batched import BatchedRectLTM
 
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
     rank, local, world = D_.init_from_env()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)

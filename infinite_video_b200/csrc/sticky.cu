@@ -66,67 +66,69 @@ sticky_hist_gauss_kernel(const float* __restrict__ mu, const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// Re-sampling.  One warp per video.
+// Re-sampling.  One CTA (4 warps) per video.
 //   1. p = sum of `parts` partial histograms (fixed order), optionally normalised twice like the
 //      reference (p/p.sum() at gibbs:203, then again inside Categorical.__init__).
-//   2. CDF exactly as torch's CPU multinomial-with-replacement: sequential fp32 running sum (lane 0),
-//      divided by the total, last entry forced to 1.
-//   3. each lane binary-searches its share of the S fp64 uniforms: first category with cdf >= u.
+//   2. CDF exactly as torch's CPU multinomial-with-replacement: sequential fp32 running sum (one
+//      thread), divided by the total, last entry forced to 1.
+//   3. every thread binary-searches its share of the S fp64 uniforms: first category with cdf >= u.
 //   4. optional ascending order of the drawn bins (Gaussian variant sorts ts, gauss:238): counting
 //      sort -- bin counts via shared atomics, exclusive warp-shuffle prefix scan, run fill.
 // ------------------------------------------------------------------------------------------------
 constexpr int MAX_CAT = 128;
+constexpr int RS_THREADS = 128;
 
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ float block_sum_128(float v, float* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  const float t = (red[0] + red[1]) + (red[2] + red[3]);      // fixed order -> reproducible
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
 resample_kernel(const float* __restrict__ hist_part, int parts, int ncat, int normalize,
                 const double* __restrict__ u, const float* __restrict__ bins,
                 const int32_t* __restrict__ bin2basis, int sort,
                 float* __restrict__ p_out, int32_t* __restrict__ b_draw, int32_t* __restrict__ b_used,
-                float* __restrict__ ts, int32_t* __restrict__ idx, int Bv, int S) {
-  __shared__ float cdf_s[4][MAX_CAT];
-  __shared__ int cnt_s[4][MAX_CAT];
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int v = blockIdx.x * 4 + wib;
-  if (v >= Bv) return;                       // warp-uniform; no block-level barrier below
-  float* cdf = cdf_s[wib];
-  int* cnt = cnt_s[wib];
+                float* __restrict__ ts, int32_t* __restrict__ idx, int S) {
+  __shared__ float cdf[MAX_CAT];
+  __shared__ int cnt[MAX_CAT];
+  __shared__ int start_s[MAX_CAT];
+  __shared__ float red[4];
+  __shared__ float total_s;
+  const int v = blockIdx.x, tid = threadIdx.x;
 
   // 1. assemble p
-  float tot = 0.f;
-  for (int i = lane; i < ncat; i += 32) {
-    float a = 0.f;
-    for (int pt = 0; pt < parts; ++pt) a += hist_part[((size_t)v * parts + pt) * ncat + i];
-    cdf[i] = a;
-    tot += a;
-  }
+  float a = 0.f;
+  if (tid < ncat)
+    for (int pt = 0; pt < parts; ++pt) a += hist_part[((size_t)v * parts + pt) * ncat + tid];
   if (normalize) {
-    tot = warp_sum(tot);
-    float tot2 = 0.f;
-    for (int i = lane; i < ncat; i += 32) { cdf[i] = __fdiv_rn(cdf[i], tot); tot2 += cdf[i]; }
-    tot2 = warp_sum(tot2);
-    for (int i = lane; i < ncat; i += 32) cdf[i] = __fdiv_rn(cdf[i], tot2);
+    const float tot = block_sum_128(a, red);
+    a = __fdiv_rn(a, tot);
+    const float tot2 = block_sum_128(tid < ncat ? a : 0.f, red);
+    a = __fdiv_rn(a, tot2);
   }
-  __syncwarp();
-  if (p_out) for (int i = lane; i < ncat; i += 32) p_out[(size_t)v * ncat + i] = cdf[i];
-  __syncwarp();
+  if (tid < ncat) {
+    cdf[tid] = a;
+    cnt[tid] = 0;
+    if (p_out) p_out[(size_t)v * ncat + tid] = a;
+  }
+  __syncthreads();
 
   // 2. sequential fp32 cumulative sum, then normalise by the total (must not be re-associated)
-  float total = 0.f;
-  if (lane == 0) {
+  if (tid == 0) {
     float s = 0.f;
     for (int i = 0; i < ncat; ++i) { s = __fadd_rn(s, cdf[i]); cdf[i] = s; }
-    total = s;
+    total_s = s;
   }
-  total = __shfl_sync(0xffffffffu, total, 0);
-  __syncwarp();
-  for (int i = lane; i < ncat; i += 32) cdf[i] = __fdiv_rn(cdf[i], total);
-  __syncwarp();
-  if (lane == 0) cdf[ncat - 1] = 1.0f;
-  for (int i = lane; i < ncat; i += 32) cnt[i] = 0;
-  __syncwarp();
+  __syncthreads();
+  if (tid < ncat) cdf[tid] = (tid == ncat - 1) ? 1.0f : __fdiv_rn(cdf[tid], total_s);
+  __syncthreads();
 
   // 3. inverse-CDF search
-  for (int s = lane; s < S; s += 32) {
+  for (int s = tid; s < S; s += RS_THREADS) {
     const double us = u[(size_t)v * S + s];
     int left = 0, right = ncat;
     while (right - left > 0) {
@@ -143,36 +145,41 @@ resample_kernel(const float* __restrict__ hist_part, int parts, int ncat, int no
       if (idx) idx[(size_t)v * S + s] = bin2basis ? bin2basis[b] : b;
     }
   }
-  if (!sort) return;
-  __syncwarp();
+  if (!sort) return;                         // block-uniform
+  __syncthreads();
 
-  // 4. counting sort: exclusive scan of the bin counts (4 bins per lane + warp shuffle scan)
-  const int per = (ncat + 31) / 32;          // <= 4
-  int local[4] = {0, 0, 0, 0};
-  int run = 0;
-  for (int t = 0; t < per; ++t) {
-    const int i = lane * per + t;
-    local[t] = (i < ncat) ? cnt[i] : 0;
-    run += local[t];
-  }
-  int incl = run;
+  // 4. counting sort: exclusive scan of the bin counts by warp 0 (4 bins per lane + warp-shuffle scan)
+  if (tid < 32) {
+    const int per = (ncat + 31) / 32;        // <= 4
+    int local[4] = {0, 0, 0, 0};
+    int run = 0;
+    for (int t = 0; t < per; ++t) {
+      const int i = tid * per + t;
+      local[t] = (i < ncat) ? cnt[i] : 0;
+      run += local[t];
+    }
+    int incl = run;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int n = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += n;
-  }
-  int start = incl - run;
-  for (int t = 0; t < per; ++t) {
-    const int i = lane * per + t;
-    if (i < ncat) {
-      const float tv = bins[i];
-      const int ix = bin2basis ? bin2basis[i] : i;
-      for (int s = start; s < start + local[t]; ++s) {
-        if (b_used) b_used[(size_t)v * S + s] = i;
-        if (ts) ts[(size_t)v * S + s] = tv;
-        if (idx) idx[(size_t)v * S + s] = ix;
-      }
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (tid >= o) incl += n;
+    }
+    int start = incl - run;
+    for (int t = 0; t < per; ++t) {
+      const int i = tid * per + t;
+      if (i < ncat) start_s[i] = start;
       start += local[t];
+    }
+  }
+  __syncthreads();
+  if (tid < ncat) {
+    const float tv = bins[tid];
+    const int ix = bin2basis ? bin2basis[tid] : tid;
+    const int s0 = start_s[tid], s1 = s0 + cnt[tid];
+    for (int s = s0; s < s1; ++s) {
+      if (b_used) b_used[(size_t)v * S + s] = tid;
+      if (ts) ts[(size_t)v * S + s] = tv;
+      if (idx) idx[(size_t)v * S + s] = ix;
     }
   }
 }
@@ -209,9 +216,8 @@ extern "C" int ltm_resample(const float* hist_part, int parts, int ncat, int nor
   LTM_REQUIRE(hist_part && u && bins, "resample: null pointer");
   LTM_REQUIRE(ncat >= 1 && ncat <= MAX_CAT, "resample: ncat=%d out of range [1,%d]", ncat, MAX_CAT);
   LTM_REQUIRE(parts >= 1 && Bv > 0 && S > 0, "resample: bad shape");
-  resample_kernel<<<(Bv + 3) / 4, 128, 0, (cudaStream_t)stream>>>(hist_part, parts, ncat, normalize, u, bins,
-                                                               bin2basis, sort, p_out, b_draw, b_used, ts, idx,
-                                                               Bv, S);
+  resample_kernel<<<Bv, RS_THREADS, 0, (cudaStream_t)stream>>>(hist_part, parts, ncat, normalize, u, bins,
+                                                            bin2basis, sort, p_out, b_draw, b_used, ts, idx, S);
   LTM_CHECK_LAUNCH("resample");
   return 0;
 }

@@ -289,3 +289,48 @@ def test_prefetched_pooling_is_bit_identical(dev):
         assert torch.equal(a.B_past, b.B_past)
     with pytest.raises(RuntimeError):
         b.prefetch(ks[0], 32); b.prefetch(ks[1], 32); b.prefetch(ks[2], 32)
+
+
+def test_step_is_cuda_graph_capturable(dev):
+    """No host synchronisation / allocation inside a step: a sticky chunk can be captured once and replayed
+    (this is how a single-video, launch-bound caller amortises the 5 launches)."""
+    from infinite_video_b200.batched import BatchedRectLTM
+    key, val = make_proj(71, 768)
+    ks, qs, us = make_inputs(72, 4, 1, 32 * 32, 768, 32)
+    ks = [k.to(dev) for k in ks]
+    qs = [q.to(dev) for q in qs]
+    us = [u.to(dev) for u in us]
+    ref = BatchedRectLTM(256, .75, *proj_tensors(key, val), device=dev)
+    want = [ref.step(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0)).clone() for c in range(4)]
+
+    eng = BatchedRectLTM(256, .75, *proj_tensors(key, val), device=dev)
+    k_s, q_s, u_s = ks[0].clone(), qs[0].clone(), us[1].clone()
+    eng.step(k_s, q_s, None, new_doc=True)                      # chunk 0 (eager)
+    k_s.copy_(ks[1]); q_s.copy_(qs[1])
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                                 # warm-up of the update path on a side stream
+        eng.step(k_s, q_s, u_s, new_doc=False)
+    torch.cuda.current_stream().wait_stream(side)
+    # rewind the state to "after chunk 0" and capture one update step; two captures alternate the ping-pong
+    eng.reset()
+    k_s.copy_(ks[0]); q_s.copy_(qs[0])
+    eng.step(k_s, q_s, None, new_doc=True)
+    a = eng._cur                                                  # buffer that holds B after chunk 0
+    graphs, outs = [], []
+    for _ in range(2):                                            # B_past ping-pong: one graph per parity
+        g = torch.cuda.CUDAGraph()
+        k_s.copy_(ks[1]); q_s.copy_(qs[1]); u_s.copy_(us[1])
+        with torch.cuda.graph(g):
+            out = eng.step(k_s, q_s, u_s, new_doc=False)
+        graphs.append(g); outs.append(out)
+    # replay from scratch: chunk 0 eager, chunks 1..3 through the graphs
+    eng.reset()
+    eng._cur = 1 - a                                              # so that chunk 0 lands in the buffer graph 0 reads
+    k_s.copy_(ks[0]); q_s.copy_(qs[0])
+    assert torch.equal(eng.step(k_s, q_s, None, new_doc=True), want[0])
+    for c in range(1, 4):
+        k_s.copy_(ks[c]); q_s.copy_(qs[c]); u_s.copy_(us[c])
+        i = (c - 1) & 1
+        graphs[i].replay()
+        assert torch.equal(outs[i], want[c]), f"graph replay differs at chunk {c}"
