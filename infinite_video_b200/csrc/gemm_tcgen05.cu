@@ -96,6 +96,33 @@ __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fe
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// commit that arrives on the barrier at the same shared-memory offset in every CTA of `mask` (cluster)
+__device__ __forceinline__ void tcgen05_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+// TMA load delivered to the same shared-memory offset (and mbarrier) of every CTA in `mask`
+__device__ __forceinline__ void tma_load_3d_mc(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1,
+                                               int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Work item -> tile origin.  CLUSTER == 1: items are tiles, n fastest.  CLUSTER == 2: a cluster of two CTAs takes
+// two vertically adjacent tiles (same n, rows m0 and m0 + 128) so that the B tile is fetched once and multicast.
+template <int CLUSTER, int BN_>
+__device__ __forceinline__ void decode_work(int w, int tiles_n, int tiles_m, int rank, int& n0, int& m0, int& bz) {
+  const int groups_m = (tiles_m + CLUSTER - 1) / CLUSTER;
+  n0 = (w % tiles_n) * BN_;
+  m0 = (((w / tiles_n) % groups_m) * CLUSTER + rank) * 128;
+  bz = w / (tiles_n * groups_m);
+}
 __device__ __forceinline__ void tcgen05_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                                  uint32_t accumulate) {
   asm volatile(
@@ -152,7 +179,7 @@ struct Cfg {
 //   warp 1      TMEM owner + tcgen05.mma issuer (one lane)
 //   warps 2-5   epilogue: tcgen05.ld -> registers -> (+bias) -> per-warp smem transpose -> 128-byte coalesced stores
 //   warps 6-9   (precision 3 only) operand splitter hi/lo
-template <int BN, int STAGES, bool SPLIT>
+template <int BN, int STAGES, bool SPLIT, int CLUSTER>
 __global__ void __launch_bounds__(Cfg<BN, STAGES, SPLIT>::THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ CUtensorMap mapB2, const GemmDev g) {
@@ -173,7 +200,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (g.K + BK - 1) / BK;
   const int tiles_n = (g.Nc + BN - 1) / BN, tiles_m = (g.M + BM - 1) / BM;
-  const int num_tiles = tiles_n * tiles_m * g.batch;
+  // static work list shared by all roles (see decode_work)
+  const int crank = (CLUSTER > 1) ? (int)(blockIdx.x % CLUSTER) : 0;
+  const int w_first = blockIdx.x / CLUSTER, w_stride = gridDim.x / CLUSTER;
+  const int num_work = tiles_n * ((tiles_m + CLUSTER - 1) / CLUSTER) * g.batch;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
@@ -181,7 +211,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (g.has_b2) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB2)) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CLUSTER);  // the MMA warps of every CTA that received a multicast into this slot
       mbar_init(split_bar(s), 128);      // every splitter thread arrives after its proxy fence
     }
     for (int b = 0; b < 2; ++b) {
@@ -198,6 +228,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();    // peers' barriers are initialised before any multicast / remote arrive
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -205,8 +236,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int n0 = (t % tiles_n) * BN, m0 = ((t / tiles_n) % tiles_m) * BM, bz = t / (tiles_n * tiles_m);
+      for (int w = w_first; w < num_work; w += w_stride) {
+        int n0, m0, bz;
+        decode_work<CLUSTER, BN>(w, tiles_n, tiles_m, crank, n0, m0, bz);
         const int za = g.a_batched ? bz : 0;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
@@ -227,7 +259,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           const CUtensorMap* mb = seg2 ? &mapB2 : &mapB;
           const int kk = seg2 ? k0 - g.K1 : k0;
           const int zb = seg2 ? (g.b2_batched ? bz : 0) : (g.b_batched ? bz : 0);
-          if (g.b_kmajor) {
+          if (CLUSTER > 1) {
+            // K-major B only (host-checked): this CTA fetches its 1/CLUSTER share of the B tile rows and
+            // multicasts it to every CTA of the cluster; the peers deliver the other shares
+            constexpr int SHARE = BN / CLUSTER;
+            tma_load_3d_mc(mb, sb + crank * (SHARE * BK * 4), full_bar(s), kk, n0 + crank * SHARE, zb,
+                           (uint16_t)((1u << CLUSTER) - 1u));
+          } else if (g.b_kmajor) {
             tma_load_3d(mb, sb, full_bar(s), kk, n0, zb);
           } else {
 #pragma unroll
@@ -248,7 +286,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                              ((uint32_t)(BM >> 4) << 24);
       const MnDesc mn{g.mn_layout, g.mn_lbo, g.mn_sbo, g.mn_kadv};
       uint32_t it = 0, tc = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tc) {
+      for (int w = w_first; w < num_work; w += w_stride, ++tc) {
         const uint32_t buf = tc & 1u, tph = (tc >> 1) & 1u;
         mbar_wait(tempty_bar(buf), tph ^ 1u);                 // epilogue has drained this accumulator
         tcgen05_fence_after();
@@ -272,7 +310,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               tcgen05_mma_tf32(tmem_acc, da, operand_desc(sb_lo, g.b_kmajor, k, mn), idesc, 1u);
             }
           }
-          tcgen05_commit(empty_bar(s));          // frees the stage once these MMAs have read it
+          // frees the stage once these MMAs have read it (in every CTA that multicasts into this slot)
+          if (CLUSTER > 1) tcgen05_commit_mc(empty_bar(s), (uint16_t)((1u << CLUSTER) - 1u));
+          else tcgen05_commit(empty_bar(s));
         }
         tcgen05_commit(tfull_bar(buf));          // accumulator of this tile complete
       }
@@ -283,8 +323,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int quarter = warp & 3;                // TMEM lanes [32*quarter, 32*quarter+32)
     float* stg = staging + quarter * (32 * STG_LD);
     uint32_t tc = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tc) {
-      const int n0 = (t % tiles_n) * BN, m0 = ((t / tiles_n) % tiles_m) * BM, bz = t / (tiles_n * tiles_m);
+    for (int w = w_first; w < num_work; w += w_stride, ++tc) {
+      int n0, m0, bz;
+      decode_work<CLUSTER, BN>(w, tiles_n, tiles_m, crank, n0, m0, bz);
       const uint32_t buf = tc & 1u, tph = (tc >> 1) & 1u;
       mbar_wait(tfull_bar(buf), tph);
       tcgen05_fence_after();
@@ -343,7 +384,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const int et = threadIdx.x - 192;          // 0..127
       constexpr int NV = (A_BYTES + C_::B_BYTES) / 16;      // float4 count of [A | B]
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int w = w_first; w < num_work; w += w_stride) {
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
@@ -371,6 +412,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
   tcgen05_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();    // no CTA may exit while a peer can still multicast into it / arrive on it
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C_::TMEM_COLS)
                  : "memory");
@@ -380,6 +422,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 // ------------------------------------------------------------------------------------------ host
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 // bring-up override of the MN-major layout parameters: {layout, lbo, sbo, kadv, tma swizzle enum}
+static int g_cluster = 2;       // 1 disables the multicast cluster variant (bring-up / A-B comparison)
 static unsigned g_mn_desc[5] = {1u, (unsigned)SLAB_BYTES, 512u, 1024u, (unsigned)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B};
 
 static int resolve_encode() {
@@ -416,14 +459,14 @@ static int encode_operand(CUtensorMap* map, const float* base, int rows, int K, 
   return 0;
 }
 
-template <int BN, int STAGES, bool SPLIT>
+template <int BN, int STAGES, bool SPLIT, int CLUSTER = 1>
 static int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mB2, const GemmDev& d,
                       int batch, cudaStream_t stream) {
   using C_ = Cfg<BN, STAGES, SPLIT>;
   static bool configured = false;
   if (!configured) {
-    LTM_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  C_::SMEM_BYTES));
+    LTM_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES, SPLIT, CLUSTER>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
     configured = true;
   }
   const long long tiles = (long long)((d.Nc + BN - 1) / BN) * ((d.M + BM - 1) / BM) * batch;
@@ -434,8 +477,30 @@ static int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const CUtens
     LTM_CUDA(cudaGetDevice(&dev));
     LTM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  if (CLUSTER > 1) {
+    // persistent clusters: CLUSTER CTAs on adjacent SMs share every B tile through TMA multicast
+    const long long tm = (d.M + BM - 1) / BM;
+    const long long work = (long long)((d.Nc + BN - 1) / BN) * ((tm + CLUSTER - 1) / CLUSTER) * batch;
+    long long clusters = num_sms / CLUSTER;
+    if (work < clusters) clusters = work;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(clusters * CLUSTER));
+    cfg.blockDim = dim3(C_::THREADS);
+    cfg.dynamicSmemBytes = C_::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    LTM_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, STAGES, SPLIT, CLUSTER>, mA, mB, mB2, d));
+    return 0;
+  }
   const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);     // persistent: one CTA per SM
-  gemm_tf32_kernel<BN, STAGES, SPLIT><<<grid, C_::THREADS, C_::SMEM_BYTES, stream>>>(mA, mB, mB2, d);
+  gemm_tf32_kernel<BN, STAGES, SPLIT, 1><<<grid, C_::THREADS, C_::SMEM_BYTES, stream>>>(mA, mB, mB2, d);
   LTM_CHECK_LAUNCH("gemm(tcgen05)");
   return 0;
 }
@@ -450,7 +515,8 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   const int K1 = two ? a.K1 : a.K;
   CUtensorMap mA, mB, mB2;
   if (encode_operand(&mA, a.A, a.M, a.K, a.lda, a.strideA, a.batch, a.a_kmajor, BM, "A")) return -1;
-  if (encode_operand(&mB, a.B, a.Nc, K1, a.ldb, a.strideB, a.batch, a.b_kmajor, bn, "B")) return -1;
+  const bool mc_pre = g_cluster >= 2 && a.b_kmajor && !two && a.M > BM;
+  if (encode_operand(&mB, a.B, a.Nc, K1, a.ldb, a.strideB, a.batch, a.b_kmajor, mc_pre ? bn / 2 : bn, "B")) return -1;
   if (two) {
     if (encode_operand(&mB2, a.B2, a.Nc, a.K - K1, a.ldb2, a.strideB2, a.batch, a.b_kmajor, bn, "B2")) return -1;
   } else {
@@ -463,14 +529,21 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   d.CT = a.CT; d.ct_cols = a.ct_cols; d.ct_group = a.ct_group;
   d.mn_layout = g_mn_desc[0]; d.mn_lbo = g_mn_desc[1]; d.mn_sbo = g_mn_desc[2]; d.mn_kadv = g_mn_desc[3];
   d.a_batched = a.strideA != 0; d.b_batched = a.strideB != 0; d.b2_batched = a.strideB2 != 0; d.has_b2 = two ? 1 : 0;
-  if (split) return launch_cfg<128, 3, true>(mA, mB, mB2, d, a.batch, stream);
-  if (bn == 256) return launch_cfg<256, 4, false>(mA, mB, mB2, d, a.batch, stream);
-  return launch_cfg<128, 6, false>(mA, mB, mB2, d, a.batch, stream);
+  // 2-CTA clusters with a multicast B tile: K-major single-segment B and at least two row tiles
+  const bool mc = g_cluster >= 2 && a.b_kmajor && !two && a.M > BM;
+  if (split) return mc ? launch_cfg<128, 3, true, 2>(mA, mB, mB2, d, a.batch, stream)
+                       : launch_cfg<128, 3, true>(mA, mB, mB2, d, a.batch, stream);
+  if (bn == 256) return mc ? launch_cfg<256, 4, false, 2>(mA, mB, mB2, d, a.batch, stream)
+                           : launch_cfg<256, 4, false>(mA, mB, mB2, d, a.batch, stream);
+  return mc ? launch_cfg<128, 6, false, 2>(mA, mB, mB2, d, a.batch, stream)
+            : launch_cfg<128, 6, false>(mA, mB, mB2, d, a.batch, stream);
 }
 
 }  // namespace ltm
 
 // Bring-up hook (not part of include/infltm.h): override the MN-major descriptor parameters.
+extern "C" void ltm_debug_set_cluster(int c) { ltm::g_cluster = c; }
+
 extern "C" void ltm_debug_set_mn_desc(unsigned layout, unsigned lbo, unsigned sbo, unsigned kadv, unsigned swz) {
   ltm::g_mn_desc[0] = layout; ltm::g_mn_desc[1] = lbo; ltm::g_mn_desc[2] = sbo; ltm::g_mn_desc[3] = kadv;
   ltm::g_mn_desc[4] = swz;

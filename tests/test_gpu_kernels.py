@@ -177,6 +177,9 @@ GEMM_CASES = [
     (128, 128, 256, 1, True, True, False, True),
     (256, 1536, 768, 1, True, True, False, True),      # K/V projection shape (per 256 coefficient rows)
     (100, 72, 40, 1, True, True, False, False),        # ragged tails everywhere
+    (384, 1536, 768, 1, True, True, False, True),      # odd number of row tiles (2-CTA multicast clusters)
+    (300, 520, 64, 2, True, True, False, True),        # ragged + batched through the cluster path
+    (1152, 256, 96, 1, False, True, False, False),     # A MN-major, B K-major multicast
     (128, 768, 256, 3, True, False, False, False),     # Psi_tab @ B_past[v]   (B MN-major, batched)
     (256, 768, 544, 2, True, False, True, False),      # G_inf^T [xm ; k]      (two K segments)
     (64, 768, 8, 2, True, False, False, False),        # G0^T k with Lk = 8
