@@ -169,8 +169,8 @@ def run_b200(args):
     torch.cuda.set_device(dev)
     lib = _capi.lib()
     _capi.check(lib.ltm_device_check(), "device_check")
-    if args.no_cluster:
-        lib.ltm_debug_set_cluster(1)
+    if args.cluster:
+        lib.ltm_debug_set_cluster(2)
     Bv, C = args.videos, args.chunks
     torch.manual_seed(0)
     key, val = torch.nn.Linear(E, D), torch.nn.Linear(E, D)
@@ -441,7 +441,7 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="do not pool chunk c+1 under chunk c's compute")
     ap.add_argument("--pool-ctas-per-sm", type=int, default=0, help="grid bound of the prefetch pooling kernel")
     ap.add_argument("--hi-prio", action="store_true", help="run the main stream at high priority")
-    ap.add_argument("--no-cluster", action="store_true", help="disable the 2-CTA multicast clusters of the GEMM")
+    ap.add_argument("--cluster", action="store_true", help="use the 2-CTA TMA-multicast variant of the GEMM")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gauss", action="store_true", help="skip the secondary Gaussian-variant measurement")
     ap.add_argument("--gauss-videos", type=int, default=32)

@@ -422,7 +422,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 // ------------------------------------------------------------------------------------------ host
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 // bring-up override of the MN-major layout parameters: {layout, lbo, sbo, kadv, tma swizzle enum}
-static int g_cluster = 2;       // 1 disables the multicast cluster variant (bring-up / A-B comparison)
+// 2 enables the 2-CTA multicast variant.  Measured on B200 (profiles/r1e): no gain over unicast -- the kernel is
+// bound by per-SM ingest (~38 B/clk/SM), not by L2 reads -- so it is off by default and kept as a tested option.
+static int g_cluster = 1;
 static unsigned g_mn_desc[5] = {1u, (unsigned)SLAB_BYTES, 512u, 1024u, (unsigned)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B};
 
 static int resolve_encode() {

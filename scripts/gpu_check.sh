@@ -21,7 +21,6 @@ if [ "$MODE" = "full" ]; then
   timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" >> $OUT/summary.txt
   B="timeout 600 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-gauss"
   $B --no-overlap > $OUT/bench_noov.json 2> $OUT/bench_noov.err
-  $B --no-overlap --no-cluster > $OUT/bench_noov_nocl.json 2> $OUT/bench_noov_nocl.err
   $B --precision tf32x3 --no-overlap > $OUT/bench_x3.json 2> $OUT/bench_x3.err
   timeout 600 python bench.py --steps 2 --warmup 3 --videos 8 --no-e2e --no-cpu-baseline --gauss-videos 8 --gauss-frames 8192 > $OUT/bench_gauss_raw.json 2> $OUT/bench_gauss_raw.err
   timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err

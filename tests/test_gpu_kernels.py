@@ -188,9 +188,21 @@ GEMM_CASES = [
 ]
 
 
+@pytest.fixture(params=[1, 2], ids=["unicast", "cluster2"])
+def gemm_cluster(request):
+    """Runs the GEMM tests with and without the 2-CTA TMA-multicast variant (bring-up hook of libinfltm)."""
+    import ctypes
+    from infinite_video_b200 import _capi
+    f = _capi.lib().ltm_debug_set_cluster
+    f.argtypes, f.restype = [ctypes.c_int], None
+    f(request.param)
+    yield request.param
+    f(1)
+
+
 @pytest.mark.parametrize("M,N,K,batch,akm,bkm,two,bias", GEMM_CASES)
 @pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
-def test_gemm_tcgen05(dev, M, N, K, batch, akm, bkm, two, bias, precision):
+def test_gemm_tcgen05(dev, gemm_cluster, M, N, K, batch, akm, bkm, two, bias, precision):
     ops = _ops()
     g = torch.Generator().manual_seed(M * 7 + N + K)
     A = torch.randn(*((M, K) if akm else (K, M)), generator=g)                  # shared across the batch
