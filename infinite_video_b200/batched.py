@@ -227,15 +227,45 @@ class BatchedRectLTM(_BatchedBase):
         done.record(self._side)
         self._pref[(k_next.data_ptr(), tuple(k_next.shape))] = (b, done)
 
-    def step(self, k, q, u=None, new_doc=False):
+    def pool(self, k):
+        """Frame pooling alone (gibbs:304): k[Bv, L*T, e] -> pooled frames [Bv, L, splits, e].  The result can be
+        handed to `step(..., pooled=...)` of SEVERAL engines: every LTM layer of a Q-former receives the same
+        `encoder_hidden_states` per chunk (2 layers in Video-LLaMA, 6 in VideoChat2), so the
+        25 MB/video chunk needs to be streamed from HBM once, not once per layer."""
+        require_cuda(k)
+        k = k.contiguous()
+        Bv, LT, e = k.shape
+        if e != self.e or LT % self.T:
+            raise ValueError(f"k must be [Bv, L*{self.T}, {self.e}]")
+        L = LT // self.T
+        units = Bv * L
+        splits = 1 if units >= 2 * SM_COUNT else max(1, min(self.T, -(-SM_COUNT * 8 // units)))
+        return ops.pool_mean(k.view(Bv, L, self.T, e), splits)
+
+    def step(self, k, q, u=None, new_doc=False, pooled=None):
         """k[Bv, L*T, e], q[Bv,Q,D] fp32 CUDA; u[Bv,S] fp64 uniforms (needed from the second chunk on when
-        sticky); new_doc: bool or per-video flags.  Returns ctx[Bv,Q,D]."""
+        sticky); new_doc: bool or per-video flags; pooled: result of `pool(k)` (then `k` is only used for its
+        shape).  Returns ctx[Bv,Q,D]."""
         require_cuda(k, q, u)
         if k.dtype != torch.float32 or q.dtype != torch.float32:
             raise ValueError("k and q must be float32")
         k, q = k.contiguous(), q.contiguous()
         Bv, L, Q, tab, tdev, flags = self._prepare(k.shape, q.shape, new_doc)
         ws = self._workspace(Bv, L, Q)
+        if pooled is not None:
+            if tuple(pooled.shape[:2]) != (Bv, L) or pooled.shape[3] != self.e or not pooled.is_contiguous():
+                raise ValueError("pooled frames do not match k")
+            if self.has_state and self.sticky:
+                if u is None or u.dtype != torch.float64 or tuple(u.shape) != (Bv, self.S):
+                    raise ValueError(f"sticky re-sampling needs u: float64 [{Bv},{self.S}]")
+                u = u.contiguous()
+            ctx = torch.empty(Bv, Q, self.D, device=self.device, dtype=torch.float32)
+            a = self._args(Bv, L, Q, ws, tab, tdev)
+            a.xpart, a.splits = pooled.data_ptr(), pooled.shape[2]
+            check(lib().ltm_rect_step(C.byref(a), None, ptr(q), ptr(u), ptr(flags), ptr(ctx),
+                                      stream_ptr(self.device)), "rect_step")
+            self._finish(ws)
+            return ctx
         if self.has_state and self.sticky:
             if u is None or u.dtype != torch.float64 or tuple(u.shape) != (Bv, self.S):
                 raise ValueError(f"sticky re-sampling needs u: float64 [{Bv},{self.S}]")

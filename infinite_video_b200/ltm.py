@@ -27,11 +27,17 @@ from .batched import BatchedGaussLTM, BatchedRectLTM
 
 
 class LongTermAttention(nn.Module):
+    # Pooled frames of the most recent chunk, shared by every instance in the process: all LTM layers of a
+    # Q-former are called with the same `encoder_hidden_states` tensor per chunk (Qformer.py:216-223 inside
+    # BertEncoder's layer loop), so only the first layer streams the chunk from HBM.
+    _shared_pool = {"key": None, "x": None}
+
     def __init__(self, head_size: int, length: int, target_len: int, attn_func: str, attn_num_basis: int,
                  continuous: bool, attn_drop: float, infinite_memory: bool, n_layers: int, n_heads: int,
                  affines: bool, mask: bool, mask_type: str, kl_regularizer: bool, proj_key, proj_value,
                  sigma_0, mu_0, sticky_memories, sigmas, tau, variant: str = "gibbs",
-                 tokens_per_frame: int = 32, precision: str = None, gemm_impl: str = "tcgen05", **kwargs):
+                 tokens_per_frame: int = 32, precision: str = None, gemm_impl: str = "tcgen05",
+                 share_pooling: bool = True, **kwargs):
         super().__init__()
         if not continuous:
             raise NotImplementedError("only the continuous-attention memory is on the LTM path (continuous=True)")
@@ -75,6 +81,7 @@ class LongTermAttention(nn.Module):
         self.tokens_per_frame = tokens_per_frame
         self.precision = precision
         self.gemm_impl = gemm_impl
+        self.share_pooling = share_pooling
         self._engine = None
         self._wver = None
 
@@ -142,7 +149,15 @@ class LongTermAttention(nn.Module):
             u = u.to(k.device, torch.float64)
         else:
             u = None
-        ctx = eng.step(k32, q32, u=u, new_doc=False)
+        pooled = None
+        if self.variant == "gibbs" and self.share_pooling:
+            key = (k.data_ptr(), tuple(k.shape), k._version, str(k.dtype), self.tokens_per_frame)
+            sp = LongTermAttention._shared_pool
+            if sp["key"] != key:
+                sp["key"], sp["x"] = key, eng.pool(k32)
+            pooled = sp["x"]
+        ctx = eng.step(k32, q32, u=u, new_doc=False, pooled=pooled) if pooled is not None else \
+            eng.step(k32, q32, u=u, new_doc=False)
         return ctx.to(out_dtype)
 
     def extra_repr(self):

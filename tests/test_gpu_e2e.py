@@ -334,3 +334,34 @@ def test_step_is_cuda_graph_capturable(dev):
         i = (c - 1) & 1
         graphs[i].replay()
         assert torch.equal(outs[i], want[c]), f"graph replay differs at chunk {c}"
+
+
+def test_layers_share_one_pooling_pass(dev):
+    """N2: two LTM layers (different projections, same encoder_hidden_states) -- the second layer must reuse the
+    pooled frames of the first and still match an instance that pools on its own, bit for bit."""
+    from infinite_video_b200 import LongTermAttention, ops
+    from oracle.ref_loader import caller_kwargs
+    layers, solo = [], []
+    for seed in (81, 82):
+        key, val = make_proj(seed, 768)
+        key, val = key.to(dev), val.to(dev)
+        layers.append(LongTermAttention(**caller_kwargs(64, .75, True, key, val)))
+        solo.append(LongTermAttention(**caller_kwargs(64, .75, True, key, val), share_pooling=False))
+    ks, qs, us = make_inputs(83, 3, 1, 8 * 32, 768, 32)
+    calls = {"n": 0}
+    real = ops.pool_mean
+
+    def counting(*a, **kw):
+        calls["n"] += 1
+        return real(*a, **kw)
+    ops.pool_mean = counting
+    try:
+        for c in range(3):
+            k = ks[c].to(dev)
+            for li in range(2):
+                got = layers[li](k, qs[c].to(dev), new_doc=(c == 0), layer_n=li, u=us[c])
+                want = solo[li](k, qs[c].to(dev), new_doc=(c == 0), layer_n=li, u=us[c])
+                assert torch.equal(got, want), (c, li)
+    finally:
+        ops.pool_mean = real
+    assert calls["n"] == 3          # one pooling pass per chunk for the two sharing layers (solo ones pool in-step)
