@@ -19,6 +19,8 @@ Differences that are deliberate (DESIGN.md section "boundary"):
   * the Video-LLaMA copy's per-call pickle of the attention density to ./alphas_uniform
     (gibbs:320-345) is not written.
 """
+import weakref
+
 import torch
 import torch.nn as nn
 
@@ -151,10 +153,15 @@ class LongTermAttention(nn.Module):
             u = None
         pooled = None
         if self.variant == "gibbs" and self.share_pooling:
-            key = (k.data_ptr(), tuple(k.shape), k._version, str(k.dtype), self.tokens_per_frame)
+            # identity of the tensor OBJECT (a weak reference) + its version counter: a data pointer alone is not
+            # a key, the caching allocator hands the same address to the next chunk
             sp = LongTermAttention._shared_pool
-            if sp["key"] != key:
-                sp["key"], sp["x"] = key, eng.pool(k32)
+            ref = sp["key"]
+            hit = (ref is not None and ref[0]() is k and ref[1] == k._version and ref[2] == self.tokens_per_frame
+                   and sp["x"] is not None and sp["x"].device == k.device)
+            if not hit:
+                sp["x"] = eng.pool(k32)
+                sp["key"] = (weakref.ref(k), k._version, self.tokens_per_frame)
             pooled = sp["x"]
         ctx = eng.step(k32, q32, u=u, new_doc=False, pooled=pooled) if pooled is not None else \
             eng.step(k32, q32, u=u, new_doc=False)
