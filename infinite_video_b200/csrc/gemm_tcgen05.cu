@@ -41,6 +41,7 @@ struct GemmDev {
   unsigned mn_layout, mn_lbo, mn_sbo, mn_kadv;
   float* CT;
   int ct_cols, ct_group;
+  int split_write_hi;
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -167,7 +168,8 @@ struct Cfg {
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;   // + 1024 B alignment slack
   static constexpr int TMEM_COLS = 2 * BN;                     // two accumulator buffers (256 or 512 columns)
-  static constexpr int THREADS = SPLIT ? 320 : 192;
+  static constexpr int SPLIT_THREADS = 256;                    // 8 splitter warps (precision 3)
+  static constexpr int THREADS = SPLIT ? 192 + SPLIT_THREADS : 192;
   static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two <= 512");
 };
 
@@ -178,7 +180,7 @@ struct Cfg {
 //   warp 0      TMA producer (one lane)
 //   warp 1      TMEM owner + tcgen05.mma issuer (one lane)
 //   warps 2-5   epilogue: tcgen05.ld -> registers -> (+bias) -> per-warp smem transpose -> 128-byte coalesced stores
-//   warps 6-9   (precision 3 only) operand splitter hi/lo
+//   warps 6-13  (precision 3 only) operand splitter hi/lo
 template <int BN, int STAGES, bool SPLIT, int CLUSTER>
 __global__ void __launch_bounds__(Cfg<BN, STAGES, SPLIT>::THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -212,7 +214,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), CLUSTER);  // the MMA warps of every CTA that received a multicast into this slot
-      mbar_init(split_bar(s), 128);      // every splitter thread arrives after its proxy fence
+      mbar_init(split_bar(s), C_::SPLIT_THREADS);   // every splitter thread arrives after its proxy fence
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);        // tcgen05.commit of the last MMA of a tile
@@ -381,7 +383,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   } else {
     // ------------------------------------------------------------------ operand splitter (precision 3)
     if (SPLIT) {
-      const int et = threadIdx.x - 192;          // 0..127
+      const int et = threadIdx.x - 192;          // 0..SPLIT_THREADS-1
       constexpr int NV = (A_BYTES + C_::B_BYTES) / 16;      // float4 count of [A | B]
       uint32_t it = 0;
       for (int w = w_first; w < num_work; w += w_stride) {
@@ -392,7 +394,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           float4* hi = reinterpret_cast<float4*>(smem_al + s * C_::STAGE_BYTES);
           float4* lo = reinterpret_cast<float4*>(smem_al + s * C_::STAGE_BYTES + A_BYTES + C_::B_BYTES);
 #pragma unroll 4
-          for (int f = et; f < NV; f += 128) {
+          for (int f = et; f < NV; f += C_::SPLIT_THREADS) {
             const float4 x = hi[f];
             float4 h, l;
             h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
@@ -400,7 +402,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
             h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
             l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
-            hi[f] = h;
+            if (g.split_write_hi) hi[f] = h;     // not needed when the tensor core truncates fp32 -> tf32 itself
             lo[f] = l;
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA)
@@ -425,6 +427,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 // 2 enables the 2-CTA multicast variant.  Measured on B200 (profiles/r1e): no gain over unicast -- the kernel is
 // bound by per-SM ingest (~38 B/clk/SM), not by L2 reads -- so it is off by default and kept as a tested option.
 static int g_cluster = 1;
+static int g_split_write_hi = 1;
 static unsigned g_mn_desc[5] = {1u, (unsigned)SLAB_BYTES, 512u, 1024u, (unsigned)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B};
 
 static int resolve_encode() {
@@ -529,6 +532,7 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   d.M = a.M; d.Nc = a.Nc; d.K = a.K; d.K1 = K1; d.batch = a.batch;
   d.a_kmajor = a.a_kmajor ? 1 : 0; d.b_kmajor = a.b_kmajor ? 1 : 0;
   d.CT = a.CT; d.ct_cols = a.ct_cols; d.ct_group = a.ct_group;
+  d.split_write_hi = g_split_write_hi;
   d.mn_layout = g_mn_desc[0]; d.mn_lbo = g_mn_desc[1]; d.mn_sbo = g_mn_desc[2]; d.mn_kadv = g_mn_desc[3];
   d.a_batched = a.strideA != 0; d.b_batched = a.strideB != 0; d.b2_batched = a.strideB2 != 0; d.has_b2 = two ? 1 : 0;
   // 2-CTA clusters with a multicast B tile: K-major single-segment B and at least two row tiles
@@ -545,6 +549,7 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
 
 // Bring-up hook (not part of include/infltm.h): override the MN-major descriptor parameters.
 extern "C" void ltm_debug_set_cluster(int c) { ltm::g_cluster = c; }
+extern "C" void ltm_debug_set_split_write_hi(int v) { ltm::g_split_write_hi = v; }
 
 extern "C" void ltm_debug_set_mn_desc(unsigned layout, unsigned lbo, unsigned sbo, unsigned kadv, unsigned swz) {
   ltm::g_mn_desc[0] = layout; ltm::g_mn_desc[1] = lbo; ltm::g_mn_desc[2] = sbo; ltm::g_mn_desc[3] = kadv;

@@ -34,4 +34,4 @@ if [ "$MODE" = "full" ]; then
       python bench.py --steps 1 --warmup 3 --videos 32 --no-e2e --no-cpu-baseline --no-gauss > $OUT/ncu_attn.log 2>&1
 fi
 cat $OUT/summary.txt
-[ -f $OUT/bench.json ] && cat $OUT/bench.json
+[ -f $OUT/bench.json ] && cat $OUT/bench.json; true
