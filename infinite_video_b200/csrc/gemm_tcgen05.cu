@@ -9,12 +9,13 @@
 //   [32 k][32 mn]); B may be the row-concatenation of two tensors (the Gaussian variant regresses
 //   [re-sampled memory ; new chunk] without materialising the concatenation,
 //   long_term_attention.py:249-250).
-// * precision 3 = split-TF32: every tile is split in shared memory into hi = tf32(x) and lo = x - hi
-//   and three MMAs (hi*hi + lo*hi + hi*lo) reproduce fp32-grade products.  Needed for the Gaussian
+// * precision 3 = split-TF32: the tensor core truncates fp32 -> tf32 (hi = tf32(x) is the loaded tile itself);
+//   8 warps write lo = x - hi into one extra buffer and three MMAs (hi*hi + lo*hi + hi*lo) reproduce
+//   fp32-grade products.  Needed for the Gaussian
 //   variant whose RBF design values reach 80 with heavy cancellation (single-pass TF32 -> 1e-2 error).
 //
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 =
-// epilogue (TMEM lane quarter = warp_id % 4), warps 6-9 = operand splitter (precision 3 only); two TMEM
+// epilogue (TMEM lane quarter = warp_id % 4), warps 6-13 = operand splitter (precision 3 only); two TMEM
 // accumulators so the epilogue of one tile overlaps the MMAs of the next.
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -41,7 +42,6 @@ struct GemmDev {
   unsigned mn_layout, mn_lbo, mn_sbo, mn_kadv;
   float* CT;
   int ct_cols, ct_group;
-  int split_write_hi;
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -164,9 +164,11 @@ constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;                 // one 32x32 fp32
 template <int BN, int STAGES, bool SPLIT>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 4;
-  static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (SPLIT ? 2 : 1);
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;        // TMA landing slot ("hi" operands are used in place)
+  static constexpr int LO_BYTES = SPLIT ? STAGE_BYTES : 0;     // one buffer of lo = x - tf32(x) (precision 3)
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES + LO_BYTES;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;   // + 1024 B alignment slack
+  static constexpr int SMEM_BYTES = RING_BYTES + STG_BYTES + BAR_BYTES + 1024;   // + 1024 B alignment slack
   static constexpr int TMEM_COLS = 2 * BN;                     // two accumulator buffers (256 or 512 columns)
   static constexpr int SPLIT_THREADS = 256;                    // 8 splitter warps (precision 3)
   static constexpr int THREADS = SPLIT ? 192 + SPLIT_THREADS : 192;
@@ -189,15 +191,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B wants 1024 B alignment
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  float* staging = reinterpret_cast<float*>(smem_al + STAGES * C_::STAGE_BYTES);
-  const uint32_t bars = smem_base + STAGES * C_::STAGE_BYTES + STG_BYTES;
+  float* staging = reinterpret_cast<float*>(smem_al + C_::RING_BYTES);
+  const uint32_t bars = smem_base + C_::RING_BYTES + STG_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto split_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
   auto tfull_bar = [&](int b) { return bars + 8u * (3 * STAGES + b); };
   auto tempty_bar = [&](int b) { return bars + 8u * (3 * STAGES + 2 + b); };
-  uint32_t* tmem_slot =
-      reinterpret_cast<uint32_t*>(smem_al + STAGES * C_::STAGE_BYTES + STG_BYTES + 8 * (3 * STAGES + 4));
+  const uint32_t lofree_bar = bars + 8u * (3 * STAGES + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_al + C_::RING_BYTES + STG_BYTES + 8 * (3 * STAGES + 5));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (g.K + BK - 1) / BK;
@@ -216,6 +218,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       mbar_init(empty_bar(s), CLUSTER);  // the MMA warps of every CTA that received a multicast into this slot
       mbar_init(split_bar(s), C_::SPLIT_THREADS);   // every splitter thread arrives after its proxy fence
     }
+    mbar_init(lofree_bar, 1);            // MMAs of a k-block done with the single lo buffer
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);        // tcgen05.commit of the last MMA of a tile
       mbar_init(tempty_bar(b), 128);     // every epilogue thread after its last tcgen05.ld of the tile
@@ -300,7 +303,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           tcgen05_fence_after();
           const uint32_t sa = smem_base + s * C_::STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
-          const uint32_t sa_lo = sb + C_::B_BYTES;
+          const uint32_t sa_lo = smem_base + STAGES * C_::STAGE_BYTES;     // the single lo buffer [A_lo | B_lo]
           const uint32_t sb_lo = sa_lo + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -312,6 +315,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               tcgen05_mma_tf32(tmem_acc, da, operand_desc(sb_lo, g.b_kmajor, k, mn), idesc, 1u);
             }
           }
+          if (SPLIT) tcgen05_commit(lofree_bar);  // the splitter may overwrite the lo buffer
           // frees the stage once these MMAs have read it (in every CTA that multicasts into this slot)
           if (CLUSTER > 1) tcgen05_commit_mc(empty_bar(s), (uint16_t)((1u << CLUSTER) - 1u));
           else tcgen05_commit(empty_bar(s));
@@ -391,8 +395,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(full_bar(s), ph);
-          float4* hi = reinterpret_cast<float4*>(smem_al + s * C_::STAGE_BYTES);
-          float4* lo = reinterpret_cast<float4*>(smem_al + s * C_::STAGE_BYTES + A_BYTES + C_::B_BYTES);
+          mbar_wait(lofree_bar, (it & 1u) ^ 1u);           // MMAs of the previous k-block have consumed lo
+          const float4* hi = reinterpret_cast<const float4*>(smem_al + s * C_::STAGE_BYTES);
+          float4* lo = reinterpret_cast<float4*>(smem_al + STAGES * C_::STAGE_BYTES);
 #pragma unroll 4
           for (int f = et; f < NV; f += C_::SPLIT_THREADS) {
             const float4 x = hi[f];
@@ -402,7 +407,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
             h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
             l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
-            if (g.split_write_hi) hi[f] = h;     // not needed when the tensor core truncates fp32 -> tf32 itself
+            // `hi` stays as loaded: the tensor core itself truncates fp32 -> tf32 (measured on B200: rewriting
+            // the masked value gives bit-identical products, scripts/split_probe.py)
             lo[f] = l;
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA)
@@ -427,7 +433,6 @@ static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 // 2 enables the 2-CTA multicast variant.  Measured on B200 (profiles/r1e): no gain over unicast -- the kernel is
 // bound by per-SM ingest (~38 B/clk/SM), not by L2 reads -- so it is off by default and kept as a tested option.
 static int g_cluster = 1;
-static int g_split_write_hi = 1;
 static unsigned g_mn_desc[5] = {1u, (unsigned)SLAB_BYTES, 512u, 1024u, (unsigned)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B};
 
 static int resolve_encode() {
@@ -516,7 +521,7 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   LTM_REQUIRE(!two || (a.K1 > 0 && a.K1 % BK == 0), "gemm: K1=%d must be a positive multiple of %d", a.K1, BK);
   LTM_REQUIRE(a.precision == 1 || a.precision == 3, "gemm: precision must be 1 (tf32) or 3 (split tf32)");
   const bool split = a.precision == 3;
-  const int bn = (!split && a.Nc > 128) ? 256 : 128;
+  const int bn = (a.Nc > 128) ? 256 : 128;
   const int K1 = two ? a.K1 : a.K;
   CUtensorMap mA, mB, mB2;
   if (encode_operand(&mA, a.A, a.M, a.K, a.lda, a.strideA, a.batch, a.a_kmajor, BM, "A")) return -1;
@@ -532,13 +537,14 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   d.M = a.M; d.Nc = a.Nc; d.K = a.K; d.K1 = K1; d.batch = a.batch;
   d.a_kmajor = a.a_kmajor ? 1 : 0; d.b_kmajor = a.b_kmajor ? 1 : 0;
   d.CT = a.CT; d.ct_cols = a.ct_cols; d.ct_group = a.ct_group;
-  d.split_write_hi = g_split_write_hi;
   d.mn_layout = g_mn_desc[0]; d.mn_lbo = g_mn_desc[1]; d.mn_sbo = g_mn_desc[2]; d.mn_kadv = g_mn_desc[3];
   d.a_batched = a.strideA != 0; d.b_batched = a.strideB != 0; d.b2_batched = a.strideB2 != 0; d.has_b2 = two ? 1 : 0;
   // 2-CTA clusters with a multicast B tile: K-major single-segment B and at least two row tiles
   const bool mc = g_cluster >= 2 && a.b_kmajor && !two && a.M > BM;
-  if (split) return mc ? launch_cfg<128, 3, true, 2>(mA, mB, mB2, d, a.batch, stream)
-                       : launch_cfg<128, 3, true>(mA, mB, mB2, d, a.batch, stream);
+  if (split && bn == 256) return mc ? launch_cfg<256, 3, true, 2>(mA, mB, mB2, d, a.batch, stream)
+                                    : launch_cfg<256, 3, true>(mA, mB, mB2, d, a.batch, stream);
+  if (split) return mc ? launch_cfg<128, 4, true, 2>(mA, mB, mB2, d, a.batch, stream)
+                       : launch_cfg<128, 4, true>(mA, mB, mB2, d, a.batch, stream);
   if (bn == 256) return mc ? launch_cfg<256, 4, false, 2>(mA, mB, mB2, d, a.batch, stream)
                            : launch_cfg<256, 4, false>(mA, mB, mB2, d, a.batch, stream);
   return mc ? launch_cfg<128, 6, false, 2>(mA, mB, mB2, d, a.batch, stream)
@@ -549,7 +555,6 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
 
 // Bring-up hook (not part of include/infltm.h): override the MN-major descriptor parameters.
 extern "C" void ltm_debug_set_cluster(int c) { ltm::g_cluster = c; }
-extern "C" void ltm_debug_set_split_write_hi(int v) { ltm::g_split_write_hi = v; }
 
 extern "C" void ltm_debug_set_mn_desc(unsigned layout, unsigned lbo, unsigned sbo, unsigned kadv, unsigned swz) {
   ltm::g_mn_desc[0] = layout; ltm::g_mn_desc[1] = lbo; ltm::g_mn_desc[2] = sbo; ltm::g_mn_desc[3] = kadv;
