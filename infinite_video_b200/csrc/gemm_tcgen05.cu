@@ -427,12 +427,333 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   }
 }
 
+// ================================================================================================
+// CTA-pair variant: tcgen05.mma.cta_group::2.  Two CTAs on one TPC compute a 256 x BN tile together:
+// CTA r holds rows [m0 + 128 r, +128) of A and rows [n0 + BN/2 r, +BN/2) of B in its shared memory, the
+// leader (rank 0) issues one M = 256 MMA that reads both CTAs' operands, and each CTA's TMEM receives its own
+// 128 accumulator rows.  Per SM this halves the B bytes that have to be ingested and it lifts the
+// single-CTA MMA rate limit (measured: cta_group::1 TF32 tops out near 550 TFLOP/s).
+//   full[s]   (leader)   precision 1: armed by the leader for both CTAs' TMA bytes (the peer's loads use the
+//                        .cta_group::2 form and signal the leader's barrier); precision 3: each CTA's own
+//   split[s]  (leader)   precision 3: 2 x 256 splitter threads (the peer's arrive remotely)
+//   empty[s], lofree, tfull[b] (both CTAs)  tcgen05.commit.cta_group::2 multicast from the leader
+//   tempty[b] (leader)   2 x 128 epilogue threads (the peer's arrive remotely)
+// ================================================================================================
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
+// bounded wait with cluster-scope acquire (barriers that receive arrivals from the peer CTA)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 0x3fffu) == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 2000000000ull) {
+        printf("libinfltm gemm(pair): mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+        asm volatile("trap;");
+      }
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* map, uint32_t dst, uint32_t bar_cluster, int c0,
+                                                 int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                      uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {     // arrives in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+template <int BN, int STAGES, bool SPLIT>
+struct PairCfg {
+  static constexpr int BH = BN / 2;                            // B rows held by each CTA
+  static constexpr int B_BYTES = BH * BK * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int LO_BYTES = SPLIT ? STAGE_BYTES : 0;
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES + LO_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = RING_BYTES + STG_BYTES + BAR_BYTES + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SPLIT_THREADS = 256;
+  static constexpr int THREADS = SPLIT ? 192 + SPLIT_THREADS : 192;
+  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two <= 512");
+};
+
+template <int BN, int STAGES, bool SPLIT>
+__global__ void __launch_bounds__(PairCfg<BN, STAGES, SPLIT>::THREADS, 1)
+gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                      const __grid_constant__ CUtensorMap mapB2, const GemmDev g) {
+  using C_ = PairCfg<BN, STAGES, SPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  float* staging = reinterpret_cast<float*>(smem_al + C_::RING_BYTES);
+  const uint32_t bars = smem_base + C_::RING_BYTES + STG_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto split_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+  auto tfull_bar = [&](int b) { return bars + 8u * (3 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bars + 8u * (3 * STAGES + 2 + b); };
+  const uint32_t lofree_bar = bars + 8u * (3 * STAGES + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_al + C_::RING_BYTES + STG_BYTES + 8 * (3 * STAGES + 5));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = blockIdx.x & 1u;
+  const bool leader = crank == 0;
+  const int num_kb = (g.K + BK - 1) / BK;
+  const int tiles_n = (g.Nc + BN - 1) / BN, tiles_m = (g.M + BM - 1) / BM;
+  const int w_first = blockIdx.x >> 1, w_stride = gridDim.x >> 1;
+  const int num_work = tiles_n * ((tiles_m + 1) / 2) * g.batch;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+    if (g.has_b2) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB2)) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(split_bar(s), 2 * C_::SPLIT_THREADS);
+    }
+    mbar_init(lofree_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 2 * 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)C_::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int w = w_first; w < num_work; w += w_stride) {
+        int n0, m0, bz;
+        decode_work<2, BN>(w, tiles_n, tiles_m, (int)crank, n0, m0, bz);
+        const int nb0 = n0 + (int)crank * C_::BH;                       // this CTA's half of the B tile
+        const int za = g.a_batched ? bz : 0;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          uint32_t bar;                                                 // shared::cluster address of the barrier
+          if (SPLIT) {
+            mbar_arrive_expect_tx(full_bar(s), C_::STAGE_BYTES);        // own barrier: the splitter waits on it
+            bar = mapa_rank(full_bar(s), crank);
+          } else {
+            if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * C_::STAGE_BYTES);
+            bar = mapa_rank(full_bar(s), 0);                            // both CTAs' bytes land on the leader's
+          }
+          const uint32_t sa = smem_base + s * C_::STAGE_BYTES;
+          const uint32_t sb = sa + A_BYTES;
+          const int k0 = kb * BK;
+          if (g.a_kmajor) {
+            tma_load_3d_pair(&mapA, sa, bar, k0, m0, za);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 32; ++i) tma_load_3d_pair(&mapA, sa + i * SLAB_BYTES, bar, m0 + 32 * i, k0, za);
+          }
+          const bool seg2 = g.has_b2 && (k0 >= g.K1);
+          const CUtensorMap* mb = seg2 ? &mapB2 : &mapB;
+          const int kk = seg2 ? k0 - g.K1 : k0;
+          const int zb = seg2 ? (g.b2_batched ? bz : 0) : (g.b_batched ? bz : 0);
+          if (g.b_kmajor) {
+            tma_load_3d_pair(mb, sb, bar, kk, nb0, zb);
+          } else {
+#pragma unroll
+            for (int i = 0; i < C_::BH / 32; ++i) tma_load_3d_pair(mb, sb + i * SLAB_BYTES, bar, nb0 + 32 * i, kk, zb);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((g.a_kmajor ? 0u : 1u) << 15) |
+                             ((g.b_kmajor ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)((2 * BM) >> 4) << 24);                       // M = 256 across the pair
+      const MnDesc mn{g.mn_layout, g.mn_lbo, g.mn_sbo, g.mn_kadv};
+      uint32_t it = 0, tc = 0;
+      for (int w = w_first; w < num_work; w += w_stride, ++tc) {
+        const uint32_t buf = tc & 1u, tph = (tc >> 1) & 1u;
+        mbar_wait_cluster(tempty_bar(buf), tph ^ 1u);          // both CTAs' epilogues have drained the accumulator
+        tcgen05_fence_after();
+        const uint32_t tmem_acc = tmem_base + buf * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          if (SPLIT) mbar_wait_cluster(split_bar(s), ph); else mbar_wait_cluster(full_bar(s), ph);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_base + s * C_::STAGE_BYTES;
+          const uint32_t sb = sa + A_BYTES;
+          const uint32_t sa_lo = smem_base + STAGES * C_::STAGE_BYTES;
+          const uint32_t sb_lo = sa_lo + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = operand_desc(sa, g.a_kmajor, k, mn);
+            const uint64_t db = operand_desc(sb, g.b_kmajor, k, mn);
+            tcgen05_mma_tf32_pair(tmem_acc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (SPLIT) {
+              tcgen05_mma_tf32_pair(tmem_acc, operand_desc(sa_lo, g.a_kmajor, k, mn), db, idesc, 1u);
+              tcgen05_mma_tf32_pair(tmem_acc, da, operand_desc(sb_lo, g.b_kmajor, k, mn), idesc, 1u);
+            }
+          }
+          if (SPLIT) tcgen05_commit_pair(lofree_bar);
+          tcgen05_commit_pair(empty_bar(s));
+        }
+        tcgen05_commit_pair(tfull_bar(buf));
+      }
+    }
+    __syncwarp();
+  } else if (warp < 6) {
+    // ------------------------------------------------------------------ epilogue warps (both CTAs, own rows)
+    const int quarter = warp & 3;
+    float* stg = staging + quarter * (32 * STG_LD);
+    uint32_t tc = 0;
+    for (int w = w_first; w < num_work; w += w_stride, ++tc) {
+      int n0, m0, bz;
+      decode_work<2, BN>(w, tiles_n, tiles_m, (int)crank, n0, m0, bz);
+      const uint32_t buf = tc & 1u, tph = (tc >> 1) & 1u;
+      mbar_wait(tfull_bar(buf), tph);
+      tcgen05_fence_after();
+      const int row0 = m0 + quarter * 32;
+      float* cbase_ptr = g.C + (size_t)bz * g.strideC;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= g.Nc) break;
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (g.CT != nullptr && n0 + c0 < g.ct_cols) {
+          const int row = row0 + lane;
+          if (row < g.M) {
+            float* dst = g.CT + (size_t)bz * g.strideC +
+                         ((size_t)(row / g.ct_group) * g.ct_cols + n0 + c0) * g.ct_group + (row % g.ct_group);
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              dst[(size_t)i * g.ct_group] = __uint_as_float(r[i]) + (g.bias ? __ldg(g.bias + n0 + c0 + i) : 0.f);
+          }
+          continue;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) stg[lane * STG_LD + i] = __uint_as_float(r[i]);
+        __syncwarp();
+        const int col = n0 + c0 + lane;
+        const bool col_ok = col < g.Nc;
+        const float bv = (g.bias != nullptr && col_ok) ? __ldg(g.bias + col) : 0.f;
+        const int ccol = col - (g.CT != nullptr ? g.ct_cols : 0);
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+          const int row = row0 + i;
+          if (row < g.M && col_ok) cbase_ptr[(size_t)row * g.ldc + ccol] = stg[i * STG_LD + lane] + bv;
+        }
+        __syncwarp();
+      }
+      tcgen05_fence_before();
+      mbar_arrive_remote(mapa_rank(tempty_bar(buf), 0));      // 2 x 128 arrivals on the leader's barrier
+    }
+  } else {
+    // ------------------------------------------------------------------ operand splitter (precision 3, both CTAs)
+    if (SPLIT) {
+      const int et = threadIdx.x - 192;
+      constexpr int NV = C_::STAGE_BYTES / 16;
+      uint32_t it = 0;
+      for (int w = w_first; w < num_work; w += w_stride) {
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(full_bar(s), ph);
+          mbar_wait(lofree_bar, (it & 1u) ^ 1u);
+          const float4* hi = reinterpret_cast<const float4*>(smem_al + s * C_::STAGE_BYTES);
+          float4* lo = reinterpret_cast<float4*>(smem_al + STAGES * C_::STAGE_BYTES);
+#pragma unroll 4
+          for (int f = et; f < NV; f += C_::SPLIT_THREADS) {
+            const float4 x = hi[f];
+            float4 l;
+            l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+            l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+            l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+            l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+            lo[f] = l;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive_remote(mapa_rank(split_bar(s), 0));    // 2 x 256 arrivals on the leader's barrier
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C_::TMEM_COLS)
+                 : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 // bring-up override of the MN-major layout parameters: {layout, lbo, sbo, kadv, tma swizzle enum}
 // 2 enables the 2-CTA multicast variant.  Measured on B200 (profiles/r1e): no gain over unicast -- the kernel is
 // bound by per-SM ingest (~38 B/clk/SM), not by L2 reads -- so it is off by default and kept as a tested option.
 static int g_cluster = 1;
+// CTA-pair (tcgen05 cta_group::2) kernel for problems with at least two row tiles
+static int g_pair = 1;
 static unsigned g_mn_desc[5] = {1u, (unsigned)SLAB_BYTES, 512u, 1024u, (unsigned)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B};
 
 static int resolve_encode() {
@@ -515,6 +836,44 @@ static int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const CUtens
   return 0;
 }
 
+template <int BN, int STAGES, bool SPLIT>
+static int launch_pair(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mB2, const GemmDev& d,
+                       int batch, cudaStream_t stream) {
+  using C_ = PairCfg<BN, STAGES, SPLIT>;
+  static bool configured = false;
+  if (!configured) {
+    LTM_CUDA(cudaFuncSetAttribute(gemm_tf32_pair_kernel<BN, STAGES, SPLIT>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
+    configured = true;
+  }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    LTM_CUDA(cudaGetDevice(&dev));
+    LTM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const long long tm = (d.M + BM - 1) / BM;
+  const long long work = (long long)((d.Nc + BN - 1) / BN) * ((tm + 1) / 2) * batch;
+  LTM_REQUIRE(work < (1ll << 31), "gemm: too many tiles");
+  long long pairs = num_sms / 2;
+  if (work < pairs) pairs = work;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(pairs * 2));
+  cfg.blockDim = dim3(C_::THREADS);
+  cfg.dynamicSmemBytes = C_::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LTM_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_pair_kernel<BN, STAGES, SPLIT>, mA, mB, mB2, d));
+  return 0;
+}
+
 static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   if (resolve_encode()) return -1;
   const bool two = a.B2 != nullptr && a.K1 < a.K;
@@ -525,10 +884,12 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   const int K1 = two ? a.K1 : a.K;
   CUtensorMap mA, mB, mB2;
   if (encode_operand(&mA, a.A, a.M, a.K, a.lda, a.strideA, a.batch, a.a_kmajor, BM, "A")) return -1;
-  const bool mc_pre = g_cluster >= 2 && a.b_kmajor && !two && a.M > BM;
-  if (encode_operand(&mB, a.B, a.Nc, K1, a.ldb, a.strideB, a.batch, a.b_kmajor, mc_pre ? bn / 2 : bn, "B")) return -1;
+  const bool pair = g_pair != 0 && a.M > BM;                    // CTA pairs need two row tiles
+  const bool mc_pre = !pair && g_cluster >= 2 && a.b_kmajor && !two && a.M > BM;
+  const int b_box = (pair || mc_pre) ? bn / 2 : bn;             // B rows fetched per TMA box
+  if (encode_operand(&mB, a.B, a.Nc, K1, a.ldb, a.strideB, a.batch, a.b_kmajor, b_box, "B")) return -1;
   if (two) {
-    if (encode_operand(&mB2, a.B2, a.Nc, a.K - K1, a.ldb2, a.strideB2, a.batch, a.b_kmajor, bn, "B2")) return -1;
+    if (encode_operand(&mB2, a.B2, a.Nc, a.K - K1, a.ldb2, a.strideB2, a.batch, a.b_kmajor, b_box, "B2")) return -1;
   } else {
     mB2 = mB;
   }
@@ -539,8 +900,14 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   d.CT = a.CT; d.ct_cols = a.ct_cols; d.ct_group = a.ct_group;
   d.mn_layout = g_mn_desc[0]; d.mn_lbo = g_mn_desc[1]; d.mn_sbo = g_mn_desc[2]; d.mn_kadv = g_mn_desc[3];
   d.a_batched = a.strideA != 0; d.b_batched = a.strideB != 0; d.b2_batched = a.strideB2 != 0; d.has_b2 = two ? 1 : 0;
+  if (pair) {
+    if (split) return bn == 256 ? launch_pair<256, 5, true>(mA, mB, mB2, d, a.batch, stream)
+                                : launch_pair<128, 6, true>(mA, mB, mB2, d, a.batch, stream);
+    return bn == 256 ? launch_pair<256, 6, false>(mA, mB, mB2, d, a.batch, stream)
+                     : launch_pair<128, 8, false>(mA, mB, mB2, d, a.batch, stream);
+  }
   // 2-CTA clusters with a multicast B tile: K-major single-segment B and at least two row tiles
-  const bool mc = g_cluster >= 2 && a.b_kmajor && !two && a.M > BM;
+  const bool mc = mc_pre;
   if (split && bn == 256) return mc ? launch_cfg<256, 3, true, 2>(mA, mB, mB2, d, a.batch, stream)
                                     : launch_cfg<256, 3, true>(mA, mB, mB2, d, a.batch, stream);
   if (split) return mc ? launch_cfg<128, 4, true, 2>(mA, mB, mB2, d, a.batch, stream)
@@ -555,6 +922,7 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
 
 // Bring-up hook (not part of include/infltm.h): override the MN-major descriptor parameters.
 extern "C" void ltm_debug_set_cluster(int c) { ltm::g_cluster = c; }
+extern "C" void ltm_debug_set_pair(int v) { ltm::g_pair = v; }
 
 extern "C" void ltm_debug_set_mn_desc(unsigned layout, unsigned lbo, unsigned sbo, unsigned kadv, unsigned swz) {
   ltm::g_mn_desc[0] = layout; ltm::g_mn_desc[1] = lbo; ltm::g_mn_desc[2] = sbo; ltm::g_mn_desc[3] = kadv;

@@ -17,10 +17,16 @@ for mode in (1, 0):
     got = ops.gemm(A.to(dev), B.to(dev), precision="tf32x3")[0].cpu().double()
     print("write_hi" if mode else "lo_only ", float((got - want).abs().max() / want.abs().max()))
 lib_set(1)
+lib.ltm_debug_set_pair.argtypes = [C.c_int]; lib.ltm_debug_set_pair.restype = None
+for pair in (0, 1):
+    lib.ltm_debug_set_pair(pair)
+    for prec in ("tf32", "tf32x3"):
+        got = ops.gemm(A.to(dev), B.to(dev), precision=prec)[0].cpu().double()
+        print("pair" if pair else "single", prec, "relerr", float((got - want).abs().max() / want.abs().max()))
 import time
 for prec in ("tf32", "tf32x3"):
     for mode in (1, 0):
-        lib_set(mode)
+        lib.ltm_debug_set_pair(mode)
         Ab = torch.randn(32768, 768, device=dev); Bb = B.to(dev); bias = torch.zeros(1536, device=dev)
         out = torch.empty(32768, 1536, device=dev)
         ops.project_kv(Ab, Bb, bias, prec, out=out); torch.cuda.synchronize()
@@ -28,5 +34,5 @@ for prec in ("tf32", "tf32x3"):
         e0.record()
         for _ in range(10): ops.project_kv(Ab, Bb, bias, prec, out=out)
         e1.record(); torch.cuda.synchronize()
-        print(prec, "write_hi" if mode else "lo_only", round(e0.elapsed_time(e1) / 10, 4), "ms")
+        print(prec, "pair" if mode else "single", round(e0.elapsed_time(e1) / 10, 4), "ms")
 lib_set(1)

@@ -188,16 +188,20 @@ GEMM_CASES = [
 ]
 
 
-@pytest.fixture(params=[1, 2], ids=["unicast", "cluster2"])
+@pytest.fixture(params=["pair", "single", "multicast"])
 def gemm_cluster(request):
-    """Runs the GEMM tests with and without the 2-CTA TMA-multicast variant (bring-up hook of libinfltm)."""
+    """Runs the GEMM tests through the three kernel variants: CTA pairs (tcgen05 cta_group::2, the default for
+    M > 128), single-CTA, and single-CTA MMAs with 2-CTA TMA multicast (bring-up hooks of libinfltm)."""
     import ctypes
     from infinite_video_b200 import _capi
-    f = _capi.lib().ltm_debug_set_cluster
-    f.argtypes, f.restype = [ctypes.c_int], None
-    f(request.param)
+    lib = _capi.lib()
+    for f in (lib.ltm_debug_set_cluster, lib.ltm_debug_set_pair):
+        f.argtypes, f.restype = [ctypes.c_int], None
+    lib.ltm_debug_set_pair(1 if request.param == "pair" else 0)
+    lib.ltm_debug_set_cluster(2 if request.param == "multicast" else 1)
     yield request.param
-    f(1)
+    lib.ltm_debug_set_pair(1)
+    lib.ltm_debug_set_cluster(1)
 
 
 @pytest.mark.parametrize("M,N,K,batch,akm,bkm,two,bias", GEMM_CASES)
