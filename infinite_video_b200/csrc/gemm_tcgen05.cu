@@ -752,8 +752,11 @@ static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 // 2 enables the 2-CTA multicast variant.  Measured on B200 (profiles/r1e): no gain over unicast -- the kernel is
 // bound by per-SM ingest (~38 B/clk/SM), not by L2 reads -- so it is off by default and kept as a tested option.
 static int g_cluster = 1;
-// CTA-pair (tcgen05 cta_group::2) kernel for problems with at least two row tiles
-static int g_pair = 1;
+// 1 selects the CTA-pair (tcgen05 cta_group::2) kernel for problems with at least two row tiles.  Measured on
+// B200 (profiles/r1f_gemm_variants.txt): same time as the single-CTA kernel in precision 1 although it ingests a
+// third fewer bytes, slower in precision 3 -- all variants sit at 46-49 % tensor-pipe activity because fp32
+// operands make shared-memory bandwidth (TMA write + MMA read of every byte) the limit.  Off by default.
+static int g_pair = 0;
 static unsigned g_mn_desc[5] = {1u, (unsigned)SLAB_BYTES, 512u, 1024u, (unsigned)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B};
 
 static int resolve_encode() {
