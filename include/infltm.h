@@ -46,6 +46,13 @@ int ltm_pool_mean_grid(const float* k, float* xpart, int Bv, int L, int T, int e
 int ltm_sticky_hist_rect(const float* scores, const int32_t* jb, const float* tb, float* hist_part,
                          int Bv, int H, int Q, int N, void* stream);
 
+/* ---- R12 side output (Video-LLaMA copy only, gibbs:320-343 -> ./alphas_uniform -> relevant_frames.py):
+ * scores[Bv,H,Q,N] -> out[Q,Bv,H,768]: Gibbs density on linspace(0,.25,256) | (.25,.5,256) | (.5,1,256), each segment
+ * normalised by its trapezoid integral (weights wd[768]), the concatenation normalised to sum 1.  jd[768] = basis
+ * index of each point (-1 none). */
+int ltm_density_rect(const float* scores, const int32_t* jd, const float* wd, float* out,
+                     int Bv, int H, int Q, int N, void* stream);
+
 /* ---- G3: sticky histogram from the previous (mu, sigma).  long_term_attention.py:220-229.
  * mu,sd[Bv,R] -> hist[Bv,128] (un-normalised). */
 int ltm_sticky_hist_gauss(const float* mu, const float* sd, const float* tb, float* hist,

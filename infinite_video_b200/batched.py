@@ -189,6 +189,7 @@ class BatchedRectLTM(_BatchedBase):
     def _finish(self, ws):
         self._cur = 1 - self._cur
         self.has_state = True
+        self._last_L = ws["xparts"][0].shape[1]
         V = ws["V"] if ws["V"] is not None else ws["KV"][:, :, self.D:]
         self.last = dict(b=ws["b_draw"], ts=ws["ts"], idx=ws["idx"], p=ws["p"], scores=ws["scores"], V=V)
 
@@ -226,6 +227,16 @@ class BatchedRectLTM(_BatchedBase):
         done = torch.cuda.Event()
         done.record(self._side)
         self._pref[(k_next.data_ptr(), tuple(k_next.shape))] = (b, done)
+
+    def density(self):
+        """alphas[Q,Bv,H,768] of the most recent call: the density side-output the Video-LLaMA copy pickles to
+        ./alphas_uniform on every forward (gibbs:320-343).  Needs `keep_scores=True`."""
+        sc = self.last.get("scores")
+        if sc is None:
+            raise RuntimeError("density() needs the scores of the last call: construct with keep_scores=True")
+        L = self._last_L
+        td = tables.rect_tables(L, self.N, self.tau, self.S).to(self.device)
+        return ops.density_rect(sc, td["jd"], td["wd"])
 
     def pool(self, k):
         """Frame pooling alone (gibbs:304): k[Bv, L*T, e] -> pooled frames [Bv, L, splits, e].  The result can be

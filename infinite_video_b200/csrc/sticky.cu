@@ -184,7 +184,64 @@ resample_kernel(const float* __restrict__ hist_part, int parts, int ncat, int no
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Density side-output of the Video-LLaMA copy (gibbs:320-343, consumed by relevant_frames.py): for every
+// (video, head, query) row the Gibbs density exp(z(t)) on 3 x 256 points, each segment normalised by its own
+// trapezoid integral, the concatenation normalised to sum 1.  One warp per row; out[q, v, h, 768].
+// ------------------------------------------------------------------------------------------------
+constexpr int DENS_PTS = 768;
+__global__ void __launch_bounds__(128)
+density_rect_kernel(const float* __restrict__ scores, const int32_t* __restrict__ jd, const float* __restrict__ wd,
+                    float* __restrict__ out, int Bv, int H, int Q, int N) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);       // (v*H + h)*Q + q
+  const int lane = threadIdx.x & 31;
+  if (row >= Bv * H * Q) return;
+  const int q = row % Q, vh = row / Q, h = vh % H, v = vh / H;
+  const float* S = scores + (size_t)row * N;
+  float e[DENS_PTS / 32];
+  float m = 0.f;
+#pragma unroll
+  for (int i = 0; i < DENS_PTS / 32; ++i) {
+    const int j = jd[i * 32 + lane];
+    e[i] = (j >= 0) ? S[j] : 0.f;
+    m = fmaxf(m, e[i]);
+  }
+  m = warp_max(m);
+  float tot = 0.f;
+#pragma unroll
+  for (int seg = 0; seg < 3; ++seg) {
+    float z = 0.f;
+#pragma unroll
+    for (int i = seg * 8; i < seg * 8 + 8; ++i) {
+      e[i] = expf(e[i] - m);
+      z += wd[i * 32 + lane] * e[i];
+    }
+    z = warp_sum(z);
+#pragma unroll
+    for (int i = seg * 8; i < seg * 8 + 8; ++i) {
+      e[i] = e[i] / z;
+      tot += e[i];
+    }
+  }
+  tot = warp_sum(tot);
+  float* dst = out + (((size_t)q * Bv + v) * H + h) * DENS_PTS;
+#pragma unroll
+  for (int i = 0; i < DENS_PTS / 32; ++i) dst[i * 32 + lane] = e[i] / tot;
+}
+
 }  // namespace ltm
+
+extern "C" int ltm_density_rect(const float* scores, const int32_t* jd, const float* wd, float* out, int Bv, int H,
+                                int Q, int N, void* stream) {
+  using namespace ltm;
+  LTM_REQUIRE(scores && jd && wd && out, "density_rect: null pointer");
+  LTM_REQUIRE(Bv > 0 && H > 0 && Q > 0 && N > 0, "density_rect: bad shape");
+  const long long rows = (long long)Bv * H * Q;
+  LTM_REQUIRE(rows < (1ll << 31), "density_rect: too many rows");
+  density_rect_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, (cudaStream_t)stream>>>(scores, jd, wd, out, Bv, H, Q, N);
+  LTM_CHECK_LAUNCH("density_rect");
+  return 0;
+}
 
 extern "C" int ltm_sticky_hist_rect(const float* scores, const int32_t* jb, const float* tb, float* hist_part,
                                     int Bv, int H, int Q, int N, void* stream) {

@@ -39,7 +39,7 @@ class LongTermAttention(nn.Module):
                  affines: bool, mask: bool, mask_type: str, kl_regularizer: bool, proj_key, proj_value,
                  sigma_0, mu_0, sticky_memories, sigmas, tau, variant: str = "gibbs",
                  tokens_per_frame: int = 32, precision: str = None, gemm_impl: str = "tcgen05",
-                 share_pooling: bool = True, **kwargs):
+                 share_pooling: bool = True, output_density: bool = False, **kwargs):
         super().__init__()
         if not continuous:
             raise NotImplementedError("only the continuous-attention memory is on the LTM path (continuous=True)")
@@ -84,6 +84,10 @@ class LongTermAttention(nn.Module):
         self.precision = precision
         self.gemm_impl = gemm_impl
         self.share_pooling = share_pooling
+        # Video-LLaMA copy: density side-output of every call (gibbs:320-343).  Off by default; when on, the
+        # result is kept on the device in `self.alphas` ([Q,B,H,768]) instead of being pickled to the cwd.
+        self.output_density = output_density
+        self.alphas = None
         self._engine = None
         self._wver = None
 
@@ -101,7 +105,8 @@ class LongTermAttention(nn.Module):
                           nb_samples=self.nb_samples, gemm_impl=self.gemm_impl, device=device)
             if self.variant == "gibbs":
                 self._engine = BatchedRectLTM(tokens_per_frame=self.tokens_per_frame,
-                                              precision=self.precision or "tf32", **common)
+                                              precision=self.precision or "tf32",
+                                              keep_scores=self.output_density, **common)
             else:
                 sig = self.sigmas if self.sigmas is not None else (0.005, 0.01)
                 self._engine = BatchedGaussLTM(sigmas=tuple(sig), precision=self.precision or "tf32x3", **common)
@@ -165,6 +170,8 @@ class LongTermAttention(nn.Module):
             pooled = sp["x"]
         ctx = eng.step(k32, q32, u=u, new_doc=False, pooled=pooled) if pooled is not None else \
             eng.step(k32, q32, u=u, new_doc=False)
+        if self.output_density and self.variant == "gibbs":
+            self.alphas = eng.density()
         return ctx.to(out_dtype)
 
     def extra_repr(self):

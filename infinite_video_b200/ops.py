@@ -50,6 +50,17 @@ def sticky_hist_rect(scores, jb, tb):
     return out
 
 
+def density_rect(scores, jd, wd):
+    """scores[Bv,H,Q,N] -> alphas[Q,Bv,H,768] (density side-output of the Video-LLaMA copy, gibbs:320-343)."""
+    require_cuda(scores, jd, wd)
+    scores = _f32c(scores)
+    Bv, H, Q, N = scores.shape
+    out = torch.empty(Q, Bv, H, 768, device=scores.device, dtype=torch.float32)
+    check(lib().ltm_density_rect(ptr(scores), ptr(jd), ptr(wd), ptr(out), Bv, H, Q, N, stream_ptr(scores.device)),
+          "density_rect")
+    return out
+
+
 def sticky_hist_gauss(mu, sd, tb):
     """mu,sd[Bv,R] -> hist[Bv,128].  long_term_attention.py:220-229."""
     require_cuda(mu, sd, tb)

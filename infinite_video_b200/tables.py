@@ -126,6 +126,9 @@ class RectTables:
     W_out: float = 0.0
     # uniform (non-sticky) resampling table: basis index of sample s (-1 none)  (gibbs:152-157,:212)
     idx_uniform: np.ndarray = None   # int32 [S]
+    # density side-output of the Video-LLaMA copy (gibbs:328-335): 3 x 256 evaluation points
+    jd: np.ndarray = None            # int32 [768] basis index at each point (-1 none)
+    wd: np.ndarray = None            # fp32  [768] trapezoid weight of the point inside its own segment
     _dev: dict = field(default_factory=dict, repr=False)
 
     def to(self, device):
@@ -133,7 +136,7 @@ class RectTables:
         if key not in self._dev:
             d = {}
             for name in ("seg_ptr0", "seg_mem0", "g0", "seg_ptr1", "seg_mem1", "g1", "tb", "jb", "bins",
-                         "bin2basis", "W", "idx_uniform"):
+                         "bin2basis", "W", "idx_uniform", "jd", "wd"):
                 d[name] = torch.from_numpy(getattr(self, name)).to(device)
             self._dev[key] = d
         return self._dev[key]
@@ -197,6 +200,19 @@ def rect_tables(L: int, N: int, tau: float, S: int = NB_SAMPLES, num_quad: int =
 
     # --- uniform re-sampling table (gibbs:152-157): psi.evaluate(t/tau) for each contracted position
     t.idx_uniform = rect_bin_of(old / tau, N).numpy()
+
+    # --- density side-output grid (gibbs:328-334): per segment, trapz weights from the actual fp32 spacings
+    jd, wd = [], []
+    for a, b in ((0.0, 0.25), (0.25, 0.5), (0.5, 1.0)):
+        ts = torch.linspace(a, b, 256)
+        jd.append(rect_bin_of(ts, N).numpy())
+        d = (ts[1:] - ts[:-1]).double().numpy()
+        w = np.zeros(256)
+        w[:-1] += d / 2
+        w[1:] += d / 2
+        wd.append(w.astype(np.float32))
+    t.jd = np.concatenate(jd).astype(np.int32)
+    t.wd = np.concatenate(wd)
     return t
 
 

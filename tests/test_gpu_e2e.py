@@ -365,3 +365,23 @@ def test_layers_share_one_pooling_pass(dev):
     finally:
         ops.pool_mean = real
     assert calls["n"] == 3          # one pooling pass per chunk for the two sharing layers (solo ones pool in-step)
+
+
+def test_density_side_output(dev):
+    """N3: `output_density=True` reproduces the alphas tensor of the Video-LLaMA copy (gibbs:320-343)."""
+    from infinite_video_b200 import LongTermAttention
+    from oracle.ref_loader import caller_kwargs
+    for N, L in ((64, 8), (256, 32)):
+        key, val = make_proj(91, 768)
+        kd, vd = make_proj(91, 768)
+        m = LongTermAttention(**caller_kwargs(N, .75, True, kd.to(dev), vd.to(dev)), output_density=True)
+        orc = O.RectLTM(N, .75, *proj_tensors(key, val), rebuild_tables=False)
+        ks, qs, us = make_inputs(92, 2, 1, L * 32, 768, 32, q_scale=3.0)
+        with torch.no_grad():
+            for c in range(2):
+                m(ks[c].to(dev), qs[c].to(dev), new_doc=(c == 0), layer_n=0, u=us[c])
+                orc.forward(ks[c], qs[c], c == 0, us[c])
+                want = O.rect_density_alphas(orc, orc.tables(L))
+                assert m.alphas.shape == (32, 1, 12, 768)
+                assert relerr(m.alphas, want) < 1e-3
+                assert abs(float(m.alphas[3, 0, 5].sum()) - 1.0) < 1e-5

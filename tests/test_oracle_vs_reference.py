@@ -91,3 +91,30 @@ def test_kat_from_survey():
                 assert abs(ctx.abs().mean().item() - want_ctx[c]) < 1e-8
     finally:
         os.chdir(cwd)
+
+
+def test_density_side_output_matches_the_pickle(tmp_path):
+    """N3: the oracle's restatement of the density dump equals what the Video-LLaMA copy pickles (gibbs:320-343)."""
+    import pickle
+    mod = RL.load_gibbs_vl()
+    key, val = make_proj(7, 768)
+    ref = mod.LongTermAttention(**RL.caller_kwargs(64, 0.75, True, key, val))
+    orc = O.RectLTM(64, 0.75, *proj_tensors(key, val))
+    ks, qs, _ = make_inputs(8, 2, 1, 8 * 32, 768, 32, q_scale=3.0)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        with torch.no_grad():
+            for c in range(2):
+                torch.manual_seed(300 + c)
+                ref(ks[c], qs[c], new_doc=(c == 0), layer_n=0)
+                torch.manual_seed(300 + c)
+                u = torch.rand(1, 512, dtype=torch.float64)
+                orc.forward(ks[c], qs[c], c == 0, u)
+                with open("alphas_uniform", "rb") as f:
+                    want = pickle.load(f)
+                got = O.rect_density_alphas(orc, orc.tables(8))
+                assert got.shape == want.shape == (32, 1, 12, 768)
+                assert torch.equal(got, want), f"chunk {c}"
+    finally:
+        os.chdir(cwd)
