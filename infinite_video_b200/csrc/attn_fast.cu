@@ -49,12 +49,14 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 template <int NB>
 __host__ __device__ constexpr int smem_floats(bool hist) {
-  // ring[2][RING] | Qt[64][32] | Rt[NB][32] | mrow[32] zrow[32] part[128] | (hist) Eb[32][130]
-  return 2 * RING + DH * QT + NB * QT + 32 + 32 + 128 + (hist ? QT * (EDGES + 1) : 0);
+  // ring[2][RING] | Qt[64][32] | Rt[NB][32] | mrow[32] zrow[32] part[128]
+  // The histogram scratch Eb[32][130] aliases Rt (written only after the histogram) when it fits (NB >= 130),
+  // otherwise it gets its own region.
+  return 2 * RING + DH * QT + NB * QT + 32 + 32 + 128 + ((hist && NB * QT < QT * (EDGES + 1)) ? QT * (EDGES + 1) : 0);
 }
 
 template <int MODE, int NB>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, (MODE == 0) ? 3 : 2)
 cont_attn_fast_kernel(const Params p) {
   static_assert(NB == 64 || NB == 128 || NB == 256, "fast path covers num_basis 64/128/256");
   constexpr int JPT = NB / 32;                 // basis columns per lane in phase 1
@@ -68,7 +70,7 @@ cont_attn_fast_kernel(const Params p) {
   float* mrow = Rt + NB * QT;
   float* zrow = mrow + 32;
   float* part = zrow + 32;
-  float* Eb = part + 128;
+  float* Eb = (NB * QT >= QT * (EDGES + 1)) ? Rt : part + 128;
 
   const int Q = p.Q, H = p.H, D = H * DH;
   const int qt = blockIdx.x, h = blockIdx.y, v = blockIdx.z;
