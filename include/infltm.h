@@ -40,6 +40,11 @@ int ltm_pool_mean(const float* k, float* xpart, int Bv, int L, int T, int e, int
 int ltm_pool_mean_grid(const float* k, float* xpart, int Bv, int L, int T, int e, int splits, int max_ctas,
                        void* stream);
 
+/* same for a 16-bit chunk (fp16 when is_bf16 == 0, else bfloat16; the VideoChat2 Q-former runs under fp16
+ * autocast): 128-bit loads of 8 elements, fp32 accumulation, fp32 output.  e % 8 == 0. */
+int ltm_pool_mean_16(const void* k, int is_bf16, float* xpart, int Bv, int L, int T, int e, int splits,
+                     void* stream);
+
 /* ---- R6: sticky histogram of the previous call's density.  gibbs:196-203 (+score :224-230,
  * compute_probability :232-249).  scores[Bv,H,Q,N] -> hist_part[Bv,H,127] (sum over q; the sum
  * over heads happens in ltm_resample).  Normally fused into ltm_cont_attn_rect. */

@@ -258,8 +258,10 @@ class BatchedRectLTM(_BatchedBase):
         sticky); new_doc: bool or per-video flags; pooled: result of `pool(k)` (then `k` is only used for its
         shape).  Returns ctx[Bv,Q,D]."""
         require_cuda(k, q, u)
-        if k.dtype != torch.float32 or q.dtype != torch.float32:
-            raise ValueError("k and q must be float32")
+        if k.dtype in (torch.float16, torch.bfloat16) and pooled is None:
+            pooled = self.pool(k)                  # 16-bit chunk: pooled straight from its 16-bit storage
+        if (k.dtype != torch.float32 and pooled is None) or q.dtype != torch.float32:
+            raise ValueError("k must be float32 / float16 / bfloat16 and q float32")
         k, q = k.contiguous(), q.contiguous()
         Bv, L, Q, tab, tdev, flags = self._prepare(k.shape, q.shape, new_doc)
         ws = self._workspace(Bv, L, Q)

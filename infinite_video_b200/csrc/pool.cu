@@ -8,6 +8,8 @@
 // policy (the chunk is read exactly once).  Partial sums over `splits` token ranges are kept
 // separate (deterministic, no atomics) and added by the consolidation kernel; splits > 1 only
 // exists to fill the 148 SMs when Bv*L is small.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace ltm {
@@ -62,7 +64,95 @@ pool_mean_persistent_kernel(const float4* __restrict__ k, float4* __restrict__ x
   for (unsigned work = blockIdx.x; work < total; work += gridDim.x) pool_unit(k, xpart, T, e4, splits, Tf, work, pol);
 }
 
+// ---- 16-bit inputs (VideoChat2 runs the Q-former under fp16 autocast, videochat2_it_mistral.py:187): the chunk is
+// read as 128-bit vectors of 8 halves / bfloat16s and accumulated in fp32 -- half the HBM bytes of the fp32 path
+// and no up-cast pass.  One thread per 8 columns.
+template <bool BF16>
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (BF16) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    } else {
+      const __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+      const float2 t = __half22float2(h);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+}
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p, uint64_t policy) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(policy));
+  return r;
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+pool_mean16_kernel(const uint4* __restrict__ k, float4* __restrict__ xpart, int T, int e8, int splits, float Tf) {
+  const uint64_t pol = policy_evict_first();
+  const unsigned work = blockIdx.x;
+  const int unit = work / splits;
+  const int sp = work - unit * splits;
+  const int r0 = (int)(((long long)T * sp) / splits);
+  const int r1 = (int)(((long long)T * (sp + 1)) / splits);
+  const uint4* base = k + (size_t)unit * T * e8;
+  for (int c = threadIdx.x; c < e8; c += blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    int r = r0;
+    for (; r + POOL_UNROLL <= r1; r += POOL_UNROLL) {
+      uint4 v[POOL_UNROLL];
+#pragma unroll
+      for (int i = 0; i < POOL_UNROLL; ++i) v[i] = ldg_stream_u4(base + (size_t)(r + i) * e8 + c, pol);
+#pragma unroll
+      for (int i = 0; i < POOL_UNROLL; ++i) {
+        float f[8];
+        unpack8<BF16>(v[i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+    }
+    for (; r < r1; ++r) {
+      float f[8];
+      unpack8<BF16>(ldg_stream_u4(base + (size_t)r * e8 + c, pol), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+    float4* dst = xpart + ((size_t)unit * splits + sp) * (2 * e8) + 2 * c;
+    dst[0] = make_float4(__fdiv_rn(acc[0], Tf), __fdiv_rn(acc[1], Tf), __fdiv_rn(acc[2], Tf), __fdiv_rn(acc[3], Tf));
+    dst[1] = make_float4(__fdiv_rn(acc[4], Tf), __fdiv_rn(acc[5], Tf), __fdiv_rn(acc[6], Tf), __fdiv_rn(acc[7], Tf));
+  }
+}
+
 }  // namespace ltm
+
+extern "C" int ltm_pool_mean_16(const void* k, int is_bf16, float* xpart, int Bv, int L, int T, int e, int splits,
+                                void* stream) {
+  using namespace ltm;
+  LTM_REQUIRE(k && xpart, "pool_mean_16: null pointer");
+  LTM_REQUIRE(Bv > 0 && L > 0 && T > 0 && e > 0, "pool_mean_16: bad shape Bv=%d L=%d T=%d e=%d", Bv, L, T, e);
+  LTM_REQUIRE(e % 8 == 0, "pool_mean_16: e=%d must be a multiple of 8 (128-bit access of 16-bit elements)", e);
+  LTM_REQUIRE(splits >= 1 && splits <= T, "pool_mean_16: splits=%d out of range [1,%d]", splits, T);
+  LTM_REQUIRE(aligned16(k) && aligned16(xpart), "pool_mean_16: pointers must be 16-byte aligned");
+  const long long units = (long long)Bv * L * splits;
+  LTM_REQUIRE(units < (1ll << 31), "pool_mean_16: too many frames");
+  const int e8 = e / 8;
+  const int threads = e8 >= 256 ? 256 : ((e8 + 31) / 32) * 32;
+  if (is_bf16)
+    pool_mean16_kernel<true><<<(unsigned)units, threads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(k), reinterpret_cast<float4*>(xpart), T, e8, splits, (float)T);
+  else
+    pool_mean16_kernel<false><<<(unsigned)units, threads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(k), reinterpret_cast<float4*>(xpart), T, e8, splits, (float)T);
+  LTM_CHECK_LAUNCH("pool_mean_16");
+  return 0;
+}
 
 extern "C" int ltm_pool_mean(const float* k, float* xpart, int Bv, int L, int T, int e, int splits,
                              void* stream) {

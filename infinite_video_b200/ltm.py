@@ -143,7 +143,8 @@ class LongTermAttention(nn.Module):
         self.device = k.device
         eng = self._get_engine(k.device)
         out_dtype = q.dtype
-        k32 = k.float().contiguous()
+        # a 16-bit chunk (fp16 autocast in VideoChat2) is pooled straight from its storage: no up-cast pass
+        k32 = k.contiguous() if k.dtype in (torch.float16, torch.bfloat16) else k.float().contiguous()
         q32 = q.float().contiguous()
         bsz = k32.size(0)
         if self.variant == "gibbs":

@@ -32,9 +32,14 @@ def _rowmajor(t):
 def pool_mean(k, splits=1):
     """k[Bv,L,T,e] -> xpart[Bv,L,splits,e] (frame means as `splits` partial sums).  gibbs:304."""
     require_cuda(k)
-    k = _f32c(k)
     Bv, L, T, e = k.shape
     out = torch.empty(Bv, L, splits, e, device=k.device, dtype=torch.float32)
+    if k.dtype in (torch.float16, torch.bfloat16):        # 16-bit chunk: read as is, accumulate in fp32
+        k = k.contiguous()
+        check(lib().ltm_pool_mean_16(ptr(k), int(k.dtype == torch.bfloat16), ptr(out), Bv, L, T, e, splits,
+                                     stream_ptr(k.device)), "pool_mean_16")
+        return out
+    k = _f32c(k)
     check(lib().ltm_pool_mean(ptr(k), ptr(out), Bv, L, T, e, splits, stream_ptr(k.device)), "pool_mean")
     return out
 

@@ -385,3 +385,23 @@ def test_density_side_output(dev):
                 assert m.alphas.shape == (32, 1, 12, 768)
                 assert relerr(m.alphas, want) < 1e-3
                 assert abs(float(m.alphas[3, 0, 5].sum()) - 1.0) < 1e-5
+
+
+def test_fp16_chunk_through_the_drop_in(dev):
+    """VideoChat2 flavour under fp16 autocast: k and q arrive as fp16; the module pools the 16-bit chunk directly
+    and must equal the fp32 oracle evaluated on the up-cast inputs; the output comes back in q's dtype."""
+    from infinite_video_b200 import LongTermAttention
+    from oracle.ref_loader import caller_kwargs
+    key, val = make_proj(95, 1024)
+    kd, vd = make_proj(95, 1024)
+    m = LongTermAttention(**caller_kwargs(64, .75, True, kd.to(dev), vd.to(dev)), tokens_per_frame=196)
+    orc = O.RectLTM(64, .75, *proj_tensors(key, val), tokens_per_frame=196, rebuild_tables=False)
+    ks, qs, us = make_inputs(96, 2, 1, 16 * 196, 1024, 96)
+    with torch.no_grad():
+        for c in range(2):
+            k16, q16 = ks[c].half(), qs[c].half()
+            got = m(k16.to(dev), q16.to(dev), new_doc=(c == 0), layer_n=0, u=us[c])
+            want = orc.forward(k16.float(), q16.float(), c == 0, us[c])
+            assert got.dtype == torch.float16 and got.shape == (1, 96, 768)
+            assert relerr(m.B_past, orc.B_past) < 1e-5
+            assert relerr(got.float(), want) < 2e-3          # output rounded to fp16 (2^-11) on top of TOL_CTX

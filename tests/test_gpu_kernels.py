@@ -38,6 +38,17 @@ def test_pool_mean(dev, Bv, L, T, e, splits):
     assert relerr(got, want) < 1e-6
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("Bv,L,T,e,splits", [(2, 8, 32, 768, 1), (1, 16, 196, 1024, 5)])
+def test_pool_mean_16bit_inputs(dev, dtype, Bv, L, T, e, splits):
+    """fp16 / bf16 chunks (VideoChat2 fp16 autocast) are pooled from their storage with fp32 accumulation."""
+    g = torch.Generator().manual_seed(2)
+    k = torch.randn(Bv, L, T, e, generator=g).to(dtype)
+    want = k.float().mean(dim=2)
+    got = _ops().pool_mean(k.to(dev), splits).sum(2).cpu()
+    assert relerr(got, want) < 1e-6
+
+
 # ---------------------------------------------------------------------------------------- R7
 @pytest.mark.parametrize("ncat,Bv,zeros,sort", [(127, 1, False, False), (127, 37, True, False),
                                                 (128, 5, False, True), (128, 4, True, True)])
