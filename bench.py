@@ -185,79 +185,87 @@ def run_b200(args):
     overlap = not args.no_overlap
     eng.pool_ctas = args.pool_ctas_per_sm * 148
 
-    def one_step():
-        out = None
-        for c in range(C):
-            if overlap:
-                eng.prefetch(ks[(c + 1) % C], Q)      # pool the next chunk under this chunk's compute
-            out = eng.step(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0))
-        if world > 1:
-            out = D_.gather_videos(out, Bv * world)       # one NCCL all_gather of per-video outputs, outside the loop
-        return out
-
-    # stage events (pool = dominant kernel) recorded inside the timed region on the launching stream
+    # ---- timed regions.  Stage events (pool = dominant kernel) are recorded on the launching streams inside them.
     import ctypes as Ct
-    n_sets = args.steps * C
-    ev_sets = []
-    for _ in range(n_sets):
-        evs = []
-        for _i in range(10):
-            h = Ct.c_void_p()
-            _capi.check(lib.ltm_event_create(Ct.byref(h)), "event_create")
-            evs.append(h)
-        ev_sets.append(evs)
+    names = ["pool", "resample", "consolidate", "project_kv", "attention"]
 
-    for _ in range(args.warmup):
-        one_step()
-    torch.cuda.synchronize(dev)
-    D_.barrier(dev)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(dev)
-    e0.record(stream)
-    i = 0
-    for _ in range(args.steps):
-        out = None
-        for c in range(C):
-            eng.prof_events = ev_sets[i]
-            if overlap and i + 1 < n_sets:
-                eng.prefetch(ks[(c + 1) % C], Q, events=ev_sets[i + 1][0:2])
-            i += 1
-            out = eng.step(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0))
-        if world > 1:
-            out = D_.gather_videos(out, Bv * world)
-    e1.record(stream)
-    torch.cuda.synchronize(dev)
-    eng.prof_events = None
-    D_.barrier(dev)
-    clocks = sampler.stop() if rank == 0 else None
-    ms = D_.max_over_ranks(e0.elapsed_time(e1), dev)
+    def timed_pass(with_overlap, sample_clocks):
+        n_sets = args.steps * C
+        ev_sets = []
+        for _ in range(n_sets):
+            evs = []
+            for _i in range(10):
+                h = Ct.c_void_p()
+                _capi.check(lib.ltm_event_create(Ct.byref(h)), "event_create")
+                evs.append(h)
+            ev_sets.append(evs)
+        eng.reset()
+        eng._pref.clear()
+        for _ in range(max(1, args.warmup if with_overlap == overlap else 1)):
+            for c in range(C):
+                if with_overlap:
+                    eng.prefetch(ks[(c + 1) % C], Q)
+                eng.step(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0))
+        torch.cuda.synchronize(dev)
+        D_.barrier(dev)
+        sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record(stream)
+        i = 0
+        for _ in range(args.steps):
+            out = None
+            for c in range(C):
+                eng.prof_events = ev_sets[i]
+                if with_overlap and i + 1 < n_sets:
+                    eng.prefetch(ks[(c + 1) % C], Q, events=ev_sets[i + 1][0:2])
+                i += 1
+                out = eng.step(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0))
+            if world > 1:
+                out = D_.gather_videos(out, Bv * world)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        eng.prof_events = None
+        D_.barrier(dev)
+        clk = sampler.stop() if sampler else None
+        ms_ = D_.max_over_ranks(e0.elapsed_time(e1), dev)
+        stage_ms = {n: [] for n in names}
+        f = Ct.c_float()
+        for si, evs in enumerate(ev_sets):
+            first = (si % C) == 0
+            for j, n in enumerate(names):
+                if n == "resample" and first:
+                    continue
+                if n == "pool" and with_overlap and si == 0:
+                    continue                          # chunk 0 of the timed region was pooled during the warm-up
+                if lib.ltm_event_elapsed_ms(evs[2 * j], evs[2 * j + 1], Ct.byref(f)) == 0:
+                    stage_ms[n].append(f.value)      # (a stage whose events were never recorded is skipped)
+        avg = {n: (sum(v) / len(v) if v else 0.0) for n, v in stage_ms.items()}
+        for evs in ev_sets:
+            for h in evs:
+                lib.ltm_event_destroy(h)
+        return ms_, avg, clk
+
+    # headline: the configured mode (pool-ahead overlap unless --no-overlap)
+    ms, stage_avg, clocks = timed_pass(overlap, True)
     calls_total = Bv * C * args.steps * world
     value = calls_total / (ms * 1e-3)
-
-    # per-stage device times (this rank)
-    names = ["pool", "resample", "consolidate", "project_kv", "attention"]
-    stage_ms = {n: [] for n in names}
-    f = Ct.c_float()
-    for si, evs in enumerate(ev_sets):
-        first = (si % C) == 0
-        for j, n in enumerate(names):
-            if n == "resample" and first:
-                continue
-            if n == "pool" and overlap and si == 0:
-                continue                          # chunk 0 of the timed region was pooled during the warm-up
-            if lib.ltm_event_elapsed_ms(evs[2 * j], evs[2 * j + 1], Ct.byref(f)) == 0:
-                stage_ms[n].append(f.value)      # (a stage whose events were never recorded is skipped)
-    stage_avg = {n: (sum(v) / len(v) if v else 0.0) for n, v in stage_ms.items()}
-    for evs in ev_sets:
-        for h in evs:
-            lib.ltm_event_destroy(h)
+    # kernel-quality pass: the same steps without overlap, so that the events around the dominant kernel bracket
+    # that kernel alone (when kernels of two streams share the GPU a kernel's own duration is no longer its cost)
+    if overlap:
+        ms_serial, stage_serial, _ = timed_pass(False, False)
+    else:
+        ms_serial, stage_serial = ms, stage_avg
 
     peak, peak_src = measured_peaks()
     pool_bytes = 4.0 * Bv * L * T * E                       # algorithmic bytes of the dominant kernel per launch
-    pool_gbs = pool_bytes / (stage_avg["pool"] * 1e-3) / 1e9 if stage_avg["pool"] > 0 else 0.0
+    pool_gbs = pool_bytes / (stage_serial["pool"] * 1e-3) / 1e9 if stage_serial["pool"] > 0 else 0.0
+    pool_gbs_ov = pool_bytes / (stage_avg["pool"] * 1e-3) / 1e9 if stage_avg["pool"] > 0 else 0.0
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/r1g_ncu_pool.txt:
+    # dram__bytes_read.sum 805.32 MB + dram__bytes_write.sum 8.0 MB per launch at 32 videos), scaled per video
+    pool_traffic = (805.32e6 + 8.0e6) / 32.0 * Bv
     step_bytes = algorithmic_bytes_per_call() * Bv * C + 4 * 2 * (E * D + D)   # + weights once per launch
     ms_per_step = ms / args.steps
     step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9
@@ -265,11 +273,17 @@ def run_b200(args):
     # ---------------- secondary arm: the Gaussian variant (north_star wording) on the same chunk shape
     gauss = None
     if rank == 0 and world == 1 and not args.no_gauss:
-        gauss = run_gauss_arm(dev, args.gauss_videos, 3, args.gauss_frames)
+        try:
+            gauss = run_gauss_arm(dev, args.gauss_videos, 3, args.gauss_frames)
+        except Exception as ex:                        # a secondary arm must never take the headline line down
+            gauss = {"error": f"{type(ex).__name__}: {ex}"}
 
     single = None
     if rank == 0 and world == 1 and not args.no_gauss:
-        single = run_single_video(dev)
+        try:
+            single = run_single_video(dev)
+        except Exception as ex:
+            single = {"error": f"{type(ex).__name__}: {ex}"}
 
     # ---------------- end to end through the host entry point (pinned host buffers, ring of 2 chunk slots)
     e2e = None
@@ -324,8 +338,14 @@ def run_b200(args):
             "data": "synthetic", "config": workload_config(Bv, C, "gibbs", overlap),
             "frame_blocks_per_s": value * L,
             "roofline": {"bound": "hbm", "kernel": "pool_mean_kernel", "achieved": pool_gbs, "peak": peak,
-                         "unit": "GB/s", "frac": pool_gbs / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": pool_bytes, "avg_launch_ms": stage_avg["pool"]},
+                         "unit": "GB/s", "frac": pool_gbs / peak, "traffic": pool_traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": pool_bytes, "avg_launch_ms": stage_serial["pool"],
+                         "measured_in": "non-overlapped timed pass of the same steps (CUDA events around this "
+                                        "kernel on its launching stream)",
+                         "achieved_while_overlapped": pool_gbs_ov,
+                         "traffic_source": "profiles/r1g_ncu_pool.txt (ncu --set full at 32 videos, per video)"},
+            "value_without_overlap": calls_total / (ms_serial * 1e-3),
+            "stage_ms_per_chunk_step_without_overlap": stage_serial,
             "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s",
                               "frac": step_gbs / peak, "algorithmic_bytes_per_step": step_bytes},
             "stage_ms_per_chunk_step": stage_avg,
