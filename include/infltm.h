@@ -108,6 +108,11 @@ typedef struct {
    * groups of ct_group consecutive rows: CT[(m / ct_group) * ct_cols + c][m % ct_group]; the remaining columns
    * c >= ct_cols go to C[m * ldc + (c - ct_cols)].  ct_cols % 32 == 0, ct_group % 32 == 0.  CT = NULL: off. */
   float* CT; int ct_cols; int ct_group;
+  /* optional two-level row mapping of C: row m lives at (m / c_group) * c_group_stride + (m % c_group) * ldc
+   * (c_group = 0: plain m * ldc).  Lets a batched product land directly in [head][video][query] style layouts. */
+  int c_group; int64_t c_group_stride;
+  /* bias of batch b starts at bias + b * bias_stride */
+  int64_t bias_stride;
 } ltm_gemm_args;
 int ltm_gemm(const ltm_gemm_args* args, void* stream);
 
@@ -199,6 +204,12 @@ int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const float* q, c
                   const uint8_t* new_doc, float* ctx, void* stream);
 int ltm_rect_step_host(const ltm_rect_step_args* a, const float* k_host, const float* q_host,
                        const double* u_host, const uint8_t* new_doc_host, float* ctx_host, void* stream);
+
+/* ---- N1 (caller, Qformer.py:279-304): row softmax of the short-term attention scores, in place.
+ * S[rows, n] <- softmax(S * scale + mask[row / rows_per_mask, :]) (mask may be NULL); and the alpha blend
+ * out = alpha * a + (1 - alpha) * b over n elements. */
+int ltm_softmax_rows(float* S, const float* mask, int rows, int n, int rows_per_mask, float scale, void* stream);
+int ltm_blend(const float* a, const float* b, float alpha, float* out, int64_t n, void* stream);
 
 /* ---- CUDA-event helpers so a ctypes host can time stages on the launching stream */
 int ltm_event_create(void** ev);

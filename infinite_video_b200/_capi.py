@@ -25,6 +25,7 @@ class GemmArgs(C.Structure):
         ("M", C.c_int), ("Nc", C.c_int), ("K", C.c_int), ("batch", C.c_int),
         ("precision", C.c_int), ("impl", C.c_int),
         ("CT", C.c_void_p), ("ct_cols", C.c_int), ("ct_group", C.c_int),
+        ("c_group", C.c_int), ("c_group_stride", C.c_int64), ("bias_stride", C.c_int64),
     ]
 
 
@@ -75,6 +76,8 @@ _SIGS = {
     "ltm_ridge_workspace_doubles": (C.c_int64, [_I, _I]),
     "ltm_ridge_solve": (C.c_int, [_P, _I, _I, _I, _P, _P, _I, C.c_double, _P, _P, _L, _P, _P]),
     "ltm_gather_rows": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "ltm_softmax_rows": (C.c_int, [_P, _P, _I, _I, _I, _F, _P]),
+    "ltm_blend": (C.c_int, [_P, _P, _F, _P, _L, _P]),
     "ltm_event_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "ltm_event_record": (C.c_int, [_P, _P]),
     "ltm_event_elapsed_ms": (C.c_int, [_P, _P, C.POINTER(C.c_float)]),

@@ -71,11 +71,12 @@ gemm_simt_kernel(const ltm_gemm_args g) {
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
       if (n < g.Nc) {
-        const float val = acc[i][j] + (g.bias ? g.bias[n] : 0.f);
+        const float val = acc[i][j] + (g.bias ? g.bias[(size_t)b * g.bias_stride + n] : 0.f);
         if (g.CT != nullptr && n < g.ct_cols)
           (g.CT + (size_t)b * g.strideC)[((size_t)(m / g.ct_group) * g.ct_cols + n) * g.ct_group + (m % g.ct_group)] = val;
         else
-          C[(size_t)m * g.ldc + n - (g.CT != nullptr ? g.ct_cols : 0)] = val;
+          C[(g.c_group > 0 ? (size_t)(m / g.c_group) * g.c_group_stride + (size_t)(m % g.c_group) * g.ldc
+                           : (size_t)m * g.ldc) + n - (g.CT != nullptr ? g.ct_cols : 0)] = val;
       }
     }
   }

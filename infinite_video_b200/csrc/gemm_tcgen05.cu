@@ -42,6 +42,8 @@ struct GemmDev {
   unsigned mn_layout, mn_lbo, mn_sbo, mn_kadv;
   float* CT;
   int ct_cols, ct_group;
+  int c_group;
+  long long c_group_stride, bias_stride;
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -362,7 +364,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                          ((size_t)(row / g.ct_group) * g.ct_cols + n0 + c0) * g.ct_group + (row % g.ct_group);
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              dst[(size_t)i * g.ct_group] = __uint_as_float(r[i]) + (g.bias ? __ldg(g.bias + n0 + c0 + i) : 0.f);
+              dst[(size_t)i * g.ct_group] = __uint_as_float(r[i]) + (g.bias ? __ldg(g.bias + (size_t)bz * g.bias_stride + n0 + c0 + i) : 0.f);
           }
           continue;
         }
@@ -372,12 +374,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         __syncwarp();
         const int col = n0 + c0 + lane;
         const bool col_ok = col < g.Nc;
-        const float bv = (g.bias != nullptr && col_ok) ? __ldg(g.bias + col) : 0.f;
+        const float bv = (g.bias != nullptr && col_ok) ? __ldg(g.bias + (size_t)bz * g.bias_stride + col) : 0.f;
         const int ccol = col - (g.CT != nullptr ? g.ct_cols : 0);
 #pragma unroll 8
         for (int i = 0; i < 32; ++i) {
           const int row = row0 + i;
-          if (row < g.M && col_ok) cbase_ptr[(size_t)row * g.ldc + ccol] = stg[i * STG_LD + lane] + bv;
+          if (row < g.M && col_ok) {
+            const size_t roff = g.c_group > 0 ? (size_t)(row / g.c_group) * g.c_group_stride +
+                                                    (size_t)(row % g.c_group) * g.ldc
+                                              : (size_t)row * g.ldc;
+            cbase_ptr[roff + ccol] = stg[i * STG_LD + lane] + bv;
+          }
         }
         __syncwarp();
       }
@@ -685,7 +692,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                          ((size_t)(row / g.ct_group) * g.ct_cols + n0 + c0) * g.ct_group + (row % g.ct_group);
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              dst[(size_t)i * g.ct_group] = __uint_as_float(r[i]) + (g.bias ? __ldg(g.bias + n0 + c0 + i) : 0.f);
+              dst[(size_t)i * g.ct_group] = __uint_as_float(r[i]) + (g.bias ? __ldg(g.bias + (size_t)bz * g.bias_stride + n0 + c0 + i) : 0.f);
           }
           continue;
         }
@@ -694,12 +701,17 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         __syncwarp();
         const int col = n0 + c0 + lane;
         const bool col_ok = col < g.Nc;
-        const float bv = (g.bias != nullptr && col_ok) ? __ldg(g.bias + col) : 0.f;
+        const float bv = (g.bias != nullptr && col_ok) ? __ldg(g.bias + (size_t)bz * g.bias_stride + col) : 0.f;
         const int ccol = col - (g.CT != nullptr ? g.ct_cols : 0);
 #pragma unroll 8
         for (int i = 0; i < 32; ++i) {
           const int row = row0 + i;
-          if (row < g.M && col_ok) cbase_ptr[(size_t)row * g.ldc + ccol] = stg[i * STG_LD + lane] + bv;
+          if (row < g.M && col_ok) {
+            const size_t roff = g.c_group > 0 ? (size_t)(row / g.c_group) * g.c_group_stride +
+                                                    (size_t)(row % g.c_group) * g.ldc
+                                              : (size_t)row * g.ldc;
+            cbase_ptr[roff + ccol] = stg[i * STG_LD + lane] + bv;
+          }
         }
         __syncwarp();
       }
@@ -901,6 +913,7 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   d.M = a.M; d.Nc = a.Nc; d.K = a.K; d.K1 = K1; d.batch = a.batch;
   d.a_kmajor = a.a_kmajor ? 1 : 0; d.b_kmajor = a.b_kmajor ? 1 : 0;
   d.CT = a.CT; d.ct_cols = a.ct_cols; d.ct_group = a.ct_group;
+  d.c_group = a.c_group; d.c_group_stride = a.c_group_stride; d.bias_stride = a.bias_stride;
   d.mn_layout = g_mn_desc[0]; d.mn_lbo = g_mn_desc[1]; d.mn_sbo = g_mn_desc[2]; d.mn_kadv = g_mn_desc[3];
   d.a_batched = a.strideA != 0; d.b_batched = a.strideB != 0; d.b2_batched = a.strideB2 != 0; d.has_b2 = two ? 1 : 0;
   if (pair) {

@@ -1,0 +1,91 @@
+// N1 -- short-term cross-attention of the caller (Qformer.py:224-304) around the tcgen05 GEMMs:
+//   scores = (q_h W_k,h / sqrt(d)) enc^T      (the key bias adds a per-row constant: softmax-invariant)
+//   P      = softmax(scores + mask)            <- ltm_softmax_rows (this file), in place
+//   ctx_h  = (P_h enc) W_v,h^T + b_v,h         (rows of P sum to 1)
+//   out    = alpha ctx + (1 - alpha) a_long    <- ltm_blend (this file)
+// so that neither K nor V of the 8192 short-term tokens is ever materialised.
+#include "common.cuh"
+
+namespace ltm {
+
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(float* __restrict__ S, const float* __restrict__ mask, int n, int rows_per_mask, float scale) {
+  __shared__ float red[8];
+  const int row = blockIdx.x;
+  float4* s4 = reinterpret_cast<float4*>(S + (size_t)row * n);
+  const float4* m4 = mask ? reinterpret_cast<const float4*>(mask + (size_t)(row / rows_per_mask) * n) : nullptr;
+  const int n4 = n >> 2, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // pass 1: max
+  float mx = -INFINITY;
+  for (int i = tid; i < n4; i += 256) {
+    float4 v = s4[i];
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    if (m4) { const float4 mm = m4[i]; v.x += mm.x; v.y += mm.y; v.z += mm.z; v.w += mm.w; }
+    mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  // pass 2: exp + sum (row stays in L1/L2: 32 KB at n = 8192)
+  float sum = 0.f;
+  for (int i = tid; i < n4; i += 256) {
+    float4 v = s4[i];
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    if (m4) { const float4 mm = m4[i]; v.x += mm.x; v.y += mm.y; v.z += mm.z; v.w += mm.w; }
+    v.x = expf(v.x - mx); v.y = expf(v.y - mx); v.z = expf(v.z - mx); v.w = expf(v.w - mx);
+    sum += (v.x + v.y) + (v.z + v.w);
+    s4[i] = v;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
+  const float inv = 1.0f / sum;
+  for (int i = tid; i < n4; i += 256) {
+    float4 v = s4[i];
+    v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+    s4[i] = v;
+  }
+}
+
+__global__ void blend_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float alpha,
+                             float4* __restrict__ out, long long n4) {
+  const float beta = 1.0f - alpha;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 x = a[i], y = b[i];
+    out[i] = make_float4(alpha * x.x + beta * y.x, alpha * x.y + beta * y.y, alpha * x.z + beta * y.z,
+                         alpha * x.w + beta * y.w);
+  }
+}
+
+}  // namespace ltm
+
+extern "C" int ltm_softmax_rows(float* S, const float* mask, int rows, int n, int rows_per_mask, float scale,
+                                void* stream) {
+  using namespace ltm;
+  LTM_REQUIRE(S != nullptr, "softmax_rows: null pointer");
+  LTM_REQUIRE(rows > 0 && n > 0 && n % 4 == 0, "softmax_rows: bad shape rows=%d n=%d (n %% 4 == 0)", rows, n);
+  LTM_REQUIRE(mask == nullptr || rows_per_mask > 0, "softmax_rows: rows_per_mask must be positive");
+  LTM_REQUIRE(aligned16(S) && aligned16(mask), "softmax_rows: 16-byte alignment");
+  softmax_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(S, mask, n, rows_per_mask > 0 ? rows_per_mask : 1, scale);
+  LTM_CHECK_LAUNCH("softmax_rows");
+  return 0;
+}
+
+extern "C" int ltm_blend(const float* a, const float* b, float alpha, float* out, int64_t n, void* stream) {
+  using namespace ltm;
+  LTM_REQUIRE(a && b && out, "blend: null pointer");
+  LTM_REQUIRE(n > 0 && n % 4 == 0, "blend: n=%lld must be a positive multiple of 4", (long long)n);
+  LTM_REQUIRE(aligned16(a) && aligned16(b) && aligned16(out), "blend: 16-byte alignment");
+  const long long n4 = n / 4;
+  const int blocks = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
+  blend_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(a),
+                                                          reinterpret_cast<const float4*>(b), alpha,
+                                                          reinterpret_cast<float4*>(out), n4);
+  LTM_CHECK_LAUNCH("blend");
+  return 0;
+}

@@ -169,6 +169,50 @@ def gemm(A, B, *, a_kmajor=True, b_kmajor=True, B2=None, bias=None, out=None, pr
     return out
 
 
+def gemm_raw(A, lda, strideA, a_kmajor, B, ldb, strideB, b_kmajor, C_, ldc, strideC, M, Nc, K, batch, *, bias=None,
+             bias_stride=0, c_group=0, c_group_stride=0, precision="tf32", impl="tcgen05", a_offset=0, b_offset=0,
+             c_offset=0):
+    """ltm_gemm with every pitch / batch stride spelled out (elements).  A, B, C_ are the base tensors; *_offset
+    shifts the start (elements).  Used where operands are strided views that tensor shapes cannot express
+    (per-head column blocks, per-head / per-video output layouts)."""
+    require_cuda(A, B, C_, bias)
+    g = GemmArgs()
+    g.A, g.lda, g.strideA, g.a_kmajor = A.data_ptr() + 4 * a_offset, lda, strideA, int(a_kmajor)
+    g.B, g.ldb, g.strideB, g.b_kmajor = B.data_ptr() + 4 * b_offset, ldb, strideB, int(b_kmajor)
+    g.B2, g.ldb2, g.strideB2, g.K1 = None, 0, 0, K
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.bias_stride = bias_stride
+    g.C, g.ldc, g.strideC = C_.data_ptr() + 4 * c_offset, ldc, strideC
+    g.M, g.Nc, g.K, g.batch = M, Nc, K, batch
+    g.precision, g.impl = PRECISION[precision], GEMM_IMPL[impl]
+    g.CT, g.ct_cols, g.ct_group = None, 0, 0
+    g.c_group, g.c_group_stride = c_group, c_group_stride
+    check(lib().ltm_gemm(C.byref(g), stream_ptr(A.device)), "gemm")
+    return C_
+
+
+def softmax_rows(S, scale=1.0, mask=None, rows_per_mask=1):
+    """In place: S[rows, n] <- softmax(S * scale + mask[row // rows_per_mask]).  Qformer.py:279-285."""
+    require_cuda(S, mask)
+    if not S.is_contiguous() or S.dtype != torch.float32:
+        raise ValueError("softmax_rows needs a contiguous float32 tensor")
+    n = S.shape[-1]
+    rows = S.numel() // n
+    check(lib().ltm_softmax_rows(ptr(S), ptr(mask), rows, n, rows_per_mask, float(scale), stream_ptr(S.device)),
+          "softmax_rows")
+    return S
+
+
+def blend(a, b, alpha, out=None):
+    """out = alpha * a + (1 - alpha) * b.  Qformer.py:303-304."""
+    require_cuda(a, b)
+    a, b = _f32c(a), _f32c(b)
+    if out is None:
+        out = torch.empty_like(a)
+    check(lib().ltm_blend(ptr(a), ptr(b), float(alpha), ptr(out), a.numel(), stream_ptr(a.device)), "blend")
+    return out
+
+
 def project_kv(Bcoef, Wkv, bkv, precision="tf32", impl="tcgen05", out=None):
     """KV[M,2D] = Bcoef[M,e] @ Wkv[2D,e]^T + bkv.  gibbs:312-313."""
     require_cuda(Bcoef, Wkv, bkv)

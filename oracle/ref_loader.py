@@ -93,6 +93,38 @@ def load_gaussian_vl():
     return mod
 
 
+def load_qformer_vl():
+    """Reference caller: ``Qformer.py`` of Video-LLaMA (``BertSelfAttention`` :115-310 constructs, triggers and
+    blends the LTM).  Written for transformers 4.x; three helpers it imports from ``transformers.modeling_utils``
+    moved / disappeared in 5.x and are aliased or stubbed (they are only used by ``prune_heads``), and its absolute
+    import of the LTM module (:50) is pointed at the isolated copy loaded above."""
+    import transformers.modeling_utils as MU
+    import transformers.pytorch_utils as PU
+
+    def _missing(name):
+        def f(*a, **k):
+            raise NotImplementedError(name)
+        return f
+    for n in ("apply_chunking_to_forward", "find_pruneable_heads_and_indices", "prune_linear_layer"):
+        if not hasattr(MU, n):
+            setattr(MU, n, getattr(PU, n, None) or _missing(n))
+    ltm = load_gibbs_vl()
+    for name in ("InfVideoLLaMA", "InfVideoLLaMA.models"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["InfVideoLLaMA.models.long_term_attention_gibbs"] = ltm
+    return _load_pkg("_ref_vl", _VL, ["Qformer"])["Qformer"]
+
+
+def bert_config(num_basis, tau, alpha, sticky=True, encoder_width=768):
+    """The HF config fields the video Q-former is built with (infinityqa.py:36-55)."""
+    from transformers.models.bert.configuration_bert import BertConfig
+    cfg = BertConfig(hidden_size=768, num_attention_heads=12)
+    cfg.encoder_width = encoder_width
+    cfg.alpha, cfg.num_basis, cfg.sticky, cfg.sigmas, cfg.tau = alpha, num_basis, sticky, None, tau
+    cfg.attention_probs_dropout_prob = 0.0
+    return cfg
+
+
 def caller_kwargs(num_basis, tau, sticky, proj_key, proj_value, sigmas=None, n_heads=12, head_size=64):
     """Keyword set the reference caller passes (Qformer.py:135-158)."""
     return dict(attn_num_basis=num_basis, head_size=head_size, length=768, target_len=768,

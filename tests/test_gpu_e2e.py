@@ -405,3 +405,32 @@ def test_fp16_chunk_through_the_drop_in(dev):
             assert got.dtype == torch.float16 and got.shape == (1, 96, 768)
             assert relerr(m.B_past, orc.B_past) < 1e-5
             assert relerr(got.float(), want) < 2e-3          # output rounded to fp16 (2^-11) on top of TOL_CTX
+
+
+@pytest.mark.parametrize("alpha,N,L,B", [(0.5, 64, 8, 2), (0.9, 256, 64, 1)])
+def test_caller_cross_attention_with_ltm_blend_on_gpu(dev, alpha, N, L, B):
+    """N1: short-term softmax attention over the chunk + (1-alpha) LTM, against the oracle of the caller
+    (bit-identical to the real BertSelfAttention, tests/test_oracle_vs_reference.py)."""
+    from infinite_video_b200.cross_attention import CrossAttentionLTM
+    torch.manual_seed(21)
+    lq, lk, lv = torch.nn.Linear(768, 768), torch.nn.Linear(768, 768), torch.nn.Linear(768, 768)
+    orcs = [O.CrossAttentionLTM(N, .75, alpha, lq.weight.detach(), lq.bias.detach(), lk.weight.detach(),
+                                lk.bias.detach(), lv.weight.detach(), lv.bias.detach(), rebuild_tables=False)
+            for _ in range(B)]
+    import copy
+    m = CrossAttentionLTM(copy.deepcopy(lq).to(dev), copy.deepcopy(lk).to(dev), copy.deepcopy(lv).to(dev), alpha, N,
+                          .75)
+    g = torch.Generator().manual_seed(22)
+    with torch.no_grad():
+        for c in range(3):
+            hidden = torch.randn(B, 32, 768, generator=g)
+            enc = torch.randn(B, L * 32, 768, generator=g)
+            u = torch.rand(B, 512, dtype=torch.float64, generator=g)
+            if c:
+                p = torch.cat([o.ltm.sticky_hist(o.ltm.tables(L)) for o in orcs])
+                u = guard_band(u, p, 5e-4)
+            want = torch.cat([orcs[v].forward(hidden[v:v + 1], enc[v:v + 1], c == 0, u[v:v + 1]) for v in range(B)])
+            got = m(hidden.to(dev), enc.to(dev), new_video=(c == 0), layer=0, u=u)
+            stm = m.short_term(torch.nn.functional.linear(hidden, lq.weight, lq.bias).to(dev), enc.to(dev))
+            assert relerr(stm, torch.cat([o.last_stm for o in orcs])) < TOL_CTX, f"short-term, chunk {c}"
+            assert relerr(got, want) < TOL_CTX, f"blend, chunk {c}"

@@ -118,3 +118,33 @@ def test_density_side_output_matches_the_pickle(tmp_path):
                 assert torch.equal(got, want), f"chunk {c}"
     finally:
         os.chdir(cwd)
+
+
+@pytest.mark.parametrize("alpha,N,L", [(0.5, 64, 8), (0.9, 256, 32)])
+def test_caller_cross_attention_with_ltm_blend(alpha, N, L, tmp_path):
+    """C1 + N1: the oracle's restatement of BertSelfAttention's cross-attention branch (short-term softmax
+    attention + (1-alpha) LTM, Qformer.py:197-310) against the real caller module."""
+    Q = RL.load_qformer_vl()
+    cfg = RL.bert_config(N, 0.75, alpha)
+    torch.manual_seed(11)
+    att = Q.BertSelfAttention(cfg, is_cross_attention=True).eval()
+    orc = O.CrossAttentionLTM(N, 0.75, alpha, att.query.weight.detach(), att.query.bias.detach(),
+                              att.key.weight.detach(), att.key.bias.detach(), att.value.weight.detach(),
+                              att.value.bias.detach())
+    g = torch.Generator().manual_seed(12)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        with torch.no_grad():
+            for c in range(3):
+                hidden = torch.randn(1, 32, 768, generator=g)
+                enc = torch.randn(1, L * 32, 768, generator=g)
+                torch.manual_seed(500 + c)
+                want = att(hidden, position_embedding_ext=torch.zeros(1), layer=0, encoder_hidden_states=enc,
+                           new_video=(c == 0))[0]
+                torch.manual_seed(500 + c)
+                u = torch.rand(1, 512, dtype=torch.float64)
+                got = orc.forward(hidden, enc, c == 0, u)
+                assert torch.equal(got, want), f"chunk {c}: {float((got - want).abs().max())}"
+    finally:
+        os.chdir(cwd)
