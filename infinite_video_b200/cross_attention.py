@@ -31,7 +31,7 @@ class CrossAttentionLTM(nn.Module):
 
     def __init__(self, query: nn.Linear, key: nn.Linear, value: nn.Linear, alpha: float, num_basis: int, tau: float,
                  sticky: bool = True, n_heads: int = 12, tokens_per_frame: int = 32, videos_per_pass: int = 8,
-                 precision: str = "tf32", **ltm_kwargs):
+                 precision: str = "tf32", score_precision: str = None, value_precision: str = None, **ltm_kwargs):
         super().__init__()
         self.query, self.key, self.value = query, key, value
         self.alpha = float(alpha)
@@ -39,6 +39,9 @@ class CrossAttentionLTM(nn.Module):
         self.d = query.out_features // n_heads
         self.videos_per_pass = videos_per_pass        # bounds the [videos, H*Q, L*T] score buffer
         self.precision = precision
+        # the two large contractions (scores = Qt enc^T, Y = probs enc); the three small ones always run split-TF32
+        self.score_precision = score_precision or precision
+        self.value_precision = value_precision or precision
         self.long_term_attention = LongTermAttention(
             head_size=self.d, length=key.in_features, target_len=key.in_features, attn_func="softmax",
             attn_num_basis=num_basis, continuous=True, attn_drop=0.1, infinite_memory=True, n_layers=2,
@@ -79,17 +82,17 @@ class CrossAttentionLTM(nn.Module):
             # (2) scores[v] = Qt[v] enc[v]^T : [H*Q, e] x [e, LT]
             S = torch.empty(nb, H * Q, LT, device=dev, dtype=torch.float32)
             ops.gemm_raw(Qt, e, H * Q * e, True, ev, e, LT * e, True, S, LT, H * Q * LT, H * Q, LT, e, nb,
-                         precision=self.precision)
+                         precision=self.score_precision)
             # (3) probs = softmax(scores / sqrt(d) + mask), in place
             m = None if mask is None else mask[v0:v0 + nb].float().contiguous()
             ops.softmax_rows(S, 1.0 / math.sqrt(d), m, H * Q)
             # (4) Yh[h][v][q][:] = probs[v][(h,q)] enc[v] : B operand = enc[v] read as [K = LT][N = e] (MN-major)
             Yh = torch.empty(H, nb, Q, e, device=dev, dtype=torch.float32)
             ops.gemm_raw(S, LT, H * Q * LT, True, ev, e, LT * e, False, Yh, e, Q * e, H * Q, e, LT, nb,
-                         c_group=Q, c_group_stride=nb * Q * e, precision=self.precision)
+                         c_group=Q, c_group_stride=nb * Q * e, precision=self.value_precision)
             # (5) ctx[:, h*d:(h+1)*d] = Yh[h] W_v,h^T + b_v,h : batch over heads
             ops.gemm_raw(Yh, e, nb * Q * e, True, wv, e, d * e, True, out, D, d, nb * Q, d, e, H,
-                         bias=bv, bias_stride=d, precision=self.precision, c_offset=v0 * Q * D)
+                         bias=bv, bias_stride=d, precision="tf32x3", c_offset=v0 * Q * D)
         return out
 
     @torch.no_grad()
