@@ -40,7 +40,9 @@ class CrossAttentionLTM(nn.Module):
         self.videos_per_pass = videos_per_pass        # bounds the [videos, H*Q, L*T] score buffer
         self.precision = precision
         # the two large contractions (scores = Qt enc^T, Y = probs enc); the three small ones always run split-TF32
-        self.score_precision = score_precision or precision
+        # measured at L*T = 8192 (scripts/stm_probe.py): scores x3 / values x1 -> 4.4e-4 at +18 % time; x1 / x1 -> 6.7e-4
+        # (1.0e-3 at L*T = 256, where fewer keys average the rounding); x3 / x3 -> 3.7e-5 at 2.2x the time
+        self.score_precision = score_precision or "tf32x3"
         self.value_precision = value_precision or precision
         self.long_term_attention = LongTermAttention(
             head_size=self.d, length=key.in_features, target_len=key.in_features, attn_func="softmax",
