@@ -44,6 +44,8 @@ struct GemmDev {
   int ct_cols, ct_group;
   int c_group;
   long long c_group_stride, bias_stride;
+  int c_vec;                                // row-major stores may be 128-bit (alignment checked on the host)
+  int dbg;                                  // bring-up only: 1 = no global stores, 2 = no TMA loads
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -126,13 +128,18 @@ __device__ __forceinline__ void decode_work(int w, int tiles_n, int tiles_m, int
   m0 = (((w / tiles_n) % groups_m) * CLUSTER + rank) * 128;
   bz = w / (tiles_n * groups_m);
 }
-__device__ __forceinline__ void tcgen05_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                                 uint32_t accumulate) {
+// The descriptors are passed as (low word, high word): only the low word (start address | LBO) changes from MMA
+// to MMA, by a constant step, so the issuing thread spends one add per operand instead of rebuilding 64-bit
+// descriptors (the first version's ~40 instructions per MMA on a single thread cost more than the MMA's 128 cycles).
+__device__ __forceinline__ void tcgen05_mma_tf32(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                 uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
@@ -159,21 +166,163 @@ __device__ __forceinline__ uint64_t operand_desc(uint32_t tile, int kmajor, int 
   return kmajor ? umma_desc(tile + k * (UMMA_K * 4), 16, 1024, 2u)
                 : umma_desc(tile + k * mn.kadv, mn.lbo, mn.sbo, mn.layout);
 }
+// The same descriptor as (low word at address 0, high word, low-word step per MMA): low word of an operand at
+// shared address `a` (a < 256 KB, 16-byte aligned) after k MMAs = lo0 + (a >> 4) + k * kstep.
+struct DescWords { uint32_t lo0, hi, kstep; };
+__device__ __forceinline__ DescWords operand_desc_words(int kmajor, const MnDesc& mn) {
+  const uint64_t d = operand_desc(0u, kmajor, 0, mn);
+  DescWords w;
+  w.lo0 = (uint32_t)d;
+  w.hi = (uint32_t)(d >> 32);
+  w.kstep = (kmajor ? (uint32_t)(UMMA_K * 4) : mn.kadv) >> 4;
+  return w;
+}
 
-constexpr int STG_LD = 33;                                    // padded row of the epilogue staging tile
-constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;                 // one 32x32 fp32 tile per epilogue warp
+// Epilogue: 8 warps (two per TMEM lane quarter, each owning half of the tile's columns) drain the accumulator in
+// chunks of 32 columns: tcgen05.ld.x32 -> 8 x STS.128 into the warp's [32 rows][32 floats] staging tile (16-byte
+// chunks XOR-swizzled with the row, so neither side has bank conflicts and no padding is needed) -> 8 x (LDS.128,
+// + bias, STG.128) with a quarter-warp per row, i.e. every store instruction writes four full 128-byte lines.
+// Row offsets (the two-level mapping needs a division) and the tile's bias values are computed / fetched once per
+// tile, before the wait for the accumulator.  The first version did that arithmetic per store on 4 warps:
+// ~28 k cycles per 128 x 256 tile, 2.3x the tile's MMA time, and that -- not shared-memory bandwidth -- was what
+// held the kernel at 47 % tensor-pipe activity.
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int EPI_COLS = 32;
+constexpr int STG_WARP_FLOATS = 32 * EPI_COLS;
+constexpr int STG_BYTES = EPI_WARPS * STG_WARP_FLOATS * 4;
+constexpr int ROLE_THREADS = 64 + EPI_THREADS;                // TMA warp + MMA warp + epilogue warps
+// Register cap: the kernel needs one CTA per SM, but frame pooling of the next chunk runs beside it on a second
+// stream (9.7 k registers per pooling CTA); 320 threads x 96 registers leave room for three of them.
+constexpr int GEMM_MAX_REGS = 96;
+
+// Drains one 128-row accumulator tile.  `ew` = epilogue warp 0..7 (its CTA warp id & 3 must be ew & 3: a warp can
+// only read its own TMEM lane quarter), `tmem_acc` = TMEM address of the tile's first column.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmDev& g, uint32_t tmem_acc, int ew, int warp_quarter, int lane,
+                                              float* stg, int m0, int n0, int bz, uint32_t tfull, uint32_t tfull_parity) {
+  const int row0 = m0 + warp_quarter * 32;
+  const int cbeg = (ew >> 2) * (BN / 2);
+  float* cbase_ptr = g.C + (size_t)bz * g.strideC;
+  const float* bias = g.bias ? g.bias + (size_t)bz * g.bias_stride : nullptr;
+  // rows this lane stores in the row-major path: 4 i + (lane >> 3); its 16-byte column chunk: lane & 7
+  const int lrow = lane >> 3, lchunk = lane & 7;
+  size_t roff[8];
+  bool rok[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = row0 + 4 * i + lrow;
+    rok[i] = row < g.M;
+    roff[i] = g.c_group > 0 ? (size_t)(row / g.c_group) * g.c_group_stride + (size_t)(row % g.c_group) * g.ldc
+                            : (size_t)row * g.ldc;
+  }
+  // transposed path: this lane owns row (row0 + lane)
+  const int trow = row0 + lane;
+  float* tbase = nullptr;
+  if (g.CT != nullptr && trow < g.M)
+    tbase = g.CT + (size_t)bz * g.strideC + (size_t)(trow / g.ct_group) * g.ct_cols * g.ct_group + (trow % g.ct_group);
+  //   row-major path: bvs[j] = bias of this lane's 4 columns in chunk j;
+  //   transposed path: btr[j] = bias[n0 + cbeg + 32 j + lane], redistributed with shuffles.
+  constexpr int NCH = BN / 2 / EPI_COLS;
+  float4 bvs[NCH];
+  float btr[NCH];
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    bvs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    btr[j] = 0.f;
+  }
+  if (bias != nullptr) {
+    if (g.CT != nullptr && n0 + cbeg < g.ct_cols) {                      // some chunks take the transposed path
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const int col = n0 + cbeg + EPI_COLS * j + lane;
+        if (col < g.Nc) btr[j] = __ldg(bias + col);
+      }
+    }
+    if (g.CT == nullptr || n0 + cbeg + BN / 2 > g.ct_cols) {             // some chunks take the row-major path
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const int col = n0 + cbeg + EPI_COLS * j + 4 * lchunk;
+        if (col + 0 < g.Nc) bvs[j].x = __ldg(bias + col + 0);
+        if (col + 1 < g.Nc) bvs[j].y = __ldg(bias + col + 1);
+        if (col + 2 < g.Nc) bvs[j].z = __ldg(bias + col + 2);
+        if (col + 3 < g.Nc) bvs[j].w = __ldg(bias + col + 3);
+      }
+    }
+  }
+  mbar_wait(tfull, tfull_parity);
+  tcgen05_fence_after();
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    const int c0 = cbeg + j * EPI_COLS;
+    if (n0 + c0 >= g.Nc) break;                    // warp-uniform
+    uint32_t r[32];
+    const uint32_t taddr = tmem_acc + ((uint32_t)(warp_quarter * 32) << 16) + (uint32_t)c0;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (g.dbg & 1) continue;
+    if (g.CT != nullptr && n0 + c0 < g.ct_cols) {
+      // transposed store (keys per head): lanes are consecutive rows of one group -> 128-byte coalesced
+      float* dst = tbase + (size_t)(n0 + c0) * g.ct_group;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float b = __shfl_sync(0xffffffffu, btr[j], i);             // all lanes take part
+        if (tbase != nullptr && !(g.dbg & 4)) dst[(size_t)i * g.ct_group] = __uint_as_float(r[i]) + b;
+      }
+      continue;
+    }
+    // row-major store through the warp's staging tile: row `lane`, chunk q at position q ^ (lane & 7)
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      *reinterpret_cast<float4*>(stg + lane * EPI_COLS + ((q ^ (lane & 7)) << 2)) =
+          make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                      __uint_as_float(r[4 * q + 3]));
+    __syncwarp();
+    const int col = n0 + c0 + 4 * lchunk;
+    const float4 bv = bvs[j];
+    const int ccol = col - (g.CT != nullptr ? g.ct_cols : 0);
+    const bool vec = g.c_vec && (col + 3 < g.Nc);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int srow = 4 * i + lrow;
+      float4 v = *reinterpret_cast<const float4*>(stg + srow * EPI_COLS + ((lchunk ^ (srow & 7)) << 2));
+      v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+      if (rok[i] && !(g.dbg & 4)) {
+        float* dst = cbase_ptr + roff[i] + ccol;
+        if (vec) {
+          *reinterpret_cast<float4*>(dst) = v;
+        } else {
+          if (col + 0 < g.Nc) dst[0] = v.x;
+          if (col + 1 < g.Nc) dst[1] = v.y;
+          if (col + 2 < g.Nc) dst[2] = v.z;
+          if (col + 3 < g.Nc) dst[3] = v.w;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
 
 template <int BN, int STAGES, bool SPLIT>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;        // TMA landing slot ("hi" operands are used in place)
-  static constexpr int LO_BYTES = SPLIT ? STAGE_BYTES : 0;     // one buffer of lo = x - tf32(x) (precision 3)
+  static constexpr int LO_BYTES = SPLIT ? 2 * STAGE_BYTES : 0; // two buffers of lo = x - tf32(x) (precision 3)
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES + LO_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = RING_BYTES + STG_BYTES + BAR_BYTES + 1024;   // + 1024 B alignment slack
   static constexpr int TMEM_COLS = 2 * BN;                     // two accumulator buffers (256 or 512 columns)
   static constexpr int SPLIT_THREADS = 256;                    // 8 splitter warps (precision 3)
-  static constexpr int THREADS = SPLIT ? 192 + SPLIT_THREADS : 192;
+  static constexpr int THREADS = SPLIT ? ROLE_THREADS + SPLIT_THREADS : ROLE_THREADS;
   static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two <= 512");
 };
 
@@ -183,10 +332,10 @@ struct Cfg {
 // double-buffered in TMEM so the epilogue of tile i drains while the MMAs of tile i+1 run.
 //   warp 0      TMA producer (one lane)
 //   warp 1      TMEM owner + tcgen05.mma issuer (one lane)
-//   warps 2-5   epilogue: tcgen05.ld -> registers -> (+bias) -> per-warp smem transpose -> 128-byte coalesced stores
-//   warps 6-13  (precision 3 only) operand splitter hi/lo
+//   warps 2-9   epilogue (see epilogue_tile)
+//   warps 10-17 (precision 3 only) operand splitter hi/lo
 template <int BN, int STAGES, bool SPLIT, int CLUSTER>
-__global__ void __launch_bounds__(Cfg<BN, STAGES, SPLIT>::THREADS, 1)
+__global__ void __maxnreg__(GEMM_MAX_REGS)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ CUtensorMap mapB2, const GemmDev g) {
   using C_ = Cfg<BN, STAGES, SPLIT>;
@@ -200,8 +349,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   auto split_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
   auto tfull_bar = [&](int b) { return bars + 8u * (3 * STAGES + b); };
   auto tempty_bar = [&](int b) { return bars + 8u * (3 * STAGES + 2 + b); };
-  const uint32_t lofree_bar = bars + 8u * (3 * STAGES + 4);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_al + C_::RING_BYTES + STG_BYTES + 8 * (3 * STAGES + 5));
+  auto lofree_bar = [&](uint32_t b) { return bars + 8u * (3 * STAGES + 4 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_al + C_::RING_BYTES + STG_BYTES + 8 * (3 * STAGES + 6));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (g.K + BK - 1) / BK;
@@ -220,10 +369,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       mbar_init(empty_bar(s), CLUSTER);  // the MMA warps of every CTA that received a multicast into this slot
       mbar_init(split_bar(s), C_::SPLIT_THREADS);   // every splitter thread arrives after its proxy fence
     }
-    mbar_init(lofree_bar, 1);            // MMAs of a k-block done with the single lo buffer
+    mbar_init(lofree_bar(0), 1);         // MMAs of a k-block done with their lo buffer (two, alternating)
+    mbar_init(lofree_bar(1), 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);        // tcgen05.commit of the last MMA of a tile
-      mbar_init(tempty_bar(b), 128);     // every epilogue thread after its last tcgen05.ld of the tile
+      mbar_init(tempty_bar(b), EPI_THREADS);   // every epilogue thread after its last tcgen05.ld of the tile
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -251,6 +401,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u);
+          if (g.dbg & 2) { mbar_arrive(full_bar(s)); continue; }
           mbar_arrive_expect_tx(full_bar(s), A_BYTES + C_::B_BYTES);
           const uint32_t sa = smem_base + s * C_::STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
@@ -292,6 +443,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                              ((g.b_kmajor ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
       const MnDesc mn{g.mn_layout, g.mn_lbo, g.mn_sbo, g.mn_kadv};
+      const DescWords wa = operand_desc_words(g.a_kmajor, mn), wb = operand_desc_words(g.b_kmajor, mn);
+      const uint32_t da0 = wa.lo0 + ((smem_base & 0x3FFFFu) >> 4), db0 = wb.lo0 + (((smem_base + A_BYTES) & 0x3FFFFu) >> 4);
+      const uint32_t dal0 = da0 + STAGES * (C_::STAGE_BYTES >> 4), dbl0 = db0 + STAGES * (C_::STAGE_BYTES >> 4);
       uint32_t it = 0, tc = 0;
       for (int w = w_first; w < num_work; w += w_stride, ++tc) {
         const uint32_t buf = tc & 1u, tph = (tc >> 1) & 1u;
@@ -303,21 +457,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(SPLIT ? split_bar(s) : full_bar(s), ph);
           tcgen05_fence_after();
-          const uint32_t sa = smem_base + s * C_::STAGE_BYTES;
-          const uint32_t sb = sa + A_BYTES;
-          const uint32_t sa_lo = smem_base + STAGES * C_::STAGE_BYTES;     // the single lo buffer [A_lo | B_lo]
-          const uint32_t sb_lo = sa_lo + A_BYTES;
+          uint32_t da = da0 + s * (C_::STAGE_BYTES >> 4), db = db0 + s * (C_::STAGE_BYTES >> 4);
+          const uint32_t lob = (it & 1u) * (C_::STAGE_BYTES >> 4);     // lo buffer [A_lo | B_lo] of this k-block
+          uint32_t dal = dal0 + lob, dbl = dbl0 + lob;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da = operand_desc(sa, g.a_kmajor, k, mn);
-            const uint64_t db = operand_desc(sb, g.b_kmajor, k, mn);
-            tcgen05_mma_tf32(tmem_acc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            tcgen05_mma_tf32(tmem_acc, da, wa.hi, db, wb.hi, idesc, (kb | k) != 0 ? 1u : 0u);
             if (SPLIT) {
-              tcgen05_mma_tf32(tmem_acc, operand_desc(sa_lo, g.a_kmajor, k, mn), db, idesc, 1u);
-              tcgen05_mma_tf32(tmem_acc, da, operand_desc(sb_lo, g.b_kmajor, k, mn), idesc, 1u);
+              tcgen05_mma_tf32(tmem_acc, dal, wa.hi, db, wb.hi, idesc, 1u);
+              tcgen05_mma_tf32(tmem_acc, da, wa.hi, dbl, wb.hi, idesc, 1u);
+              dal += wa.kstep; dbl += wb.kstep;
             }
+            da += wa.kstep; db += wb.kstep;
           }
-          if (SPLIT) tcgen05_commit(lofree_bar);  // the splitter may overwrite the lo buffer
+          if (SPLIT) tcgen05_commit(lofree_bar(it & 1u));  // the splitter may overwrite this lo buffer
           // frees the stage once these MMAs have read it (in every CTA that multicasts into this slot)
           if (CLUSTER > 1) tcgen05_commit_mc(empty_bar(s), (uint16_t)((1u << CLUSTER) - 1u));
           else tcgen05_commit(empty_bar(s));
@@ -326,75 +479,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
     }
     __syncwarp();
-  } else if (warp < 6) {
+  } else if (warp < 2 + EPI_WARPS) {
     // ------------------------------------------------------------------ epilogue warps
-    const int quarter = warp & 3;                // TMEM lanes [32*quarter, 32*quarter+32)
-    float* stg = staging + quarter * (32 * STG_LD);
+    const int ew = warp - 2;
+    float* stg = staging + ew * STG_WARP_FLOATS;
     uint32_t tc = 0;
     for (int w = w_first; w < num_work; w += w_stride, ++tc) {
       int n0, m0, bz;
       decode_work<CLUSTER, BN>(w, tiles_n, tiles_m, crank, n0, m0, bz);
       const uint32_t buf = tc & 1u, tph = (tc >> 1) & 1u;
-      mbar_wait(tfull_bar(buf), tph);
-      tcgen05_fence_after();
-      const int row0 = m0 + quarter * 32;
-      float* cbase_ptr = g.C + (size_t)bz * g.strideC;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (n0 + c0 >= g.Nc) break;              // warp-uniform
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr)
-            : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        // thread `lane` holds row (row0 + lane), columns c0..c0+31
-        if (g.CT != nullptr && n0 + c0 < g.ct_cols) {
-          // transposed store (keys per head): lanes are consecutive rows of one group -> 128-byte coalesced
-          const int row = row0 + lane;
-          if (row < g.M) {
-            float* dst = g.CT + (size_t)bz * g.strideC +
-                         ((size_t)(row / g.ct_group) * g.ct_cols + n0 + c0) * g.ct_group + (row % g.ct_group);
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              dst[(size_t)i * g.ct_group] = __uint_as_float(r[i]) + (g.bias ? __ldg(g.bias + (size_t)bz * g.bias_stride + n0 + c0 + i) : 0.f);
-          }
-          continue;
-        }
-        // row-major store: transpose through the warp's staging tile so that lanes become columns
-#pragma unroll
-        for (int i = 0; i < 32; ++i) stg[lane * STG_LD + i] = __uint_as_float(r[i]);
-        __syncwarp();
-        const int col = n0 + c0 + lane;
-        const bool col_ok = col < g.Nc;
-        const float bv = (g.bias != nullptr && col_ok) ? __ldg(g.bias + (size_t)bz * g.bias_stride + col) : 0.f;
-        const int ccol = col - (g.CT != nullptr ? g.ct_cols : 0);
-#pragma unroll 8
-        for (int i = 0; i < 32; ++i) {
-          const int row = row0 + i;
-          if (row < g.M && col_ok) {
-            const size_t roff = g.c_group > 0 ? (size_t)(row / g.c_group) * g.c_group_stride +
-                                                    (size_t)(row % g.c_group) * g.ldc
-                                              : (size_t)row * g.ldc;
-            cbase_ptr[roff + ccol] = stg[i * STG_LD + lane] + bv;
-          }
-        }
-        __syncwarp();
-      }
+      epilogue_tile<BN>(g, tmem_base + buf * BN, ew, warp & 3, lane, stg, m0, n0, bz, tfull_bar(buf), tph);
       tcgen05_fence_before();
-      mbar_arrive(tempty_bar(buf));              // 128 arrivals hand the accumulator back to the MMA warp
+      mbar_arrive(tempty_bar(buf));              // EPI_THREADS arrivals hand the accumulator back to the MMA warp
     }
   } else {
     // ------------------------------------------------------------------ operand splitter (precision 3)
     if (SPLIT) {
-      const int et = threadIdx.x - 192;          // 0..SPLIT_THREADS-1
+      const int et = threadIdx.x - ROLE_THREADS;  // 0..SPLIT_THREADS-1
       constexpr int NV = (A_BYTES + C_::B_BYTES) / 16;      // float4 count of [A | B]
       uint32_t it = 0;
       for (int w = w_first; w < num_work; w += w_stride) {
@@ -402,9 +503,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(full_bar(s), ph);
-          mbar_wait(lofree_bar, (it & 1u) ^ 1u);           // MMAs of the previous k-block have consumed lo
+          mbar_wait(lofree_bar(it & 1u), ((it >> 1) & 1u) ^ 1u);   // MMAs of k-block it - 2 have consumed this lo buffer
           const float4* hi = reinterpret_cast<const float4*>(smem_al + s * C_::STAGE_BYTES);
-          float4* lo = reinterpret_cast<float4*>(smem_al + STAGES * C_::STAGE_BYTES);
+          float4* lo = reinterpret_cast<float4*>(smem_al + (STAGES + (it & 1u)) * C_::STAGE_BYTES);
 #pragma unroll 4
           for (int f = et; f < NV; f += C_::SPLIT_THREADS) {
             const float4 x = hi[f];
@@ -490,13 +591,15 @@ __device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* map, uint32_
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-__device__ __forceinline__ void tcgen05_mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                                      uint32_t accumulate) {
+__device__ __forceinline__ void tcgen05_mma_tf32_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                      uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {     // arrives in both CTAs of the pair
@@ -509,18 +612,18 @@ struct PairCfg {
   static constexpr int BH = BN / 2;                            // B rows held by each CTA
   static constexpr int B_BYTES = BH * BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int LO_BYTES = SPLIT ? STAGE_BYTES : 0;
+  static constexpr int LO_BYTES = SPLIT ? 2 * STAGE_BYTES : 0;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES + LO_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = RING_BYTES + STG_BYTES + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int SPLIT_THREADS = 256;
-  static constexpr int THREADS = SPLIT ? 192 + SPLIT_THREADS : 192;
+  static constexpr int THREADS = SPLIT ? ROLE_THREADS + SPLIT_THREADS : ROLE_THREADS;
   static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two <= 512");
 };
 
 template <int BN, int STAGES, bool SPLIT>
-__global__ void __launch_bounds__(PairCfg<BN, STAGES, SPLIT>::THREADS, 1)
+__global__ void __maxnreg__(GEMM_MAX_REGS)
 gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                       const __grid_constant__ CUtensorMap mapB2, const GemmDev g) {
   using C_ = PairCfg<BN, STAGES, SPLIT>;
@@ -534,8 +637,8 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   auto split_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
   auto tfull_bar = [&](int b) { return bars + 8u * (3 * STAGES + b); };
   auto tempty_bar = [&](int b) { return bars + 8u * (3 * STAGES + 2 + b); };
-  const uint32_t lofree_bar = bars + 8u * (3 * STAGES + 4);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_al + C_::RING_BYTES + STG_BYTES + 8 * (3 * STAGES + 5));
+  auto lofree_bar = [&](uint32_t b) { return bars + 8u * (3 * STAGES + 4 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_al + C_::RING_BYTES + STG_BYTES + 8 * (3 * STAGES + 6));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = blockIdx.x & 1u;
@@ -554,10 +657,11 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       mbar_init(empty_bar(s), 1);
       mbar_init(split_bar(s), 2 * C_::SPLIT_THREADS);
     }
-    mbar_init(lofree_bar, 1);
+    mbar_init(lofree_bar(0), 1);
+    mbar_init(lofree_bar(1), 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 2 * 128);
+      mbar_init(tempty_bar(b), 2 * EPI_THREADS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -586,6 +690,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u);
+          if (g.dbg & 2) { if (SPLIT || leader) mbar_arrive(full_bar(s)); continue; }
           uint32_t bar;                                                 // shared::cluster address of the barrier
           if (SPLIT) {
             mbar_arrive_expect_tx(full_bar(s), C_::STAGE_BYTES);        // own barrier: the splitter waits on it
@@ -624,6 +729,9 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                              ((g.b_kmajor ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)((2 * BM) >> 4) << 24);                       // M = 256 across the pair
       const MnDesc mn{g.mn_layout, g.mn_lbo, g.mn_sbo, g.mn_kadv};
+      const DescWords wa = operand_desc_words(g.a_kmajor, mn), wb = operand_desc_words(g.b_kmajor, mn);
+      const uint32_t da0 = wa.lo0 + ((smem_base & 0x3FFFFu) >> 4), db0 = wb.lo0 + (((smem_base + A_BYTES) & 0x3FFFFu) >> 4);
+      const uint32_t dal0 = da0 + STAGES * (C_::STAGE_BYTES >> 4), dbl0 = db0 + STAGES * (C_::STAGE_BYTES >> 4);
       uint32_t it = 0, tc = 0;
       for (int w = w_first; w < num_work; w += w_stride, ++tc) {
         const uint32_t buf = tc & 1u, tph = (tc >> 1) & 1u;
@@ -635,93 +743,43 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           const uint32_t ph = (it / STAGES) & 1u;
           if (SPLIT) mbar_wait_cluster(split_bar(s), ph); else mbar_wait_cluster(full_bar(s), ph);
           tcgen05_fence_after();
-          const uint32_t sa = smem_base + s * C_::STAGE_BYTES;
-          const uint32_t sb = sa + A_BYTES;
-          const uint32_t sa_lo = smem_base + STAGES * C_::STAGE_BYTES;
-          const uint32_t sb_lo = sa_lo + A_BYTES;
+          uint32_t da = da0 + s * (C_::STAGE_BYTES >> 4), db = db0 + s * (C_::STAGE_BYTES >> 4);
+          const uint32_t lob = (it & 1u) * (C_::STAGE_BYTES >> 4);     // lo buffer [A_lo | B_lo] of this k-block
+          uint32_t dal = dal0 + lob, dbl = dbl0 + lob;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da = operand_desc(sa, g.a_kmajor, k, mn);
-            const uint64_t db = operand_desc(sb, g.b_kmajor, k, mn);
-            tcgen05_mma_tf32_pair(tmem_acc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            tcgen05_mma_tf32_pair(tmem_acc, da, wa.hi, db, wb.hi, idesc, (kb | k) != 0 ? 1u : 0u);
             if (SPLIT) {
-              tcgen05_mma_tf32_pair(tmem_acc, operand_desc(sa_lo, g.a_kmajor, k, mn), db, idesc, 1u);
-              tcgen05_mma_tf32_pair(tmem_acc, da, operand_desc(sb_lo, g.b_kmajor, k, mn), idesc, 1u);
+              tcgen05_mma_tf32_pair(tmem_acc, dal, wa.hi, db, wb.hi, idesc, 1u);
+              tcgen05_mma_tf32_pair(tmem_acc, da, wa.hi, dbl, wb.hi, idesc, 1u);
+              dal += wa.kstep; dbl += wb.kstep;
             }
+            da += wa.kstep; db += wb.kstep;
           }
-          if (SPLIT) tcgen05_commit_pair(lofree_bar);
+          if (SPLIT) tcgen05_commit_pair(lofree_bar(it & 1u));
           tcgen05_commit_pair(empty_bar(s));
         }
         tcgen05_commit_pair(tfull_bar(buf));
       }
     }
     __syncwarp();
-  } else if (warp < 6) {
+  } else if (warp < 2 + EPI_WARPS) {
     // ------------------------------------------------------------------ epilogue warps (both CTAs, own rows)
-    const int quarter = warp & 3;
-    float* stg = staging + quarter * (32 * STG_LD);
+    const int ew = warp - 2;
+    float* stg = staging + ew * STG_WARP_FLOATS;
     uint32_t tc = 0;
     for (int w = w_first; w < num_work; w += w_stride, ++tc) {
       int n0, m0, bz;
       decode_work<2, BN>(w, tiles_n, tiles_m, (int)crank, n0, m0, bz);
       const uint32_t buf = tc & 1u, tph = (tc >> 1) & 1u;
-      mbar_wait(tfull_bar(buf), tph);
-      tcgen05_fence_after();
-      const int row0 = m0 + quarter * 32;
-      float* cbase_ptr = g.C + (size_t)bz * g.strideC;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (n0 + c0 >= g.Nc) break;
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr)
-            : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (g.CT != nullptr && n0 + c0 < g.ct_cols) {
-          const int row = row0 + lane;
-          if (row < g.M) {
-            float* dst = g.CT + (size_t)bz * g.strideC +
-                         ((size_t)(row / g.ct_group) * g.ct_cols + n0 + c0) * g.ct_group + (row % g.ct_group);
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              dst[(size_t)i * g.ct_group] = __uint_as_float(r[i]) + (g.bias ? __ldg(g.bias + (size_t)bz * g.bias_stride + n0 + c0 + i) : 0.f);
-          }
-          continue;
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) stg[lane * STG_LD + i] = __uint_as_float(r[i]);
-        __syncwarp();
-        const int col = n0 + c0 + lane;
-        const bool col_ok = col < g.Nc;
-        const float bv = (g.bias != nullptr && col_ok) ? __ldg(g.bias + (size_t)bz * g.bias_stride + col) : 0.f;
-        const int ccol = col - (g.CT != nullptr ? g.ct_cols : 0);
-#pragma unroll 8
-        for (int i = 0; i < 32; ++i) {
-          const int row = row0 + i;
-          if (row < g.M && col_ok) {
-            const size_t roff = g.c_group > 0 ? (size_t)(row / g.c_group) * g.c_group_stride +
-                                                    (size_t)(row % g.c_group) * g.ldc
-                                              : (size_t)row * g.ldc;
-            cbase_ptr[roff + ccol] = stg[i * STG_LD + lane] + bv;
-          }
-        }
-        __syncwarp();
-      }
+      epilogue_tile<BN>(g, tmem_base + buf * BN, ew, warp & 3, lane, stg, m0, n0, bz, tfull_bar(buf), tph);
       tcgen05_fence_before();
-      mbar_arrive_remote(mapa_rank(tempty_bar(buf), 0));      // 2 x 128 arrivals on the leader's barrier
+      mbar_arrive_remote(mapa_rank(tempty_bar(buf), 0));      // 2 x EPI_THREADS arrivals on the leader's barrier
     }
   } else {
     // ------------------------------------------------------------------ operand splitter (precision 3, both CTAs)
     if (SPLIT) {
-      const int et = threadIdx.x - 192;
+      const int et = threadIdx.x - ROLE_THREADS;
       constexpr int NV = C_::STAGE_BYTES / 16;
       uint32_t it = 0;
       for (int w = w_first; w < num_work; w += w_stride) {
@@ -729,9 +787,9 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(full_bar(s), ph);
-          mbar_wait(lofree_bar, (it & 1u) ^ 1u);
+          mbar_wait(lofree_bar(it & 1u), ((it >> 1) & 1u) ^ 1u);
           const float4* hi = reinterpret_cast<const float4*>(smem_al + s * C_::STAGE_BYTES);
-          float4* lo = reinterpret_cast<float4*>(smem_al + STAGES * C_::STAGE_BYTES);
+          float4* lo = reinterpret_cast<float4*>(smem_al + (STAGES + (it & 1u)) * C_::STAGE_BYTES);
 #pragma unroll 4
           for (int f = et; f < NV; f += C_::SPLIT_THREADS) {
             const float4 x = hi[f];
@@ -769,6 +827,7 @@ static int g_cluster = 1;
 // third fewer bytes, slower in precision 3 -- all variants sit at 46-49 % tensor-pipe activity because fp32
 // operands make shared-memory bandwidth (TMA write + MMA read of every byte) the limit.  Off by default.
 static int g_pair = 0;
+static int g_dbg = 0;
 static unsigned g_mn_desc[5] = {1u, (unsigned)SLAB_BYTES, 512u, 1024u, (unsigned)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B};
 
 static int resolve_encode() {
@@ -915,17 +974,20 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   d.CT = a.CT; d.ct_cols = a.ct_cols; d.ct_group = a.ct_group;
   d.c_group = a.c_group; d.c_group_stride = a.c_group_stride; d.bias_stride = a.bias_stride;
   d.mn_layout = g_mn_desc[0]; d.mn_lbo = g_mn_desc[1]; d.mn_sbo = g_mn_desc[2]; d.mn_kadv = g_mn_desc[3];
+  d.dbg = g_dbg;
+  d.c_vec = (a.ldc % 4 == 0 && a.strideC % 4 == 0 && a.c_group_stride % 4 == 0 && aligned16(a.C) &&
+             (a.CT == nullptr || a.ct_cols % 4 == 0)) ? 1 : 0;
   d.a_batched = a.strideA != 0; d.b_batched = a.strideB != 0; d.b2_batched = a.strideB2 != 0; d.has_b2 = two ? 1 : 0;
   if (pair) {
-    if (split) return bn == 256 ? launch_pair<256, 5, true>(mA, mB, mB2, d, a.batch, stream)
+    if (split) return bn == 256 ? launch_pair<256, 4, true>(mA, mB, mB2, d, a.batch, stream)
                                 : launch_pair<128, 6, true>(mA, mB, mB2, d, a.batch, stream);
     return bn == 256 ? launch_pair<256, 6, false>(mA, mB, mB2, d, a.batch, stream)
                      : launch_pair<128, 8, false>(mA, mB, mB2, d, a.batch, stream);
   }
   // 2-CTA clusters with a multicast B tile: K-major single-segment B and at least two row tiles
   const bool mc = mc_pre;
-  if (split && bn == 256) return mc ? launch_cfg<256, 3, true, 2>(mA, mB, mB2, d, a.batch, stream)
-                                    : launch_cfg<256, 3, true>(mA, mB, mB2, d, a.batch, stream);
+  if (split && bn == 256) return mc ? launch_cfg<256, 2, true, 2>(mA, mB, mB2, d, a.batch, stream)
+                                    : launch_cfg<256, 2, true>(mA, mB, mB2, d, a.batch, stream);
   if (split) return mc ? launch_cfg<128, 4, true, 2>(mA, mB, mB2, d, a.batch, stream)
                        : launch_cfg<128, 4, true>(mA, mB, mB2, d, a.batch, stream);
   if (bn == 256) return mc ? launch_cfg<256, 4, false, 2>(mA, mB, mB2, d, a.batch, stream)
@@ -939,6 +1001,7 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
 // Bring-up hook (not part of include/infltm.h): override the MN-major descriptor parameters.
 extern "C" void ltm_debug_set_cluster(int c) { ltm::g_cluster = c; }
 extern "C" void ltm_debug_set_pair(int v) { ltm::g_pair = v; }
+extern "C" void ltm_debug_set_gemm_flags(int v) { ltm::g_dbg = v; }
 
 extern "C" void ltm_debug_set_mn_desc(unsigned layout, unsigned lbo, unsigned sbo, unsigned kadv, unsigned swz) {
   ltm::g_mn_desc[0] = layout; ltm::g_mn_desc[1] = lbo; ltm::g_mn_desc[2] = sbo; ltm::g_mn_desc[3] = kadv;
