@@ -113,6 +113,9 @@ typedef struct {
   int c_group; int64_t c_group_stride;
   /* bias of batch b starts at bias + b * bias_stride */
   int64_t bias_stride;
+  /* != 0: round the stored row-major results to the tf32 grid (round to nearest), for products that feed another
+   * tf32 tensor-core contraction (the tensor core itself would truncate, which biases sums of products) */
+  int round_tf32;
 } ltm_gemm_args;
 int ltm_gemm(const ltm_gemm_args* args, void* stream);
 
@@ -151,6 +154,20 @@ int ltm_cont_attn_rect_t(const float* q, const float* Kt, const float* V, int64_
 int ltm_cont_attn_gauss_t(const float* q, const float* Kt, const float* V, int64_t ldv, const float* basis_mu,
                           const float* basis_sigma, float* ctx, float* scores_out, float* mu_out, float* sd_out,
                           int Bv, int Q, int N, int H, int d, void* stream);
+
+/* ---- tensor-core path of the rect attention for num_basis in {128,256}, head_size 64 (csrc/attn_tc.cu): both
+ * contractions as tf32 UMMAs.  K[Bv*N, ldkv], V[Bv*N, ldkv] row-major (head h at column h*64; e.g. the two halves
+ * of ltm_project_kv's KV, ldkv = 2D), already rounded to tf32 (ltm_gemm round_tf32 / ltm_project_kv_r).
+ * X[N,32]: extra operand rows (1, hi/lo of c_j/W_j; infinite_video_b200/tables.py), c_none: trapezoid node weight
+ * of the sticky edges outside every basis.  Outputs as ltm_cont_attn_rect. */
+int ltm_attn_tc_supported(int N, int d);
+int ltm_cont_attn_rect_tc(const float* q, const float* K, const float* V, int64_t ldkv, const float* X,
+                          const float* W, float W_out, float c_none, const int32_t* jb, const float* tb,
+                          float* ctx, float* scores_out, float* hist_part,
+                          int Bv, int Q, int N, int H, int d, void* stream);
+/* ltm_project_kv with the stored K and V rounded to tf32 */
+int ltm_project_kv_r(const float* Bcoef, const float* Wkv, const float* bkv, float* KV,
+                     int M, int e, int D2, int precision, int impl, void* stream);
 
 /* ---- G1: Gaussian RBF evaluation.  basis_functions.py:158-164.
  * out[p, j] (ld) = N(t_p; mu_j, sigma_j^2); t may be gathered: t_p = tvals[tidx[p]] when tidx != NULL. */
@@ -199,6 +216,8 @@ typedef struct {
   /* optional cudaEvent_t pairs recorded on `stream` around each stage (NULL = skip):
    * [0,1] pool  [2,3] re-sample  [4,5] consolidate  [6,7] K/V projection  [8,9] attention */
   void* prof_events[10];
+  /* tensor-core attention (used when X != NULL, KV != NULL, precision == 1 and ltm_attn_tc_supported(N, d)) */
+  const float* X; float c_none;
 } ltm_rect_step_args;
 int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const float* q, const double* u,
                   const uint8_t* new_doc, float* ctx, void* stream);

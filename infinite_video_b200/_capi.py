@@ -26,6 +26,7 @@ class GemmArgs(C.Structure):
         ("precision", C.c_int), ("impl", C.c_int),
         ("CT", C.c_void_p), ("ct_cols", C.c_int), ("ct_group", C.c_int),
         ("c_group", C.c_int), ("c_group_stride", C.c_int64), ("bias_stride", C.c_int64),
+        ("round_tf32", C.c_int),
     ]
 
 
@@ -48,6 +49,7 @@ class RectStepArgs(C.Structure):
         ("k_dev", C.c_void_p), ("q_dev", C.c_void_p), ("u_dev", C.c_void_p), ("new_doc_dev", C.c_void_p),
         ("ctx_dev", C.c_void_p),
         ("prof_events", C.c_void_p * 10),
+        ("X", C.c_void_p), ("c_none", C.c_float),
     ]
 
 
@@ -67,7 +69,10 @@ _SIGS = {
     "ltm_gemm": (C.c_int, [C.POINTER(GemmArgs), _P]),
     "ltm_project_kv": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_project_kv_t": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "ltm_project_kv_r": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_attn_fast_supported": (C.c_int, [_I, _I]),
+    "ltm_attn_tc_supported": (C.c_int, [_I, _I]),
+    "ltm_cont_attn_rect_tc": (C.c_int, [_P, _P, _P, _L, _P, _P, _F, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_cont_attn_rect_t": (C.c_int, [_P, _P, _P, _L, _P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_cont_attn_gauss_t": (C.c_int, [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_cont_attn_rect": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),

@@ -81,13 +81,16 @@ class BatchedRectLTM(_BatchedBase):
 
     def __init__(self, num_basis, tau, w_key, b_key, w_value, b_value, *, n_heads=12, head_size=64,
                  tokens_per_frame=32, sticky=True, nb_samples=tables.NB_SAMPLES, precision="tf32",
-                 gemm_impl="tcgen05", device="cuda", keep_scores=False, fast_attn=True):
+                 gemm_impl="tcgen05", device="cuda", keep_scores=False, fast_attn=True, tc_attn=True):
         super().__init__(num_basis, tau, w_key, b_key, w_value, b_value, n_heads, head_size, sticky, nb_samples,
                          precision, gemm_impl, device)
         self.T = int(tokens_per_frame)
         self.keep_scores = keep_scores
         # transposed-key attention path (num_basis 64/128/256, head size 64); `fast_attn=False` forces the generic one
         self.fast_attn = bool(fast_attn) and ops.attn_fast_supported(self.N, self.d)
+        # tensor-core attention (csrc/attn_tc.cu): num_basis 128/256, head size 64, single-pass tf32 projection
+        self.tc_attn = (bool(tc_attn) and bool(fast_attn) and precision == "tf32" and gemm_impl == "tcgen05"
+                        and ops.attn_tc_supported(self.N, self.d))
         self.prof_events = None       # optional list of 10 cudaEvent_t handles (bench.py stage timing)
         self._side = None             # side stream for pooling the next chunk ahead of time
         self._pref = {}               # pending prefetches: (data_ptr, shape) -> (buffer index, done event)
@@ -113,9 +116,9 @@ class BatchedRectLTM(_BatchedBase):
                 splits=splits,
                 xparts=[torch.empty(Bv, L, splits, self.e, **f32), torch.empty(Bv, L, splits, self.e, **f32)],
                 xi=0, xnext=0,
-                KV=None if self.fast_attn else torch.empty(Bv, self.N, 2 * self.D, **f32),
-                Kt=torch.empty(Bv, self.H, self.d, self.N, **f32) if self.fast_attn else None,
-                V=torch.empty(Bv, self.N, self.D, **f32) if self.fast_attn else None,
+                KV=torch.empty(Bv, self.N, 2 * self.D, **f32) if (self.tc_attn or not self.fast_attn) else None,
+                Kt=torch.empty(Bv, self.H, self.d, self.N, **f32) if (self.fast_attn and not self.tc_attn) else None,
+                V=torch.empty(Bv, self.N, self.D, **f32) if (self.fast_attn and not self.tc_attn) else None,
                 b_draw=torch.empty(Bv, self.S, **i32), idx=torch.empty(Bv, self.S, **i32),
                 ts=torch.empty(Bv, self.S, **f32), p=torch.empty(Bv, 127, **f32),
                 scores=torch.empty(Bv, self.H, Q, self.N, **f32) if self.keep_scores else None,
@@ -148,6 +151,10 @@ class BatchedRectLTM(_BatchedBase):
                      "idx_uniform", "W"):
             setattr(a, name, tdev[name].data_ptr())
         a.W_out = tab.W_out
+        if self.tc_attn:
+            if tdev["X"] is None:
+                raise RuntimeError("tensor-core attention needs a quadrature point in every basis (tc_attn=False)")
+            a.X, a.c_none = tdev["X"].data_ptr(), tab.c_none
         a.Wkv, a.bkv = self.Wkv.data_ptr(), self.bkv.data_ptr()
         a.B_past = self._B[self._cur].data_ptr() if self.has_state else None
         a.B_new = self._B[1 - self._cur].data_ptr()

@@ -1,0 +1,425 @@
+// Continuous attention over rectangular bases (R10/R11 + R6) on the tcgen05 tensor cores.
+// long_term_attention_gibbs.py:224-286 (expected value by quadrature), :196-203 (sticky histogram of the next call).
+//
+// Same mathematics as attn.cu / attn_fast.cu (closed form of the 1000-point quadrature,
+// r_j = W_j e^{S_j} / (sum_i W_i e^{S_i} + W_out)), but both contractions run as tf32 UMMAs with the basis index j
+// on the TMEM lanes, one CTA per (query tile of 32, head, video):
+//
+//   S^T[j, q] = K_h[j, :] . q_h[q, :]          A = K_h  (TMA, K-major, SWIZZLE_128B, [NB j][64 d]),
+//                                              B = q_h/sqrt(d) rounded to tf32, written by the CTA (K-major)
+//   thread j:  e[q] = W_j exp(S[j,q] - m_q),   m_q = max(0, max_j S[j,q])  (redux.sync + one smem exchange)
+//   D[m, q]   = sum_j A2[m, j] e[j, q]         A2 = [V_h^T ; X^T ; *]  (TMA, MN-major, SWIZZLE_128B_ATOM_32B):
+//                 rows  0..63  V_h[:, d]                 -> un-normalised context
+//                 row   64     1                         -> quadrature normaliser  sum_j e[j,q]
+//                 rows  65,66  c_j / W_j  (hi, lo)       -> trapezoid integral of the sticky-edge density
+//               B = e^T rounded to tf32, written by the CTA in the K-major SWIZZLE_128B layout
+//   ctx[q, d]  = D[d, q] / (D[64, q] + W_out e^{-m_q})
+//   histogram: p_i = dt_{i+1}/2 (G[jb_{i+1}] + G[jb_{i+2}]),  G[j] = sum_q exp(S[j,q] - m_q) / Z_q  -- the per-row
+//              trapezoid of rect_hist.cuh regrouped by basis (every edge value is the weight of one basis or of
+//              "no basis"), so no cross-thread reduction is left: the column sums come out of the tensor core.
+//
+// The FMA kernels spend 2 x 524 k FMAs per CTA on 85 registers x 768 threads per SM; here the SM's register file
+// and issue slots stay almost free (288 threads), which is what lets the frame pooling of the next chunk run
+// beside it (BatchedRectLTM.prefetch).  K and V must already be tf32-rounded (ltm_gemm round_tf32) so that the
+// tensor core's own fp32 -> tf32 truncation does not bias the scores.
+#include "rect_hist.cuh"
+#include "tcgen05.cuh"
+
+namespace ltm {
+namespace tc {
+
+constexpr int DH = 64;
+constexpr int QT = 32;
+constexpr int THREADS = 288;             // 8 compute warps (TMEM lane quarter = warp % 4) + 1 TMA / MMA warp
+constexpr int TMEM_COLS = 128;           // S^T: NB/128 x 32 columns at 0; D: 32 columns at 64
+
+struct Params {
+  const float* q;        // [Bv,Q,D]
+  const float* W;        // [NB] quadrature weight per basis
+  const float* tb;       // [129] sticky edges
+  const int32_t* jb;     // [129] basis at each edge (-1: none)
+  float W_out, c_none;
+  float* ctx;            // [Bv,Q,D]
+  float* scores_out;     // optional [Bv,H,Q,NB]
+  float* hist_part;      // optional [Bv, H*q_tiles, 127]
+  int Q, H;
+};
+
+template <int NB>
+struct Lay {
+  static constexpr int SLAB = NB * 128;              // NB rows x 32 floats
+  static constexpr int K_OFF = 0;                    // 2 slabs: d 0..31 | d 32..63        (K-major rows = j)
+  static constexpr int V_OFF = 2 * SLAB;             // 3 slabs: V d 0..31 | V d 32..63 | X (MN-major rows = j)
+  static constexpr int R_OFF = 5 * SLAB;             // e^T: [NB/32 k-blocks][32 q][32 j]; also "slab 3" of A2
+  static constexpr int Q_OFF = 6 * SLAB;             // q tile: [2 k-blocks][32 q][32 d]
+  static constexpr int MISC_OFF = Q_OFF + 2 * 4096;
+  static constexpr int MISC_FLOATS = 8 * 32 + 3 * 32 + NB + 32;
+  static constexpr int BYTES = MISC_OFF + MISC_FLOATS * 4 + 64 + 1024;   // + 6 barriers, TMEM slot, alignment slack
+};
+
+__device__ __forceinline__ void cw_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 compute warps
+
+// q tile of one work item, scaled by 1/sqrt(d) (gibbs:226; a power of two, exact) and rounded to tf32, in the
+// K-major SWIZZLE_128B layout: element (q, d) at [d >> 5][q][((d & 31) >> 2) ^ (q & 7)][d & 3].  256 threads; the
+// global loads are issued one item ahead (load_q) so that their latency is off the item's critical path.
+struct QRegs { float4 a, b; };
+__device__ __forceinline__ QRegs load_q(const float* qbase, int rows, int D, int tid) {
+  const int qq = tid >> 3, dch = tid & 7;                          // 8 consecutive d per thread
+  QRegs r;
+  r.a = make_float4(0.f, 0.f, 0.f, 0.f);
+  r.b = r.a;
+  if (qq < rows) {
+    const float4* src = reinterpret_cast<const float4*>(qbase + (size_t)qq * D + dch * 8);
+    r.a = __ldg(src);
+    r.b = __ldg(src + 1);
+  }
+  return r;
+}
+__device__ __forceinline__ void store_q_tile(uint8_t* dstq, const QRegs& r, int tid) {
+  const int qq = tid >> 3, dch = tid & 7;
+  const float sc = 0.125f;
+  const float4 a = make_float4(tf32_rna(r.a.x * sc), tf32_rna(r.a.y * sc), tf32_rna(r.a.z * sc), tf32_rna(r.a.w * sc));
+  const float4 b = make_float4(tf32_rna(r.b.x * sc), tf32_rna(r.b.y * sc), tf32_rna(r.b.z * sc), tf32_rna(r.b.w * sc));
+  uint8_t* row = dstq + (dch >> 2) * 4096 + qq * 128;
+  const int c0 = (dch & 3) * 2;
+  *reinterpret_cast<float4*>(row + (((c0) ^ (qq & 7)) << 4)) = a;
+  *reinterpret_cast<float4*>(row + (((c0 + 1) ^ (qq & 7)) << 4)) = b;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// Persistent: CTA b walks the work items w = b, b + grid, ... (w -> query tile, head, video; head fastest).
+// Per item, warp 8 (one lane) issues  S MMAs -> [K buffer free] TMA K(next) -> PV MMAs -> [V buffer free] TMA V(next)
+// and the 8 compute warps run  read S -> write q(next) -> weights -> write e^T -> read D -> outputs,  so the next
+// item's keys land during this item's weight phase and its values during the output phase + the next score MMAs.
+//   bar_k / bar_v   TMA bytes of this item's K / V (+ X once)            bar_s / bar_pv   tcgen05.commit
+//   bar_q           256 arrivals: q tile of the next item is in place (and S has been read out of TMEM)
+//   bar_r           256 arrivals: e^T is in place (and D of the previous item has been read out of TMEM)
+template <int NB>
+__global__ void __launch_bounds__(THREADS, 1)
+cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV,
+                    const __grid_constant__ CUtensorMap mapX, const Params p, const int q_tiles, const int total) {
+  static_assert(NB == 128 || NB == 256, "the tensor-core path covers num_basis 128 / 256");
+  using L_ = Lay<NB>;
+  constexpr int HALVES = NB / 128;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (sbase - smem_u32(smem_raw));
+  float* misc = reinterpret_cast<float*>(sm + L_::MISC_OFF);
+  float* wmax = misc;                       // [8][32]
+  float* mcol = wmax + 8 * 32;              // [32]
+  float* zq = mcol + 32;                    // [32]
+  float* rzh = zq + 32;                     // [32]
+  float* Gs = rzh + 32;                     // [NB + 1]
+  const uint32_t bars = sbase + L_::MISC_OFF + L_::MISC_FLOATS * 4;
+  const uint32_t bar_k = bars, bar_v = bars + 8, bar_s = bars + 16, bar_pv = bars + 24, bar_q = bars + 32,
+                 bar_r = bars + 40;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L_::MISC_OFF + L_::MISC_FLOATS * 4 + 48);
+
+  const int Q = p.Q, H = p.H, D = H * DH;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sK = sbase + L_::K_OFF, sV = sbase + L_::V_OFF, sR = sbase + L_::R_OFF, sQ = sbase + L_::Q_OFF;
+  auto decode = [&](int w, int& qt, int& h, int& v) {
+    h = w % H;
+    qt = (w / H) % q_tiles;
+    v = w / (H * q_tiles);
+  };
+  const int w0 = blockIdx.x, wstride = gridDim.x;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapK)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapV)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapX)) : "memory");
+      mbar_init(bar_k, 1);
+      mbar_init(bar_v, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_pv, 1);
+      mbar_init(bar_q, 256);
+      mbar_init(bar_r, 256);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      int qt, h, v;
+      decode(w0, qt, h, v);
+      mbar_arrive_expect_tx(bar_k, 2 * L_::SLAB);
+      tma_load_2d(&mapK, sK, bar_k, h * DH, v * NB);
+      tma_load_2d(&mapK, sK + L_::SLAB, bar_k, h * DH + 32, v * NB);
+      mbar_arrive_expect_tx(bar_v, 3 * L_::SLAB);
+      tma_load_2d(&mapV, sV, bar_v, h * DH, v * NB);
+      tma_load_2d(&mapV, sV + L_::SLAB, bar_v, h * DH + 32, v * NB);
+      tma_load_2d(&mapX, sV + 2 * L_::SLAB, bar_v, 0, 0);
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();                       // barriers initialised, TMEM allocated
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // instruction descriptors: D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2, a_major bit 15 (1 = MN-major),
+  // N>>3 [17,23), M>>4 [24,29)
+  constexpr uint32_t IDESC_S = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(QT >> 3) << 17) | ((128u >> 4) << 24);
+  constexpr uint32_t IDESC_PV = IDESC_S | (1u << 15);
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ TMA + MMA issue (one lane)
+    if (lane == 0) {
+      // descriptor words: only the start-address field of the low word changes between MMAs (compile-time offsets)
+      const uint64_t dK = umma_desc(sK, 16, 1024, 2u), dQ = umma_desc(sQ, 16, 1024, 2u);
+      const uint64_t dV = umma_desc(sV, L_::SLAB, 512, 1u), dR = umma_desc(sR, 16, 1024, 2u);
+      const uint32_t dk_lo = (uint32_t)dK, dk_hi = (uint32_t)(dK >> 32), dq_lo = (uint32_t)dQ;
+      const uint32_t dv_lo = (uint32_t)dV, dv_hi = (uint32_t)(dV >> 32), dr_lo = (uint32_t)dR;
+      uint32_t it = 0;
+      for (int w = w0; w < total; w += wstride, ++it) {
+        const uint32_t ph = it & 1u;
+        const int wn = w + wstride;
+        int qtn = 0, hn = 0, vn = 0;
+        if (wn < total) decode(wn, qtn, hn, vn);
+        mbar_wait(bar_q, ph);                          // this item's q tile written, S free
+        mbar_wait(bar_k, ph);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int hf = 0; hf < HALVES; ++hf) {
+#pragma unroll
+          for (int ks = 0; ks < DH / 8; ++ks)
+            tcgen05_mma_tf32(tmem_base + hf * QT,
+                             dk_lo + (uint32_t)(((ks >> 2) * L_::SLAB + hf * (128 * 128) + (ks & 3) * 32) >> 4), dk_hi,
+                             dq_lo + (uint32_t)(((ks >> 2) * 4096 + (ks & 3) * 32) >> 4), dk_hi, IDESC_S,
+                             ks != 0 ? 1u : 0u);
+        }
+        tcgen05_commit(bar_s);
+        mbar_wait(bar_s, ph);                          // the K buffer has been read
+        if (wn < total) {
+          mbar_arrive_expect_tx(bar_k, 2 * L_::SLAB);
+          tma_load_2d(&mapK, sK, bar_k, hn * DH, vn * NB);
+          tma_load_2d(&mapK, sK + L_::SLAB, bar_k, hn * DH + 32, vn * NB);
+        }
+        mbar_wait(bar_r, ph);                          // e^T written, D free
+        mbar_wait(bar_v, ph);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < NB / 8; ++ks)
+          tcgen05_mma_tf32(tmem_base + 64, dv_lo + (uint32_t)((ks * 1024) >> 4), dv_hi,
+                           dr_lo + (uint32_t)(((ks >> 2) * 4096 + (ks & 3) * 32) >> 4), dk_hi, IDESC_PV,
+                           ks != 0 ? 1u : 0u);
+        tcgen05_commit(bar_pv);
+        mbar_wait(bar_pv, ph);                         // the V buffer (and e^T) have been read
+        if (wn < total) {
+          mbar_arrive_expect_tx(bar_v, 2 * L_::SLAB);
+          tma_load_2d(&mapV, sV, bar_v, hn * DH, vn * NB);
+          tma_load_2d(&mapV, sV + L_::SLAB, bar_v, hn * DH + 32, vn * NB);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ compute warps
+    const bool active = warp < 4 * HALVES;
+    const int j = (warp >> 2) * 128 + (warp & 3) * 32 + lane;      // this thread's basis in the weight phase
+    const int quarter = warp & 3, chalf = warp >> 2;
+    const float Wj = active ? __ldg(p.W + j) : 0.f;
+    {
+      int qt, h, v;
+      decode(w0, qt, h, v);
+      const QRegs qr = load_q(p.q + ((size_t)v * Q + qt * QT) * D + h * DH, min(QT, Q - qt * QT), D, tid);
+      store_q_tile(sm + L_::Q_OFF, qr, tid);
+      mbar_arrive(bar_q);
+    }
+    uint32_t it = 0;
+    for (int w = w0; w < total; w += wstride, ++it) {
+      const uint32_t ph = it & 1u;
+      int qt, h, v;
+      decode(w, qt, h, v);
+      const int q0 = qt * QT;
+      const int rows = min(QT, Q - q0);
+      float e[32];
+      const int wn = w + wstride;
+      QRegs qnext;
+      if (wn < total) {
+        int qtn, hn, vn;
+        decode(wn, qtn, hn, vn);
+        qnext = load_q(p.q + ((size_t)vn * Q + qtn * QT) * D + hn * DH, min(QT, Q - qtn * QT), D, tid);
+      }
+      mbar_wait(bar_s, ph);
+      tcgen05_fence_after();
+      if (active) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(chalf * QT);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < 32; ++c) e[c] = __uint_as_float(r[c]);
+      }
+      // the score MMAs are complete (bar_s): the q tile can take the next item's queries
+      if (wn < total) store_q_tile(sm + L_::Q_OFF, qnext, tid);
+      tcgen05_fence_before();
+      mbar_arrive(bar_q);
+      if (active) {
+        uint32_t mine = 0u;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          // non-negative floats order like their bit patterns: one redux.sync per column
+          const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(e[c], 0.f)));
+          if (lane == c) mine = mx;
+        }
+        wmax[warp * 32 + lane] = __uint_as_float(mine);
+        if (p.scores_out) {
+          float* dst = p.scores_out + (((size_t)v * H + h) * Q + q0) * NB + j;
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c < rows) dst[(size_t)c * NB] = e[c];
+        }
+      }
+      cw_sync();                                                                           // column maxima
+      if (active) {
+        float M = 0.f;                                 // per-row shift m = max(0, max_j S_j): it cancels exactly
+#pragma unroll
+        for (int ww = 0; ww < 4 * HALVES; ++ww) M = fmaxf(M, wmax[ww * 32 + lane]);
+        if (warp == 0) mcol[lane] = M;
+        uint8_t* rblk = sm + L_::R_OFF + (j >> 5) * 4096 + (lane & 3) * 4;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float m = __shfl_sync(0xffffffffu, M, c);
+          e[c] = Wj * __expf(e[c] - m);
+          // e^T element (q = c, j): row c of k-block j >> 5, chunk ((j & 31) >> 2) ^ (c & 7)
+          *reinterpret_cast<float*>(rblk + c * 128 + ((((lane >> 2) ^ (c & 7))) << 4)) = tf32_rna(e[c]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      }
+      tcgen05_fence_before();
+      mbar_arrive(bar_r);
+
+      // ---- outputs: D[lane m][q]; warp (quarter, chalf) reads 16 columns
+      mbar_wait(bar_pv, ph);
+      tcgen05_fence_after();
+      float dv[16];
+      {
+        uint32_t r[16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + 64u + (uint32_t)(chalf * 16);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dv[i] = __uint_as_float(r[i]);
+      }
+      if (quarter == 2) {
+        // lanes 0,1,2 hold rows 64 (sum_j e), 65, 66 (sum_j c_j/W_j e, hi + lo)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float hi = __shfl_sync(0xffffffffu, dv[i], 1);
+          const float lo = __shfl_sync(0xffffffffu, dv[i], 2);
+          if (lane == 0) {
+            const int c = chalf * 16 + i;
+            const float em = expf(-mcol[c]);
+            zq[c] = dv[i] + p.W_out * em;
+            rzh[c] = (c < rows) ? 1.0f / (hi + lo + p.c_none * em) : 0.f;
+          }
+        }
+      }
+      cw_sync();                                                                           // normalisers
+      if (quarter < 2) {
+        const int dd = quarter * 32 + lane;
+        float* dst = p.ctx + ((size_t)v * Q + q0 + chalf * 16) * D + h * DH + dd;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (chalf * 16 + i < rows) dst[(size_t)i * D] = dv[i] / zq[chalf * 16 + i];
+      }
+      if (p.hist_part != nullptr) {
+        if (active) {
+          // G[j] = sum_q exp(S[j,q] - m_q) / Z_q = (1 / W_j) sum_q e[q] / Z_q
+          float g = 0.f;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) g = fmaf(e[c], rzh[c], g);
+          Gs[j] = g / Wj;
+        }
+        if (tid == 255 || (HALVES == 1 && tid == 128)) {
+          float g = 0.f;
+          for (int c = 0; c < 32; ++c) g = fmaf(expf(-mcol[c]), rzh[c], g);
+          Gs[NB] = g;                                  // edges outside every basis: score 0
+        }
+        cw_sync();                                                                         // G complete
+        if (tid < EDGES - 2) {
+          const int a = __ldg(p.jb + tid + 1), b = __ldg(p.jb + tid + 2);
+          const float dt = __ldg(p.tb + tid + 2) - __ldg(p.tb + tid + 1);
+          const float val = dt * (Gs[a < 0 ? NB : a] + Gs[b < 0 ? NB : b]) * 0.5f;
+          p.hist_part[((size_t)v * (H * q_tiles) + h * q_tiles + qt) * (EDGES - 2) + tid] = val;
+        }
+        cw_sync();                                     // Gs / mcol / rzh are rewritten by the next item
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+template <int NB>
+static int launch(const CUtensorMap& mK, const CUtensorMap& mV, const CUtensorMap& mX, const Params& p, int Bv,
+                  cudaStream_t stream) {
+  static bool configured = false;
+  static int num_sms = 0;
+  if (!configured) {
+    LTM_CUDA(cudaFuncSetAttribute(cont_attn_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Lay<NB>::BYTES));
+    int dev = 0;
+    LTM_CUDA(cudaGetDevice(&dev));
+    LTM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    configured = true;
+  }
+  const int q_tiles = (p.Q + QT - 1) / QT;
+  const long long total = (long long)q_tiles * p.H * Bv;
+  LTM_REQUIRE(total < (1ll << 31), "cont_attn_rect_tc: too many work items");
+  const unsigned grid = (unsigned)(total < num_sms ? total : num_sms);
+  cont_attn_tc_kernel<NB><<<grid, THREADS, Lay<NB>::BYTES, stream>>>(mK, mV, mX, p, q_tiles, (int)total);
+  LTM_CHECK_LAUNCH("cont_attn_rect_tc");
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace ltm
+
+extern "C" int ltm_attn_tc_supported(int N, int d) { return (d == 64 && (N == 128 || N == 256)) ? 1 : 0; }
+
+extern "C" int ltm_cont_attn_rect_tc(const float* q, const float* K, const float* V, int64_t ldkv, const float* X,
+                                     const float* W, float W_out, float c_none, const int32_t* jb, const float* tb,
+                                     float* ctx, float* scores_out, float* hist_part, int Bv, int Q, int N, int H,
+                                     int d, void* stream) {
+  using namespace ltm;
+  LTM_REQUIRE(q && K && V && X && W && ctx, "cont_attn_rect_tc: null pointer");
+  LTM_REQUIRE(hist_part == nullptr || (jb && tb), "cont_attn_rect_tc: histogram requested without edge tables");
+  LTM_REQUIRE(ltm_attn_tc_supported(N, d), "cont_attn_rect_tc: unsupported num_basis=%d / head_size=%d", N, d);
+  LTM_REQUIRE(Bv > 0 && Bv <= 65535 && Q > 0 && H > 0 && H <= 65535 && ldkv % 4 == 0 && ldkv >= (int64_t)H * d,
+              "cont_attn_rect_tc: bad shape");
+  LTM_REQUIRE(aligned16(q) && aligned16(ctx), "cont_attn_rect_tc: 16-byte alignment");
+  CUtensorMap mK, mV, mX;
+  const unsigned long long rows = (unsigned long long)Bv * N;
+  if (tma_encode_2d(&mK, K, (unsigned long long)H * d, rows, (unsigned long long)ldkv, 32, (unsigned)N, 0, "attn K"))
+    return -1;
+  if (tma_encode_2d(&mV, V, (unsigned long long)H * d, rows, (unsigned long long)ldkv, 32, (unsigned)N, 1, "attn V"))
+    return -1;
+  if (tma_encode_2d(&mX, X, 32, (unsigned long long)N, 32, 32, (unsigned)N, 1, "attn X")) return -1;
+  tc::Params p{};
+  p.q = q; p.W = W; p.tb = tb; p.jb = jb; p.W_out = W_out; p.c_none = c_none; p.ctx = ctx;
+  p.scores_out = scores_out; p.hist_part = hist_part; p.Q = Q; p.H = H;
+  return N == 256 ? tc::launch<256>(mK, mV, mX, p, Bv, (cudaStream_t)stream)
+                  : tc::launch<128>(mK, mV, mX, p, Bv, (cudaStream_t)stream);
+}

@@ -84,8 +84,14 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
   if (rc) return rc;
   LTM_PROF(5);
   LTM_PROF(6);
-  const bool fast = a->Kt != nullptr && a->V != nullptr && ltm_attn_fast_supported(a->N, a->d);
-  if (fast)
+  // tensor-core attention: row-major tf32-rounded K|V from the projection, both attention contractions as UMMAs
+  const bool tcp = a->X != nullptr && a->KV != nullptr && a->precision == 1 && a->gemm_impl == 0 &&
+                   ltm_attn_tc_supported(a->N, a->d);
+  const bool fast = !tcp && a->Kt != nullptr && a->V != nullptr && ltm_attn_fast_supported(a->N, a->d);
+  if (tcp)
+    rc = ltm_project_kv_r(a->B_new, a->Wkv, a->bkv, a->KV, a->Bv * a->N, a->e, 2 * D, a->precision, a->gemm_impl,
+                          stream);
+  else if (fast)
     rc = ltm_project_kv_t(a->B_new, a->Wkv, a->bkv, a->Kt, a->V, a->Bv * a->N, a->e, D, a->N, a->precision,
                           a->gemm_impl, stream);
   else
@@ -94,7 +100,10 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
   if (rc) return rc;
   LTM_PROF(7);
   LTM_PROF(8);
-  if (fast)
+  if (tcp)
+    rc = ltm_cont_attn_rect_tc(q, a->KV, a->KV + D, 2 * D, a->X, a->W, a->W_out, a->c_none, a->jb, a->tb, ctx,
+                               a->scores, a->sticky ? a->hist_part : nullptr, a->Bv, a->Q, a->N, a->H, a->d, stream);
+  else if (fast)
     rc = ltm_cont_attn_rect_t(q, a->Kt, a->V, D, a->W, a->W_out, a->jb, a->tb, ctx, a->scores,
                               a->sticky ? a->hist_part : nullptr, a->Bv, a->Q, a->N, a->H, a->d, stream);
   else

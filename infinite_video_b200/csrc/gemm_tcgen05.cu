@@ -21,6 +21,7 @@
 #include <cudaTypedefs.h>
 
 #include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace ltm {
 
@@ -44,81 +45,11 @@ struct GemmDev {
   int ct_cols, ct_group;
   int c_group;
   long long c_group_stride, bias_stride;
+  int round_tf32;                           // round stored row-major results to the tf32 grid
   int c_vec;                                // row-major stores may be 128-bit (alignment checked on the host)
   int dbg;                                  // bring-up only: 1 = no global stores, 2 = no TMA loads
 };
 
-// ------------------------------------------------------------------------------------------ PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(done)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return done;
-}
-// Bounded wait: a broken pipeline traps (launch error) after ~2 s instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  unsigned long long t0;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3fffu) == 0) {
-      unsigned long long t1;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 2000000000ull) {
-        printf("libinfltm gemm: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y,
-               blockIdx.z, threadIdx.x);
-        asm volatile("trap;");
-      }
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1,
-                                            int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// commit that arrives on the barrier at the same shared-memory offset in every CTA of `mask` (cluster)
-__device__ __forceinline__ void tcgen05_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(mask) : "memory");
-}
-// TMA load delivered to the same shared-memory offset (and mbarrier) of every CTA in `mask`
-__device__ __forceinline__ void tma_load_3d_mc(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1,
-                                               int c2, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 // Work item -> tile origin.  CLUSTER == 1: items are tiles, n fastest.  CLUSTER == 2: a cluster of two CTAs takes
 // two vertically adjacent tiles (same n, rows m0 and m0 + 128) so that the B tile is fetched once and multicast.
 template <int CLUSTER, int BN_>
@@ -127,33 +58,6 @@ __device__ __forceinline__ void decode_work(int w, int tiles_n, int tiles_m, int
   n0 = (w % tiles_n) * BN_;
   m0 = (((w / tiles_n) % groups_m) * CLUSTER + rank) * 128;
   bz = w / (tiles_n * groups_m);
-}
-// The descriptors are passed as (low word, high word): only the low word (start address | LBO) changes from MMA
-// to MMA, by a constant step, so the issuing thread spends one add per operand instead of rebuilding 64-bit
-// descriptors (the first version's ~40 instructions per MMA on a single thread cost more than the MMA's 128 cycles).
-__device__ __forceinline__ void tcgen05_mma_tf32(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
-                                                 uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-      "setp.ne.b32 p, %6, 0;\n\t"
-      "mov.b64 da, {%1, %2};\n\t"
-      "mov.b64 db, {%3, %4};\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
-      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-// UMMA shared-memory matrix descriptor (sm_100): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
-// version=1 [46,48) | layout type [61,64): SWIZZLE_128B = 2, SWIZZLE_128B_BASE32B = 1.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                              uint32_t layout) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= 1ull << 46;
-  d |= (uint64_t)layout << 61;
-  return d;
 }
 // MN-major descriptor parameters.  For 32-bit (tf32) MN-major operands the only legal canonical layout is
 // the 128-byte swizzle with 32-byte atoms (TMA: SWIZZLE_128B_ATOM_32B): atoms of [4 k][32 mn], i.e. the
@@ -296,6 +200,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& g, uint32_t tmem_ac
       const int srow = 4 * i + lrow;
       float4 v = *reinterpret_cast<const float4*>(stg + srow * EPI_COLS + ((lchunk ^ (srow & 7)) << 2));
       v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+      if (g.round_tf32) v = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
       if (rok[i] && !(g.dbg & 4)) {
         float* dst = cbase_ptr + roff[i] + ccol;
         if (vec) {
@@ -864,6 +769,24 @@ static int encode_operand(CUtensorMap* map, const float* base, int rows, int K, 
   return 0;
 }
 
+int tma_encode_2d(CUtensorMap* map, const float* base, unsigned long long inner, unsigned long long outer,
+                  unsigned long long pitch_elems, unsigned box_inner, unsigned box_outer, int swizzle32b_atom,
+                  const char* what) {
+  if (resolve_encode()) return -1;
+  LTM_REQUIRE(aligned16(base) && pitch_elems % 4 == 0 && pitch_elems >= inner, "%s: tensor map needs a 16-byte aligned base and pitch", what);
+  LTM_REQUIRE(box_inner * 4 == 128 && box_outer >= 1 && box_outer <= 256, "%s: bad TMA box", what);
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 4ull};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle32b_atom ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LTM_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled failed with CUresult %d", what, (int)r);
+  return 0;
+}
+
 template <int BN, int STAGES, bool SPLIT, int CLUSTER = 1>
 static int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mB2, const GemmDev& d,
                       int batch, cudaStream_t stream) {
@@ -975,6 +898,7 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   d.c_group = a.c_group; d.c_group_stride = a.c_group_stride; d.bias_stride = a.bias_stride;
   d.mn_layout = g_mn_desc[0]; d.mn_lbo = g_mn_desc[1]; d.mn_sbo = g_mn_desc[2]; d.mn_kadv = g_mn_desc[3];
   d.dbg = g_dbg;
+  d.round_tf32 = a.round_tf32;
   d.c_vec = (a.ldc % 4 == 0 && a.strideC % 4 == 0 && a.c_group_stride % 4 == 0 && aligned16(a.C) &&
              (a.CT == nullptr || a.ct_cols % 4 == 0)) ? 1 : 0;
   d.a_batched = a.strideA != 0; d.b_batched = a.strideB != 0; d.b2_batched = a.strideB2 != 0; d.has_b2 = two ? 1 : 0;
@@ -1041,8 +965,8 @@ extern "C" int ltm_project_kv_t(const float* Bcoef, const float* Wkv, const floa
   return ltm_gemm(&a, stream);
 }
 
-extern "C" int ltm_project_kv(const float* Bcoef, const float* Wkv, const float* bkv, float* KV, int M, int e,
-                              int D2, int precision, int impl, void* stream) {
+static int project_kv_impl(const float* Bcoef, const float* Wkv, const float* bkv, float* KV, int M, int e, int D2,
+                           int precision, int impl, int round_tf32, void* stream) {
   ltm_gemm_args a;
   memset(&a, 0, sizeof(a));
   a.A = Bcoef; a.lda = e; a.strideA = 0; a.a_kmajor = 1;
@@ -1051,6 +975,16 @@ extern "C" int ltm_project_kv(const float* Bcoef, const float* Wkv, const float*
   a.bias = bkv;
   a.C = KV; a.ldc = D2; a.strideC = 0;
   a.M = M; a.Nc = D2; a.K = e; a.batch = 1;
-  a.precision = precision; a.impl = impl;
+  a.precision = precision; a.impl = impl; a.round_tf32 = round_tf32;
   return ltm_gemm(&a, stream);
+}
+extern "C" int ltm_project_kv(const float* Bcoef, const float* Wkv, const float* bkv, float* KV, int M, int e,
+                              int D2, int precision, int impl, void* stream) {
+  return project_kv_impl(Bcoef, Wkv, bkv, KV, M, e, D2, precision, impl, 0, stream);
+}
+extern "C" int ltm_project_kv_r(const float* Bcoef, const float* Wkv, const float* bkv, float* KV, int M, int e,
+                                int D2, int precision, int impl, void* stream) {
+  using namespace ltm;
+  LTM_REQUIRE(impl == 0, "project_kv_r: the rounding epilogue exists in the tcgen05 kernel only");
+  return project_kv_impl(Bcoef, Wkv, bkv, KV, M, e, D2, precision, impl, 1, stream);
 }

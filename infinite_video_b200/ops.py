@@ -230,6 +230,41 @@ def attn_fast_supported(N, d=64):
     return bool(lib().ltm_attn_fast_supported(int(N), int(d)))
 
 
+def attn_tc_supported(N, d=64):
+    return bool(lib().ltm_attn_tc_supported(int(N), int(d)))
+
+
+def project_kv_r(Bcoef, Wkv, bkv, precision="tf32", out=None):
+    """`project_kv` with the stored K|V rounded to the tf32 grid (operands of the tensor-core attention)."""
+    require_cuda(Bcoef, Wkv, bkv)
+    Bc = _f32c(Bcoef).reshape(-1, Bcoef.shape[-1])
+    M, e = Bc.shape
+    D2 = Wkv.shape[0]
+    if out is None:
+        out = torch.empty(M, D2, device=Bc.device, dtype=torch.float32)
+    check(lib().ltm_project_kv_r(ptr(Bc), ptr(Wkv), ptr(bkv), ptr(out), M, e, D2, PRECISION[precision],
+                                 GEMM_IMPL["tcgen05"], stream_ptr(Bc.device)), "project_kv_r")
+    return out
+
+
+def cont_attn_rect_tc(q, KV, X, W, W_out, c_none, jb=None, tb=None, want_scores=False, want_hist=True, n_heads=12):
+    """Tensor-core path (num_basis 128/256): q[Bv,Q,D], KV[Bv,N,2D] (tf32-rounded) -> (ctx, scores|None, hist|None)."""
+    require_cuda(q, KV, X, W, jb, tb)
+    q = _f32c(q)
+    Bv, Q, D = q.shape
+    N = KV.shape[1]
+    H, d = n_heads, D // n_heads
+    ctx = torch.empty(Bv, Q, D, device=q.device, dtype=torch.float32)
+    scores = torch.empty(Bv, H, Q, N, device=q.device, dtype=torch.float32) if want_scores else None
+    hist = (torch.empty(Bv, H * ((Q + 31) // 32), STICKY_EDGES - 2, device=q.device, dtype=torch.float32)
+            if want_hist else None)
+    kv = KV.reshape(Bv * N, 2 * D)
+    check(lib().ltm_cont_attn_rect_tc(ptr(q), ptr(kv), C.c_void_p(kv.data_ptr() + 4 * D), 2 * D, ptr(X), ptr(W),
+                                      float(W_out), float(c_none), ptr(jb), ptr(tb), ptr(ctx), ptr(scores), ptr(hist),
+                                      Bv, Q, N, H, d, stream_ptr(q.device)), "cont_attn_rect_tc")
+    return ctx, scores, hist
+
+
 def project_kv_t(Bcoef, Wkv, bkv, N, precision="tf32", impl="tcgen05"):
     """Same projection with the keys stored transposed per head: -> (Kt[Bv,H,64,N], V[Bv,N,D])."""
     require_cuda(Bcoef, Wkv, bkv)

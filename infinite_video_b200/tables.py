@@ -124,6 +124,8 @@ class RectTables:
     # quadrature of expected_value: r_j = W_j e^{S_j} / (sum_i W_i e^{S_i} + W_out)
     W: np.ndarray = None             # fp32 [N]
     W_out: float = 0.0
+    X: np.ndarray = None             # fp32 [N,32] extra operand rows of the tensor-core attention (or None)
+    c_none: float = 0.0              # trapezoid node weight of the sticky edges outside every basis
     # uniform (non-sticky) resampling table: basis index of sample s (-1 none)  (gibbs:152-157,:212)
     idx_uniform: np.ndarray = None   # int32 [S]
     # density side-output of the Video-LLaMA copy (gibbs:328-335): 3 x 256 evaluation points
@@ -138,6 +140,7 @@ class RectTables:
             for name in ("seg_ptr0", "seg_mem0", "g0", "seg_ptr1", "seg_mem1", "g1", "tb", "jb", "bins",
                          "bin2basis", "W", "idx_uniform", "jd", "wd"):
                 d[name] = torch.from_numpy(getattr(self, name)).to(device)
+            d["X"] = torch.from_numpy(self.X).to(device) if self.X is not None else None
             self._dev[key] = d
         return self._dev[key]
 
@@ -197,6 +200,29 @@ def rect_tables(L: int, N: int, tau: float, S: int = NB_SAMPLES, num_quad: int =
     np.add.at(W, jq[jq >= 0], wt[jq >= 0])
     t.W = W.astype(np.float32)
     t.W_out = float(wt[jq < 0].sum())
+
+    # --- operand rows appended to V^T by the tensor-core attention (csrc/attn_tc.cu): with the un-normalised
+    # weights e_j = W_j exp(S_j - m) as the other operand, row 0 (ones) yields the quadrature normaliser
+    # sum_j e_j and rows 1+2 (hi + lo, each exact in tf32) the trapezoid integral of the sticky histogram,
+    # Z = sum_i w_i E_i = sum_j c_j exp(S_j - m) + c_none exp(-m), c_j = sum of the node weights w_i of the
+    # edges that fall into basis j (gibbs:197-202,:248), as sum_j (c_j / W_j) e_j.
+    tbd = t.tb.astype(np.float64)
+    wn = np.zeros(tbd.shape[0])
+    wn[:-1] += np.diff(tbd) / 2
+    wn[1:] += np.diff(tbd) / 2
+    cj = np.zeros(N)
+    np.add.at(cj, t.jb[t.jb >= 0], wn[t.jb >= 0])
+    t.c_none = float(wn[t.jb < 0].sum())
+    X = np.zeros((N, 32), dtype=np.float32)
+    if (W > 0).all():
+        ratio = (cj / W).astype(np.float32)
+        hi = (ratio.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+        X[:, 0] = 1.0
+        X[:, 1] = hi
+        X[:, 2] = (ratio.astype(np.float64) - hi.astype(np.float64)).astype(np.float32)
+        t.X = X
+    else:
+        t.X = None                     # a basis without quadrature points: the tensor-core path is not used
 
     # --- uniform re-sampling table (gibbs:152-157): psi.evaluate(t/tau) for each contracted position
     t.idx_uniform = rect_bin_of(old / tau, N).numpy()

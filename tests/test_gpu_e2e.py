@@ -246,7 +246,9 @@ def test_full_size_properties(dev):
     solo = BatchedRectLTM(N, .75, *proj_tensors(key, val), device=dev)
     s0 = solo.step(k0[3:4], q[3:4], None, new_doc=True)
     s1 = solo.step(k1[3:4], q[3:4], u[3:4], new_doc=False)
-    assert relerr(s0[0], c0[3]) < 1e-5 and relerr(s1[0], c1[3]) < 1e-5
+    # (a solo video pools with a different split count: 1e-7 differences in B can cross a tf32 rounding boundary of
+    # K, V or the attention weights, each worth 2^-12 relative on one element)
+    assert relerr(s0[0], c0[3]) < 1e-4 and relerr(s1[0], c1[3]) < 1e-4
     # (iii) linearity of the regression in the chunk: B(2k) == 2 B(k) exactly (power-of-two scaling)
     eng.step(2 * k0, q, None, new_doc=True)
     assert torch.equal(eng.B_past, 2 * B0)
@@ -265,7 +267,8 @@ def test_full_size_properties(dev):
     W = tables.rect_tables(L, N, .75).to(dev)["W"]
     want = torch.einsum("j,vjd->vd", W / (W.sum() + tables.rect_tables(L, N, .75).W_out), V)
     got = eng.step(k0, torch.zeros_like(q), None, new_doc=True)
-    assert relerr(got[:, 0], want) < 1e-5 and relerr(got[:, 31], want) < 1e-5
+    # (the tensor-core attention rounds the weights W_j and the values to tf32: 2^-12 relative per element)
+    assert relerr(got[:, 0], want) < 2e-4 and relerr(got[:, 31], want) < 2e-4
 
 
 def test_prefetched_pooling_is_bit_identical(dev):

@@ -107,8 +107,15 @@ def _rect_case(N, L, Q, seed, q_scale):
     return key, val, ks[0], qs[0], outs
 
 
+def _tf32_rna(x):
+    """Round-to-nearest (ties away) onto the tf32 grid, like cvt.rna.tf32.f32."""
+    b = x.contiguous().view(torch.int32)
+    return ((b + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 @pytest.mark.parametrize("N,L,Q,q_scale", [(64, 8, 32, 1.0), (256, 16, 32, 8.0), (512, 16, 32, 4.0),
-                                           (64, 8, 96, 2.0), (100, 30, 40, 2.0)])
+                                           (64, 8, 96, 2.0), (100, 30, 40, 2.0), (128, 16, 32, 2.0),
+                                           (256, 8, 40, 1.0)])
 def test_cont_attn_rect_and_fused_histogram(dev, N, L, Q, q_scale):
     ops, T = _ops(), _tables()
     key, val, k, q, outs = _rect_case(N, L, Q, 7, q_scale)
@@ -146,6 +153,18 @@ def test_cont_attn_rect_and_fused_histogram(dev, N, L, Q, q_scale):
         assert relerr(got3["p"], want_p) < 2e-5
         ctx4, _, _ = ops.cont_attn_rect_t(q.to(dev), Kt.to(dev), Vv.to(dev), td["W"], tab.W_out, want_hist=False)
         assert torch.equal(ctx4, ctx3)
+    # tensor-core path: both contractions as tf32 UMMAs over tf32-rounded K|V (tolerances are tf32's: operands carry
+    # 2^-12 relative rounding; the scores enter an exponential, so ctx / p are held to 1e-3 like the e2e tests)
+    if ops.attn_tc_supported(N):
+        KVr = _tf32_rna(KV).to(dev)
+        ctx5, scores5, hist5 = ops.cont_attn_rect_tc(q.to(dev), KVr, td["X"], td["W"], tab.W_out, tab.c_none,
+                                                     td["jb"], td["tb"], want_scores=True, want_hist=True)
+        assert relerr(scores5, want_S) < 5e-4
+        assert relerr(ctx5, want_ctx) < 1e-3
+        got5 = ops.resample(hist5, u, bins, td["bin2basis"], normalize=True)
+        assert relerr(got5["p"], want_p) < 1e-3
+        ctx6, _, _ = ops.cont_attn_rect_tc(q.to(dev), KVr, td["X"], td["W"], tab.W_out, tab.c_none, want_hist=False)
+        assert torch.equal(ctx6, ctx5)
 
 
 # ---------------------------------------------------------------------------------------- R3/R5/R8
