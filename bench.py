@@ -65,11 +65,18 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark(self):
+        """Start of the timed region: only samples that arrive after this moment are reported.  (The sampler is
+        started before the warm-up: nvidia-smi's start-up holds driver locks for ~100 ms and must not fall into
+        the timed region.)"""
+        self.t0 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t1 = time.time() + 0.03           # the line of a sample taken at the end of the region arrives a little later
         time.sleep(0.15)
         self.proc.terminate()
         try:
@@ -77,7 +84,11 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
-        for r in self.rows:
+        t0 = getattr(self, "t0", 0.0)
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1]
+        if not rows:                      # region shorter than the sampling period: the nearest sample after its start
+            rows = [r for (t, r) in self.rows if t >= t0][:1] or [r for (_t, r) in self.rows[-1:]]
+        for r in rows:
             try:
                 sm.append(float(r[1])); smax.append(float(r[2]))
             except Exception:
@@ -201,6 +212,9 @@ def run_b200(args):
             ev_sets.append(evs)
         eng.reset()
         eng._pref.clear()
+        sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
+        if sampler:
+            sampler.start()
         for _ in range(max(1, args.warmup if with_overlap == overlap else 1)):
             for c in range(C):
                 if with_overlap:
@@ -208,11 +222,10 @@ def run_b200(args):
                 eng.step(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0))
         torch.cuda.synchronize(dev)
         D_.barrier(dev)
-        sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
-        if sampler:
-            sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(dev)
+        if sampler:
+            sampler.mark()
         e0.record(stream)
         i = 0
         for _ in range(args.steps):

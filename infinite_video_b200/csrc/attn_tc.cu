@@ -31,6 +31,8 @@ namespace tc {
 constexpr int DH = 64;
 constexpr int QT = 32;
 constexpr int THREADS = 288;             // 8 compute warps (TMEM lane quarter = warp % 4) + 1 TMA / MMA warp
+// register cap: 288 threads x 96 leave room for three frame-pooling CTAs of the next chunk beside this kernel
+constexpr int TC_MAX_REGS = 96;
 constexpr int TMEM_COLS = 128;           // S^T: NB/128 x 32 columns at 0; D: 32 columns at 64
 
 struct Params {
@@ -95,7 +97,7 @@ __device__ __forceinline__ void store_q_tile(uint8_t* dstq, const QRegs& r, int 
 //   bar_q           256 arrivals: q tile of the next item is in place (and S has been read out of TMEM)
 //   bar_r           256 arrivals: e^T is in place (and D of the previous item has been read out of TMEM)
 template <int NB>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __maxnreg__(TC_MAX_REGS)
 cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV,
                     const __grid_constant__ CUtensorMap mapX, const Params p, const int q_tiles, const int total) {
   static_assert(NB == 128 || NB == 256, "the tensor-core path covers num_basis 128 / 256");
@@ -107,7 +109,7 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
   float* misc = reinterpret_cast<float*>(sm + L_::MISC_OFF);
   float* wmax = misc;                       // [8][32]
   float* mcol = wmax + 8 * 32;              // [32]
-  float* zq = mcol + 32;                    // [32]
+  float* zq = mcol + 32;                    // [32] reciprocal of the quadrature normaliser
   float* rzh = zq + 32;                     // [32]
   float* Gs = rzh + 32;                     // [NB + 1]
   const uint32_t bars = sbase + L_::MISC_OFF + L_::MISC_FLOATS * 4;
@@ -118,10 +120,13 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
   const int Q = p.Q, H = p.H, D = H * DH;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sK = sbase + L_::K_OFF, sV = sbase + L_::V_OFF, sR = sbase + L_::R_OFF, sQ = sbase + L_::Q_OFF;
+  // videos are walked last-to-first: the projection kernel that ran just before wrote K|V first-to-last, so the
+  // most recently written rows are the ones still resident in L2
+  const int nvid = total / (H * q_tiles);
   auto decode = [&](int w, int& qt, int& h, int& v) {
     h = w % H;
     qt = (w / H) % q_tiles;
-    v = w / (H * q_tiles);
+    v = nvid - 1 - w / (H * q_tiles);
   };
   const int w0 = blockIdx.x, wstride = gridDim.x;
 
@@ -227,6 +232,14 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
       store_q_tile(sm + L_::Q_OFF, qr, tid);
       mbar_arrive(bar_q);
     }
+    QRegs qnext;                                       // queries of item it + 1, fetched during item it - 1
+    qnext.a = make_float4(0.f, 0.f, 0.f, 0.f);
+    qnext.b = qnext.a;
+    if (w0 + wstride < total) {
+      int qtn, hn, vn;
+      decode(w0 + wstride, qtn, hn, vn);
+      qnext = load_q(p.q + ((size_t)vn * Q + qtn * QT) * D + hn * DH, min(QT, Q - qtn * QT), D, tid);
+    }
     uint32_t it = 0;
     for (int w = w0; w < total; w += wstride, ++it) {
       const uint32_t ph = it & 1u;
@@ -236,12 +249,6 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
       const int rows = min(QT, Q - q0);
       float e[32];
       const int wn = w + wstride;
-      QRegs qnext;
-      if (wn < total) {
-        int qtn, hn, vn;
-        decode(wn, qtn, hn, vn);
-        qnext = load_q(p.q + ((size_t)vn * Q + qtn * QT) * D + hn * DH, min(QT, Q - qtn * QT), D, tid);
-      }
       mbar_wait(bar_s, ph);
       tcgen05_fence_after();
       if (active) {
@@ -299,6 +306,11 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
       }
       tcgen05_fence_before();
       mbar_arrive(bar_r);
+      if (wn + wstride < total) {                      // queries of item it + 2: consumed after the next bar_s
+        int qtn, hn, vn;
+        decode(wn + wstride, qtn, hn, vn);
+        qnext = load_q(p.q + ((size_t)vn * Q + qtn * QT) * D + hn * DH, min(QT, Q - qtn * QT), D, tid);
+      }
 
       // ---- outputs: D[lane m][q]; warp (quarter, chalf) reads 16 columns
       mbar_wait(bar_pv, ph);
@@ -327,7 +339,7 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
           if (lane == 0) {
             const int c = chalf * 16 + i;
             const float em = expf(-mcol[c]);
-            zq[c] = dv[i] + p.W_out * em;
+            zq[c] = 1.0f / (dv[i] + p.W_out * em);
             rzh[c] = (c < rows) ? 1.0f / (hi + lo + p.c_none * em) : 0.f;
           }
         }
@@ -338,7 +350,7 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
         float* dst = p.ctx + ((size_t)v * Q + q0 + chalf * 16) * D + h * DH + dd;
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (chalf * 16 + i < rows) dst[(size_t)i * D] = dv[i] / zq[chalf * 16 + i];
+          if (chalf * 16 + i < rows) dst[(size_t)i * D] = dv[i] * zq[chalf * 16 + i];
       }
       if (p.hist_part != nullptr) {
         if (active) {
