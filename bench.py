@@ -298,6 +298,13 @@ def run_b200(args):
         except Exception as ex:
             single = {"error": f"{type(ex).__name__}: {ex}"}
 
+    caller = None
+    if rank == 0 and world == 1 and not args.no_gauss:
+        try:
+            caller = run_caller_arm(dev)
+        except Exception as ex:
+            caller = {"error": f"{type(ex).__name__}: {ex}"}
+
     # ---------------- end to end through the host entry point (pinned host buffers, ring of 2 chunk slots)
     e2e = None
     if not args.no_e2e:
@@ -363,7 +370,7 @@ def run_b200(args):
                               "frac": step_gbs / peak, "algorithmic_bytes_per_step": step_bytes},
             "stage_ms_per_chunk_step": stage_avg,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "variant_gaussian": gauss, "single_video": single,
+            "variant_gaussian": gauss, "single_video": single, "caller_cross_attention": caller,
         }
         print(json.dumps(line))
     if world > 1:
@@ -418,6 +425,41 @@ def run_gauss_arm(dev, Bv, C, Lk, steps=3):
             "roofline": {"bound": "tensor", "achieved": tfl, "peak": peak_tf32, "unit": "TFLOP/s",
                          "frac": tfl / peak_tf32, "note": "algorithmic (single-product) flops; the split-TF32 path "
                          "issues 3 MMAs per product; peak = 1/2 of the measured bf16 GEMM"}}
+
+
+def run_caller_arm(dev, Bv=16, C=3, steps=3):
+    """the whole cross-attention branch of the Q-former's BertSelfAttention
+    (query projection, short-term attention over the L*T chunk tokens, LTM, alpha blend) per video chunk."""
+    from infinite_video_b200.cross_attention import CrossAttentionLTM
+    torch.manual_seed(0)
+    lin = lambda: torch.nn.Linear(E, D).to(dev)
+    mod = CrossAttentionLTM(lin(), lin(), lin(), alpha=0.9, num_basis=NB, tau=TAU, sticky=True, n_heads=H)
+    g = torch.Generator(device=dev).manual_seed(7)
+    ks = [torch.randn(Bv, L * T, E, device=dev, generator=g) for _ in range(C)]
+    hs = [torch.randn(Bv, Q, D, device=dev, generator=g) for _ in range(C)]
+    us = [torch.rand(Bv, S, dtype=torch.float64, generator=g, device=dev) for _ in range(C)]
+
+    def one():
+        for c in range(C):
+            out = mod(hs[c], ks[c], new_video=(c == 0), u=us[c] if c else None)
+        return out
+    one()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(steps):
+        out = one()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    calls = Bv * C
+    # flops of the re-associated short-term half: scores + P.enc over H*Q rows, L*T keys, e columns
+    fl = 4.0 * H * Q * (L * T) * E
+    tfl = fl * calls / (ms * 1e-3) / 1e12
+    return {"value": calls / (ms * 1e-3), "unit": "chunks/s", "videos": Bv, "chunks": C, "ms_per_step": ms,
+            "finite": bool(torch.isfinite(out).all()), "short_term_tflops": tfl,
+            "note": "Qformer.py:197-310 eval path: q = query(h); LTM(enc, q); softmax(q K^T) V over L*T = 8192 "
+                    "tokens without forming K, V (scores split-TF32, values TF32); alpha blend"}
 
 
 def run_single_video(dev, reps=200):
