@@ -155,7 +155,7 @@ def run_reference_impl(args):
         "e2e": {"value": val, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -372,7 +372,7 @@ def run_b200(args):
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "variant_gaussian": gauss, "single_video": single, "caller_cross_attention": caller,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0
@@ -502,7 +502,28 @@ def run_single_video(dev, reps=200):
             "note": "one video, CUDA-graph replay of a sticky update call (k re-read from L2: 25 MB < 126 MB L2)"}
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: keep a private handle to it and point fd 1 at stderr for the rest of
+    the run, so that library banners written by native code (NCCL prints its version at communicator creation)
+    cannot precede or follow the line."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
