@@ -90,7 +90,11 @@ __device__ __forceinline__ DescWords operand_desc_words(int kmajor, const MnDesc
 // tile, before the wait for the accumulator.  The first version did that arithmetic per store on 4 warps:
 // ~28 k cycles per 128 x 256 tile, 2.3x the tile's MMA time, and that -- not shared-memory bandwidth -- was what
 // held the kernel at 47 % tensor-pipe activity.
-constexpr int EPI_WARPS = 8;
+#ifndef LTM_GEMM_EPI_WARPS
+#define LTM_GEMM_EPI_WARPS 8
+#endif
+constexpr int EPI_WARPS = LTM_GEMM_EPI_WARPS;          // 4 or 8 (each TMEM lane quarter is served by EPI_WARPS / 4 warps)
+constexpr int EPI_SPLIT = EPI_WARPS / 4;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int EPI_COLS = 32;
 constexpr int STG_WARP_FLOATS = 32 * EPI_COLS;
@@ -106,7 +110,8 @@ template <int BN>
 __device__ __forceinline__ void epilogue_tile(const GemmDev& g, uint32_t tmem_acc, int ew, int warp_quarter, int lane,
                                               float* stg, int m0, int n0, int bz, uint32_t tfull, uint32_t tfull_parity) {
   const int row0 = m0 + warp_quarter * 32;
-  const int cbeg = (ew >> 2) * (BN / 2);
+  constexpr int WCOLS = BN / EPI_SPLIT;            // columns drained by this warp
+  const int cbeg = (ew >> 2) * WCOLS;
   float* cbase_ptr = g.C + (size_t)bz * g.strideC;
   const float* bias = g.bias ? g.bias + (size_t)bz * g.bias_stride : nullptr;
   // rows this lane stores in the row-major path: 4 i + (lane >> 3); its 16-byte column chunk: lane & 7
@@ -127,7 +132,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& g, uint32_t tmem_ac
     tbase = g.CT + (size_t)bz * g.strideC + (size_t)(trow / g.ct_group) * g.ct_cols * g.ct_group + (trow % g.ct_group);
   //   row-major path: bvs[j] = bias of this lane's 4 columns in chunk j;
   //   transposed path: btr[j] = bias[n0 + cbeg + 32 j + lane], redistributed with shuffles.
-  constexpr int NCH = BN / 2 / EPI_COLS;
+  constexpr int NCH = WCOLS / EPI_COLS;
   float4 bvs[NCH];
   float btr[NCH];
 #pragma unroll
@@ -143,7 +148,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& g, uint32_t tmem_ac
         if (col < g.Nc) btr[j] = __ldg(bias + col);
       }
     }
-    if (g.CT == nullptr || n0 + cbeg + BN / 2 > g.ct_cols) {             // some chunks take the row-major path
+    if (g.CT == nullptr || n0 + cbeg + WCOLS > g.ct_cols) {             // some chunks take the row-major path
 #pragma unroll
       for (int j = 0; j < NCH; ++j) {
         const int col = n0 + cbeg + EPI_COLS * j + 4 * lchunk;
