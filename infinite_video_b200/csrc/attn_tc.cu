@@ -30,10 +30,10 @@ namespace tc {
 
 constexpr int DH = 64;
 constexpr int QT = 32;
-constexpr int THREADS = 288;             // 8 compute warps (TMEM lane quarter = warp % 4) + 1 TMA / MMA warp
-// register cap: 288 threads x 96 leave room for three frame-pooling CTAs of the next chunk beside this kernel
+constexpr int THREADS = 320;             // 8 compute warps (TMEM lane quarter = warp % 4) + 2 issuing warps
+// register cap: 320 threads x 96 leave room for three frame-pooling CTAs of the next chunk beside this kernel
 constexpr int TC_MAX_REGS = 96;
-constexpr int TMEM_COLS = 128;           // S^T: NB/128 x 32 columns at 0; D: 32 columns at 64
+constexpr int TMEM_COLS = 128;           // S^T: NB/128 x 32 columns at 0; D: 2 x 32 columns at 64 (one per issuer)
 
 struct Params {
   const float* q;        // [Bv,Q,D]
@@ -45,6 +45,7 @@ struct Params {
   float* scores_out;     // optional [Bv,H,Q,NB]
   float* hist_part;      // optional [Bv, H*q_tiles, 127]
   int Q, H;
+  unsigned long long* trace;   // bring-up: CTA 0 writes globaltimer stamps [item][16] (NULL = off)
 };
 
 template <int NB>
@@ -55,10 +56,17 @@ struct Lay {
   static constexpr int R_OFF = 5 * SLAB;             // e^T: [NB/32 k-blocks][32 q][32 j]; also "slab 3" of A2
   static constexpr int Q_OFF = 6 * SLAB;             // q tile: [2 k-blocks][32 q][32 d]
   static constexpr int MISC_OFF = Q_OFF + 2 * 4096;
-  static constexpr int MISC_FLOATS = 8 * 32 + 3 * 32 + NB + 32;
+  static constexpr int MISC_FLOATS = 8 * 32 + 4 * 32 + 96 + NB + 32;
   static constexpr int BYTES = MISC_OFF + MISC_FLOATS * 4 + 64 + 1024;   // + 6 barriers, TMEM slot, alignment slack
 };
 
+__device__ __forceinline__ void stamp(unsigned long long* trace, uint32_t it, int slot) {
+  if (trace != nullptr && blockIdx.x == 0 && it < 16) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    trace[it * 16 + slot] = t;
+  }
+}
 __device__ __forceinline__ void cw_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 compute warps
 
 // q tile of one work item, scaled by 1/sqrt(d) (gibbs:226; a power of two, exact) and rounded to tf32, in the
@@ -71,9 +79,13 @@ __device__ __forceinline__ QRegs load_q(const float* qbase, int rows, int D, int
   r.a = make_float4(0.f, 0.f, 0.f, 0.f);
   r.b = r.a;
   if (qq < rows) {
+    // volatile asm: the loads stay where they are written (one item ahead of their use) instead of being sunk
+    // next to the first use by the scheduler
     const float4* src = reinterpret_cast<const float4*>(qbase + (size_t)qq * D + dch * 8);
-    r.a = __ldg(src);
-    r.b = __ldg(src + 1);
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w) : "l"(src));
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(src + 1));
   }
   return r;
 }
@@ -111,7 +123,9 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
   float* mcol = wmax + 8 * 32;              // [32]
   float* zq = mcol + 32;                    // [32] reciprocal of the quadrature normaliser
   float* rzh = zq + 32;                     // [32]
-  float* Gs = rzh + 32;                     // [NB + 1]
+  float* ems = rzh + 32;                    // [32] e^{-m_q} / Z_q (histogram)
+  float* nrm = ems + 32;                    // [2][3][16] scratch of the normaliser rows
+  float* Gs = nrm + 96;                     // [NB + 1]
   const uint32_t bars = sbase + L_::MISC_OFF + L_::MISC_FLOATS * 4;
   const uint32_t bar_k = bars, bar_v = bars + 8, bar_s = bars + 16, bar_pv = bars + 24, bar_q = bars + 32,
                  bar_r = bars + 40;
@@ -138,7 +152,7 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
       mbar_init(bar_k, 1);
       mbar_init(bar_v, 1);
       mbar_init(bar_s, 1);
-      mbar_init(bar_pv, 1);
+      mbar_init(bar_pv, 2);                            // one commit per issuing warp
       mbar_init(bar_q, 256);
       mbar_init(bar_r, 256);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -176,15 +190,11 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
       const uint64_t dV = umma_desc(sV, L_::SLAB, 512, 1u), dR = umma_desc(sR, 16, 1024, 2u);
       const uint32_t dk_lo = (uint32_t)dK, dk_hi = (uint32_t)(dK >> 32), dq_lo = (uint32_t)dQ;
       const uint32_t dv_lo = (uint32_t)dV, dv_hi = (uint32_t)(dV >> 32), dr_lo = (uint32_t)dR;
-      uint32_t it = 0;
-      for (int w = w0; w < total; w += wstride, ++it) {
-        const uint32_t ph = it & 1u;
-        const int wn = w + wstride;
-        int qtn = 0, hn = 0, vn = 0;
-        if (wn < total) decode(wn, qtn, hn, vn);
-        mbar_wait(bar_q, ph);                          // this item's q tile written, S free
+      auto issue_scores = [&](uint32_t ph, uint32_t sit) {            // S^T of the item whose K tile / q tile carry parity ph
+        mbar_wait(bar_q, ph);                          // q tile written, S read out of TMEM
         mbar_wait(bar_k, ph);
         tcgen05_fence_after();
+        if (threadIdx.x == 256) stamp(p.trace, sit, 5);
 #pragma unroll
         for (int hf = 0; hf < HALVES; ++hf) {
 #pragma unroll
@@ -195,27 +205,65 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
                              ks != 0 ? 1u : 0u);
         }
         tcgen05_commit(bar_s);
+      };
+      uint32_t it = 0;
+      issue_scores(0u, 0u);
+      for (int w = w0; w < total; w += wstride, ++it) {
+        const uint32_t ph = it & 1u;
+        const int wn = w + wstride;
+        int qtn = 0, hn = 0, vn = 0;
+        if (wn < total) decode(wn, qtn, hn, vn);
         mbar_wait(bar_s, ph);                          // the K buffer has been read
+        stamp(p.trace, it, 0);
         if (wn < total) {
           mbar_arrive_expect_tx(bar_k, 2 * L_::SLAB);
           tma_load_2d(&mapK, sK, bar_k, hn * DH, vn * NB);
           tma_load_2d(&mapK, sK + L_::SLAB, bar_k, hn * DH + 32, vn * NB);
         }
         mbar_wait(bar_r, ph);                          // e^T written, D free
+        stamp(p.trace, it, 1);
         mbar_wait(bar_v, ph);
+        stamp(p.trace, it, 2);
         tcgen05_fence_after();
+        // this warp contracts the first half of the basis range into D0, warp 9 the second half into D1: the issue
+        // of 32 small MMAs by one thread (~33 ns each) was 1.05 us of the item's 4.7 us
 #pragma unroll
-        for (int ks = 0; ks < NB / 8; ++ks)
+        for (int ks = 0; ks < NB / 16; ++ks)
           tcgen05_mma_tf32(tmem_base + 64, dv_lo + (uint32_t)((ks * 1024) >> 4), dv_hi,
                            dr_lo + (uint32_t)(((ks >> 2) * 4096 + (ks & 3) * 32) >> 4), dk_hi, IDESC_PV,
                            ks != 0 ? 1u : 0u);
         tcgen05_commit(bar_pv);
+        stamp(p.trace, it, 3);
+        // the next item's scores go out right behind: its keys landed during this item's weight phase, so S is
+        // ready by the time the compute warps have written this item's outputs
+        if (wn < total) issue_scores(ph ^ 1u, it + 1);
         mbar_wait(bar_pv, ph);                         // the V buffer (and e^T) have been read
+        stamp(p.trace, it, 4);
         if (wn < total) {
           mbar_arrive_expect_tx(bar_v, 2 * L_::SLAB);
           tma_load_2d(&mapV, sV, bar_v, hn * DH, vn * NB);
           tma_load_2d(&mapV, sV + L_::SLAB, bar_v, hn * DH + 32, vn * NB);
         }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ second MMA issuer (one lane)
+    if (lane == 0) {
+      const uint64_t dV = umma_desc(sV, L_::SLAB, 512, 1u), dR = umma_desc(sR, 16, 1024, 2u);
+      const uint32_t dv_lo = (uint32_t)dV, dv_hi = (uint32_t)(dV >> 32), dr_lo = (uint32_t)dR, dr_hi = (uint32_t)(dR >> 32);
+      uint32_t it = 0;
+      for (int w = w0; w < total; w += wstride, ++it) {
+        const uint32_t ph = it & 1u;
+        mbar_wait(bar_r, ph);
+        mbar_wait(bar_v, ph);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int ks = NB / 16; ks < NB / 8; ++ks)
+          tcgen05_mma_tf32(tmem_base + 96, dv_lo + (uint32_t)((ks * 1024) >> 4), dv_hi,
+                           dr_lo + (uint32_t)(((ks >> 2) * 4096 + (ks & 3) * 32) >> 4), dr_hi, IDESC_PV,
+                           ks != NB / 16 ? 1u : 0u);
+        tcgen05_commit(bar_pv);
       }
     }
     __syncwarp();
@@ -225,6 +273,16 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
     const int j = (warp >> 2) * 128 + (warp & 3) * 32 + lane;      // this thread's basis in the weight phase
     const int quarter = warp & 3, chalf = warp >> 2;
     const float Wj = active ? __ldg(p.W + j) : 0.f;
+    const float rWj = active ? 1.0f / Wj : 0.f;
+    // histogram bin of this thread (tid < 127): p_i = dt_{i+1}/2 (G[jb_{i+1}] + G[jb_{i+2}])
+    int hja = NB, hjb = NB;
+    float hdt = 0.f;
+    if (tid < EDGES - 2 && p.hist_part != nullptr) {
+      const int a = __ldg(p.jb + tid + 1), b = __ldg(p.jb + tid + 2);
+      hja = a < 0 ? NB : a;
+      hjb = b < 0 ? NB : b;
+      hdt = 0.5f * (__ldg(p.tb + tid + 2) - __ldg(p.tb + tid + 1));
+    }
     {
       int qt, h, v;
       decode(w0, qt, h, v);
@@ -250,6 +308,7 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
       float e[32];
       const int wn = w + wstride;
       mbar_wait(bar_s, ph);
+      if (tid == 0) stamp(p.trace, it, 8);
       tcgen05_fence_after();
       if (active) {
         uint32_t r[32];
@@ -289,6 +348,7 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
         }
       }
       cw_sync();                                                                           // column maxima
+      if (tid == 0) stamp(p.trace, it, 9);
       if (active) {
         float M = 0.f;                                 // per-row shift m = max(0, max_j S_j): it cancels exactly
 #pragma unroll
@@ -306,6 +366,7 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
       }
       tcgen05_fence_before();
       mbar_arrive(bar_r);
+      if (tid == 0) stamp(p.trace, it, 10);
       if (wn + wstride < total) {                      // queries of item it + 2: consumed after the next bar_s
         int qtn, hn, vn;
         decode(wn + wstride, qtn, hn, vn);
@@ -314,6 +375,7 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
 
       // ---- outputs: D[lane m][q]; warp (quarter, chalf) reads 16 columns
       mbar_wait(bar_pv, ph);
+      if (tid == 0) stamp(p.trace, it, 11);
       tcgen05_fence_after();
       float dv[16];
       {
@@ -326,25 +388,39 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
               "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
             : "r"(taddr)
             : "memory");
+        uint32_t r2[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7]),
+              "=r"(r2[8]), "=r"(r2[9]), "=r"(r2[10]), "=r"(r2[11]), "=r"(r2[12]), "=r"(r2[13]), "=r"(r2[14]),
+              "=r"(r2[15])
+            : "r"(taddr + 32u)
+            : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int i = 0; i < 16; ++i) dv[i] = __uint_as_float(r[i]);
+        for (int i = 0; i < 16; ++i) dv[i] = __uint_as_float(r[i]) + __uint_as_float(r2[i]);
       }
       if (quarter == 2) {
-        // lanes 0,1,2 hold rows 64 (sum_j e), 65, 66 (sum_j c_j/W_j e, hi + lo)
+        // lanes 0,1,2 hold rows 64 (sum_j e), 65, 66 (sum_j c_j/W_j e, hi + lo) of this warp's 16 columns: through
+        // a small scratch so that 16 lanes finish one column each
+        float* sc = nrm + chalf * 48;
+        if (lane < 3) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float hi = __shfl_sync(0xffffffffu, dv[i], 1);
-          const float lo = __shfl_sync(0xffffffffu, dv[i], 2);
-          if (lane == 0) {
-            const int c = chalf * 16 + i;
-            const float em = expf(-mcol[c]);
-            zq[c] = 1.0f / (dv[i] + p.W_out * em);
-            rzh[c] = (c < rows) ? 1.0f / (hi + lo + p.c_none * em) : 0.f;
-          }
+          for (int i = 0; i < 16; ++i) sc[lane * 16 + i] = dv[i];
+        }
+        __syncwarp();
+        if (lane < 16) {
+          const int c = chalf * 16 + lane;
+          const float em = expf(-mcol[c]);
+          zq[c] = 1.0f / (sc[lane] + p.W_out * em);
+          const float rz = (c < rows) ? 1.0f / (sc[16 + lane] + sc[32 + lane] + p.c_none * em) : 0.f;
+          rzh[c] = rz;
+          ems[c] = em * rz;
         }
       }
       cw_sync();                                                                           // normalisers
+      if (tid == 0) stamp(p.trace, it, 12);
       if (quarter < 2) {
         const int dd = quarter * 32 + lane;
         float* dst = p.ctx + ((size_t)v * Q + q0 + chalf * 16) * D + h * DH + dd;
@@ -358,21 +434,19 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
           float g = 0.f;
 #pragma unroll
           for (int c = 0; c < 32; ++c) g = fmaf(e[c], rzh[c], g);
-          Gs[j] = g / Wj;
+          Gs[j] = g * rWj;
         }
-        if (tid == 255 || (HALVES == 1 && tid == 128)) {
-          float g = 0.f;
-          for (int c = 0; c < 32; ++c) g = fmaf(expf(-mcol[c]), rzh[c], g);
-          Gs[NB] = g;                                  // edges outside every basis: score 0
+        if (warp == 3) {                               // edges outside every basis (score 0): sum_q e^{-m_q} / Z_q
+          const float g = warp_sum(ems[lane]);
+          if (lane == 0) Gs[NB] = g;
         }
         cw_sync();                                                                         // G complete
-        if (tid < EDGES - 2) {
-          const int a = __ldg(p.jb + tid + 1), b = __ldg(p.jb + tid + 2);
-          const float dt = __ldg(p.tb + tid + 2) - __ldg(p.tb + tid + 1);
-          const float val = dt * (Gs[a < 0 ? NB : a] + Gs[b < 0 ? NB : b]) * 0.5f;
-          p.hist_part[((size_t)v * (H * q_tiles) + h * q_tiles + qt) * (EDGES - 2) + tid] = val;
-        }
-        cw_sync();                                     // Gs / mcol / rzh are rewritten by the next item
+        if (tid < EDGES - 2)
+          p.hist_part[((size_t)v * (H * q_tiles) + h * q_tiles + qt) * (EDGES - 2) + tid] =
+              hdt * (Gs[hja] + Gs[hjb]);
+        // no barrier before the next item: everything above is rewritten only behind the next item's first
+        // cw_sync, which no thread passes before all of them have finished this item
+        if (tid == 0) stamp(p.trace, it, 13);
       }
     }
   }
@@ -406,8 +480,10 @@ static int launch(const CUtensorMap& mK, const CUtensorMap& mV, const CUtensorMa
   return 0;
 }
 
+static unsigned long long* g_trace = nullptr;
 }  // namespace tc
 }  // namespace ltm
+extern "C" void ltm_debug_set_attn_trace(void* p) { ltm::tc::g_trace = (unsigned long long*)p; }
 
 extern "C" int ltm_attn_tc_supported(int N, int d) { return (d == 64 && (N == 128 || N == 256)) ? 1 : 0; }
 
@@ -432,6 +508,7 @@ extern "C" int ltm_cont_attn_rect_tc(const float* q, const float* K, const float
   tc::Params p{};
   p.q = q; p.W = W; p.tb = tb; p.jb = jb; p.W_out = W_out; p.c_none = c_none; p.ctx = ctx;
   p.scores_out = scores_out; p.hist_part = hist_part; p.Q = Q; p.H = H;
+  p.trace = tc::g_trace;
   return N == 256 ? tc::launch<256>(mK, mV, mX, p, Bv, (cudaStream_t)stream)
                   : tc::launch<128>(mK, mV, mX, p, Bv, (cudaStream_t)stream);
 }

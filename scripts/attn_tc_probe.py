@@ -34,3 +34,19 @@ def timeit(f, n=20):
     return e0.elapsed_time(e1) / n
 print("fma  ms", timeit(lambda: ops.cont_attn_rect_t(q, Kt, V, td["W"], tab.W_out, td["jb"], td["tb"])))
 print("tc   ms", timeit(lambda: ops.cont_attn_rect_tc(q, KVr, td["X"], td["W"], tab.W_out, tab.c_none, td["jb"], td["tb"])))
+# ---- per-item timeline of CTA 0 (bring-up trace)
+import ctypes as C
+from infinite_video_b200 import _capi
+lib = _capi.lib()
+lib.ltm_debug_set_attn_trace.argtypes = [C.c_void_p]; lib.ltm_debug_set_attn_trace.restype = None
+tr = torch.zeros(16 * 16, dtype=torch.int64, device=dev)
+lib.ltm_debug_set_attn_trace(C.c_void_p(tr.data_ptr()))
+ops.cont_attn_rect_tc(q, KVr, td["X"], td["W"], tab.W_out, tab.c_none, td["jb"], td["tb"])
+torch.cuda.synchronize()
+lib.ltm_debug_set_attn_trace(None)
+t = tr.cpu().view(16, 16).numpy()
+names = {5: "S issue (K,q ready)", 8: "CW sees S", 0: "IS sees S done", 9: "maxima exchanged", 10: "e^T written", 1: "IS sees e^T", 2: "V ready", 3: "PV issued", 11: "CW sees PV", 4: "IS sees PV", 12: "normalisers", 13: "item end"}
+t0 = t[0][5]
+for it in range(min(8, Bv * 12 // 148 + 1)):
+    ev = sorted((int(t[it][k] - t0), names[k]) for k in names if t[it][k] > 0)
+    print(f"item {it}: " + " | ".join(f"{n} {dt/1000:.2f}" for dt, n in ev))

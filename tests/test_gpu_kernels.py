@@ -280,6 +280,19 @@ def test_project_kv(dev):
 
 
 # ---------------------------------------------------------------------------------------- variant G kernels
+def test_project_kv_rounded_to_tf32(dev):
+    """`ltm_project_kv_r`: the same product as `ltm_project_kv`, stored on the tf32 grid (round to nearest)."""
+    ops = _ops()
+    torch.manual_seed(3)
+    Bc = torch.randn(512, 768, device=dev)
+    Wkv = torch.randn(1536, 768, device=dev) * 0.05
+    bkv = torch.randn(1536, device=dev)
+    plain = ops.project_kv(Bc, Wkv, bkv)
+    rounded = ops.project_kv_r(Bc, Wkv, bkv)
+    assert torch.equal(rounded, _tf32_rna(plain))
+    assert int((rounded.view(torch.int32) & 0x1FFF).abs().max()) == 0
+
+
 def test_rbf_eval_and_sticky_hist_gauss(dev):
     ops = _ops()
     psi = O.GaussBasis(256, [0.005, 0.01])
