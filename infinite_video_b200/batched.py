@@ -233,7 +233,7 @@ class BatchedRectLTM(_BatchedBase):
             check(lib().ltm_event_record(events[1], sp), "event_record")
         done = torch.cuda.Event()
         done.record(self._side)
-        self._pref[(k_next.data_ptr(), tuple(k_next.shape))] = (b, done)
+        self._pref[(k_next.data_ptr(), tuple(k_next.shape))] = (b, done, torch.cuda.is_current_stream_capturing())
 
     def density(self):
         """alphas[Q,Bv,H,768] of the most recent call: the density side-output the Video-LLaMA copy pickles to
@@ -299,7 +299,10 @@ class BatchedRectLTM(_BatchedBase):
             ws["xi"] = hit[0]
             run = self._compute                      # fork: high-priority compute stream, joined below
             run.wait_stream(main)
-            run.wait_event(hit[1])
+            # (a graph capture cannot wait on an event recorded before it began: the capturing host has synchronised,
+            # and on replay the buffer is the one the previous replay's last prefetch filled)
+            if hit[2] or not torch.cuda.is_current_stream_capturing():
+                run.wait_event(hit[1])
         else:
             ws["xi"] = ws["xnext"]
             ws["xnext"] = 1 - ws["xnext"]
