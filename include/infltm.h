@@ -224,6 +224,23 @@ int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const float* q, c
 int ltm_rect_step_host(const ltm_rect_step_args* a, const float* k_host, const float* q_host,
                        const double* u_host, const uint8_t* new_doc_host, float* ctx_host, void* stream);
 
+/* ---- the same step with the frame pooling of the NEXT chunk issued beside it (two-stream schedule in one call):
+ *   side:     wait(main) -> pool(k_next -> xpart_next) -> record ev_pooled_next
+ *   compute:  wait(main), wait(ev_pooled_cur) -> re-sample / consolidate / project / attention of this chunk
+ *             (a->xpart holds this chunk's pooled frames, filled by the previous call's side-stream pooling)
+ *   main:     wait(compute)
+ * Frame pooling does not depend on the memory state and is the HBM-bound 93 % of a call's bytes; the other kernels
+ * are tensor- / latency-bound.  Streams and (timing-disabled) events are the caller's; the events are re-recorded
+ * on every call.  k_next == NULL issues no pooling; ev_pooled_cur == NULL waits for nothing.  The pooling of the
+ * next chunk is bracketed by a->prof_events[0,1] when those are set. */
+typedef struct {
+  void *main_stream, *side_stream, *compute_stream;
+  void *ev_fork_pool, *ev_pooled_cur, *ev_pooled_next, *ev_fork, *ev_join;
+  const float* k_next; float* xpart_next; int pool_ctas;
+} ltm_overlap;
+int ltm_rect_step_overlap(const ltm_rect_step_args* a, const ltm_overlap* o, const float* q, const double* u,
+                          const uint8_t* new_doc, float* ctx);
+
 /* ---- N1 (caller, Qformer.py:279-304): row softmax of the short-term attention scores, in place.
  * S[rows, n] <- softmax(S * scale + mask[row / rows_per_mask, :]) (mask may be NULL); and the alpha blend
  * out = alpha * a + (1 - alpha) * b over n elements. */
@@ -232,7 +249,9 @@ int ltm_blend(const float* a, const float* b, float alpha, float* out, int64_t n
 
 /* ---- CUDA-event helpers so a ctypes host can time stages on the launching stream */
 int ltm_event_create(void** ev);
+int ltm_event_create_sync(void** ev);                             /* no timing: stream fork / join only */
 int ltm_event_record(void* ev, void* stream);
+int ltm_stream_wait_event(void* stream, void* ev);
 int ltm_event_elapsed_ms(void* start, void* stop, float* ms);   /* synchronises on `stop` */
 int ltm_event_destroy(void* ev);
 

@@ -53,6 +53,15 @@ class RectStepArgs(C.Structure):
     ]
 
 
+class Overlap(C.Structure):
+    _fields_ = [
+        ("main_stream", C.c_void_p), ("side_stream", C.c_void_p), ("compute_stream", C.c_void_p),
+        ("ev_fork_pool", C.c_void_p), ("ev_pooled_cur", C.c_void_p), ("ev_pooled_next", C.c_void_p),
+        ("ev_fork", C.c_void_p), ("ev_join", C.c_void_p),
+        ("k_next", C.c_void_p), ("xpart_next", C.c_void_p), ("pool_ctas", C.c_int),
+    ]
+
+
 _I, _F, _P, _L = C.c_int, C.c_float, C.c_void_p, C.c_int64
 _SIGS = {
     "ltm_version": (C.c_int, []),
@@ -84,10 +93,13 @@ _SIGS = {
     "ltm_softmax_rows": (C.c_int, [_P, _P, _I, _I, _I, _F, _P]),
     "ltm_blend": (C.c_int, [_P, _P, _F, _P, _L, _P]),
     "ltm_event_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "ltm_event_create_sync": (C.c_int, [C.POINTER(C.c_void_p)]),
     "ltm_event_record": (C.c_int, [_P, _P]),
+    "ltm_stream_wait_event": (C.c_int, [_P, _P]),
     "ltm_event_elapsed_ms": (C.c_int, [_P, _P, C.POINTER(C.c_float)]),
     "ltm_event_destroy": (C.c_int, [_P]),
     "ltm_rect_step": (C.c_int, [C.POINTER(RectStepArgs), _P, _P, _P, _P, _P, _P]),
+    "ltm_rect_step_overlap": (C.c_int, [C.POINTER(RectStepArgs), C.POINTER(Overlap), _P, _P, _P, _P]),
     "ltm_rect_step_host": (C.c_int, [C.POINTER(RectStepArgs), _P, _P, _P, _P, _P, _P]),
 }
 EXPORTED = tuple(_SIGS)

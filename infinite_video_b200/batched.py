@@ -15,7 +15,7 @@ import math
 import torch
 
 from . import ops, tables
-from ._capi import RectStepArgs, check, lib, ptr, require_cuda, stream_ptr
+from ._capi import Overlap, RectStepArgs, check, lib, ptr, require_cuda, stream_ptr
 
 SM_COUNT = 148
 
@@ -94,6 +94,7 @@ class BatchedRectLTM(_BatchedBase):
         self.prof_events = None       # optional list of 10 cudaEvent_t handles (bench.py stage timing)
         self._side = None             # side stream for pooling the next chunk ahead of time
         self._pref = {}               # pending prefetches: (data_ptr, shape) -> (buffer index, done event)
+        self._evs = None              # persistent fork / join events of the two-stream schedule
         self.pool_ctas = 0            # grid bound of the side-stream pooling kernel (0 = one CTA per frame)
         self._ws = {}
         self._B = None
@@ -215,25 +216,42 @@ class BatchedRectLTM(_BatchedBase):
             # pooling runs at the lowest priority, the compute-bound kernels of `step` on a high-priority stream:
             # the block scheduler then places regression / projection / attention CTAs as soon as resources free
             # up and the streaming kernel fills whatever is left
+            import os
+            flat = os.environ.get("LTM_FLAT_PRIORITY") == "1"        # bring-up: both streams at the default priority
             self._side = torch.cuda.Stream(device=self.device, priority=0)
-            self._compute = torch.cuda.Stream(device=self.device, priority=-1)
+            self._compute = torch.cuda.Stream(device=self.device, priority=0 if flat else -1)
         if len(self._pref) >= 2:
             raise RuntimeError("at most two chunks may be in flight (the pooled frames are double-buffered)")
         main = torch.cuda.current_stream(self.device)
-        self._side.wait_stream(main)          # the target buffer was last read by work already queued on `main`
-        k_next.record_stream(self._side)
+        ev = self._sync_events()
         b = ws["xnext"]
         ws["xnext"] = 1 - b
         sp = C.c_void_p(self._side.cuda_stream)
+        mp = C.c_void_p(main.cuda_stream)
+        # fork: the target buffer was last read by work already queued on `main`.  Persistent events (re-recorded
+        # every call) instead of torch's wait_stream, which creates and destroys a CUDA event per call: with four of
+        # those per chunk-step the host enqueue time of a step varied between 0.9 and 8 ms from run to run
+        check(lib().ltm_event_record(ev["fork_pool"][b], mp), "event_record")
+        check(lib().ltm_stream_wait_event(sp, ev["fork_pool"][b]), "stream_wait_event")
+        k_next.record_stream(self._side)
         if events is not None:
             check(lib().ltm_event_record(events[0], sp), "event_record")
         check(lib().ltm_pool_mean_grid(ptr(k_next), ptr(ws["xparts"][b]), Bv, L, self.T, self.e, ws["splits"],
                                        int(self.pool_ctas), sp), "pool_mean")
         if events is not None:
             check(lib().ltm_event_record(events[1], sp), "event_record")
-        done = torch.cuda.Event()
-        done.record(self._side)
-        self._pref[(k_next.data_ptr(), tuple(k_next.shape))] = (b, done, torch.cuda.is_current_stream_capturing())
+        check(lib().ltm_event_record(ev["pooled"][b], sp), "event_record")
+        self._pref[(k_next.data_ptr(), tuple(k_next.shape))] = (b, ev["pooled"][b],
+                                                                 torch.cuda.is_current_stream_capturing())
+
+    def _sync_events(self):
+        if self._evs is None:
+            def mk():
+                h = C.c_void_p()
+                check(lib().ltm_event_create_sync(C.byref(h)), "event_create_sync")
+                return h
+            self._evs = {"fork_pool": [mk(), mk()], "pooled": [mk(), mk()], "fork": mk(), "join": mk()}
+        return self._evs
 
     def density(self):
         """alphas[Q,Bv,H,768] of the most recent call: the density side-output the Video-LLaMA copy pickles to
@@ -298,11 +316,14 @@ class BatchedRectLTM(_BatchedBase):
         if pooled:
             ws["xi"] = hit[0]
             run = self._compute                      # fork: high-priority compute stream, joined below
-            run.wait_stream(main)
+            ev = self._sync_events()
+            rp, mp = C.c_void_p(run.cuda_stream), C.c_void_p(main.cuda_stream)
+            check(lib().ltm_event_record(ev["fork"], mp), "event_record")
+            check(lib().ltm_stream_wait_event(rp, ev["fork"]), "stream_wait_event")
             # (a graph capture cannot wait on an event recorded before it began: the capturing host has synchronised,
             # and on replay the buffer is the one the previous replay's last prefetch filled)
             if hit[2] or not torch.cuda.is_current_stream_capturing():
-                run.wait_event(hit[1])
+                check(lib().ltm_stream_wait_event(rp, hit[1]), "stream_wait_event")
         else:
             ws["xi"] = ws["xnext"]
             ws["xnext"] = 1 - ws["xnext"]
@@ -310,7 +331,56 @@ class BatchedRectLTM(_BatchedBase):
         check(lib().ltm_rect_step(C.byref(a), None if pooled else ptr(k), ptr(q), ptr(u), ptr(flags), ptr(ctx),
                                   C.c_void_p(run.cuda_stream)), "rect_step")
         if pooled:
-            main.wait_stream(run)
+            check(lib().ltm_event_record(ev["join"], rp), "event_record")
+            check(lib().ltm_stream_wait_event(mp, ev["join"]), "stream_wait_event")
+        self._finish(ws)
+        return ctx
+
+    def step_overlapped(self, k, q, u=None, new_doc=False, k_next=None):
+        """`step(k, ...)` with the frame pooling of `k_next` issued beside it, in ONE library call
+        (`ltm_rect_step_overlap`: side stream pools the next chunk, a high-priority stream runs this chunk's
+        regression / projection / attention, the current stream joins both).  `k` must be the tensor handed over as
+        `k_next` by the previous call (or to `prefetch`); the first chunk of a stream is pooled here.  Same results as
+        `step`, bit for bit."""
+        require_cuda(k, q, u, k_next)
+        if k.dtype != torch.float32 or q.dtype != torch.float32 or (k_next is not None and k_next.dtype != torch.float32):
+            raise ValueError("step_overlapped takes float32 tensors")
+        k, q = k.contiguous(), q.contiguous()
+        Bv, L, Q, tab, tdev, flags = self._prepare(k.shape, q.shape, new_doc)
+        ws = self._workspace(Bv, L, Q)
+        if self.has_state and self.sticky:
+            if u is None or u.dtype != torch.float64 or tuple(u.shape) != (Bv, self.S):
+                raise ValueError(f"sticky re-sampling needs u: float64 [{Bv},{self.S}]")
+            u = u.contiguous()
+        key = (k.data_ptr(), tuple(k.shape))
+        if key not in self._pref:
+            self.prefetch(k, Q)
+        hit = self._pref.pop(key)
+        ev = self._sync_events()
+        main = torch.cuda.current_stream(self.device)
+        capturing = torch.cuda.is_current_stream_capturing()
+        ws["xi"] = hit[0]
+        o = Overlap()
+        o.main_stream, o.side_stream, o.compute_stream = main.cuda_stream, self._side.cuda_stream, self._compute.cuda_stream
+        o.ev_fork, o.ev_join = ev["fork"], ev["join"]
+        o.ev_pooled_cur = hit[1] if (hit[2] or not capturing) else None
+        o.pool_ctas = int(self.pool_ctas)
+        if k_next is not None:
+            k_next = k_next.contiguous()
+            if tuple(k_next.shape) != tuple(k.shape):
+                raise ValueError("k_next must have the shape of k")
+            if len(self._pref) >= 1:
+                raise RuntimeError("at most two chunks may be in flight (the pooled frames are double-buffered)")
+            b = ws["xnext"]
+            ws["xnext"] = 1 - b
+            o.k_next, o.xpart_next = k_next.data_ptr(), ws["xparts"][b].data_ptr()
+            o.ev_fork_pool, o.ev_pooled_next = ev["fork_pool"][b], ev["pooled"][b]
+            k_next.record_stream(self._side)
+            self._pref[(k_next.data_ptr(), tuple(k_next.shape))] = (b, ev["pooled"][b], capturing)
+        ctx = torch.empty(Bv, Q, self.D, device=self.device, dtype=torch.float32)   # main joins the compute stream
+        a = self._args(Bv, L, Q, ws, tab, tdev)
+        check(lib().ltm_rect_step_overlap(C.byref(a), C.byref(o), ptr(q), ptr(u), ptr(flags), ptr(ctx)),
+              "rect_step_overlap")
         self._finish(ws)
         return ctx
 

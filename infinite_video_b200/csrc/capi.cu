@@ -1,6 +1,8 @@
 // C-ABI glue: error reporting, device check, and the fused per-chunk step of variant R.
 #include <stdarg.h>
 
+#include <time.h>
+
 #include "common.cuh"
 
 namespace ltm {
@@ -114,12 +116,77 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
   return rc;
 }
 
+// bring-up: host time spent in the sections of ltm_rect_step_overlap (sum and max, seconds)
+static double g_ov_sum[6] = {0, 0, 0, 0, 0, 0}, g_ov_max[6] = {0, 0, 0, 0, 0, 0};
+static inline double now_s() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+extern "C" void ltm_debug_overlap_times(double* sum6, double* max6, int reset) {
+  for (int i = 0; i < 6; ++i) {
+    if (sum6) sum6[i] = g_ov_sum[i];
+    if (max6) max6[i] = g_ov_max[i];
+    if (reset) g_ov_sum[i] = g_ov_max[i] = 0.0;
+  }
+}
+#define LTM_OV_MARK(i) do { const double t_ = now_s(); const double d_ = t_ - t_prev; g_ov_sum[i] += d_; \
+                            if (d_ > g_ov_max[i]) g_ov_max[i] = d_; t_prev = t_; } while (0)
+
+extern "C" int ltm_rect_step_overlap(const ltm_rect_step_args* a, const ltm_overlap* o, const float* q,
+                                     const double* u, const uint8_t* new_doc, float* ctx) {
+  using namespace ltm;
+  LTM_REQUIRE(a && o && q && ctx, "rect_step_overlap: null pointer");
+  LTM_REQUIRE(o->ev_fork && o->ev_join, "rect_step_overlap: fork / join events missing");
+  cudaStream_t ms = (cudaStream_t)o->main_stream, ss = (cudaStream_t)o->side_stream,
+               cs = (cudaStream_t)o->compute_stream;
+  double t_prev = now_s();
+  if (o->k_next != nullptr) {
+    LTM_REQUIRE(o->xpart_next && o->ev_fork_pool && o->ev_pooled_next, "rect_step_overlap: prefetch target missing");
+    // the target buffer was last read by work already queued on the main stream
+    LTM_CUDA(cudaEventRecord((cudaEvent_t)o->ev_fork_pool, ms));
+    LTM_CUDA(cudaStreamWaitEvent(ss, (cudaEvent_t)o->ev_fork_pool, 0));
+    LTM_OV_MARK(0);
+    if (a->prof_events[0]) cudaEventRecord((cudaEvent_t)a->prof_events[0], ss);
+    int rc = ltm_pool_mean_grid(o->k_next, o->xpart_next, a->Bv, a->L, a->T, a->e, a->splits, o->pool_ctas, ss);
+    if (rc) return rc;
+    if (a->prof_events[1]) cudaEventRecord((cudaEvent_t)a->prof_events[1], ss);
+    LTM_OV_MARK(1);
+    LTM_CUDA(cudaEventRecord((cudaEvent_t)o->ev_pooled_next, ss));
+    LTM_OV_MARK(2);
+  }
+  LTM_CUDA(cudaEventRecord((cudaEvent_t)o->ev_fork, ms));
+  LTM_CUDA(cudaStreamWaitEvent(cs, (cudaEvent_t)o->ev_fork, 0));
+  if (o->ev_pooled_cur) LTM_CUDA(cudaStreamWaitEvent(cs, (cudaEvent_t)o->ev_pooled_cur, 0));
+  LTM_OV_MARK(3);
+  int rc = ltm_rect_step(a, nullptr, q, u, new_doc, ctx, cs);
+  if (rc) return rc;
+  LTM_OV_MARK(4);
+  LTM_CUDA(cudaEventRecord((cudaEvent_t)o->ev_join, cs));
+  LTM_CUDA(cudaStreamWaitEvent(ms, (cudaEvent_t)o->ev_join, 0));
+  LTM_OV_MARK(5);
+  return 0;
+}
+
 extern "C" int ltm_event_create(void** ev) {
   using namespace ltm;
   LTM_REQUIRE(ev != nullptr, "event_create: null pointer");
   cudaEvent_t e;
   LTM_CUDA(cudaEventCreate(&e));
   *ev = (void*)e;
+  return 0;
+}
+extern "C" int ltm_event_create_sync(void** ev) {
+  using namespace ltm;
+  LTM_REQUIRE(ev != nullptr, "event_create_sync: null pointer");
+  cudaEvent_t e;
+  LTM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  *ev = (void*)e;
+  return 0;
+}
+extern "C" int ltm_stream_wait_event(void* stream, void* ev) {
+  using namespace ltm;
+  LTM_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)ev, 0));
   return 0;
 }
 extern "C" int ltm_event_record(void* ev, void* stream) {

@@ -294,6 +294,28 @@ def test_prefetched_pooling_is_bit_identical(dev):
         b.prefetch(ks[0], 32); b.prefetch(ks[1], 32); b.prefetch(ks[2], 32)
 
 
+def test_overlapped_step_is_bit_identical(dev):
+    """`step_overlapped` (one library call: this chunk's kernels on a high-priority stream, the next chunk's frame
+    pooling on a side stream, joined into the caller's stream) == `step`, bit for bit, over a whole stream of chunks,
+    including a second video that starts without a pending prefetch."""
+    from infinite_video_b200.batched import BatchedRectLTM
+    key, val = make_proj(63, 768)
+    a = BatchedRectLTM(256, .75, *proj_tensors(key, val), device=dev)
+    b = BatchedRectLTM(256, .75, *proj_tensors(key, val), device=dev)
+    ks, qs, us = make_inputs(64, 5, 3, 64 * 32, 768, 32)
+    ks = [k.to(dev) for k in ks]
+    qs = [q.to(dev) for q in qs]
+    us = [u.to(dev) for u in us]
+    for rep in range(2):
+        for c in range(5):
+            x = a.step(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0))
+            nxt = ks[c + 1] if c + 1 < 5 else None
+            y = b.step_overlapped(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0), k_next=nxt)
+            assert torch.equal(x, y), f"rep {rep} chunk {c}"
+            assert torch.equal(a.B_past, b.B_past)
+    torch.cuda.synchronize()
+
+
 def test_step_is_cuda_graph_capturable(dev):
     """No host synchronisation / allocation inside a step: a sticky chunk can be captured once and replayed
     (this is how a single-video, launch-bound caller amortises the 5 launches)."""
