@@ -144,6 +144,29 @@ class BatchedRectLTM(_BatchedBase):
 
     # ------------------------------------------------------------------ one chunk
     def _args(self, Bv, L, Q, ws, tab, tdev):
+        # the argument block is built once per workspace / table set / weights and only its per-call fields are
+        # rewritten afterwards (the ~40 ctypes assignments were a third of the host time of a chunk)
+        sig = (id(tdev), self.Wkv.data_ptr(), self.bkv.data_ptr(), self._hist.data_ptr(), self.sticky,
+               self.precision, self.gemm_impl, ws["k_dev"] is None)
+        a = ws.get("_args")
+        if a is None or ws.get("_args_sig") != sig:
+            a = self._args_full(Bv, L, Q, ws, tab, tdev)
+            ws["_args"], ws["_args_sig"], ws["_args_prof"] = a, sig, False
+        a.splits = ws["splits"]
+        a.B_past = self._B[self._cur].data_ptr() if self.has_state else None
+        a.B_new = self._B[1 - self._cur].data_ptr()
+        a.xpart = ws["xparts"][ws["xi"]].data_ptr()
+        if self.prof_events is not None:
+            for i, ev in enumerate(self.prof_events):
+                a.prof_events[i] = ev
+            ws["_args_prof"] = True
+        elif ws["_args_prof"]:
+            for i in range(10):
+                a.prof_events[i] = None
+            ws["_args_prof"] = False
+        return a
+
+    def _args_full(self, Bv, L, Q, ws, tab, tdev):
         a = RectStepArgs()
         a.Bv, a.L, a.T, a.e, a.N, a.Q, a.H, a.d, a.S = Bv, L, self.T, self.e, self.N, Q, self.H, self.d, self.S
         a.splits, a.sticky = ws["splits"], int(self.sticky)
@@ -170,9 +193,6 @@ class BatchedRectLTM(_BatchedBase):
         for f, n in (("k_dev", "k_dev"), ("q_dev", "q_dev"), ("u_dev", "u_dev"), ("new_doc_dev", "nd_dev"),
                      ("ctx_dev", "ctx_dev")):
             setattr(a, f, ws[n].data_ptr() if ws[n] is not None else None)
-        if self.prof_events is not None:
-            for i, ev in enumerate(self.prof_events):
-                a.prof_events[i] = ev
         return a
 
     def _prepare(self, kshape, qshape, new_doc):
@@ -198,8 +218,11 @@ class BatchedRectLTM(_BatchedBase):
         self._cur = 1 - self._cur
         self.has_state = True
         self._last_L = ws["xparts"][0].shape[1]
-        V = ws["V"] if ws["V"] is not None else ws["KV"][:, :, self.D:]
-        self.last = dict(b=ws["b_draw"], ts=ws["ts"], idx=ws["idx"], p=ws["p"], scores=ws["scores"], V=V)
+        last = ws.get("_last")
+        if last is None:
+            V = ws["V"] if ws["V"] is not None else ws["KV"][:, :, self.D:]
+            last = ws["_last"] = dict(b=ws["b_draw"], ts=ws["ts"], idx=ws["idx"], p=ws["p"], scores=ws["scores"], V=V)
+        self.last = last
 
     def prefetch(self, k_next, Q, events=None):
         """Pool the frames of the NEXT chunk now, on a side stream, into the alternate buffer.
