@@ -696,7 +696,7 @@ def main():
     ap.add_argument("--cluster", action="store_true", help="use the 2-CTA TMA-multicast variant of the GEMM")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gauss", action="store_true", help="skip the secondary Gaussian-variant measurement")
-    ap.add_argument("--gauss-videos", type=int, default=32)
+    ap.add_argument("--gauss-videos", type=int, default=128)
     ap.add_argument("--gauss-frames", type=int, default=256, help="Lk of the Gaussian arm (k is consumed un-pooled)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

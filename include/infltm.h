@@ -59,9 +59,10 @@ int ltm_density_rect(const float* scores, const int32_t* jd, const float* wd, fl
                      int Bv, int H, int Q, int N, void* stream);
 
 /* ---- G3: sticky histogram from the previous (mu, sigma).  long_term_attention.py:220-229.
- * mu,sd[Bv,R] -> hist[Bv,128] (un-normalised). */
-int ltm_sticky_hist_gauss(const float* mu, const float* sd, const float* tb, float* hist,
-                          int Bv, int R, void* stream);
+ * mu,sd[Bv,R] -> hist_part[Bv,parts,128] (un-normalised): part p sums a contiguous share of the R rows;
+ * ltm_resample adds the parts in a fixed order. */
+int ltm_sticky_hist_gauss(const float* mu, const float* sd, const float* tb, float* hist_part,
+                          int Bv, int R, int parts, void* stream);
 
 /* ---- R7/G3: inverse-CDF re-sampling == Categorical(p).sample((S,)) with explicit uniforms.
  * gibbs:204-208, gauss:230-238.  hist_part[Bv,parts,ncat] is summed over `parts` in a fixed

@@ -72,7 +72,7 @@ _SIGS = {
     "ltm_pool_mean_grid": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ltm_sticky_hist_rect": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ltm_density_rect": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
-    "ltm_sticky_hist_gauss": (C.c_int, [_P, _P, _P, _P, _I, _I, _P]),
+    "ltm_sticky_hist_gauss": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "ltm_resample": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _P]),
     "ltm_consolidate_rect": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ltm_gemm": (C.c_int, [C.POINTER(GemmArgs), _P]),

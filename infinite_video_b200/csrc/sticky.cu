@@ -45,24 +45,34 @@ sticky_hist_rect_kernel(const float* __restrict__ scores, const int32_t* __restr
 
 // ------------------------------------------------------------------------------------------------
 // Gaussian variant histogram: p_i = sum_r Phi((tb_{i+1}-mu_r)/sd_r) - Phi((tb_i-mu_r)/sd_r), i<128
-// (Normal.cdf of torch: 0.5*(1+erf((x-loc)*(1/scale)/sqrt(2)))).  One CTA per video.
+// (Normal.cdf of torch: 0.5*(1+erf((x-loc)*(1/scale)/sqrt(2)))).  grid (video, part): each CTA sums a
+// contiguous share of the R rows (in order) into its own partial histogram -- the re-sampling kernel adds the
+// partials in a fixed order -- and thread i evaluates the CDF at EDGE i once per row: the upper edge of
+// interval i is the lower edge of interval i+1 (one erff per edge instead of two per interval).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+constexpr int HG_THREADS = 160;              // 129 edges
+__global__ void __launch_bounds__(HG_THREADS)
 sticky_hist_gauss_kernel(const float* __restrict__ mu, const float* __restrict__ sd,
-                         const float* __restrict__ tb, float* __restrict__ hist, int R) {
-  const int v = blockIdx.x;
-  const int i = threadIdx.x;               // interval 0..127
-  const float lo = tb[i], hi = tb[i + 1];
+                         const float* __restrict__ tb, float* __restrict__ hist_part, int R, int parts) {
+  __shared__ float phi[2][EDGES + 3];
+  const int v = blockIdx.x, pt = blockIdx.y;
+  const int i = threadIdx.x;               // edge 0..128 (threads beyond idle), interval 0..127
+  const int per = (R + parts - 1) / parts;
+  const int r0 = pt * per, r1 = min(R, r0 + per);
+  const float edge = (i < EDGES) ? tb[i] : 0.f;
   const float* m = mu + (size_t)v * R;
   const float* s = sd + (size_t)v * R;
   float acc = 0.f;
-  for (int r = 0; r < R; ++r) {
-    const float inv = __frcp_rn(s[r]);
-    const float chi = 0.5f * (1.f + erff(__fdiv_rn((hi - m[r]) * inv, 1.4142135623730951f)));
-    const float clo = 0.5f * (1.f + erff(__fdiv_rn((lo - m[r]) * inv, 1.4142135623730951f)));
-    acc += chi - clo;
+  for (int r = r0; r < r1; ++r) {
+    float* ph = phi[(r - r0) & 1];
+    if (i < EDGES) {
+      const float inv = __frcp_rn(s[r]);
+      ph[i] = 0.5f * (1.f + erff(__fdiv_rn((edge - m[r]) * inv, 1.4142135623730951f)));
+    }
+    __syncthreads();                       // (the other buffer is rewritten only after the next barrier)
+    if (i < EDGES - 1) acc += ph[i + 1] - ph[i];
   }
-  hist[(size_t)v * (EDGES - 1) + i] = acc;
+  if (i < EDGES - 1) hist_part[((size_t)v * parts + pt) * (EDGES - 1) + i] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -255,12 +265,14 @@ extern "C" int ltm_sticky_hist_rect(const float* scores, const int32_t* jb, cons
   return 0;
 }
 
-extern "C" int ltm_sticky_hist_gauss(const float* mu, const float* sd, const float* tb, float* hist,
-                                     int Bv, int R, void* stream) {
+extern "C" int ltm_sticky_hist_gauss(const float* mu, const float* sd, const float* tb, float* hist_part,
+                                     int Bv, int R, int parts, void* stream) {
   using namespace ltm;
-  LTM_REQUIRE(mu && sd && tb && hist, "sticky_hist_gauss: null pointer");
-  LTM_REQUIRE(Bv > 0 && R > 0, "sticky_hist_gauss: bad shape");
-  sticky_hist_gauss_kernel<<<Bv, EDGES - 1, 0, (cudaStream_t)stream>>>(mu, sd, tb, hist, R);
+  LTM_REQUIRE(mu && sd && tb && hist_part, "sticky_hist_gauss: null pointer");
+  LTM_REQUIRE(Bv > 0 && Bv <= 2147483647 && R > 0 && parts >= 1 && parts <= 65535 && parts <= R,
+              "sticky_hist_gauss: bad shape");
+  sticky_hist_gauss_kernel<<<dim3(Bv, parts), HG_THREADS, 0, (cudaStream_t)stream>>>(mu, sd, tb, hist_part, R,
+                                                                                       parts);
   LTM_CHECK_LAUNCH("sticky_hist_gauss");
   return 0;
 }

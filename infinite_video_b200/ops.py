@@ -66,13 +66,15 @@ def density_rect(scores, jd, wd):
     return out
 
 
-def sticky_hist_gauss(mu, sd, tb):
-    """mu,sd[Bv,R] -> hist[Bv,128].  long_term_attention.py:220-229."""
+def sticky_hist_gauss(mu, sd, tb, parts=None):
+    """mu,sd[Bv,R] -> hist_part[Bv,parts,128] (feed to `resample`).  long_term_attention.py:220-229."""
     require_cuda(mu, sd, tb)
     mu, sd = _f32c(mu), _f32c(sd)
     Bv, R = mu.shape
-    out = torch.empty(Bv, STICKY_EDGES - 1, device=mu.device, dtype=torch.float32)
-    check(lib().ltm_sticky_hist_gauss(ptr(mu), ptr(sd), ptr(tb), ptr(out), Bv, R, stream_ptr(mu.device)),
+    if parts is None:
+        parts = max(1, min(8, R // 48))          # ~48 rows per CTA: 8 CTAs per video at R = H*Q = 384
+    out = torch.empty(Bv, parts, STICKY_EDGES - 1, device=mu.device, dtype=torch.float32)
+    check(lib().ltm_sticky_hist_gauss(ptr(mu), ptr(sd), ptr(tb), ptr(out), Bv, R, parts, stream_ptr(mu.device)),
           "sticky_hist_gauss")
     return out
 
