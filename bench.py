@@ -250,6 +250,8 @@ def run_b200(args):
     _capi.check(lib.ltm_device_check(), "device_check")
     if args.cluster:
         lib.ltm_debug_set_cluster(2)
+    if args.pair:
+        lib.ltm_debug_set_pair(1)
     Bv, C = args.videos, args.chunks
     torch.manual_seed(0)
     key, val = torch.nn.Linear(E, D), torch.nn.Linear(E, D)
@@ -688,6 +690,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="do not pool chunk c+1 under chunk c's compute")
     ap.add_argument("--pool-ctas-per-sm", type=int, default=0, help="grid bound of the prefetch pooling kernel")
+    ap.add_argument("--pair", action="store_true", help="K/V projection on the CTA-pair (cta_group::2) GEMM kernel")
     ap.add_argument("--repeats", type=int, default=3, help="timed regions of K steps each; the fastest is reported")
     ap.add_argument("--graph", action="store_true",
                     help="also time the K steps replayed from one CUDA graph per step (measured: 160 k vs 175 k eager -- "

@@ -732,11 +732,10 @@ static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 // 2 enables the 2-CTA multicast variant.  Measured on B200 (profiles/r1e): no gain over unicast -- the kernel is
 // bound by per-SM ingest (~38 B/clk/SM), not by L2 reads -- so it is off by default and kept as a tested option.
 static int g_cluster = 1;
-// 1 selects the CTA-pair (tcgen05 cta_group::2) kernel for problems with at least two row tiles.  Measured on
-// B200 (profiles/r1f_gemm_variants.txt): same time as the single-CTA kernel in precision 1 although it ingests a
-// third fewer bytes, slower in precision 3 -- all variants sit at 46-49 % tensor-pipe activity because fp32
-// operands make shared-memory bandwidth (TMA write + MMA read of every byte) the limit.  Off by default.
-static int g_pair = 0;
+// CTA-pair (tcgen05 cta_group::2) kernel for problems with at least two row tiles: -1 = automatic (single-pass
+// TF32 only: 130 vs 135 us on the K/V projection and one third fewer operand bytes ingested per SM, which the
+// frame pooling running beside it can use; in split-TF32 the pair is slower, 384 vs 358 us), 0 = never, 1 = always.
+static int g_pair = -1;
 static int g_dbg = 0;
 static unsigned g_mn_desc[5] = {1u, (unsigned)SLAB_BYTES, 512u, 1024u, (unsigned)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B};
 
@@ -886,7 +885,7 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   const int K1 = two ? a.K1 : a.K;
   CUtensorMap mA, mB, mB2;
   if (encode_operand(&mA, a.A, a.M, a.K, a.lda, a.strideA, a.batch, a.a_kmajor, BM, "A")) return -1;
-  const bool pair = g_pair != 0 && a.M > BM;                    // CTA pairs need two row tiles
+  const bool pair = (g_pair > 0 || (g_pair < 0 && !split)) && a.M > BM;        // CTA pairs need two row tiles
   const bool mc_pre = !pair && g_cluster >= 2 && a.b_kmajor && !two && a.M > BM;
   const int b_box = (pair || mc_pre) ? bn / 2 : bn;             // B rows fetched per TMA box
   if (encode_operand(&mB, a.B, a.Nc, K1, a.ldb, a.strideB, a.batch, a.b_kmajor, b_box, "B")) return -1;
