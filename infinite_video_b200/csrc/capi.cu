@@ -116,6 +116,27 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
   return rc;
 }
 
+// bring-up: a persistent kernel with a chosen footprint (threads, <= 96 registers, dynamic shared memory) that only
+// spins for `us` microseconds: measures what a co-resident footprint alone costs the streaming kernels beside it
+__global__ void __maxnreg__(96) footprint_spin_kernel(unsigned long long ns, float* sink) {
+  extern __shared__ float fs[];
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  if (threadIdx.x == 0) fs[0] = 1.f;
+  do {
+    __nanosleep(200);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+  } while (t1 - t0 < ns);
+  if (sink != nullptr && threadIdx.x == 0 && fs[0] == 2.f) sink[0] = 1.f;
+}
+extern "C" int ltm_debug_footprint_spin(int ctas, int threads, int smem_bytes, int us, void* stream) {
+  using namespace ltm;
+  LTM_CUDA(cudaFuncSetAttribute(footprint_spin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  footprint_spin_kernel<<<ctas, threads, smem_bytes, (cudaStream_t)stream>>>((unsigned long long)us * 1000ull, nullptr);
+  LTM_CHECK_LAUNCH("footprint_spin");
+  return 0;
+}
+
 // bring-up: host time spent in the sections of ltm_rect_step_overlap (sum and max, seconds)
 static double g_ov_sum[6] = {0, 0, 0, 0, 0, 0}, g_ov_max[6] = {0, 0, 0, 0, 0, 0};
 static inline double now_s() {
