@@ -502,8 +502,8 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": value, "unit": "chunks/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (tf32 tensor-core products for the K/V projection, fp32 accumulate)"
-            if args.precision == "tf32" else "f32 (split-tf32 x3 tensor-core products, fp32 accumulate)",
+            "vs_baseline": None, "dtype": "f32 (tf32 tensor-core products for the K/V projection and the two attention contractions, fp32 accumulate)"
+            if args.precision == "tf32" else "f32 (split-tf32 x3 tensor-core projection, fp32 FMA attention)",
             "data": "synthetic", "config": workload_config(Bv, C, "gibbs", overlap),
             "frame_blocks_per_s": value * L,
             "roofline": {"bound": "hbm", "kernel": "pool_mean_kernel", "achieved": pool_gbs, "peak": peak,
