@@ -86,6 +86,13 @@ int ltm_consolidate_rect(const float* B_past, const float* xpart, const int32_t*
                          const int32_t* seg_ptr0, const int32_t* seg_mem0, const float* g0,
                          const int32_t* seg_ptr1, const int32_t* seg_mem1, const float* g1,
                          float* B_new, int Bv, int N, int e, int L, int splits, int S, void* stream);
+/* same, additionally writing B_new as IEEE fp16 to B_half[Bv,N,e] (round to nearest; NULL = off): the operand of
+ * the fp16 K/V projection (ltm_gemm ab_fp16) */
+int ltm_consolidate_rect_h(const float* B_past, const float* xpart, const int32_t* idx,
+                           const uint8_t* new_doc,
+                           const int32_t* seg_ptr0, const int32_t* seg_mem0, const float* g0,
+                           const int32_t* seg_ptr1, const int32_t* seg_mem1, const float* g1,
+                           float* B_new, void* B_half, int Bv, int N, int e, int L, int splits, int S, void* stream);
 
 /* ---- batched GEMM on tcgen05 tensor cores (kind::tf32, fp32 operands fed by TMA, fp32
  * accumulate in TMEM).  C[b] (M x Nc, ldc) = A[b] (M x K) * B[b] (K x Nc) (+ bias[Nc]).
@@ -117,6 +124,10 @@ typedef struct {
   /* != 0: round the stored row-major results to the tf32 grid (round to nearest), for products that feed another
    * tf32 tensor-core contraction (the tensor core itself would truncate, which biases sums of products) */
   int round_tf32;
+  /* != 0: A, B (and B2) point to IEEE fp16 data (leading dimensions / strides in elements, multiples of 8), both
+   * K-major; the products run as kind::f16 UMMAs with fp32 accumulation -- the same 11-bit significand as tf32 at
+   * half the operand bytes and twice the MMA rate, for operands whose range fits fp16 (precision must be 1) */
+  int ab_fp16;
 } ltm_gemm_args;
 int ltm_gemm(const ltm_gemm_args* args, void* stream);
 
@@ -219,6 +230,10 @@ typedef struct {
   void* prof_events[10];
   /* tensor-core attention (used when X != NULL, KV != NULL, precision == 1 and ltm_attn_tc_supported(N, d)) */
   const float* X; float c_none;
+  /* fp16 operands of the K/V projection (used with the tensor-core attention when both are set): B_half[Bv,N,e]
+   * workspace (written by the consolidation), Wkv_half[2D,e] = Wkv in fp16.  Coefficients beyond the fp16 range
+   * (|B| > 65504) become inf and propagate visibly; leave NULL for fp32 (tf32) operands. */
+  void* B_half; const void* Wkv_half;
 } ltm_rect_step_args;
 int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const float* q, const double* u,
                   const uint8_t* new_doc, float* ctx, void* stream);

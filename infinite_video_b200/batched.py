@@ -81,7 +81,8 @@ class BatchedRectLTM(_BatchedBase):
 
     def __init__(self, num_basis, tau, w_key, b_key, w_value, b_value, *, n_heads=12, head_size=64,
                  tokens_per_frame=32, sticky=True, nb_samples=tables.NB_SAMPLES, precision="tf32",
-                 gemm_impl="tcgen05", device="cuda", keep_scores=False, fast_attn=True, tc_attn=True):
+                 gemm_impl="tcgen05", device="cuda", keep_scores=False, fast_attn=True, tc_attn=True,
+                 proj_operands="fp32"):
         super().__init__(num_basis, tau, w_key, b_key, w_value, b_value, n_heads, head_size, sticky, nb_samples,
                          precision, gemm_impl, device)
         self.T = int(tokens_per_frame)
@@ -91,6 +92,14 @@ class BatchedRectLTM(_BatchedBase):
         # tensor-core attention (csrc/attn_tc.cu): num_basis 128/256, head size 64, single-pass tf32 projection
         self.tc_attn = (bool(tc_attn) and bool(fast_attn) and precision == "tf32" and gemm_impl == "tcgen05"
                         and ops.attn_tc_supported(self.N, self.d))
+        # operands of the K/V projection on the tensor-core path: "fp32" (default: tf32 UMMAs straight from the fp32
+        # tensors) or "fp16" (coefficients and weights rounded to fp16: tf32's 11-bit significand at half the bytes
+        # and twice the MMA rate -- projection 0.134 -> 0.108 ms, serial step +3 %, overlapped step +0.7 % at 128
+        # videos -- but coefficients beyond 65504 turn into inf, which is why it is opt-in)
+        if proj_operands not in ("fp16", "fp32"):
+            raise ValueError("proj_operands must be 'fp16' or 'fp32'")
+        self.half_ops = self.tc_attn and proj_operands == "fp16" and self.e % 8 == 0
+        self._Wkv_h = None
         self.prof_events = None       # optional list of 10 cudaEvent_t handles (bench.py stage timing)
         self._side = None             # side stream for pooling the next chunk ahead of time
         self._pref = {}               # pending prefetches: (data_ptr, shape) -> (buffer index, done event)
@@ -123,6 +132,7 @@ class BatchedRectLTM(_BatchedBase):
                 b_draw=torch.empty(Bv, self.S, **i32), idx=torch.empty(Bv, self.S, **i32),
                 ts=torch.empty(Bv, self.S, **f32), p=torch.empty(Bv, 127, **f32),
                 scores=torch.empty(Bv, self.H, Q, self.N, **f32) if self.keep_scores else None,
+                B_half=torch.empty(Bv, self.N, self.e, device=dev, dtype=torch.float16) if self.half_ops else None,
                 k_dev=None, q_dev=None, u_dev=None, nd_dev=None, ctx_dev=None,
             )
             self._ws = {key: ws}          # one live shape at a time
@@ -180,6 +190,10 @@ class BatchedRectLTM(_BatchedBase):
                 raise RuntimeError("tensor-core attention needs a quadrature point in every basis (tc_attn=False)")
             a.X, a.c_none = tdev["X"].data_ptr(), tab.c_none
         a.Wkv, a.bkv = self.Wkv.data_ptr(), self.bkv.data_ptr()
+        if self.half_ops:
+            if self._Wkv_h is None or self._Wkv_h_src != self.Wkv.data_ptr():
+                self._Wkv_h, self._Wkv_h_src = self.Wkv.to(torch.float16).contiguous(), self.Wkv.data_ptr()
+            a.B_half, a.Wkv_half = ws["B_half"].data_ptr(), self._Wkv_h.data_ptr()
         a.B_past = self._B[self._cur].data_ptr() if self.has_state else None
         a.B_new = self._B[1 - self._cur].data_ptr()
         a.hist_part = self._hist.data_ptr()

@@ -81,16 +81,28 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
     idx = a->idx;
   }
   LTM_PROF(4);
-  rc = ltm_consolidate_rect(B_past, a->xpart, idx, new_doc, a->seg_ptr0, a->seg_mem0, a->g0, a->seg_ptr1,
-                            a->seg_mem1, a->g1, a->B_new, a->Bv, a->N, a->e, a->L, a->splits, a->S, stream);
-  if (rc) return rc;
-  LTM_PROF(5);
-  LTM_PROF(6);
   // tensor-core attention: row-major tf32-rounded K|V from the projection, both attention contractions as UMMAs
   const bool tcp = a->X != nullptr && a->KV != nullptr && a->precision == 1 && a->gemm_impl == 0 &&
                    ltm_attn_tc_supported(a->N, a->d);
+  const bool half_ops = tcp && a->B_half != nullptr && a->Wkv_half != nullptr && a->e % 8 == 0;
+  rc = ltm_consolidate_rect_h(B_past, a->xpart, idx, new_doc, a->seg_ptr0, a->seg_mem0, a->g0, a->seg_ptr1,
+                              a->seg_mem1, a->g1, a->B_new, half_ops ? a->B_half : nullptr, a->Bv, a->N, a->e, a->L,
+                              a->splits, a->S, stream);
+  if (rc) return rc;
+  LTM_PROF(5);
+  LTM_PROF(6);
   const bool fast = !tcp && a->Kt != nullptr && a->V != nullptr && ltm_attn_fast_supported(a->N, a->d);
-  if (tcp)
+  if (half_ops) {
+    ltm_gemm_args ga;
+    memset(&ga, 0, sizeof(ga));
+    ga.A = reinterpret_cast<const float*>(a->B_half); ga.lda = a->e; ga.a_kmajor = 1;
+    ga.B = reinterpret_cast<const float*>(a->Wkv_half); ga.ldb = a->e; ga.b_kmajor = 1;
+    ga.K1 = a->e; ga.bias = a->bkv;
+    ga.C = a->KV; ga.ldc = 2 * D;
+    ga.M = a->Bv * a->N; ga.Nc = 2 * D; ga.K = a->e; ga.batch = 1;
+    ga.precision = 1; ga.impl = 0; ga.round_tf32 = 1; ga.ab_fp16 = 1;
+    rc = ltm_gemm(&ga, stream);
+  } else if (tcp)
     rc = ltm_project_kv_r(a->B_new, a->Wkv, a->bkv, a->KV, a->Bv * a->N, a->e, 2 * D, a->precision, a->gemm_impl,
                           stream);
   else if (fast)

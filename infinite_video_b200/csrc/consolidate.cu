@@ -6,6 +6,8 @@
 // fall into bin j: contracted re-samples of the old memory -- rows of B_past gathered through the
 // sticky sample indices, i.e. the one-hot product B_past^T Psi^T of :208-210 -- followed by the
 // new pooled frames.  One CTA produces one coefficient row; one thread one 128-bit column group.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace ltm {
@@ -17,7 +19,8 @@ consolidate_rect_kernel(const float4* __restrict__ B_past, const float4* __restr
                         const float* __restrict__ g0,
                         const int32_t* __restrict__ seg_ptr1, const int32_t* __restrict__ seg_mem1,
                         const float* __restrict__ g1,
-                        float4* __restrict__ B_new, int N, int e4, int L, int splits, int S) {
+                        float4* __restrict__ B_new, uint2* __restrict__ B_half, int N, int e4, int L, int splits,
+                        int S) {
   const int j = blockIdx.x;
   const int v = blockIdx.y;
   const bool first = (B_past == nullptr) || (new_doc != nullptr && new_doc[v] != 0);
@@ -43,6 +46,13 @@ consolidate_rect_kernel(const float4* __restrict__ B_past, const float4* __restr
     }
     acc.x *= g; acc.y *= g; acc.z *= g; acc.w *= g;
     B_new[((size_t)v * N + j) * e4 + c] = acc;
+    if (B_half != nullptr) {                    // fp16 copy: operand of the K/V projection (kind::f16 UMMAs)
+      const __half2 lo = __floats2half2_rn(acc.x, acc.y), hi = __floats2half2_rn(acc.z, acc.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+      B_half[((size_t)v * N + j) * e4 + c] = pk;
+    }
   }
 }
 
@@ -66,7 +76,18 @@ extern "C" int ltm_consolidate_rect(const float* B_past, const float* xpart, con
                                     const int32_t* seg_ptr0, const int32_t* seg_mem0, const float* g0,
                                     const int32_t* seg_ptr1, const int32_t* seg_mem1, const float* g1,
                                     float* B_new, int Bv, int N, int e, int L, int splits, int S, void* stream) {
+  return ltm_consolidate_rect_h(B_past, xpart, idx, new_doc, seg_ptr0, seg_mem0, g0, seg_ptr1, seg_mem1, g1, B_new,
+                                nullptr, Bv, N, e, L, splits, S, stream);
+}
+
+extern "C" int ltm_consolidate_rect_h(const float* B_past, const float* xpart, const int32_t* idx,
+                                      const uint8_t* new_doc,
+                                      const int32_t* seg_ptr0, const int32_t* seg_mem0, const float* g0,
+                                      const int32_t* seg_ptr1, const int32_t* seg_mem1, const float* g1,
+                                      float* B_new, void* B_half, int Bv, int N, int e, int L, int splits, int S,
+                                      void* stream) {
   using namespace ltm;
+  LTM_REQUIRE(B_half == nullptr || (reinterpret_cast<uintptr_t>(B_half) & 7u) == 0, "consolidate_rect: B_half alignment");
   LTM_REQUIRE(xpart && B_new && seg_ptr0 && seg_mem0 && g0, "consolidate_rect: null pointer");
   LTM_REQUIRE(B_past == nullptr || (idx && seg_ptr1 && seg_mem1 && g1),
               "consolidate_rect: update tables / sample indices missing");
@@ -80,7 +101,8 @@ extern "C" int ltm_consolidate_rect(const float* B_past, const float* xpart, con
   dim3 grid(N, Bv);
   consolidate_rect_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4*>(B_past), reinterpret_cast<const float4*>(xpart), idx, new_doc,
-      seg_ptr0, seg_mem0, g0, seg_ptr1, seg_mem1, g1, reinterpret_cast<float4*>(B_new), N, e4, L, splits, S);
+      seg_ptr0, seg_mem0, g0, seg_ptr1, seg_mem1, g1, reinterpret_cast<float4*>(B_new),
+      reinterpret_cast<uint2*>(B_half), N, e4, L, splits, S);
   LTM_CHECK_LAUNCH("consolidate_rect");
   return 0;
 }

@@ -45,6 +45,7 @@ struct GemmDev {
   int ct_cols, ct_group;
   int c_group;
   long long c_group_stride, bias_stride;
+  int ab_half;                              // operands are fp16 (kind::f16, 64 K-elements per 128-byte row)
   int round_tf32;                           // round stored row-major results to the tf32 grid
   int c_vec;                                // row-major stores may be 128-bit (alignment checked on the host)
   int dbg;                                  // bring-up only: 1 = no global stores, 2 = no TMA loads
@@ -263,7 +264,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_al + C_::RING_BYTES + STG_BYTES + 8 * (3 * STAGES + 6));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb = (g.K + BK - 1) / BK;
+  const int bke = g.ab_half ? 2 * BK : BK;        // K-elements per 128-byte swizzle row
+  const int num_kb = (g.K + bke - 1) / bke;
   const int tiles_n = (g.Nc + BN - 1) / BN, tiles_m = (g.M + BM - 1) / BM;
   // static work list shared by all roles (see decode_work)
   const int crank = (CLUSTER > 1) ? (int)(blockIdx.x % CLUSTER) : 0;
@@ -315,7 +317,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           mbar_arrive_expect_tx(full_bar(s), A_BYTES + C_::B_BYTES);
           const uint32_t sa = smem_base + s * C_::STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
-          const int k0 = kb * BK;
+          const int k0 = kb * bke;
           if (g.a_kmajor) {
             tma_load_3d(&mapA, sa, full_bar(s), k0, m0, za);
           } else {
@@ -349,7 +351,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (lane == 0) {
       // instruction descriptor: D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2, a_major bit15,
       // b_major bit16 (1 = MN-major), N>>3 [17,23), M>>4 [24,29)
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((g.a_kmajor ? 0u : 1u) << 15) |
+      const uint32_t fmt = g.ab_half ? 0u : 2u;         // operand format: 0 = f16 (kind::f16), 2 = tf32
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((g.a_kmajor ? 0u : 1u) << 15) |
                              ((g.b_kmajor ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
       const MnDesc mn{g.mn_layout, g.mn_lbo, g.mn_sbo, g.mn_kadv};
@@ -372,7 +375,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           uint32_t dal = dal0 + lob, dbl = dbl0 + lob;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            tcgen05_mma_tf32(tmem_acc, da, wa.hi, db, wb.hi, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (g.ab_half) tcgen05_mma_f16(tmem_acc, da, wa.hi, db, wb.hi, idesc, (kb | k) != 0 ? 1u : 0u);
+            else tcgen05_mma_tf32(tmem_acc, da, wa.hi, db, wb.hi, idesc, (kb | k) != 0 ? 1u : 0u);
             if (SPLIT) {
               tcgen05_mma_tf32(tmem_acc, dal, wa.hi, db, wb.hi, idesc, 1u);
               tcgen05_mma_tf32(tmem_acc, da, wa.hi, dbl, wb.hi, idesc, 1u);
@@ -512,6 +516,17 @@ __device__ __forceinline__ void tcgen05_mma_tf32_pair(uint32_t tmem_d, uint32_t 
       ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tcgen05_mma_f16_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                     uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {     // arrives in both CTAs of the pair
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"((uint16_t)3) : "memory");
@@ -553,7 +568,8 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = blockIdx.x & 1u;
   const bool leader = crank == 0;
-  const int num_kb = (g.K + BK - 1) / BK;
+  const int bke = g.ab_half ? 2 * BK : BK;        // K-elements per 128-byte swizzle row
+  const int num_kb = (g.K + bke - 1) / bke;
   const int tiles_n = (g.Nc + BN - 1) / BN, tiles_m = (g.M + BM - 1) / BM;
   const int w_first = blockIdx.x >> 1, w_stride = gridDim.x >> 1;
   const int num_work = tiles_n * ((tiles_m + 1) / 2) * g.batch;
@@ -611,7 +627,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           }
           const uint32_t sa = smem_base + s * C_::STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
-          const int k0 = kb * BK;
+          const int k0 = kb * bke;
           if (g.a_kmajor) {
             tma_load_3d_pair(&mapA, sa, bar, k0, m0, za);
           } else {
@@ -635,7 +651,8 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (leader && lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((g.a_kmajor ? 0u : 1u) << 15) |
+      const uint32_t fmt = g.ab_half ? 0u : 2u;         // operand format: 0 = f16 (kind::f16), 2 = tf32
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((g.a_kmajor ? 0u : 1u) << 15) |
                              ((g.b_kmajor ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)((2 * BM) >> 4) << 24);                       // M = 256 across the pair
       const MnDesc mn{g.mn_layout, g.mn_lbo, g.mn_sbo, g.mn_kadv};
@@ -658,7 +675,8 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           uint32_t dal = dal0 + lob, dbl = dbl0 + lob;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            tcgen05_mma_tf32_pair(tmem_acc, da, wa.hi, db, wb.hi, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (g.ab_half) tcgen05_mma_f16_pair(tmem_acc, da, wa.hi, db, wb.hi, idesc, (kb | k) != 0 ? 1u : 0u);
+            else tcgen05_mma_tf32_pair(tmem_acc, da, wa.hi, db, wb.hi, idesc, (kb | k) != 0 ? 1u : 0u);
             if (SPLIT) {
               tcgen05_mma_tf32_pair(tmem_acc, dal, wa.hi, db, wb.hi, idesc, 1u);
               tcgen05_mma_tf32_pair(tmem_acc, da, wa.hi, dbl, wb.hi, idesc, 1u);
@@ -753,7 +771,23 @@ static int resolve_encode() {
 // rows x K operand.  kmajor: memory [rows][K] -> dims {K, rows, batch}, box {32, box_rows, 1};
 // otherwise memory [K][rows] -> dims {rows, K, batch}, box {32, 32, 1}.
 static int encode_operand(CUtensorMap* map, const float* base, int rows, int K, long long ld, long long bstride,
-                          int batch, int kmajor, int box_rows, const char* what) {
+                          int batch, int kmajor, int box_rows, const char* what, int half = 0) {
+  if (half) {
+    // fp16 operand, K-major only: memory [rows][K] halves -> dims {K, rows, batch}, box {64, box_rows, 1}
+    LTM_REQUIRE(kmajor, "gemm: fp16 operands must be K-major (%s)", what);
+    LTM_REQUIRE(aligned16(base) && ld % 8 == 0 && ld >= K && bstride % 8 == 0,
+                "gemm: fp16 %s needs a 16-byte aligned base and pitches that are multiples of 8 elements", what);
+    const int nbh = (bstride == 0) ? 1 : batch;
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)nbh};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2ull, (cuuint64_t)((bstride == 0 ? ld * (long long)rows : bstride) * 2ll)};
+    cuuint32_t box[3] = {64u, (cuuint32_t)box_rows, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<float*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LTM_REQUIRE(r == CUDA_SUCCESS, "gemm: cuTensorMapEncodeTiled(%s, fp16) failed with CUresult %d", what, (int)r);
+    return 0;
+  }
   LTM_REQUIRE(aligned16(base), "gemm: %s base pointer must be 16-byte aligned", what);
   LTM_REQUIRE(ld % 4 == 0 && ld > 0, "gemm: %s leading dimension %lld must be a positive multiple of 4", what, ld);
   LTM_REQUIRE(bstride % 4 == 0, "gemm: %s batch stride %lld must be a multiple of 4", what, bstride);
@@ -878,19 +912,23 @@ static int launch_pair(const CUtensorMap& mA, const CUtensorMap& mB, const CUten
 static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   if (resolve_encode()) return -1;
   const bool two = a.B2 != nullptr && a.K1 < a.K;
-  LTM_REQUIRE(!two || (a.K1 > 0 && a.K1 % BK == 0), "gemm: K1=%d must be a positive multiple of %d", a.K1, BK);
+  const int half = a.ab_fp16 ? 1 : 0;
+  const int bke = half ? 2 * BK : BK;
+  LTM_REQUIRE(!two || (a.K1 > 0 && a.K1 % bke == 0), "gemm: K1=%d must be a positive multiple of %d", a.K1, bke);
+  LTM_REQUIRE(!half || (a.precision == 1 && a.a_kmajor && a.b_kmajor),
+              "gemm: fp16 operands need precision 1 and K-major A and B");
   LTM_REQUIRE(a.precision == 1 || a.precision == 3, "gemm: precision must be 1 (tf32) or 3 (split tf32)");
   const bool split = a.precision == 3;
   const int bn = (a.Nc > 128) ? 256 : 128;
   const int K1 = two ? a.K1 : a.K;
   CUtensorMap mA, mB, mB2;
-  if (encode_operand(&mA, a.A, a.M, a.K, a.lda, a.strideA, a.batch, a.a_kmajor, BM, "A")) return -1;
+  if (encode_operand(&mA, a.A, a.M, a.K, a.lda, a.strideA, a.batch, a.a_kmajor, BM, "A", half)) return -1;
   const bool pair = (g_pair > 0 || (g_pair < 0 && !split)) && a.M > BM;        // CTA pairs need two row tiles
   const bool mc_pre = !pair && g_cluster >= 2 && a.b_kmajor && !two && a.M > BM;
   const int b_box = (pair || mc_pre) ? bn / 2 : bn;             // B rows fetched per TMA box
-  if (encode_operand(&mB, a.B, a.Nc, K1, a.ldb, a.strideB, a.batch, a.b_kmajor, b_box, "B")) return -1;
+  if (encode_operand(&mB, a.B, a.Nc, K1, a.ldb, a.strideB, a.batch, a.b_kmajor, b_box, "B", half)) return -1;
   if (two) {
-    if (encode_operand(&mB2, a.B2, a.Nc, a.K - K1, a.ldb2, a.strideB2, a.batch, a.b_kmajor, b_box, "B2")) return -1;
+    if (encode_operand(&mB2, a.B2, a.Nc, a.K - K1, a.ldb2, a.strideB2, a.batch, a.b_kmajor, b_box, "B2", half)) return -1;
   } else {
     mB2 = mB;
   }
@@ -903,6 +941,7 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   d.mn_layout = g_mn_desc[0]; d.mn_lbo = g_mn_desc[1]; d.mn_sbo = g_mn_desc[2]; d.mn_kadv = g_mn_desc[3];
   d.dbg = g_dbg;
   d.round_tf32 = a.round_tf32;
+  d.ab_half = half;
   d.c_vec = (a.ldc % 4 == 0 && a.strideC % 4 == 0 && a.c_group_stride % 4 == 0 && aligned16(a.C) &&
              (a.CT == nullptr || a.ct_cols % 4 == 0)) ? 1 : 0;
   d.a_batched = a.strideA != 0; d.b_batched = a.strideB != 0; d.b2_batched = a.strideB2 != 0; d.has_b2 = two ? 1 : 0;

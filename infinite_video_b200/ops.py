@@ -193,6 +193,28 @@ def gemm_raw(A, lda, strideA, a_kmajor, B, ldb, strideB, b_kmajor, C_, ldc, stri
     return C_
 
 
+def gemm_fp16(A, B, bias=None, out=None, round_tf32=False):
+    """C[M,Nc] fp32 = A[M,K] fp16 @ B[Nc,K]^T fp16 (+ bias): kind::f16 UMMAs, fp32 accumulation (`ab_fp16`)."""
+    require_cuda(A, B, bias)
+    if A.dtype != torch.float16 or B.dtype != torch.float16 or not A.is_contiguous() or not B.is_contiguous():
+        raise ValueError("gemm_fp16 takes contiguous float16 operands")
+    M, K = A.shape
+    Nc = B.shape[0]
+    if out is None:
+        out = torch.empty(M, Nc, device=A.device, dtype=torch.float32)
+    g = GemmArgs()
+    g.A, g.lda, g.strideA, g.a_kmajor = A.data_ptr(), K, 0, 1
+    g.B, g.ldb, g.strideB, g.b_kmajor = B.data_ptr(), K, 0, 1
+    g.B2, g.ldb2, g.strideB2, g.K1 = None, 0, 0, K
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.C, g.ldc, g.strideC = out.data_ptr(), Nc, 0
+    g.M, g.Nc, g.K, g.batch = M, Nc, K, 1
+    g.precision, g.impl = 1, 0
+    g.round_tf32, g.ab_fp16 = int(bool(round_tf32)), 1
+    check(lib().ltm_gemm(C.byref(g), stream_ptr(A.device)), "gemm(fp16)")
+    return out
+
+
 def softmax_rows(S, scale=1.0, mask=None, rows_per_mask=1):
     """In place: S[rows, n] <- softmax(S * scale + mask[row // rows_per_mask]).  Qformer.py:279-285."""
     require_cuda(S, mask)

@@ -24,3 +24,10 @@ for (M, N, K) in ((32768, 1536, 768), (8192, 8192, 8192), (32768, 1536, 4096)):
     fl = 2.0 * M * N * K
     print(f"M={M} N={N} K={K}: cublas tf32 {t_lib*1e3:.1f} us {fl/t_lib/1e9:.0f} TF/s | own tf32 {t_own*1e3:.1f} us "
           f"{fl/t_own/1e9:.0f} TF/s | cublas bf16 {t_bf*1e3:.1f} us {fl/t_bf/1e9:.0f} TF/s", flush=True)
+# ---- fp16-operand path of the own kernel at the K/V projection shape
+M, N, K = 32768, 1536, 768
+A = torch.randn(M, K, device=dev); W = torch.randn(N, K, device=dev) * 0.03; bias = torch.zeros(N, device=dev)
+Ah, Wh = A.half(), W.half(); out = torch.empty(M, N, device=dev)
+t = timeit(lambda: ops.gemm_fp16(Ah, Wh, bias, out=out, round_tf32=True))
+t1 = timeit(lambda: ops.project_kv_r(A, W, bias, out=out))
+print(f"own fp16 operands {t*1e3:.1f} us ({2.0*M*N*K/t/1e9:.0f} TF/s) | own tf32 {t1*1e3:.1f} us")

@@ -15,7 +15,7 @@ def dev(cuda_device):
 
 
 def _run_rect(dev, N, L, C, Bv, T=32, e=768, Q=32, tau=.75, sticky=True, q_scale=1.0, seed=31, precision="tf32",
-              eps=None, fast_attn=True):
+              eps=None, fast_attn=True, proj_operands="fp32"):
     # The sampled bins are bit-exact GIVEN (p, u) (tests/test_gpu_kernels.py).  End to end, p itself carries the
     # rounding of the K/V projection (single-pass TF32: ~3e-4 relative on K, more on exp(q.K) for peaky
     # queries), so uniforms closer than `eps` to a CDF edge of the oracle's p are moved to the middle of a bin.
@@ -23,7 +23,7 @@ def _run_rect(dev, N, L, C, Bv, T=32, e=768, Q=32, tau=.75, sticky=True, q_scale
     from infinite_video_b200.batched import BatchedRectLTM
     key, val = make_proj(seed, e)
     eng = BatchedRectLTM(N, tau, *proj_tensors(key, val), tokens_per_frame=T, sticky=sticky, precision=precision,
-                         device=dev, keep_scores=True, fast_attn=fast_attn)
+                         device=dev, keep_scores=True, fast_attn=fast_attn, proj_operands=proj_operands)
     orcs = [O.RectLTM(N, tau, *proj_tensors(key, val), tokens_per_frame=T, sticky=sticky, rebuild_tables=False)
             for _ in range(Bv)]
     ks, qs, us = make_inputs(seed + 1, C, Bv, L * T, e, Q, q_scale)
@@ -314,6 +314,14 @@ def test_overlapped_step_is_bit_identical(dev):
             assert torch.equal(x, y), f"rep {rep} chunk {c}"
             assert torch.equal(a.B_past, b.B_past)
     torch.cuda.synchronize()
+
+
+def test_fp16_projection_operands(dev):
+    """`proj_operands="fp16"`: coefficients and weights enter the K/V projection as fp16 (kind::f16 UMMAs, fp32
+    accumulation).  Same tolerances as the default path; the coefficients themselves stay fp32."""
+    for kw in (dict(N=256, L=64, C=3, Bv=2), dict(N=128, L=16, C=3, Bv=2, Q=40)):
+        w = _run_rect(dev, proj_operands="fp16", **kw)
+        assert w["B"] < 1e-5 and w["ctx"] < TOL_CTX, w
 
 
 def test_step_is_cuda_graph_capturable(dev):

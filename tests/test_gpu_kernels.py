@@ -281,6 +281,19 @@ def test_project_kv(dev):
 
 
 # ---------------------------------------------------------------------------------------- variant G kernels
+@pytest.mark.parametrize("M,N,K", [(512, 1536, 768), (300, 200, 136), (128, 256, 64)])
+def test_gemm_fp16_operands(dev, gemm_cluster, M, N, K):
+    """kind::f16 path of the tcgen05 GEMM: fp16 operands are exact inputs, products accumulate in fp32."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).half()
+    B = (torch.randn(N, K, generator=g) * 0.05).half()
+    bias = torch.randn(N, generator=g)
+    want = A.double() @ B.double().t() + bias.double()
+    got = ops.gemm_fp16(A.to(dev), B.to(dev), bias.to(dev))
+    assert relerr(got, want.float()) < 2e-6
+
+
 def test_project_kv_rounded_to_tf32(dev):
     """`ltm_project_kv_r`: the same product as `ltm_project_kv`, stored on the tf32 grid (round to nearest)."""
     ops = _ops()
