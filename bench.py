@@ -256,7 +256,8 @@ def run_b200(args):
     torch.manual_seed(0)
     key, val = torch.nn.Linear(E, D), torch.nn.Linear(E, D)
     eng = BatchedRectLTM(NB, TAU, key.weight.detach(), key.bias.detach(), val.weight.detach(), val.bias.detach(),
-                         tokens_per_frame=T, sticky=True, precision=args.precision, device=dev)
+                         tokens_per_frame=T, sticky=True, precision=args.precision, device=dev,
+                         proj_operands=args.proj_operands)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     ks = [torch.randn(Bv, L * T, E, device=dev, generator=g) for _ in range(C)]
     qs = [torch.randn(Bv, Q, D, device=dev, generator=g) for _ in range(C)]
@@ -690,6 +691,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="do not pool chunk c+1 under chunk c's compute")
     ap.add_argument("--pool-ctas-per-sm", type=int, default=0, help="grid bound of the prefetch pooling kernel")
+    ap.add_argument("--proj-operands", choices=["fp32", "fp16"], default="fp32",
+                    help="operands of the K/V projection on the tensor-core path (fp16: kind::f16 UMMAs, opt-in)")
     ap.add_argument("--pair", action="store_true", help="K/V projection on the CTA-pair (cta_group::2) GEMM kernel")
     ap.add_argument("--repeats", type=int, default=3, help="timed regions of K steps each; the fastest is reported")
     ap.add_argument("--graph", action="store_true",
