@@ -252,6 +252,8 @@ def run_b200(args):
         lib.ltm_debug_set_cluster(2)
     if args.pair:
         lib.ltm_debug_set_pair(1)
+    if args.no_pair:
+        lib.ltm_debug_set_pair(0)
     Bv, C = args.videos, args.chunks
     torch.manual_seed(0)
     key, val = torch.nn.Linear(E, D), torch.nn.Linear(E, D)
@@ -693,6 +695,7 @@ def main():
     ap.add_argument("--pool-ctas-per-sm", type=int, default=0, help="grid bound of the prefetch pooling kernel")
     ap.add_argument("--proj-operands", choices=["fp32", "fp16"], default="fp32",
                     help="operands of the K/V projection on the tensor-core path (fp16: kind::f16 UMMAs, opt-in)")
+    ap.add_argument("--no-pair", action="store_true", help="K/V projection on the single-CTA GEMM kernel")
     ap.add_argument("--pair", action="store_true", help="K/V projection on the CTA-pair (cta_group::2) GEMM kernel")
     ap.add_argument("--repeats", type=int, default=3, help="timed regions of K steps each; the fastest is reported")
     ap.add_argument("--graph", action="store_true",

@@ -750,10 +750,10 @@ static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 // 2 enables the 2-CTA multicast variant.  Measured on B200 (profiles/r1e): no gain over unicast -- the kernel is
 // bound by per-SM ingest (~38 B/clk/SM), not by L2 reads -- so it is off by default and kept as a tested option.
 static int g_cluster = 1;
-// CTA-pair (tcgen05 cta_group::2) kernel for problems with at least two row tiles: -1 = automatic (single-pass
-// TF32 only: 130 vs 135 us on the K/V projection and one third fewer operand bytes ingested per SM, which the
-// frame pooling running beside it can use; in split-TF32 the pair is slower, 384 vs 358 us), 0 = never, 1 = always.
-static int g_pair = -1;
+// CTA-pair (tcgen05 cta_group::2) kernel for problems with at least two row tiles: 0 = off (default), 1 = always,
+// -1 = for single-pass TF32 only.  Measured on two B200s: 130 vs 135 us (pair wins) on one, 152 vs 146 us (pair
+// loses) on the other -- no robust winner, so the simpler single-CTA kernel stays the default.
+static int g_pair = 0;
 static int g_dbg = 0;
 static unsigned g_mn_desc[5] = {1u, (unsigned)SLAB_BYTES, 512u, 1024u, (unsigned)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B};
 

@@ -220,8 +220,7 @@ GEMM_CASES = [
 
 @pytest.fixture(params=["pair", "single", "multicast"])
 def gemm_cluster(request):
-    """Runs the GEMM tests through the three kernel variants: CTA pairs (tcgen05 cta_group::2; the default for single-pass
-    TF32), single-CTA (the default for split-TF32), and single-CTA MMAs with 2-CTA TMA multicast (bring-up hooks)."""
+    """Runs the GEMM tests through the three kernel variants: CTA pairs (tcgen05 cta_group::2), single-CTA (the default), and single-CTA MMAs with 2-CTA TMA multicast (bring-up hooks)."""
     import ctypes
     from infinite_video_b200 import _capi
     lib = _capi.lib()
@@ -230,7 +229,7 @@ def gemm_cluster(request):
     lib.ltm_debug_set_pair(1 if request.param == "pair" else 0)
     lib.ltm_debug_set_cluster(2 if request.param == "multicast" else 1)
     yield request.param
-    lib.ltm_debug_set_pair(-1)                 # back to the automatic choice
+    lib.ltm_debug_set_pair(0)                  # back to the default
     lib.ltm_debug_set_cluster(1)
 
 
