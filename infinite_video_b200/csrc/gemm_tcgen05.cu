@@ -10,13 +10,14 @@
 //   [re-sampled memory ; new chunk] without materialising the concatenation,
 //   long_term_attention.py:249-250).
 // * precision 3 = split-TF32: the tensor core truncates fp32 -> tf32 (hi = tf32(x) is the loaded tile itself);
-//   8 warps write lo = x - hi into one extra buffer and three MMAs (hi*hi + lo*hi + hi*lo) reproduce
-//   fp32-grade products.  Needed for the Gaussian
-//   variant whose RBF design values reach 80 with heavy cancellation (single-pass TF32 -> 1e-2 error).
+//   8 warps write lo = x - hi into two alternating buffers and three MMAs (hi*hi + lo*hi + hi*lo) reproduce
+//   fp32-grade products.  Needed for the Gaussian variant whose RBF design values reach 80 with heavy
+//   cancellation (single-pass TF32 -> 1e-2 error).
+// * ab_fp16: both operands IEEE fp16 (64 K-elements per 128-byte row, kind::f16, K = 16 per MMA), same pipeline.
 //
-// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 =
-// epilogue (TMEM lane quarter = warp_id % 4), warps 6-13 = operand splitter (precision 3 only); two TMEM
-// accumulators so the epilogue of one tile overlaps the MMAs of the next.
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-9 =
+// epilogue (TMEM lane quarter = warp_id % 4, two warps per quarter), warps 10-17 = operand splitter (precision 3
+// only); two TMEM accumulators so the epilogue of one tile overlaps the MMAs of the next.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -919,7 +920,10 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
               "gemm: fp16 operands need precision 1 and K-major A and B");
   LTM_REQUIRE(a.precision == 1 || a.precision == 3, "gemm: precision must be 1 (tf32) or 3 (split tf32)");
   const bool split = a.precision == 3;
-  const int bn = (a.Nc > 128) ? 256 : 128;
+  // 256-wide tiles (128 x 256 x 8 atoms) unless the problem is too small to give every SM a tile: then 128-wide
+  // tiles double the CTA count and halve each tile's MMA time (one video: 12 -> 24 tiles)
+  const long long tiles256 = (long long)((a.Nc + 255) / 256) * ((a.M + BM - 1) / BM) * a.batch;
+  const int bn = (a.Nc > 128 && tiles256 >= 74) ? 256 : 128;
   const int K1 = two ? a.K1 : a.K;
   CUtensorMap mA, mB, mB2;
   if (encode_operand(&mA, a.A, a.M, a.K, a.lda, a.strideA, a.batch, a.a_kmajor, BM, "A", half)) return -1;
