@@ -39,11 +39,15 @@ class CrossAttentionLTM(nn.Module):
         self.d = query.out_features // n_heads
         self.videos_per_pass = videos_per_pass        # bounds the [videos, H*Q, L*T] score buffer
         self.precision = precision
-        # the two large contractions (scores = Qt enc^T, Y = probs enc); the three small ones always run split-TF32
-        # measured at L*T = 8192 (scripts/stm_probe.py): scores x3 / values x1 -> 4.4e-4 at +18 % time; x1 / x1 -> 6.7e-4
-        # (1.0e-3 at L*T = 256, where fewer keys average the rounding); x3 / x3 -> 3.7e-5 at 2.2x the time
-        self.score_precision = score_precision or "tf32x3"
-        self.value_precision = value_precision or precision
+        # the two large contractions (scores = Qt enc^T, Y = probs enc); the three small ones always run split-TF32.
+        # Measured (scripts/stm_probe.py, error vs fp64 at L*T = 8192 / 256, time at 16 videos):
+        #   scores x1 (Qt rounded to tf32) / values x3   2.6e-4 / 2.1e-4   0.80 ms   <- default
+        #   scores x3 / values x1                         4.5e-4 / 9.4e-4   0.87 ms
+        #   x1 / x1                                       5.8e-4 / 9.2e-4   0.59 ms
+        #   x3 / x3                                       3.9e-5 / 1.2e-5   1.08 ms
+        # (the value contraction reads the raw chunk, which the tensor core truncates: its bias is the larger error)
+        self.score_precision = score_precision or precision
+        self.value_precision = value_precision or "tf32x3"
         self.long_term_attention = LongTermAttention(
             head_size=self.d, length=key.in_features, target_len=key.in_features, attn_func="softmax",
             attn_num_basis=num_basis, continuous=True, attn_drop=0.1, infinite_memory=True, n_layers=2,
@@ -80,7 +84,8 @@ class CrossAttentionLTM(nn.Module):
             #     read as [K = d][N = e] (MN-major); rows m = (v, q) land at (v*H + h)*Q + q
             Qt = torch.empty(nb, H, Q, e, device=dev, dtype=torch.float32)
             ops.gemm_raw(qv, D, d, True, wk, e, d * e, False, Qt, e, Q * e, nb * Q, e, d, H,
-                         c_group=Q, c_group_stride=H * Q * e, precision="tf32x3")
+                         c_group=Q, c_group_stride=H * Q * e, precision="tf32x3",
+                         round_tf32=(self.score_precision == "tf32"))   # rounded (not truncated) operand of (2)
             # (2) scores[v] = Qt[v] enc[v]^T : [H*Q, e] x [e, LT]
             S = torch.empty(nb, H * Q, LT, device=dev, dtype=torch.float32)
             ops.gemm_raw(Qt, e, H * Q * e, True, ev, e, LT * e, True, S, LT, H * Q * LT, H * Q, LT, e, nb,

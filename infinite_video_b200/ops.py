@@ -173,7 +173,7 @@ def gemm(A, B, *, a_kmajor=True, b_kmajor=True, B2=None, bias=None, out=None, pr
 
 def gemm_raw(A, lda, strideA, a_kmajor, B, ldb, strideB, b_kmajor, C_, ldc, strideC, M, Nc, K, batch, *, bias=None,
              bias_stride=0, c_group=0, c_group_stride=0, precision="tf32", impl="tcgen05", a_offset=0, b_offset=0,
-             c_offset=0):
+             c_offset=0, round_tf32=False):
     """ltm_gemm with every pitch / batch stride spelled out (elements).  A, B, C_ are the base tensors; *_offset
     shifts the start (elements).  Used where operands are strided views that tensor shapes cannot express
     (per-head column blocks, per-head / per-video output layouts)."""
@@ -189,6 +189,7 @@ def gemm_raw(A, lda, strideA, a_kmajor, B, ldb, strideB, b_kmajor, C_, ldc, stri
     g.precision, g.impl = PRECISION[precision], GEMM_IMPL[impl]
     g.CT, g.ct_cols, g.ct_group = None, 0, 0
     g.c_group, g.c_group_stride = c_group, c_group_stride
+    g.round_tf32 = int(bool(round_tf32))
     check(lib().ltm_gemm(C.byref(g), stream_ptr(A.device)), "gemm")
     return C_
 

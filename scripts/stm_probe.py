@@ -8,7 +8,7 @@ dev = torch.device("cuda:0")
 torch.manual_seed(21)
 lq, lk, lv = torch.nn.Linear(768, 768), torch.nn.Linear(768, 768), torch.nn.Linear(768, 768)
 g = torch.Generator().manual_seed(22)
-B, L = 2, 256
+B, L = int(sys.argv[1]) if len(sys.argv) > 1 else 2, int(sys.argv[2]) if len(sys.argv) > 2 else 256
 hidden = torch.randn(B, 32, 768, generator=g); enc = torch.randn(B, L * 32, 768, generator=g)
 q = torch.nn.functional.linear(hidden, lq.weight, lq.bias)
 def ref():
