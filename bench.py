@@ -616,7 +616,7 @@ def run_caller_arm(dev, Bv=16, C=3, steps=3):
     return {"value": calls / (ms * 1e-3), "unit": "chunks/s", "videos": Bv, "chunks": C, "ms_per_step": ms,
             "finite": bool(torch.isfinite(out).all()), "short_term_tflops": tfl,
             "note": "Qformer.py:197-310 eval path: q = query(h); LTM(enc, q); softmax(q K^T) V over L*T = 8192 "
-                    "tokens without forming K, V (scores split-TF32, values TF32); alpha blend"}
+                    "tokens without forming K, V (scores TF32 on a rounded operand, values split-TF32); alpha blend"}
 
 
 def run_single_video(dev, reps=200):

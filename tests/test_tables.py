@@ -73,3 +73,24 @@ def test_gauss_tables_shapes():
     assert t.trim1 == 260 and t.trim0 == 4
     with pytest.raises(ValueError):
         T.gauss_tables(7, 64, .75)
+
+
+@pytest.mark.parametrize("N,L", [(256, 256), (128, 16)])
+def test_tensor_core_attention_operand_rows(N, L):
+    """tables.X (rows appended to V^T by csrc/attn_tc.cu): with e_j = W_j exp(S_j - m) as the other operand, column 0
+    gives the quadrature normaliser and columns 1 + 2 (hi + lo, hi exact in tf32) the trapezoid integral of the
+    sticky-edge density, Z = trapz(E, tb) with E_i = exp(S[jb_i] - m) (0 score where no basis is active)."""
+    t = T.rect_tables(L, N, .75)
+    assert t.X is not None and t.X.shape == (N, 32) and (t.X[:, 0] == 1).all() and (t.X[:, 3:] == 0).all()
+    hi_bits = t.X[:, 1].view(np.uint32)
+    assert (hi_bits & np.uint32(0x1FFF) == 0).all()                    # exact on the tf32 grid
+    rng = np.random.default_rng(3)
+    S = rng.normal(size=N) * 3.0
+    m = max(0.0, S.max())
+    E = np.where(t.jb >= 0, np.exp(S[np.maximum(t.jb, 0)] - m), np.exp(-m))
+    tb = t.tb.astype(np.float64)
+    want = float(np.sum((tb[1:] - tb[:-1]) * (E[1:] + E[:-1]) * 0.5))
+    e = t.W.astype(np.float64) * np.exp(S - m)
+    got = float(((t.X[:, 1].astype(np.float64) + t.X[:, 2]) * e).sum() + t.c_none * np.exp(-m))
+    assert abs(got - want) < 1e-6 * want
+    assert abs(float((t.X[:, 0] * e).sum()) - float(e.sum())) < 1e-12
