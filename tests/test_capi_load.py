@@ -45,6 +45,17 @@ def test_version_and_error_convention(lib):
     assert rc < 0 and b"resample" in lib.ltm_last_error()
     g = _capi.GemmArgs()
     assert lib.ltm_gemm(C.byref(g), None) < 0
+    # entry points added with the tensor-core attention / overlapped step: validation before any CUDA call
+    rc = lib.ltm_cont_attn_rect_tc(None, None, None, 1536, None, None, 0.0, 0.0, None, None, None, None, None,
+                                   1, 32, 256, 12, 64, None)
+    assert rc < 0 and b"cont_attn_rect_tc" in lib.ltm_last_error()
+    assert lib.ltm_attn_tc_supported(256, 64) == 1 and lib.ltm_attn_tc_supported(64, 64) == 0
+    assert lib.ltm_attn_tc_supported(256, 128) == 0
+    a, o = _capi.RectStepArgs(), _capi.Overlap()
+    rc = lib.ltm_rect_step_overlap(C.byref(a), C.byref(o), None, None, None, None)
+    assert rc < 0 and b"rect_step_overlap" in lib.ltm_last_error()
+    rc = lib.ltm_sticky_hist_gauss(None, None, None, None, 1, 384, 8, None)
+    assert rc < 0 and b"sticky_hist_gauss" in lib.ltm_last_error()
 
 
 def test_ctypes_structs_match_c_layout(tmp_path):
