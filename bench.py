@@ -355,6 +355,7 @@ def run_b200(args):
         e0.record(stream)
         t_host = time.perf_counter()
         i = 0
+        gathers = []
         for _ in range(args.steps):
             out = None
             for c in range(C):
@@ -368,7 +369,14 @@ def run_b200(args):
                 else:
                     out = eng.step(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0))
             if world > 1:
-                out = D_.gather_videos(out, Bv * world)
+                # gather of this step's outputs: asynchronous, so that the next step's kernels are not held up;
+                # every gather is complete before the end of the timed region
+                out, wk = D_.gather_videos(out, Bv * world, async_op=True)
+                gathers.append((out, wk))
+        for _o, wk in gathers:
+            if wk is not None:
+                wk.wait()
+        gathers.clear()
         e1.record(stream)
         host_ms[0] = (time.perf_counter() - t_host) * 1e3 / args.steps      # time the host needed to enqueue a step
         if with_overlap and os.environ.get("BENCH_DEBUG") == "1":

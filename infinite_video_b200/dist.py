@@ -30,13 +30,24 @@ def init_from_env(backend=None):
     return rank, local, world
 
 
-def gather_videos(local: torch.Tensor, n_videos: int, group=None) -> torch.Tensor:
-    """local[n_local, ...] on every rank -> [n_videos, ...] on every rank, in video order."""
+def gather_videos(local: torch.Tensor, n_videos: int, group=None, async_op: bool = False):
+    """local[n_local, ...] on every rank -> [n_videos, ...] on every rank, in video order.
+
+    Equal shards (n_videos divisible by the world size) are gathered straight into the result; ragged shards go
+    through a padded buffer.  async_op=True (equal shards only) returns (result, work): the collective runs on
+    NCCL's stream behind the work already queued on the current stream, and the caller `work.wait()`s before it
+    reads the result -- the next chunk's kernels are not held up by the gather."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return local
+        return (local, None) if async_op else local
     world = dist.get_world_size(group)
     counts = [shard_range(n_videos, r, world) for r in range(world)]
     most = max(e - s for s, e in counts)
+    if all(e - s == most for s, e in counts):
+        out = torch.empty((world * most,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        work = dist.all_gather_into_tensor(out, local.contiguous(), group=group, async_op=async_op)
+        return (out, work) if async_op else out
+    if async_op:
+        raise ValueError("async gather needs equal shards")
     pad = torch.zeros((most,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
     out = torch.empty((world * most,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
