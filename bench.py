@@ -436,7 +436,7 @@ def run_b200(args):
     pool_bytes = 4.0 * Bv * L * T * E                       # algorithmic bytes of the dominant kernel per launch
     pool_gbs = pool_bytes / (stage_serial["pool"] * 1e-3) / 1e9 if stage_serial["pool"] > 0 else 0.0
     pool_gbs_ov = pool_bytes / (stage_avg["pool"] * 1e-3) / 1e9 if stage_avg["pool"] > 0 else 0.0
-    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/r1j_ncu_pool.txt:
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/r1l_ncu_pool.txt:
     # dram__bytes_read.sum 805.32 MB + dram__bytes_write.sum 8.0 MB per launch at 32 videos), scaled per video
     pool_traffic = (805.32e6 + 8.0e6) / 32.0 * Bv
     step_bytes = algorithmic_bytes_per_call() * Bv * C + 4 * 2 * (E * D + D)   # + weights once per launch
@@ -523,7 +523,7 @@ def run_b200(args):
                          "measured_in": "non-overlapped timed pass of the same steps (CUDA events around this "
                                         "kernel on its launching stream)",
                          "achieved_while_overlapped": pool_gbs_ov,
-                         "traffic_source": "profiles/r1j_ncu_pool.txt (ncu --set full at 32 videos, per video)"},
+                         "traffic_source": "profiles/r1l_ncu_pool.txt (ncu --set full at 32 videos, per video)"},
             "value_without_overlap": calls_total / (ms_serial * 1e-3),
             "value_eager_launch": value_eager, "host_enqueue_ms_per_step_eager": host_enqueue_ms,
             "repeats": {"n": len(reps), "reported": "fastest", "ms_per_step": [r[0] / args.steps for r in reps],
