@@ -2,7 +2,8 @@
 
 Public surface:
   LongTermAttention  -- drop-in for the reference module (same ctor / forward signature)
-  BatchedLTM         -- the same path for Bv independent videos with explicit state and uniforms
+  BatchedRectLTM / BatchedGaussLTM -- the same path for Bv independent videos with explicit state and uniforms
+  CrossAttentionLTM  -- the caller's whole cross-attention branch (short-term attention + LTM + alpha blend)
 """
 __version__ = "0.1.0"
 
@@ -14,7 +15,13 @@ def __getattr__(name):
     if name in ("LongTermAttention",):
         from .ltm import LongTermAttention
         return LongTermAttention
-    if name in ("BatchedLTM", "BatchedRectLTM", "BatchedGaussLTM"):
+    if name in ("BatchedRectLTM", "BatchedGaussLTM"):
         from . import batched
         return getattr(batched, name)
+    if name == "BatchedLTM":                       # the live (rect / "gibbs") variant
+        from .batched import BatchedRectLTM
+        return BatchedRectLTM
+    if name == "CrossAttentionLTM":
+        from .cross_attention import CrossAttentionLTM
+        return CrossAttentionLTM
     raise AttributeError(name)
