@@ -280,6 +280,27 @@ def test_project_kv(dev):
 
 
 # ---------------------------------------------------------------------------------------- variant G kernels
+@pytest.mark.parametrize("Bv,N,Q,H,L", [(3, 256, 1, 12, 64), (2, 128, 96, 16, 16), (1, 256, 33, 8, 32),
+                                        (5, 128, 32, 1, 16)])
+def test_tensor_core_attention_shapes(dev, Bv, N, Q, H, L):
+    """The tensor-core attention against the fp32 FMA kernel on identical (tf32-rounded) K|V for shapes the end-to-end
+    cases do not reach: a single query, several / partial query tiles, 1, 8 and 16 heads."""
+    ops, T = _ops(), _tables()
+    g = torch.Generator().manual_seed(Bv * 1000 + N + Q + H)
+    D = H * 64
+    tab = T.rect_tables(L, N, .75)
+    td = tab.to(dev)
+    KVr = _tf32_rna(torch.randn(Bv, N, 2 * D, generator=g)).to(dev)
+    q = (torch.randn(Bv, Q, D, generator=g) * 2).to(dev)
+    Kt = KVr[:, :, :D].reshape(Bv, N, H, 64).permute(0, 2, 3, 1).contiguous()
+    V = KVr[:, :, D:].contiguous()
+    c0, s0, h0 = ops.cont_attn_rect_t(q, Kt, V, td["W"], tab.W_out, td["jb"], td["tb"], want_scores=True)
+    c1, s1, h1 = ops.cont_attn_rect_tc(q, KVr, td["X"], td["W"], tab.W_out, tab.c_none, td["jb"], td["tb"],
+                                       want_scores=True, n_heads=H)
+    assert relerr(s1, s0) < 5e-4 and relerr(c1, c0) < 1e-3 and relerr(h1, h0) < 1e-3
+    assert bool(torch.isfinite(c1).all())
+
+
 @pytest.mark.parametrize("M,N,K", [(512, 1536, 768), (300, 200, 136), (128, 256, 64)])
 def test_gemm_fp16_operands(dev, gemm_cluster, M, N, K):
     """kind::f16 path of the tcgen05 GEMM: fp16 operands are exact inputs, products accumulate in fp32."""
