@@ -167,7 +167,7 @@ int ltm_cont_attn_gauss_t(const float* q, const float* Kt, const float* V, int64
                           const float* basis_sigma, float* ctx, float* scores_out, float* mu_out, float* sd_out,
                           int Bv, int Q, int N, int H, int d, void* stream);
 
-/* ---- tensor-core path of the rect attention for num_basis in {128,256}, head_size 64 (csrc/attn_tc.cu): both
+/* ---- tensor-core path of the rect attention for num_basis in {64,128,256}, head_size 64 (csrc/attn_tc.cu): both
  * contractions as tf32 UMMAs.  K[Bv*N, ldkv], V[Bv*N, ldkv] row-major (head h at column h*64; e.g. the two halves
  * of ltm_project_kv's KV, ldkv = 2D), already rounded to tf32 (ltm_gemm round_tf32 / ltm_project_kv_r).
  * X[N,32]: extra operand rows (1, hi/lo of c_j/W_j; infinite_video_b200/tables.py), c_none: trapezoid node weight

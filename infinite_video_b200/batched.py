@@ -89,7 +89,7 @@ class BatchedRectLTM(_BatchedBase):
         self.keep_scores = keep_scores
         # transposed-key attention path (num_basis 64/128/256, head size 64); `fast_attn=False` forces the generic one
         self.fast_attn = bool(fast_attn) and ops.attn_fast_supported(self.N, self.d)
-        # tensor-core attention (csrc/attn_tc.cu): num_basis 128/256, head size 64, single-pass tf32 projection
+        # tensor-core attention (csrc/attn_tc.cu): num_basis 64/128/256, head size 64, single-pass tf32 projection
         self.tc_attn = (bool(tc_attn) and bool(fast_attn) and precision == "tf32" and gemm_impl == "tcgen05"
                         and ops.attn_tc_supported(self.N, self.d))
         # operands of the K/V projection on the tensor-core path: "fp32" (default: tf32 UMMAs straight from the fp32

@@ -112,9 +112,11 @@ template <int NB>
 __global__ void __maxnreg__(TC_MAX_REGS)
 cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV,
                     const __grid_constant__ CUtensorMap mapX, const Params p, const int q_tiles, const int total) {
-  static_assert(NB == 128 || NB == 256, "the tensor-core path covers num_basis 128 / 256");
+  static_assert(NB == 64 || NB == 128 || NB == 256, "the tensor-core path covers num_basis 64 / 128 / 256");
   using L_ = Lay<NB>;
-  constexpr int HALVES = NB / 128;
+  constexpr int HALVES = (NB + 127) / 128;   // score MMAs (M = 128 each); NB = 64: the upper 64 rows read past the
+                                             // K tile (finite or not, they only reach accumulator rows nobody reads)
+  constexpr int JWARPS = NB / 32;            // compute warps that own a basis (the others only help with the outputs)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (sbase - smem_u32(smem_raw));
@@ -269,7 +271,7 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ compute warps
-    const bool active = warp < 4 * HALVES;
+    const bool active = warp < JWARPS;
     const int j = (warp >> 2) * 128 + (warp & 3) * 32 + lane;      // this thread's basis in the weight phase
     const int quarter = warp & 3, chalf = warp >> 2;
     const float Wj = active ? __ldg(p.W + j) : 0.f;
@@ -352,7 +354,7 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
       if (active) {
         float M = 0.f;                                 // per-row shift m = max(0, max_j S_j): it cancels exactly
 #pragma unroll
-        for (int ww = 0; ww < 4 * HALVES; ++ww) M = fmaxf(M, wmax[ww * 32 + lane]);
+        for (int ww = 0; ww < JWARPS; ++ww) M = fmaxf(M, wmax[ww * 32 + lane]);
         if (warp == 0) mcol[lane] = M;
         uint8_t* rblk = sm + L_::R_OFF + (j >> 5) * 4096 + (lane & 3) * 4;
 #pragma unroll
@@ -485,7 +487,7 @@ static unsigned long long* g_trace = nullptr;
 }  // namespace ltm
 extern "C" void ltm_debug_set_attn_trace(void* p) { ltm::tc::g_trace = (unsigned long long*)p; }
 
-extern "C" int ltm_attn_tc_supported(int N, int d) { return (d == 64 && (N == 128 || N == 256)) ? 1 : 0; }
+extern "C" int ltm_attn_tc_supported(int N, int d) { return (d == 64 && (N == 64 || N == 128 || N == 256)) ? 1 : 0; }
 
 extern "C" int ltm_cont_attn_rect_tc(const float* q, const float* K, const float* V, int64_t ldkv, const float* X,
                                      const float* W, float W_out, float c_none, const int32_t* jb, const float* tb,
@@ -509,6 +511,7 @@ extern "C" int ltm_cont_attn_rect_tc(const float* q, const float* K, const float
   p.q = q; p.W = W; p.tb = tb; p.jb = jb; p.W_out = W_out; p.c_none = c_none; p.ctx = ctx;
   p.scores_out = scores_out; p.hist_part = hist_part; p.Q = Q; p.H = H;
   p.trace = tc::g_trace;
-  return N == 256 ? tc::launch<256>(mK, mV, mX, p, Bv, (cudaStream_t)stream)
-                  : tc::launch<128>(mK, mV, mX, p, Bv, (cudaStream_t)stream);
+  if (N == 256) return tc::launch<256>(mK, mV, mX, p, Bv, (cudaStream_t)stream);
+  if (N == 128) return tc::launch<128>(mK, mV, mX, p, Bv, (cudaStream_t)stream);
+  return tc::launch<64>(mK, mV, mX, p, Bv, (cudaStream_t)stream);
 }

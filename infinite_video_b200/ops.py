@@ -273,7 +273,7 @@ def project_kv_r(Bcoef, Wkv, bkv, precision="tf32", out=None):
 
 
 def cont_attn_rect_tc(q, KV, X, W, W_out, c_none, jb=None, tb=None, want_scores=False, want_hist=True, n_heads=12):
-    """Tensor-core path (num_basis 128/256): q[Bv,Q,D], KV[Bv,N,2D] (tf32-rounded) -> (ctx, scores|None, hist|None)."""
+    """Tensor-core path (num_basis 64/128/256): q[Bv,Q,D], KV[Bv,N,2D] (tf32-rounded) -> (ctx, scores|None, hist|None)."""
     require_cuda(q, KV, X, W, jb, tb)
     q = _f32c(q)
     Bv, Q, D = q.shape
