@@ -197,6 +197,44 @@ def cpu_arm(chunks, budget_s, max_videos):
     return orc, ks, qs, us
 
 
+def parity_check(dev, chunks, eps=5e-4):
+    """One video of the bench shape through the CUDA path and through the oracle on the same inputs (the checker,
+    not the thing measured): sampled bins must be identical, coefficients and context vectors within 1e-3.
+    Uniforms closer than `eps` to a CDF edge of the oracle's histogram are moved to the middle of a bin first
+    (the sampled bin is bit-exact given (p, u); p itself carries the tf32 rounding of the projection)."""
+    from oracle import ltm_oracle as O
+    from infinite_video_b200.batched import BatchedRectLTM
+    torch.manual_seed(0)
+    key, val = torch.nn.Linear(E, D), torch.nn.Linear(E, D)
+    w = (key.weight.detach(), key.bias.detach(), val.weight.detach(), val.bias.detach())
+    orc = O.RectLTM(NB, TAU, *w, tokens_per_frame=T, sticky=True, rebuild_tables=False)
+    eng = BatchedRectLTM(NB, TAU, *w, tokens_per_frame=T, sticky=True, device=dev)
+    ks, qs, us = make_cpu_inputs(chunks, seed=4321)
+    worst_ctx, worst_B, bins_equal = 0.0, 0.0, True
+    rel = lambda a, b: float((a.double().cpu() - b.double()).abs().max() / b.double().abs().max())
+    with torch.no_grad():
+        for c in range(chunks):
+            u = us[c]
+            if c > 0:
+                p64 = orc.sticky_hist(orc.tables(L)).double()
+                cdf = torch.cumsum(p64, -1) / p64.sum(-1, keepdim=True)
+                u = u.clone()
+                close = (u[0].unsqueeze(1) - cdf[0].unsqueeze(0)).abs().min(1).values < eps
+                if close.any():
+                    edges = torch.cat([torch.zeros(1, dtype=torch.float64), cdf[0]])
+                    big = (edges[1:] - edges[:-1]).argmax()
+                    u[0][close] = (edges[big] + edges[big + 1]) / 2
+            want = orc.forward(ks[c], qs[c], c == 0, u)
+            got = eng.step(ks[c].to(dev), qs[c].to(dev), u.to(dev) if c > 0 else None, new_doc=(c == 0))
+            worst_ctx = max(worst_ctx, rel(got, want))
+            worst_B = max(worst_B, rel(eng.B_past, orc.B_past))
+            if c > 0:
+                bins_equal = bins_equal and bool(torch.equal(eng.last["b"].cpu().long(), orc.last["b"]))
+    return {"videos": 1, "chunks": chunks, "ctx_max_relerr": worst_ctx, "coeff_max_relerr": worst_B,
+            "sampled_bins_identical": bins_equal, "tolerance": 1e-3, "guard_band": eps,
+            "ok": bool(bins_equal and worst_ctx < 1e-3 and worst_B < 1e-3)}
+
+
 def run_reference_impl(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -508,6 +546,13 @@ def run_b200(args):
                "sample": f"{n_calls // C} video(s) x {C} chunks of the same shape, batch 1 sequential, "
                          f"oracle port of long_term_attention_gibbs.py (tables rebuilt per call, 1000-pt quadrature)"}
 
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            parity = parity_check(dev, C)
+        except Exception as ex:
+            parity = {"error": f"{type(ex).__name__}: {ex}"}
+
     if rank == 0:
         launches = args.steps * (C * 5 - 1)
         line = {
@@ -534,7 +579,7 @@ def run_b200(args):
             "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s",
                               "frac": step_gbs / peak, "algorithmic_bytes_per_step": step_bytes},
             "stage_ms_per_chunk_step": stage_avg,
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "variant_gaussian": gauss, "single_video": single, "caller_cross_attention": caller,
         }
         emit(line)
