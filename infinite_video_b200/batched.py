@@ -162,6 +162,7 @@ class BatchedRectLTM(_BatchedBase):
         if a is None or ws.get("_args_sig") != sig:
             a = self._args_full(Bv, L, Q, ws, tab, tdev)
             ws["_args"], ws["_args_sig"], ws["_args_prof"] = a, sig, False
+            ws["_args_keep"] = (tdev, self.Wkv, self.bkv, self._hist)     # the block holds raw pointers into these
         a.splits = ws["splits"]
         a.B_past = self._B[self._cur].data_ptr() if self.has_state else None
         a.B_new = self._B[1 - self._cur].data_ptr()
