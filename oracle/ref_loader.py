@@ -22,7 +22,13 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("INFLTM_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# /root/reference exists only in the dev container; `oracle/install_ref.py` puts verbatim copies of the path's files
+# under baseline/_ref/ (git-ignored, travels with the gpurun snapshot) so the same loader works on the GPU box
+_CANDIDATES = [os.environ.get("INFLTM_REFERENCE_ROOT"), "/root/reference",
+               os.path.join(os.path.dirname(_HERE), "baseline", "_ref")]
+REF_ROOT = next((c for c in _CANDIDATES if c and os.path.isfile(os.path.join(
+    c, "infty-Video-LLaMA", "InfVideoLLaMA", "models", "long_term_attention_gibbs.py"))), "/root/reference")
 _VL = os.path.join(REF_ROOT, "infty-Video-LLaMA", "InfVideoLLaMA", "models")
 _VC = os.path.join(REF_ROOT, "infty-VideoChat2", "models", "blip2")
 

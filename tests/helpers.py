@@ -40,6 +40,25 @@ def load_golden(name):
     return {k: z[k] for k in z.files}
 
 
+def compare_draws(b_got, b_want, u, p, delta):
+    """Sampled bins of the implementation under test vs the oracle's own draws from the same uniforms, NO guard band.
+    Returns (flips, draws).  A draw may only differ where it is a numerical tie: every CDF edge of the oracle's `p`
+    (fp32 [B,C]) that separates the two bins must lie within `delta` of the uniform -- i.e. the two histograms
+    differ by less than `delta` there.  Anything else raises."""
+    b_got, b_want = torch.as_tensor(b_got).long().cpu(), torch.as_tensor(b_want).long().cpu()
+    diff = b_got != b_want
+    flips = int(diff.sum())
+    if flips:
+        p64 = torch.as_tensor(p).double().cpu()
+        cdf = torch.cumsum(p64, -1) / p64.sum(-1, keepdim=True)
+        for v, s in diff.nonzero().tolist():
+            lo, hi = sorted((int(b_got[v, s]), int(b_want[v, s])))
+            uu = float(u[v, s])
+            assert cdf[v, lo] > uu - delta and cdf[v, hi - 1] < uu + delta, \
+                f"draw {s} of video {v}: bins {int(b_got[v, s])} vs {int(b_want[v, s])} is not a tie within {delta}"
+    return flips, b_got.numel()
+
+
 def guard_band(u, p, eps=2e-6):
     """Move uniforms that sit within `eps` of a CDF edge of p (fp32 [B,C]) to the middle of their bin, so
     ulp-level differences between two correct implementations of p cannot flip a draw.  Returns a copy."""

@@ -4,7 +4,8 @@ import pytest
 import torch
 
 from oracle import ltm_oracle as O
-from tests.helpers import (TOL_B, TOL_CTX, guard_band, load_golden, make_inputs, make_proj, proj_tensors, relerr)
+from tests.helpers import (TOL_B, TOL_CTX, compare_draws, guard_band, load_golden, make_inputs, make_proj, proj_tensors,
+                           relerr)
 
 pytestmark = pytest.mark.gpu
 
@@ -14,36 +15,46 @@ def dev(cuda_device):
     return cuda_device
 
 
+# Sampled bins are compared with the oracle's own draws from the SAME uniforms, no guard band.  The sampling kernel is
+# bit-exact given (p, u) (tests/test_gpu_kernels.py); end to end p carries the rounding of everything upstream, so a
+# uniform that sits on a CDF edge can land in the neighbouring bin.  Such flips are counted (and reported by bench.py),
+# each one must be a tie within TIE[precision] (`compare_draws`), and the oracle then continues from the bins the CUDA
+# path used so that coefficients / contexts of every later chunk are still compared like for like.
+TIE = {"tf32": 1e-3, "tf32x3": 2e-5}
+FLIPS = {}          # test id -> (flips, draws): printed in the summary line of the session
+
+
 def _run_rect(dev, N, L, C, Bv, T=32, e=768, Q=32, tau=.75, sticky=True, q_scale=1.0, seed=31, precision="tf32",
-              eps=None, fast_attn=True, proj_operands="fp32"):
-    # The sampled bins are bit-exact GIVEN (p, u) (tests/test_gpu_kernels.py).  End to end, p itself carries the
-    # rounding of the K/V projection (single-pass TF32: ~3e-4 relative on K, more on exp(q.K) for peaky
-    # queries), so uniforms closer than `eps` to a CDF edge of the oracle's p are moved to the middle of a bin.
-    eps = eps if eps is not None else (5e-4 if precision == "tf32" else 2e-5)
+              fast_attn=True, proj_operands="fp32", tag=None, **eng_kw):
     from infinite_video_b200.batched import BatchedRectLTM
     key, val = make_proj(seed, e)
     eng = BatchedRectLTM(N, tau, *proj_tensors(key, val), tokens_per_frame=T, sticky=sticky, precision=precision,
-                         device=dev, keep_scores=True, fast_attn=fast_attn, proj_operands=proj_operands)
+                         device=dev, keep_scores=True, fast_attn=fast_attn, proj_operands=proj_operands, **eng_kw)
     orcs = [O.RectLTM(N, tau, *proj_tensors(key, val), tokens_per_frame=T, sticky=sticky, rebuild_tables=False)
             for _ in range(Bv)]
     ks, qs, us = make_inputs(seed + 1, C, Bv, L * T, e, Q, q_scale)
-    worst = dict(B=0.0, ctx=0.0)
+    worst = dict(B=0.0, ctx=0.0, flips=0, draws=0)
     with torch.no_grad():
         for c in range(C):
             u = us[c]
-            if c > 0 and sticky:
-                p = torch.cat([o.sticky_hist(o.tables(L)) for o in orcs])
-                u = guard_band(u, p, eps)
-            want = torch.cat([orcs[v].forward(ks[c][v:v + 1], qs[c][v:v + 1], c == 0, u[v:v + 1]) for v in range(Bv)])
-            got = eng.step(ks[c].to(dev), qs[c].to(dev), u.to(dev) if c > 0 and sticky else None, new_doc=(c == 0))
-            if c > 0 and sticky:
-                want_b = torch.cat([o.last["b"] for o in orcs])
-                assert torch.equal(eng.last["b"].cpu().long(), want_b), f"sampled bins differ at chunk {c}"
+            upd = c > 0 and sticky
+            got = eng.step(ks[c].to(dev), qs[c].to(dev), u.to(dev) if upd else None, new_doc=(c == 0))
+            b_got = eng.last["b"].cpu().long() if upd else None
+            want = torch.cat([orcs[v].forward(ks[c][v:v + 1], qs[c][v:v + 1], c == 0, u[v:v + 1],
+                                              b_override=b_got[v:v + 1] if upd else None) for v in range(Bv)])
+            if upd:
+                f, d = compare_draws(b_got, torch.cat([o.last["b_own"] for o in orcs]), u,
+                                     torch.cat([o.last["p"] for o in orcs]), TIE[precision])
+                worst["flips"] += f
+                worst["draws"] += d
                 assert torch.equal(eng.last["ts"].cpu(), torch.cat([o.last["ts"] for o in orcs]))
                 assert torch.equal(eng.last["idx"].cpu().long(), torch.stack([o.last["idx"] for o in orcs]))
             wantB = torch.cat([o.B_past for o in orcs])
             worst["B"] = max(worst["B"], relerr(eng.B_past, wantB))
             worst["ctx"] = max(worst["ctx"], relerr(got, want))
+    if tag:
+        FLIPS[tag] = (worst["flips"], worst["draws"])
+        print(f"[flips] {tag}: {worst['flips']} of {worst['draws']} draws")
     return worst
 
 
@@ -54,15 +65,17 @@ def _run_rect(dev, N, L, C, Bv, T=32, e=768, Q=32, tau=.75, sticky=True, q_scale
     ("cfg3", dict(N=64, L=16, C=3, Bv=1, T=196, e=1024, Q=96)),             # BASELINE configs[2] (VideoChat2)
     ("cfg4", dict(N=512, L=32, C=3, Bv=2)),                                 # num_basis=512 stress
     ("peaky", dict(N=64, L=8, C=3, Bv=2, q_scale=8.0, precision="tf32x3")),  # far-from-uniform sticky histogram
-    ("peaky_tf32", dict(N=64, L=8, C=3, Bv=2, q_scale=8.0, eps=2e-2)),
+    ("peaky_tf32", dict(N=64, L=8, C=3, Bv=2, q_scale=8.0)),
     ("odd", dict(N=64, L=7, C=3, Bv=1)),
     ("nonpow2", dict(N=100, L=30, C=3, Bv=2, tau=.5)),                      # positions that fall in no bin
     ("uniform", dict(N=64, L=8, C=3, Bv=2, sticky=False)),                  # non-sticky re-sampling
 ])
 def test_rect_matches_oracle_over_chunks(dev, name, kw):
-    w = _run_rect(dev, **kw)
+    w = _run_rect(dev, tag=name, **kw)
     assert w["B"] < 1e-5, w            # the segmented mean is fp32 exact up to summation order
     assert w["ctx"] < TOL_CTX, w       # single-pass TF32 projection, fp32 accumulate
+    # ties are rare: at most 1 % of the draws even for the peaky TF32 case (measured rates: bench.py `parity`)
+    assert w["flips"] <= 0.01 * max(w["draws"], 1), w
 
 
 @pytest.mark.parametrize("kw", [dict(N=256, L=32, C=3, Bv=2), dict(N=64, L=8, C=3, Bv=2, Q=96),
@@ -78,21 +91,62 @@ def test_rect_split_tf32_is_fp32_grade(dev):
     assert w["B"] < 1e-5 and w["ctx"] < 2e-5, w
 
 
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
 @pytest.mark.parametrize("name", ["gibbs_vl_cfg1.npz", "gibbs_vl_cfg2.npz", "gibbs_vl_peaky.npz",
-                                  "gibbs_vc_cfg3.npz"])
-def test_rect_reproduces_reference_goldens(dev, name):
-    """CUDA path vs outputs of the real reference module (tests/golden, generated in the dev container)."""
+                                  "gibbs_vc_cfg3.npz", "gibbs_vl_cfg4.npz"])
+def test_rect_reproduces_reference_goldens(dev, name, precision):
+    """CUDA path vs outputs of the real reference module (tests/golden, generated in the dev container) fed with
+    the uniforms the reference itself consumed -- no guard band: the sampled bins must equal the reference's
+    (`b`, observed through Categorical.sample by make_golden.py), and with them coefficients and contexts."""
     from infinite_video_b200.batched import BatchedRectLTM
     g = load_golden(name)
     N, L, C, seed, T, e, Q = (int(x) for x in g["meta"])
     key, val = make_proj(seed, e)
-    eng = BatchedRectLTM(N, float(g["tau"]), *proj_tensors(key, val), tokens_per_frame=T, device=dev)
+    eng = BatchedRectLTM(N, float(g["tau"]), *proj_tensors(key, val), tokens_per_frame=T, device=dev,
+                         precision=precision)
     ks, qs, _ = make_inputs(seed + 1, C, 1, L * T, e, Q, float(g["q_scale"]))
     for c in range(C):
         u = torch.from_numpy(g["u"][c]).to(dev)
         ctx = eng.step(ks[c].to(dev), qs[c].to(dev), u if c else None, new_doc=(c == 0))
+        if c:
+            b_ref = torch.from_numpy(g["b"][c])
+            flips, _ = compare_draws(eng.last["b"], b_ref, g["u"][c], g["p"][c], TIE[precision])
+            assert flips == 0, f"{name}/{precision}: {flips} sampled bins differ from the reference's at chunk {c}"
+            assert relerr(eng.last["p"], g["p"][c]) < (2e-3 if precision == "tf32" else 2e-5)
         assert relerr(eng.B_past[0, :, :96], g["B_cols"][c]) < TOL_B, f"{name}: B, chunk {c}"
         assert relerr(ctx[0], g["ctx"][c]) < TOL_CTX, f"{name}: ctx, chunk {c}"
+
+
+def test_cfg4_at_full_size(dev):
+    """BASELINE configs[3]: num_basis=512, 64 videos, chunks of 256 frames, sticky re-sampling on every chunk.  The
+    CUDA path runs the whole batch; the oracle checks a spread of its videos (a CPU call at this size takes ~1 s)."""
+    N, L, Bv, C = 512, 256, 64, 3
+    from infinite_video_b200.batched import BatchedRectLTM
+    key, val = make_proj(15, 768)
+    eng = BatchedRectLTM(N, .75, *proj_tensors(key, val), device=dev)
+    check = [0, 21, 42, 63]
+    orcs = {v: O.RectLTM(N, .75, *proj_tensors(key, val), rebuild_tables=False, faithful_quadrature=False)
+            for v in check}
+    g = torch.Generator().manual_seed(16)
+    flips = draws = 0
+    with torch.no_grad():
+        for c in range(C):
+            k = torch.randn(Bv, L * 32, 768, generator=g)
+            q = torch.randn(Bv, 32, 768, generator=g)
+            u = torch.rand(Bv, 512, dtype=torch.float64, generator=g)
+            got = eng.step(k.to(dev), q.to(dev), u.to(dev) if c else None, new_doc=(c == 0)).cpu()
+            assert torch.isfinite(got).all()
+            b_got = eng.last["b"].cpu().long()
+            for v in check:
+                o = orcs[v]
+                want = o.forward(k[v:v + 1], q[v:v + 1], c == 0, u[v:v + 1], b_override=b_got[v:v + 1] if c else None)
+                if c:
+                    f, d = compare_draws(b_got[v:v + 1], o.last["b_own"], u[v:v + 1], o.last["p"], TIE["tf32"])
+                    flips, draws = flips + f, draws + d
+                assert relerr(eng.B_past[v], o.B_past[0]) < 1e-5, (c, v)
+                assert relerr(got[v], want[0]) < TOL_CTX, (c, v)
+    print(f"[flips] cfg4 full size: {flips} of {draws} draws")
+    assert flips <= 0.01 * draws
 
 
 def test_host_entry_point_equals_device_entry_point(dev):
@@ -459,11 +513,13 @@ def test_caller_cross_attention_with_ltm_blend_on_gpu(dev, alpha, N, L, B):
             hidden = torch.randn(B, 32, 768, generator=g)
             enc = torch.randn(B, L * 32, 768, generator=g)
             u = torch.rand(B, 512, dtype=torch.float64, generator=g)
-            if c:
-                p = torch.cat([o.ltm.sticky_hist(o.ltm.tables(L)) for o in orcs])
-                u = guard_band(u, p, 5e-4)
-            want = torch.cat([orcs[v].forward(hidden[v:v + 1], enc[v:v + 1], c == 0, u[v:v + 1]) for v in range(B)])
             got = m(hidden.to(dev), enc.to(dev), new_video=(c == 0), layer=0, u=u)
+            b_got = m.long_term_attention._engine.last["b"].cpu().long() if c else None
+            want = torch.cat([orcs[v].forward(hidden[v:v + 1], enc[v:v + 1], c == 0, u[v:v + 1],
+                                              b_override=b_got[v:v + 1] if c else None) for v in range(B)])
+            if c:
+                compare_draws(b_got, torch.cat([o.ltm.last["b_own"] for o in orcs]), u,
+                              torch.cat([o.ltm.last["p"] for o in orcs]), TIE["tf32"])
             stm = m.short_term(torch.nn.functional.linear(hidden, lq.weight, lq.bias).to(dev), enc.to(dev))
             assert relerr(stm, torch.cat([o.last_stm for o in orcs])) < TOL_CTX, f"short-term, chunk {c}"
             assert relerr(got, want) < TOL_CTX, f"blend, chunk {c}"
