@@ -370,12 +370,6 @@ def run_b200(args):
     torch.cuda.set_device(dev)
     lib = _capi.lib()
     _capi.check(lib.ltm_device_check(), "device_check")
-    if args.cluster:
-        lib.ltm_debug_set_cluster(2)
-    if args.pair:
-        lib.ltm_debug_set_pair(1)
-    if args.no_pair:
-        lib.ltm_debug_set_pair(0)
     Bv, C = args.videos, args.chunks
     torch.manual_seed(0)
     key, val = torch.nn.Linear(E, D), torch.nn.Linear(E, D)
@@ -471,9 +465,6 @@ def run_b200(args):
         torch.cuda.synchronize(dev)
         if sampler:
             sampler.mark()
-        if with_overlap and os.environ.get("BENCH_DEBUG") == "1":
-            lib.ltm_debug_overlap_times.argtypes = [Ct.c_void_p, Ct.c_void_p, Ct.c_int]
-            lib.ltm_debug_overlap_times(None, None, 1)
         e0.record(stream)
         t_host = time.perf_counter()
         i = 0
@@ -501,13 +492,6 @@ def run_b200(args):
         gathers.clear()
         e1.record(stream)
         host_ms[0] = (time.perf_counter() - t_host) * 1e3 / args.steps      # time the host needed to enqueue a step
-        if with_overlap and os.environ.get("BENCH_DEBUG") == "1":
-            sm6, mx6 = (Ct.c_double * 6)(), (Ct.c_double * 6)()
-            lib.ltm_debug_overlap_times.argtypes = [Ct.c_void_p, Ct.c_void_p, Ct.c_int]
-            lib.ltm_debug_overlap_times(sm6, mx6, 1)
-            sys.stderr.write("overlap host sections [fork_pool, pool, pooled, fork, step, join] sum ms: "
-                             + " ".join(f"{x*1e3:.2f}" for x in sm6) + " | max ms: "
-                             + " ".join(f"{x*1e3:.2f}" for x in mx6) + f" | loop {host_ms[0]*args.steps:.1f} ms\n")
         torch.cuda.synchronize(dev)
         eng.prof_events = None
         D_.barrier(dev)
@@ -835,14 +819,11 @@ def main():
     ap.add_argument("--pool-ctas-per-sm", type=int, default=0, help="grid bound of the prefetch pooling kernel")
     ap.add_argument("--proj-operands", choices=["fp32", "fp16"], default="fp32",
                     help="operands of the K/V projection on the tensor-core path (fp16: kind::f16 UMMAs, opt-in)")
-    ap.add_argument("--no-pair", action="store_true", help="K/V projection on the single-CTA GEMM kernel")
-    ap.add_argument("--pair", action="store_true", help="K/V projection on the CTA-pair (cta_group::2) GEMM kernel")
     ap.add_argument("--repeats", type=int, default=3, help="timed regions of K steps each; the fastest is reported")
     ap.add_argument("--graph", action="store_true",
                     help="also time the K steps replayed from one CUDA graph per step (measured: 160 k vs 175 k eager -- "
                          "the host needs 0.8 ms to enqueue a 5.9 ms step, and graph kernel nodes lose the stream priorities)")
     ap.add_argument("--hi-prio", action="store_true", help="run the main stream at high priority")
-    ap.add_argument("--cluster", action="store_true", help="use the 2-CTA TMA-multicast variant of the GEMM")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gauss", action="store_true", help="skip the secondary Gaussian-variant measurement")
     ap.add_argument("--gauss-videos", type=int, default=128)

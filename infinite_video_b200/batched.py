@@ -10,14 +10,31 @@ State per video
   variant G: B_past[N,e]; (mu, sigma)[H*Q] of the previous call
 """
 import ctypes as C
+import functools
 import math
+import weakref
 
 import torch
 
 from . import ops, tables
 from ._capi import Overlap, RectStepArgs, check, lib, ptr, require_cuda, stream_ptr
 
-SM_COUNT = 148
+@functools.lru_cache(maxsize=None)
+def _sm_count(index):
+    return torch.cuda.get_device_properties(index).multi_processor_count
+
+
+def _on_device(fn):
+    """Run a method with the engine's device current: the library launches on the stream handle it is given, and
+    handles of one device are invalid while another device is current (a model sharded over several GPUs of one
+    process)."""
+    @functools.wraps(fn)
+    def wrapped(self, *a, **kw):
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *a, **kw)
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **kw)
+    return wrapped
 
 
 def _as_flags(new_doc, Bv, device):
@@ -45,6 +62,9 @@ class _BatchedBase:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ValueError("the LTM consolidation path runs on CUDA devices only (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.sm_count = _sm_count(self.device.index)
         self.N = int(num_basis)
         self.tau = float(tau)
         self.H, self.d = int(n_heads), int(head_size)
@@ -102,7 +122,7 @@ class BatchedRectLTM(_BatchedBase):
         self._Wkv_h = None
         self.prof_events = None       # optional list of 10 cudaEvent_t handles (bench.py stage timing)
         self._side = None             # side stream for pooling the next chunk ahead of time
-        self._pref = {}               # pending prefetches: (data_ptr, shape) -> (buffer index, done event)
+        self._pref = []               # pending prefetches, oldest first (see `prefetch`)
         self._evs = None              # persistent fork / join events of the two-stream schedule
         self.pool_ctas = 0            # grid bound of the side-stream pooling kernel (0 = one CTA per frame)
         self._ws = {}
@@ -119,13 +139,13 @@ class BatchedRectLTM(_BatchedBase):
             units = Bv * L
             # split the token range of a frame over several CTAs only when there are too few frames to fill the
             # 148 SMs (small batches); otherwise one CTA per frame, one pass, no partial sums
-            splits = 1 if units >= 2 * SM_COUNT else max(1, min(self.T, -(-SM_COUNT * 8 // units)))
+            splits = self._splits(units)
             f32 = dict(device=dev, dtype=torch.float32)
             i32 = dict(device=dev, dtype=torch.int32)
             ws = dict(
                 splits=splits,
                 xparts=[torch.empty(Bv, L, splits, self.e, **f32), torch.empty(Bv, L, splits, self.e, **f32)],
-                xi=0, xnext=0,
+                xi=0,
                 KV=torch.empty(Bv, self.N, 2 * self.D, **f32) if (self.tc_attn or not self.fast_attn) else None,
                 Kt=torch.empty(Bv, self.H, self.d, self.N, **f32) if (self.fast_attn and not self.tc_attn) else None,
                 V=torch.empty(Bv, self.N, self.D, **f32) if (self.fast_attn and not self.tc_attn) else None,
@@ -137,6 +157,37 @@ class BatchedRectLTM(_BatchedBase):
             )
             self._ws = {key: ws}          # one live shape at a time
         return ws
+
+    def _splits(self, units):
+        return 1 if units >= 2 * self.sm_count else max(1, min(self.T, -(-self.sm_count * 8 // units)))
+
+    def reset(self):
+        """Forget every video (new_doc for all) and every pending prefetch."""
+        super().reset()
+        self._pref.clear()
+
+    def cancel_prefetch(self):
+        """Drop the chunks pooled ahead of time that were never consumed by a `step`."""
+        self._pref.clear()
+
+    # pending prefetches are identified by the tensor OBJECT (weak reference) and its version counter: a data pointer
+    # is not a key, the caching allocator hands the same address to the next chunk (and an in-place write changes
+    # the contents behind an unchanged pointer)
+    def _pref_take(self, k):
+        for i, ent in enumerate(self._pref):
+            if ent["ref"]() is k and ent["ver"] == k._version:
+                return self._pref.pop(i)
+        return None
+
+    def _pref_buffer(self, ws):
+        """Buffer for the next prefetch: one that no pending prefetch holds, preferably not the one the most recent
+        step consumes.  An abandoned prefetch (tensor gone, or never stepped) is evicted, oldest first."""
+        self._pref[:] = [e for e in self._pref if e["ref"]() is not None]
+        while len(self._pref) >= 2:
+            self._pref.pop(0)
+        held = {e["buf"] for e in self._pref}
+        pref = 1 - ws["xi"]
+        return pref if pref not in held else 1 - pref
 
     def _state(self, Bv, Q):
         qt = (Q + 31) // 32
@@ -239,6 +290,7 @@ class BatchedRectLTM(_BatchedBase):
             last = ws["_last"] = dict(b=ws["b_draw"], ts=ws["ts"], idx=ws["idx"], p=ws["p"], scores=ws["scores"], V=V)
         self.last = last
 
+    @_on_device
     def prefetch(self, k_next, Q, events=None):
         """Pool the frames of the NEXT chunk now, on a side stream, into the alternate buffer.
 
@@ -246,7 +298,8 @@ class BatchedRectLTM(_BatchedBase):
         call's bytes, while regression / projection / attention of the current chunk are compute-bound; issuing
         it one chunk ahead lets the two overlap.  The following `step(k_next, ...)` must pass the same tensor."""
         require_cuda(k_next)
-        k_next = k_next.contiguous()
+        if not k_next.is_contiguous():
+            raise ValueError("prefetch needs a contiguous chunk (the following step must be given the same tensor)")
         Bv, LT, e = k_next.shape
         L = LT // self.T
         ws = self._workspace(Bv, L, Q)
@@ -258,12 +311,9 @@ class BatchedRectLTM(_BatchedBase):
             flat = os.environ.get("LTM_FLAT_PRIORITY") == "1"        # bring-up: both streams at the default priority
             self._side = torch.cuda.Stream(device=self.device, priority=0)
             self._compute = torch.cuda.Stream(device=self.device, priority=0 if flat else -1)
-        if len(self._pref) >= 2:
-            raise RuntimeError("at most two chunks may be in flight (the pooled frames are double-buffered)")
         main = torch.cuda.current_stream(self.device)
         ev = self._sync_events()
-        b = ws["xnext"]
-        ws["xnext"] = 1 - b
+        b = self._pref_buffer(ws)
         sp = C.c_void_p(self._side.cuda_stream)
         mp = C.c_void_p(main.cuda_stream)
         # fork: the target buffer was last read by work already queued on `main`.  Persistent events (re-recorded
@@ -279,8 +329,8 @@ class BatchedRectLTM(_BatchedBase):
         if events is not None:
             check(lib().ltm_event_record(events[1], sp), "event_record")
         check(lib().ltm_event_record(ev["pooled"][b], sp), "event_record")
-        self._pref[(k_next.data_ptr(), tuple(k_next.shape))] = (b, ev["pooled"][b],
-                                                                 torch.cuda.is_current_stream_capturing())
+        self._pref.append(dict(ref=weakref.ref(k_next), ver=k_next._version, buf=b, event=ev["pooled"][b],
+                               captured=torch.cuda.is_current_stream_capturing()))
 
     def _sync_events(self):
         if self._evs is None:
@@ -291,6 +341,7 @@ class BatchedRectLTM(_BatchedBase):
             self._evs = {"fork_pool": [mk(), mk()], "pooled": [mk(), mk()], "fork": mk(), "join": mk()}
         return self._evs
 
+    @_on_device
     def density(self):
         """alphas[Q,Bv,H,768] of the most recent call: the density side-output the Video-LLaMA copy pickles to
         ./alphas_uniform on every forward (gibbs:320-343).  Needs `keep_scores=True`."""
@@ -301,6 +352,7 @@ class BatchedRectLTM(_BatchedBase):
         td = tables.rect_tables(L, self.N, self.tau, self.S).to(self.device)
         return ops.density_rect(sc, td["jd"], td["wd"])
 
+    @_on_device
     def pool(self, k):
         """Frame pooling alone (gibbs:304): k[Bv, L*T, e] -> pooled frames [Bv, L, splits, e].  The result can be
         handed to `step(..., pooled=...)` of SEVERAL engines: every LTM layer of a Q-former receives the same
@@ -312,10 +364,9 @@ class BatchedRectLTM(_BatchedBase):
         if e != self.e or LT % self.T:
             raise ValueError(f"k must be [Bv, L*{self.T}, {self.e}]")
         L = LT // self.T
-        units = Bv * L
-        splits = 1 if units >= 2 * SM_COUNT else max(1, min(self.T, -(-SM_COUNT * 8 // units)))
-        return ops.pool_mean(k.view(Bv, L, self.T, e), splits)
+        return ops.pool_mean(k.view(Bv, L, self.T, e), self._splits(Bv * L))
 
+    @_on_device
     def step(self, k, q, u=None, new_doc=False, pooled=None):
         """k[Bv, L*T, e], q[Bv,Q,D] fp32 CUDA; u[Bv,S] fp64 uniforms (needed from the second chunk on when
         sticky); new_doc: bool or per-video flags; pooled: result of `pool(k)` (then `k` is only used for its
@@ -347,12 +398,12 @@ class BatchedRectLTM(_BatchedBase):
                 raise ValueError(f"sticky re-sampling needs u: float64 [{Bv},{self.S}]")
             u = u.contiguous()
         ctx = torch.empty(Bv, Q, self.D, device=self.device, dtype=torch.float32)
-        hit = self._pref.pop((k.data_ptr(), tuple(k.shape)), None)
+        hit = self._pref_take(k)
         pooled = hit is not None
         main = torch.cuda.current_stream(self.device)
         run = main
         if pooled:
-            ws["xi"] = hit[0]
+            ws["xi"] = hit["buf"]
             run = self._compute                      # fork: high-priority compute stream, joined below
             ev = self._sync_events()
             rp, mp = C.c_void_p(run.cuda_stream), C.c_void_p(main.cuda_stream)
@@ -360,11 +411,13 @@ class BatchedRectLTM(_BatchedBase):
             check(lib().ltm_stream_wait_event(rp, ev["fork"]), "stream_wait_event")
             # (a graph capture cannot wait on an event recorded before it began: the capturing host has synchronised,
             # and on replay the buffer is the one the previous replay's last prefetch filled)
-            if hit[2] or not torch.cuda.is_current_stream_capturing():
-                check(lib().ltm_stream_wait_event(rp, hit[1]), "stream_wait_event")
+            if hit["captured"] or not torch.cuda.is_current_stream_capturing():
+                check(lib().ltm_stream_wait_event(rp, hit["event"]), "stream_wait_event")
         else:
-            ws["xi"] = ws["xnext"]
-            ws["xnext"] = 1 - ws["xnext"]
+            held = {e["buf"] for e in self._pref}          # never pool over frames a pending prefetch still owns
+            ws["xi"] = (1 - ws["xi"]) if (1 - ws["xi"]) not in held else ws["xi"]
+            if ws["xi"] in held:
+                self._pref[:] = [e for e in self._pref if e["buf"] != ws["xi"]]
         a = self._args(Bv, L, Q, ws, tab, tdev)
         check(lib().ltm_rect_step(C.byref(a), None if pooled else ptr(k), ptr(q), ptr(u), ptr(flags), ptr(ctx),
                                   C.c_void_p(run.cuda_stream)), "rect_step")
@@ -374,6 +427,7 @@ class BatchedRectLTM(_BatchedBase):
         self._finish(ws)
         return ctx
 
+    @_on_device
     def step_overlapped(self, k, q, u=None, new_doc=False, k_next=None):
         """`step(k, ...)` with the frame pooling of `k_next` issued beside it, in ONE library call
         (`ltm_rect_step_overlap`: side stream pools the next chunk, a high-priority stream runs this chunk's
@@ -390,31 +444,28 @@ class BatchedRectLTM(_BatchedBase):
             if u is None or u.dtype != torch.float64 or tuple(u.shape) != (Bv, self.S):
                 raise ValueError(f"sticky re-sampling needs u: float64 [{Bv},{self.S}]")
             u = u.contiguous()
-        key = (k.data_ptr(), tuple(k.shape))
-        if key not in self._pref:
+        hit = self._pref_take(k)
+        if hit is None:
             self.prefetch(k, Q)
-        hit = self._pref.pop(key)
+            hit = self._pref_take(k)
         ev = self._sync_events()
         main = torch.cuda.current_stream(self.device)
         capturing = torch.cuda.is_current_stream_capturing()
-        ws["xi"] = hit[0]
+        ws["xi"] = hit["buf"]
         o = Overlap()
         o.main_stream, o.side_stream, o.compute_stream = main.cuda_stream, self._side.cuda_stream, self._compute.cuda_stream
         o.ev_fork, o.ev_join = ev["fork"], ev["join"]
-        o.ev_pooled_cur = hit[1] if (hit[2] or not capturing) else None
+        o.ev_pooled_cur = hit["event"] if (hit["captured"] or not capturing) else None
         o.pool_ctas = int(self.pool_ctas)
         if k_next is not None:
-            k_next = k_next.contiguous()
-            if tuple(k_next.shape) != tuple(k.shape):
-                raise ValueError("k_next must have the shape of k")
-            if len(self._pref) >= 1:
-                raise RuntimeError("at most two chunks may be in flight (the pooled frames are double-buffered)")
-            b = ws["xnext"]
-            ws["xnext"] = 1 - b
+            if not k_next.is_contiguous() or tuple(k_next.shape) != tuple(k.shape):
+                raise ValueError("k_next must be contiguous and have the shape of k")
+            b = self._pref_buffer(ws)
             o.k_next, o.xpart_next = k_next.data_ptr(), ws["xparts"][b].data_ptr()
             o.ev_fork_pool, o.ev_pooled_next = ev["fork_pool"][b], ev["pooled"][b]
             k_next.record_stream(self._side)
-            self._pref[(k_next.data_ptr(), tuple(k_next.shape))] = (b, ev["pooled"][b], capturing)
+            self._pref.append(dict(ref=weakref.ref(k_next), ver=k_next._version, buf=b, event=ev["pooled"][b],
+                                   captured=capturing))
         ctx = torch.empty(Bv, Q, self.D, device=self.device, dtype=torch.float32)   # main joins the compute stream
         a = self._args(Bv, L, Q, ws, tab, tdev)
         check(lib().ltm_rect_step_overlap(C.byref(a), C.byref(o), ptr(q), ptr(u), ptr(flags), ptr(ctx)),
@@ -422,6 +473,7 @@ class BatchedRectLTM(_BatchedBase):
         self._finish(ws)
         return ctx
 
+    @_on_device
     def step_host(self, k_host, q_host, u_host=None, new_doc=False, out=None):
         """Same as `step` but through HOST buffers (ideally pinned): the C entry point enqueues the H2D copies,
         the kernels and the D2H copy of ctx on the current stream.  Returns the host ctx tensor; the caller
@@ -440,8 +492,10 @@ class BatchedRectLTM(_BatchedBase):
         if out is None:
             out = torch.empty(Bv, Q, self.D, dtype=torch.float32, pin_memory=True)
         need_u = self.has_state and self.sticky
-        if need_u and (u_host is None or u_host.dtype != torch.float64):
-            raise ValueError("sticky re-sampling needs u_host: float64 [Bv,S]")
+        if need_u and (u_host is None or u_host.dtype != torch.float64 or tuple(u_host.shape) != (Bv, self.S)):
+            raise ValueError(f"sticky re-sampling needs u_host: float64 [{Bv},{self.S}]")
+        if k_host.dtype != torch.float32 or q_host.dtype != torch.float32:
+            raise ValueError("step_host takes float32 k and q")
         a = self._args(Bv, L, Q, ws, tab, tdev)
         nd_host = None
         if flags is not None:
@@ -475,6 +529,7 @@ class BatchedGaussLTM(_BatchedBase):
         self.last = {}
 
     # ------------------------------------------------------------------ constant operators
+    @_on_device
     def operators(self, L):
         """Device tables + ridge operators for chunk length L (solved once, fp64, on the device)."""
         op = self._ops.get(L)
@@ -493,6 +548,7 @@ class BatchedGaussLTM(_BatchedBase):
             self._ops[L] = op
         return op
 
+    @_on_device
     def set_operators(self, L, G0=None, G_inf=None):
         """Inject ridge operators ([L,N] / [S+L,N]) computed elsewhere (used by the parity tests to share
         the reference's fp32 `.inverse()` result)."""
@@ -506,6 +562,7 @@ class BatchedGaussLTM(_BatchedBase):
     def B_past(self):
         return self._B if self.has_state else None
 
+    @_on_device
     def step(self, k, q, u=None, new_doc=False):
         """k[Bv,Lk,e], q[Bv,Q,D], u[Bv,S] fp64.  Returns ctx[Bv,Q,D]."""
         require_cuda(k, q, u)

@@ -297,11 +297,8 @@ template <int MODE>
 static int launch_attn(const AttnParams& p, int Bv, cudaStream_t stream, const char* name) {
   const size_t smem = attn_smem_bytes(p.N);
   LTM_REQUIRE(smem <= 227 * 1024, "%s: num_basis=%d needs %zu B of shared memory (> 227 KB)", name, p.N, smem);
-  static size_t configured[2] = {0, 0};
-  if (smem > configured[MODE]) {
-    LTM_CUDA(cudaFuncSetAttribute(cont_attn_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[MODE] = smem;
-  }
+  static PerDevice pd = {};
+  if (int rc = kernel_setup(cont_attn_kernel<MODE>, smem, pd, nullptr)) return rc;
   dim3 grid((p.Q + QT - 1) / QT, p.H, Bv);
   cont_attn_kernel<MODE><<<grid, ATTN_THREADS, smem, stream>>>(p);
   LTM_CHECK_LAUNCH(name);

@@ -323,12 +323,8 @@ cont_attn_fast_kernel(const Params p) {
 template <int MODE, int NB>
 static int launch(const Params& p, int Bv, bool hist, cudaStream_t stream, const char* name) {
   const size_t smem = sizeof(float) * smem_floats<NB>(MODE == 0);
-  static bool configured = false;
-  if (!configured) {
-    LTM_CUDA(cudaFuncSetAttribute(cont_attn_fast_kernel<MODE, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    configured = true;
-  }
+  static PerDevice pd = {};
+  if (int rc = kernel_setup(cont_attn_fast_kernel<MODE, NB>, smem, pd, nullptr)) return rc;
   (void)hist;
   dim3 grid((p.Q + QT - 1) / QT, p.H, Bv);
   cont_attn_fast_kernel<MODE, NB><<<grid, THREADS, smem, stream>>>(p);

@@ -61,6 +61,10 @@ struct Lay {
 };
 
 __device__ __forceinline__ void stamp(unsigned long long* trace, uint32_t it, int slot) {
+#ifndef LTM_BRINGUP
+  (void)trace; (void)it; (void)slot;          // the per-item timeline exists in bring-up builds only
+  return;
+#endif
   if (trace != nullptr && blockIdx.x == 0 && it < 16) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -463,16 +467,9 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
 template <int NB>
 static int launch(const CUtensorMap& mK, const CUtensorMap& mV, const CUtensorMap& mX, const Params& p, int Bv,
                   cudaStream_t stream) {
-  static bool configured = false;
-  static int num_sms = 0;
-  if (!configured) {
-    LTM_CUDA(cudaFuncSetAttribute(cont_attn_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Lay<NB>::BYTES));
-    int dev = 0;
-    LTM_CUDA(cudaGetDevice(&dev));
-    LTM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    configured = true;
-  }
+  static PerDevice pd = {};
+  int num_sms = 0;
+  if (int rc = kernel_setup(cont_attn_tc_kernel<NB>, (size_t)Lay<NB>::BYTES, pd, &num_sms)) return rc;
   const int q_tiles = (p.Q + QT - 1) / QT;
   const long long total = (long long)q_tiles * p.H * Bv;
   LTM_REQUIRE(total < (1ll << 31), "cont_attn_rect_tc: too many work items");
@@ -485,7 +482,9 @@ static int launch(const CUtensorMap& mK, const CUtensorMap& mV, const CUtensorMa
 static unsigned long long* g_trace = nullptr;
 }  // namespace tc
 }  // namespace ltm
+#ifdef LTM_BRINGUP
 extern "C" void ltm_debug_set_attn_trace(void* p) { ltm::tc::g_trace = (unsigned long long*)p; }
+#endif
 
 extern "C" int ltm_attn_tc_supported(int N, int d) { return (d == 64 && (N == 64 || N == 128 || N == 256)) ? 1 : 0; }
 

@@ -128,6 +128,7 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
   return rc;
 }
 
+#ifdef LTM_BRINGUP
 // bring-up: a persistent kernel with a chosen footprint (threads, <= 96 registers, dynamic shared memory) that only
 // spins for `us` microseconds: measures what a co-resident footprint alone costs the streaming kernels beside it
 __global__ void __maxnreg__(96) footprint_spin_kernel(unsigned long long ns, float* sink) {
@@ -165,6 +166,11 @@ extern "C" void ltm_debug_overlap_times(double* sum6, double* max6, int reset) {
 }
 #define LTM_OV_MARK(i) do { const double t_ = now_s(); const double d_ = t_ - t_prev; g_ov_sum[i] += d_; \
                             if (d_ > g_ov_max[i]) g_ov_max[i] = d_; t_prev = t_; } while (0)
+#define LTM_OV_START() double t_prev = now_s()
+#else
+#define LTM_OV_MARK(i) do { } while (0)
+#define LTM_OV_START() do { } while (0)
+#endif
 
 extern "C" int ltm_rect_step_overlap(const ltm_rect_step_args* a, const ltm_overlap* o, const float* q,
                                      const double* u, const uint8_t* new_doc, float* ctx) {
@@ -173,7 +179,7 @@ extern "C" int ltm_rect_step_overlap(const ltm_rect_step_args* a, const ltm_over
   LTM_REQUIRE(o->ev_fork && o->ev_join, "rect_step_overlap: fork / join events missing");
   cudaStream_t ms = (cudaStream_t)o->main_stream, ss = (cudaStream_t)o->side_stream,
                cs = (cudaStream_t)o->compute_stream;
-  double t_prev = now_s();
+  LTM_OV_START();
   if (o->k_next != nullptr) {
     LTM_REQUIRE(o->xpart_next && o->ev_fork_pool && o->ev_pooled_next, "rect_step_overlap: prefetch target missing");
     // the target buffer was last read by work already queued on the main stream

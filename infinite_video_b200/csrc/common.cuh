@@ -39,6 +39,28 @@ void set_error(const char* fmt, ...);
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// The dynamic-shared-memory opt-in of a kernel and the SM count are properties of a DEVICE, so their one-time setup
+// is cached per device ordinal (a process may drive several GPUs: a Q-former sharded with device_map).
+constexpr int LTM_MAX_DEVICES = 64;
+struct PerDevice {
+  size_t smem[LTM_MAX_DEVICES];      // largest dynamic shared memory size opted into so far
+  int num_sms[LTM_MAX_DEVICES];
+};
+template <class Kern>
+static inline int kernel_setup(Kern kern, size_t smem_bytes, PerDevice& pd, int* num_sms) {
+  int dev = 0;
+  LTM_CUDA(cudaGetDevice(&dev));
+  LTM_REQUIRE(dev >= 0 && dev < LTM_MAX_DEVICES, "device ordinal %d out of range", dev);
+  if (smem_bytes > pd.smem[dev]) {
+    LTM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    pd.smem[dev] = smem_bytes;
+  }
+  if (pd.num_sms[dev] == 0)
+    LTM_CUDA(cudaDeviceGetAttribute(&pd.num_sms[dev], cudaDevAttrMultiProcessorCount, dev));
+  if (num_sms) *num_sms = pd.num_sms[dev];
+  return 0;
+}
+
 #ifdef __CUDACC__
 // 128-bit streaming load: read-only path, no L1 allocation, L2 evict-first (data is touched once).
 __device__ __forceinline__ float4 ldg_stream(const float4* p, uint64_t policy) {

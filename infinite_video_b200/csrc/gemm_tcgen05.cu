@@ -49,8 +49,15 @@ struct GemmDev {
   int ab_half;                              // operands are fp16 (kind::f16, 64 K-elements per 128-byte row)
   int round_tf32;                           // round stored row-major results to the tf32 grid
   int c_vec;                                // row-major stores may be 128-bit (alignment checked on the host)
-  int dbg;                                  // bring-up only: 1 = no global stores, 2 = no TMA loads
+  int dbg;                                  // bring-up builds only (-DLTM_BRINGUP): 1 = no global stores, 2 = no TMA loads
 };
+// The bring-up switches exist only in builds made with -DLTM_BRINGUP (scripts/*_probe.py); the product library
+// neither exports the setters nor carries the branches.
+#ifdef LTM_BRINGUP
+#define LTM_DBG(g) ((g).dbg)
+#else
+#define LTM_DBG(g) 0
+#endif
 
 // Work item -> tile origin.  CLUSTER == 1: items are tiles, n fastest.  CLUSTER == 2: a cluster of two CTAs takes
 // two vertically adjacent tiles (same n, rows m0 and m0 + 128) so that the B tile is fetched once and multicast.
@@ -180,14 +187,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& g, uint32_t tmem_ac
         : "r"(taddr)
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (g.dbg & 1) continue;
+    if (LTM_DBG(g) & 1) continue;
     if (g.CT != nullptr && n0 + c0 < g.ct_cols) {
       // transposed store (keys per head): lanes are consecutive rows of one group -> 128-byte coalesced
       float* dst = tbase + (size_t)(n0 + c0) * g.ct_group;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const float b = __shfl_sync(0xffffffffu, btr[j], i);             // all lanes take part
-        if (tbase != nullptr && !(g.dbg & 4)) dst[(size_t)i * g.ct_group] = __uint_as_float(r[i]) + b;
+        if (tbase != nullptr && !(LTM_DBG(g) & 4)) dst[(size_t)i * g.ct_group] = __uint_as_float(r[i]) + b;
       }
       continue;
     }
@@ -208,7 +215,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& g, uint32_t tmem_ac
       float4 v = *reinterpret_cast<const float4*>(stg + srow * EPI_COLS + ((lchunk ^ (srow & 7)) << 2));
       v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
       if (g.round_tf32) v = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-      if (rok[i] && !(g.dbg & 4)) {
+      if (rok[i] && !(LTM_DBG(g) & 4)) {
         float* dst = cbase_ptr + roff[i] + ccol;
         if (vec) {
           *reinterpret_cast<float4*>(dst) = v;
@@ -314,7 +321,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u);
-          if (g.dbg & 2) { mbar_arrive(full_bar(s)); continue; }
+          if (LTM_DBG(g) & 2) { mbar_arrive(full_bar(s)); continue; }
           mbar_arrive_expect_tx(full_bar(s), A_BYTES + C_::B_BYTES);
           const uint32_t sa = smem_base + s * C_::STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
@@ -450,6 +457,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   }
 }
 
+#ifdef LTM_BRINGUP   // the CTA-pair and multicast variants measured no robust gain: bring-up builds only
 // ================================================================================================
 // CTA-pair variant: tcgen05.mma.cta_group::2.  Two CTAs on one TPC compute a 256 x BN tile together:
 // CTA r holds rows [m0 + 128 r, +128) of A and rows [n0 + BN/2 r, +BN/2) of B in its shared memory, the
@@ -617,7 +625,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u);
-          if (g.dbg & 2) { if (SPLIT || leader) mbar_arrive(full_bar(s)); continue; }
+          if (LTM_DBG(g) & 2) { if (SPLIT || leader) mbar_arrive(full_bar(s)); continue; }
           uint32_t bar;                                                 // shared::cluster address of the barrier
           if (SPLIT) {
             mbar_arrive_expect_tx(full_bar(s), C_::STAGE_BYTES);        // own barrier: the splitter waits on it
@@ -745,17 +753,23 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   }
 }
 
+#endif  // LTM_BRINGUP
+
 // ------------------------------------------------------------------------------------------ host
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 // bring-up override of the MN-major layout parameters: {layout, lbo, sbo, kadv, tma swizzle enum}
 // 2 enables the 2-CTA multicast variant.  Measured on B200 (profiles/r1e): no gain over unicast -- the kernel is
 // bound by per-SM ingest (~38 B/clk/SM), not by L2 reads -- so it is off by default and kept as a tested option.
+#ifdef LTM_BRINGUP
 static int g_cluster = 1;
 // CTA-pair (tcgen05 cta_group::2) kernel for problems with at least two row tiles: 0 = off (default), 1 = always,
 // -1 = for single-pass TF32 only.  Measured on two B200s: 130 vs 135 us (pair wins) on one, 152 vs 146 us (pair
 // loses) on the other -- no robust winner, so the simpler single-CTA kernel stays the default.
 static int g_pair = 0;
 static int g_dbg = 0;
+#else
+constexpr int g_cluster = 1, g_pair = 0, g_dbg = 0;
+#endif
 static unsigned g_mn_desc[5] = {1u, (unsigned)SLAB_BYTES, 512u, 1024u, (unsigned)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B};
 
 static int resolve_encode() {
@@ -830,20 +844,12 @@ template <int BN, int STAGES, bool SPLIT, int CLUSTER = 1>
 static int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mB2, const GemmDev& d,
                       int batch, cudaStream_t stream) {
   using C_ = Cfg<BN, STAGES, SPLIT>;
-  static bool configured = false;
-  if (!configured) {
-    LTM_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES, SPLIT, CLUSTER>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
-    configured = true;
-  }
+  static PerDevice pd = {};
+  int num_sms = 0;
+  if (int rc = kernel_setup(gemm_tf32_kernel<BN, STAGES, SPLIT, CLUSTER>, (size_t)C_::SMEM_BYTES, pd, &num_sms))
+    return rc;
   const long long tiles = (long long)((d.Nc + BN - 1) / BN) * ((d.M + BM - 1) / BM) * batch;
   LTM_REQUIRE(tiles < (1ll << 31), "gemm: too many tiles");
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    LTM_CUDA(cudaGetDevice(&dev));
-    LTM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
   if (CLUSTER > 1) {
     // persistent clusters: CLUSTER CTAs on adjacent SMs share every B tile through TMA multicast
     const long long tm = (d.M + BM - 1) / BM;
@@ -872,22 +878,14 @@ static int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const CUtens
   return 0;
 }
 
+#ifdef LTM_BRINGUP
 template <int BN, int STAGES, bool SPLIT>
 static int launch_pair(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mB2, const GemmDev& d,
                        int batch, cudaStream_t stream) {
   using C_ = PairCfg<BN, STAGES, SPLIT>;
-  static bool configured = false;
-  if (!configured) {
-    LTM_CUDA(cudaFuncSetAttribute(gemm_tf32_pair_kernel<BN, STAGES, SPLIT>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
-    configured = true;
-  }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    LTM_CUDA(cudaGetDevice(&dev));
-    LTM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  static PerDevice pd = {};
+  int num_sms = 0;
+  if (int rc = kernel_setup(gemm_tf32_pair_kernel<BN, STAGES, SPLIT>, (size_t)C_::SMEM_BYTES, pd, &num_sms)) return rc;
   const long long tm = (d.M + BM - 1) / BM;
   const long long work = (long long)((d.Nc + BN - 1) / BN) * ((tm + 1) / 2) * batch;
   LTM_REQUIRE(work < (1ll << 31), "gemm: too many tiles");
@@ -909,6 +907,8 @@ static int launch_pair(const CUtensorMap& mA, const CUtensorMap& mB, const CUten
   LTM_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_pair_kernel<BN, STAGES, SPLIT>, mA, mB, mB2, d));
   return 0;
 }
+
+#endif
 
 static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   if (resolve_encode()) return -1;
@@ -949,6 +949,7 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   d.c_vec = (a.ldc % 4 == 0 && a.strideC % 4 == 0 && a.c_group_stride % 4 == 0 && aligned16(a.C) &&
              (a.CT == nullptr || a.ct_cols % 4 == 0)) ? 1 : 0;
   d.a_batched = a.strideA != 0; d.b_batched = a.strideB != 0; d.b2_batched = a.strideB2 != 0; d.has_b2 = two ? 1 : 0;
+#ifdef LTM_BRINGUP
   if (pair) {
     if (split) return bn == 256 ? launch_pair<256, 4, true>(mA, mB, mB2, d, a.batch, stream)
                                 : launch_pair<128, 6, true>(mA, mB, mB2, d, a.batch, stream);
@@ -956,20 +957,24 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
                      : launch_pair<128, 8, false>(mA, mB, mB2, d, a.batch, stream);
   }
   // 2-CTA clusters with a multicast B tile: K-major single-segment B and at least two row tiles
-  const bool mc = mc_pre;
-  if (split && bn == 256) return mc ? launch_cfg<256, 2, true, 2>(mA, mB, mB2, d, a.batch, stream)
-                                    : launch_cfg<256, 2, true>(mA, mB, mB2, d, a.batch, stream);
-  if (split) return mc ? launch_cfg<128, 4, true, 2>(mA, mB, mB2, d, a.batch, stream)
-                       : launch_cfg<128, 4, true>(mA, mB, mB2, d, a.batch, stream);
-  if (bn == 256) return mc ? launch_cfg<256, 4, false, 2>(mA, mB, mB2, d, a.batch, stream)
-                           : launch_cfg<256, 4, false>(mA, mB, mB2, d, a.batch, stream);
-  return mc ? launch_cfg<128, 6, false, 2>(mA, mB, mB2, d, a.batch, stream)
-            : launch_cfg<128, 6, false>(mA, mB, mB2, d, a.batch, stream);
+  if (mc_pre) {
+    if (split && bn == 256) return launch_cfg<256, 2, true, 2>(mA, mB, mB2, d, a.batch, stream);
+    if (split) return launch_cfg<128, 4, true, 2>(mA, mB, mB2, d, a.batch, stream);
+    if (bn == 256) return launch_cfg<256, 4, false, 2>(mA, mB, mB2, d, a.batch, stream);
+    return launch_cfg<128, 6, false, 2>(mA, mB, mB2, d, a.batch, stream);
+  }
+#endif
+  if (split && bn == 256) return launch_cfg<256, 2, true>(mA, mB, mB2, d, a.batch, stream);
+  if (split) return launch_cfg<128, 4, true>(mA, mB, mB2, d, a.batch, stream);
+  if (bn == 256) return launch_cfg<256, 4, false>(mA, mB, mB2, d, a.batch, stream);
+  return launch_cfg<128, 6, false>(mA, mB, mB2, d, a.batch, stream);
 }
 
 }  // namespace ltm
 
-// Bring-up hook (not part of include/infltm.h): override the MN-major descriptor parameters.
+// Bring-up hooks (not part of include/infltm.h, compiled only with -DLTM_BRINGUP): kernel variant selection,
+// store / load suppression, override of the MN-major descriptor parameters.
+#ifdef LTM_BRINGUP
 extern "C" void ltm_debug_set_cluster(int c) { ltm::g_cluster = c; }
 extern "C" void ltm_debug_set_pair(int v) { ltm::g_pair = v; }
 extern "C" void ltm_debug_set_gemm_flags(int v) { ltm::g_dbg = v; }
@@ -978,6 +983,7 @@ extern "C" void ltm_debug_set_mn_desc(unsigned layout, unsigned lbo, unsigned sb
   ltm::g_mn_desc[0] = layout; ltm::g_mn_desc[1] = lbo; ltm::g_mn_desc[2] = sbo; ltm::g_mn_desc[3] = kadv;
   ltm::g_mn_desc[4] = swz;
 }
+#endif
 
 extern "C" int ltm_gemm(const ltm_gemm_args* args, void* stream) {
   using namespace ltm;

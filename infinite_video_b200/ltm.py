@@ -144,13 +144,18 @@ class LongTermAttention(nn.Module):
         eng = self._get_engine(k.device)
         out_dtype = q.dtype
         # a 16-bit chunk (fp16 autocast in VideoChat2) is pooled straight from its storage: no up-cast pass
-        k32 = k.contiguous() if k.dtype in (torch.float16, torch.bfloat16) else k.float().contiguous()
+        # (variant R only: variant G consumes k un-pooled through the fp32 GEMMs)
+        half_in = self.variant == "gibbs" and k.dtype in (torch.float16, torch.bfloat16)
+        k32 = k.contiguous() if half_in else k.float().contiguous()
         q32 = q.float().contiguous()
         bsz = k32.size(0)
         if self.variant == "gibbs":
             self.length = k32.size(1) // self.tokens_per_frame            # gibbs:291-292
         if new_doc:
             eng.reset()                                                    # gibbs:300-302
+            LongTermAttention._shared_pool.update(key=None, x=None)       # do not keep the last video's frames alive
+        if eng.Bv is not None and eng.Bv != bsz:
+            eng.reset()            # a different batch size starts from scratch: decide that BEFORE touching the RNG
         if eng.has_state and eng.sticky:
             if u is None:
                 u = self._draw_uniforms(bsz, generator)

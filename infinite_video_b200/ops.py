@@ -405,3 +405,27 @@ def gather_rows(src, idx, out=None):
         out = torch.empty(Bv, S, e, device=src.device, dtype=torch.float32)
     check(lib().ltm_gather_rows(ptr(src), ptr(idx), ptr(out), Bv, R, S, e, stream_ptr(src.device)), "gather_rows")
     return out
+
+
+def _device_guarded(fn):
+    """Make the device of the first CUDA tensor argument current for the call (stream handles of one device are
+    invalid while another device is current)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*a, **kw):
+        for t in list(a) + list(kw.values()):
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                if t.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(t.device):
+                        return fn(*a, **kw)
+                break
+        return fn(*a, **kw)
+    return wrapped
+
+
+for _name, _fn in list(globals().items()):
+    if callable(_fn) and getattr(_fn, "__module__", None) == __name__ and not _name.startswith("_") \
+            and not _name.endswith("_supported") and isinstance(_fn, type(_device_guarded)):
+        globals()[_name] = _device_guarded(_fn)
+

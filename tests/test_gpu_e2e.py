@@ -344,8 +344,59 @@ def test_prefetched_pooling_is_bit_identical(dev):
         y = b.step(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0))
         assert torch.equal(x, y), f"chunk {c}"
         assert torch.equal(a.B_past, b.B_past)
-    with pytest.raises(RuntimeError):
-        b.prefetch(ks[0], 32); b.prefetch(ks[1], 32); b.prefetch(ks[2], 32)
+
+
+def test_prefetch_bookkeeping_survives_abandoned_and_interleaved_chunks(dev):
+    """Pending prefetches are keyed on tensor identity + version, never on the data pointer: an abandoned prefetch,
+    a non-prefetched step in between, a recycled address or an in-place rewrite must not make a step consume stale
+    pooled frames (results stay bit-identical to plain `step`)."""
+    from infinite_video_b200.batched import BatchedRectLTM
+    key, val = make_proj(65, 768)
+    a = BatchedRectLTM(64, .75, *proj_tensors(key, val), device=dev)
+    b = BatchedRectLTM(64, .75, *proj_tensors(key, val), device=dev)
+    ks, qs, us = make_inputs(66, 6, 2, 8 * 32, 768, 32)
+    ks = [k.to(dev) for k in ks]
+    qs = [q.to(dev) for q in qs]
+    us = [u.to(dev) for u in us]
+
+    def both(c, first, **kw):
+        x = a.step(ks[c], qs[c], None if first else us[c], new_doc=first)
+        y = b.step(ks[c], qs[c], None if first else us[c], new_doc=first, **kw)
+        assert torch.equal(x, y), f"chunk {c}"
+    # (c) prefetch(A) -> plain step(B) -> prefetch(C) -> step(A) -> step(C): A's pooled frames must survive
+    b.prefetch(ks[1], 32)
+    both(0, True)
+    b.prefetch(ks[2], 32)
+    both(1, False)
+    both(2, False)
+    # (a) an abandoned prefetch, then a NEW tensor that recycles its address and shape
+    junk = torch.randn_like(ks[3])
+    b.prefetch(junk, 32)
+    addr = junk.data_ptr()
+    del junk
+    fresh = ks[3].clone()
+    if fresh.data_ptr() == addr:                       # the caching allocator usually hands the block back
+        x = a.step(ks[3], qs[3], us[3])
+        y = b.step(fresh, qs[3], us[3])
+        assert torch.equal(x, y)
+    else:
+        both(3, False)
+    # in-place rewrite behind an unchanged pointer: the version counter invalidates the prefetch
+    buf = ks[4].clone()
+    b.prefetch(buf, 32)
+    buf.copy_(ks[5])
+    x = a.step(ks[5], qs[4], us[4])
+    y = b.step(buf, qs[4], us[4])
+    assert torch.equal(x, y)
+    # (b) more prefetches than buffers: the oldest is evicted, nothing raises, and reset() forgets them all
+    for c in range(4):
+        b.prefetch(ks[c], 32)
+    assert len(b._pref) == 2
+    b.reset(); a.reset()
+    assert not b._pref
+    both(0, True)
+    with pytest.raises(ValueError):
+        b.prefetch(ks[0].transpose(1, 2), 32)          # a copy made by .contiguous() could never be matched later
 
 
 def test_overlapped_step_is_bit_identical(dev):

@@ -224,6 +224,12 @@ def gemm_cluster(request):
     import ctypes
     from infinite_video_b200 import _capi
     lib = _capi.lib()
+    if not hasattr(lib, "ltm_debug_set_pair"):
+        # product build: the variant kernels and their selection hooks are compiled only with INFLTM_BRINGUP=1
+        if request.param != "single":
+            pytest.skip("kernel variant exists in bring-up builds only")
+        yield request.param
+        return
     for f in (lib.ltm_debug_set_cluster, lib.ltm_debug_set_pair):
         f.argtypes, f.restype = [ctypes.c_int], None
     lib.ltm_debug_set_pair(1 if request.param == "pair" else 0)
