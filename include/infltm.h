@@ -94,6 +94,23 @@ int ltm_consolidate_rect_h(const float* B_past, const float* xpart, const int32_
                            const int32_t* seg_ptr1, const int32_t* seg_mem1, const float* g1,
                            float* B_new, void* B_half, int Bv, int N, int e, int L, int splits, int S, void* stream);
 
+/* ---- projected-memory state (the K/V projection is affine and the memory contraction is linear): the keys / values
+ * of the bins that hold only re-sampled memory follow from the previous call's keys / values,
+ *   KV_new[v,j,:] = g[j] * sum_{p in seg(j), idx[v,p] >= 0} KV_past[v, idx[v,p], :] + (1 - g[j] * cnt) * bkv      j < jf
+ * (cnt = number of members with a valid index), so that only the rows j >= jf that receive new frames go through the
+ * projection GEMM (a quarter of them at tau = 0.75).  Same launch as ltm_consolidate_rect_h: B_new is produced as
+ * before; the KV rows j < jf are written only for videos that take the update branch.  round_tf32 != 0 stores the KV
+ * rows rounded to the tf32 grid (operands of the tensor-core attention).  idx_stride: elements between the index
+ * rows of consecutive videos (S; 0 = one row shared by all videos, the uniform re-sampling table).
+ * KV_past / KV_new: [Bv, N, ldkv] with ldkv = 2D; KV_past == NULL: coefficients only. */
+int ltm_consolidate_rect_kv(const float* B_past, const float* xpart, const int32_t* idx, int64_t idx_stride,
+                            const uint8_t* new_doc,
+                            const int32_t* seg_ptr0, const int32_t* seg_mem0, const float* g0,
+                            const int32_t* seg_ptr1, const int32_t* seg_mem1, const float* g1,
+                            float* B_new, void* B_half,
+                            const float* KV_past, float* KV_new, const float* bkv, int ldkv, int jf, int round_tf32,
+                            int Bv, int N, int e, int L, int splits, int S, void* stream);
+
 /* ---- batched GEMM on tcgen05 tensor cores (kind::tf32, fp32 operands fed by TMA, fp32
  * accumulate in TMEM).  C[b] (M x Nc, ldc) = A[b] (M x K) * B[b] (K x Nc) (+ bias[Nc]).
  *   a_kmajor: A[b] stored [M][K] (K contiguous, lda = row pitch) else [K][M] (lda = pitch of a K row)
@@ -128,6 +145,11 @@ typedef struct {
    * K-major; the products run as kind::f16 UMMAs with fp32 accumulation -- the same 11-bit significand as tf32 at
    * half the operand bytes and twice the MMA rate, for operands whose range fits fp16 (precision must be 1) */
   int ab_fp16;
+  /* optional two-level row mapping of A (K-major A, batch == 1): row m lives at
+   * A + (m / a_group) * a_group_stride + (m % a_group) * lda  -- e.g. the rows [jf, N) of every video's coefficient
+   * matrix as one flat problem (A = B_new + jf * e, a_group = N - jf, a_group_stride = N * e).  a_group must divide
+   * 128 or be a multiple of 128, and M % a_group == 0 (one TMA box spans 128 / a_group groups).  0 = plain m * lda. */
+  int a_group; int64_t a_group_stride;
 } ltm_gemm_args;
 int ltm_gemm(const ltm_gemm_args* args, void* stream);
 
@@ -234,6 +256,11 @@ typedef struct {
    * workspace (written by the consolidation), Wkv_half[2D,e] = Wkv in fp16.  Coefficients beyond the fp16 range
    * (|B| > 65504) become inf and propagate visibly; leave NULL for fp32 (tf32) operands. */
   void* B_half; const void* Wkv_half;
+  /* projected-memory state (ltm_consolidate_rect_kv): KV_past[Bv,N,2D] = the previous call's K|V (ping-pong with KV,
+   * caller swaps after the call), jf = first bin that holds a new frame in the update tables.  Used when KV_past != NULL,
+   * jf > 0, every video takes the update branch (B_past != NULL, new_doc == NULL) and N - jf tiles 128 rows evenly;
+   * otherwise all N rows are projected.  proj_precision: precision of the K/V projection GEMM (0 = `precision`). */
+  const float* KV_past; int jf; int proj_precision;
 } ltm_rect_step_args;
 int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const float* q, const double* u,
                   const uint8_t* new_doc, float* ctx, void* stream);

@@ -12,15 +12,29 @@
 
 namespace ltm {
 
+struct KvState {
+  const float4* KV_past;      // [Bv, N, ldkv4] previous call's K|V (NULL: coefficients only)
+  float4* KV_new;
+  const float4* bkv;          // [ldkv4]
+  int ldkv4, jf, round_tf32;
+};
+
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 __global__ void __launch_bounds__(256)
 consolidate_rect_kernel(const float4* __restrict__ B_past, const float4* __restrict__ xpart,
-                        const int32_t* __restrict__ idx, const uint8_t* __restrict__ new_doc,
+                        const int32_t* __restrict__ idx, const long long idx_stride,
+                        const uint8_t* __restrict__ new_doc,
                         const int32_t* __restrict__ seg_ptr0, const int32_t* __restrict__ seg_mem0,
                         const float* __restrict__ g0,
                         const int32_t* __restrict__ seg_ptr1, const int32_t* __restrict__ seg_mem1,
                         const float* __restrict__ g1,
-                        float4* __restrict__ B_new, uint2* __restrict__ B_half, int N, int e4, int L, int splits,
-                        int S) {
+                        float4* __restrict__ B_new, uint2* __restrict__ B_half, const KvState kv, int N, int e4, int L,
+                        int splits, int S) {
   const int j = blockIdx.x;
   const int v = blockIdx.y;
   const bool first = (B_past == nullptr) || (new_doc != nullptr && new_doc[v] != 0);
@@ -31,7 +45,7 @@ consolidate_rect_kernel(const float4* __restrict__ B_past, const float4* __restr
   const int frame_base = first ? 0 : S;       // member ids >= frame_base are frames
   const float4* xv = xpart + (size_t)v * L * splits * e4;
   const float4* bv = first ? nullptr : B_past + (size_t)v * N * e4;
-  const int32_t* iv = first ? nullptr : idx + (size_t)v * S;
+  const int32_t* iv = first ? nullptr : idx + (size_t)v * idx_stride;
   for (int c = threadIdx.x; c < e4; c += blockDim.x) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int m = m0; m < m1; ++m) {
@@ -52,6 +66,27 @@ consolidate_rect_kernel(const float4* __restrict__ B_past, const float4* __restr
       pk.x = *reinterpret_cast<const uint32_t*>(&lo);
       pk.y = *reinterpret_cast<const uint32_t*>(&hi);
       B_half[((size_t)v * N + j) * e4 + c] = pk;
+    }
+  }
+  // projected memory: a bin below jf holds re-sampled memory only, and K|V = B W^T + b is affine in B, so its
+  // keys / values are the same segmented mean taken over the previous call's K|V rows (the bias enters once:
+  // g sum_p (KV_past[p] - b) + b).  Rows >= jf are left to the projection GEMM.
+  if (kv.KV_past != nullptr && !first && j < kv.jf) {
+    const float4* kvp = kv.KV_past + (size_t)v * N * kv.ldkv4;
+    int cnt = 0;
+    for (int m = m0; m < m1; ++m) cnt += (iv[seg_mem[m]] >= 0) ? 1 : 0;
+    const float bw = 1.f - g * (float)cnt;
+    for (int c = threadIdx.x; c < kv.ldkv4; c += blockDim.x) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int m = m0; m < m1; ++m) {
+        const int row = iv[seg_mem[m]];
+        if (row >= 0) f4_add(acc, kvp[(size_t)row * kv.ldkv4 + c]);
+      }
+      const float4 b = kv.bkv[c];
+      acc.x = fmaf(acc.x, g, bw * b.x); acc.y = fmaf(acc.y, g, bw * b.y);
+      acc.z = fmaf(acc.z, g, bw * b.z); acc.w = fmaf(acc.w, g, bw * b.w);
+      if (kv.round_tf32) acc = make_float4(tf32_round(acc.x), tf32_round(acc.y), tf32_round(acc.z), tf32_round(acc.w));
+      kv.KV_new[((size_t)v * N + j) * kv.ldkv4 + c] = acc;
     }
   }
 }
@@ -86,6 +121,17 @@ extern "C" int ltm_consolidate_rect_h(const float* B_past, const float* xpart, c
                                       const int32_t* seg_ptr1, const int32_t* seg_mem1, const float* g1,
                                       float* B_new, void* B_half, int Bv, int N, int e, int L, int splits, int S,
                                       void* stream) {
+  return ltm_consolidate_rect_kv(B_past, xpart, idx, S, new_doc, seg_ptr0, seg_mem0, g0, seg_ptr1, seg_mem1, g1, B_new,
+                                 B_half, nullptr, nullptr, nullptr, 0, 0, 0, Bv, N, e, L, splits, S, stream);
+}
+
+extern "C" int ltm_consolidate_rect_kv(const float* B_past, const float* xpart, const int32_t* idx, int64_t idx_stride,
+                                       const uint8_t* new_doc,
+                                       const int32_t* seg_ptr0, const int32_t* seg_mem0, const float* g0,
+                                       const int32_t* seg_ptr1, const int32_t* seg_mem1, const float* g1,
+                                       float* B_new, void* B_half,
+                                       const float* KV_past, float* KV_new, const float* bkv, int ldkv, int jf,
+                                       int round_tf32, int Bv, int N, int e, int L, int splits, int S, void* stream) {
   using namespace ltm;
   LTM_REQUIRE(B_half == nullptr || (reinterpret_cast<uintptr_t>(B_half) & 7u) == 0, "consolidate_rect: B_half alignment");
   LTM_REQUIRE(xpart && B_new && seg_ptr0 && seg_mem0 && g0, "consolidate_rect: null pointer");
@@ -96,13 +142,25 @@ extern "C" int ltm_consolidate_rect_h(const float* B_past, const float* xpart, c
               "consolidate_rect: bad shape Bv=%d N=%d e=%d L=%d splits=%d", Bv, N, e, L, splits);
   LTM_REQUIRE(Bv <= 65535, "consolidate_rect: Bv=%d exceeds grid.y", Bv);
   LTM_REQUIRE(aligned16(B_past) && aligned16(xpart) && aligned16(B_new), "consolidate_rect: 16-byte alignment");
+  LTM_REQUIRE(idx_stride == 0 || idx_stride >= S, "consolidate_rect: idx_stride=%lld", (long long)idx_stride);
+  KvState kv{};
+  if (KV_past != nullptr) {
+    LTM_REQUIRE(B_past != nullptr && KV_new && bkv && KV_past != KV_new, "consolidate_rect_kv: K|V state needs B_past, "
+                "KV_new (distinct from KV_past) and the bias");
+    LTM_REQUIRE(ldkv > 0 && ldkv % 4 == 0 && jf >= 0 && jf <= N, "consolidate_rect_kv: bad ldkv=%d / jf=%d", ldkv, jf);
+    LTM_REQUIRE(aligned16(KV_past) && aligned16(KV_new) && aligned16(bkv), "consolidate_rect_kv: 16-byte alignment");
+    kv.KV_past = reinterpret_cast<const float4*>(KV_past);
+    kv.KV_new = reinterpret_cast<float4*>(KV_new);
+    kv.bkv = reinterpret_cast<const float4*>(bkv);
+    kv.ldkv4 = ldkv / 4; kv.jf = jf; kv.round_tf32 = round_tf32;
+  }
   const int e4 = e / 4;
   const int threads = e4 >= 256 ? 256 : ((e4 + 31) / 32) * 32;
   dim3 grid(N, Bv);
   consolidate_rect_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float4*>(B_past), reinterpret_cast<const float4*>(xpart), idx, new_doc,
-      seg_ptr0, seg_mem0, g0, seg_ptr1, seg_mem1, g1, reinterpret_cast<float4*>(B_new),
-      reinterpret_cast<uint2*>(B_half), N, e4, L, splits, S);
+      reinterpret_cast<const float4*>(B_past), reinterpret_cast<const float4*>(xpart), idx, (long long)idx_stride,
+      new_doc, seg_ptr0, seg_mem0, g0, seg_ptr1, seg_mem1, g1, reinterpret_cast<float4*>(B_new),
+      reinterpret_cast<uint2*>(B_half), kv, N, e4, L, splits, S);
   LTM_CHECK_LAUNCH("consolidate_rect");
   return 0;
 }

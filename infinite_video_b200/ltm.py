@@ -153,7 +153,9 @@ class LongTermAttention(nn.Module):
             self.length = k32.size(1) // self.tokens_per_frame            # gibbs:291-292
         if new_doc:
             eng.reset()                                                    # gibbs:300-302
-            LongTermAttention._shared_pool.update(key=None, x=None)       # do not keep the last video's frames alive
+            sp = LongTermAttention._shared_pool
+            if sp["key"] is None or sp["key"][0]() is not k:               # do not keep the last video's frames alive
+                sp.update(key=None, x=None)
         if eng.Bv is not None and eng.Bv != bsz:
             eng.reset()            # a different batch size starts from scratch: decide that BEFORE touching the RNG
         if eng.has_state and eng.sticky:

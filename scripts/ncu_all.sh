@@ -1,0 +1,14 @@
+#!/bin/bash
+# `ncu --set full` capture of every kernel of the library (one launch each, the last of the workload), summaries
+# into gpurun_out/ncu_<name>.txt (copied to profiles/<tag>_ncu_<name>.txt by scripts/save_profiles.sh).
+# usage: scripts/ncu_all.sh [kernel-name-regex ...]
+OUT=gpurun_out
+mkdir -p $OUT
+KERNELS=${@:-"pool_mean_kernel resample_kernel consolidate gemm_tf32_kernel cont_attn_tc_kernel cont_attn_fast_kernel cont_attn_kernel sticky_hist_gauss_kernel rbf_eval_kernel gather_rows_kernel density_rect_kernel ridge"}
+for k in $KERNELS; do
+  which=rect
+  case $k in sticky_hist_gauss*|rbf_eval*|gather_rows*|ridge*) which=gauss;; esac
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -c 3 -f -o $OUT/prof_$k \
+      python scripts/ncu_workload.py $which > $OUT/ncu_$k.log 2>&1
+  echo "$k rc=$?" >> $OUT/summary.txt
+done

@@ -1,0 +1,35 @@
+"""Small workload that launches every kernel of the library once or twice, for `ncu -k regex:<kernel>` captures
+(scripts/ncu_all.sh).  32 videos of the NExT-QA shape: rect path in tf32 (tensor-core attention) and tf32x3
+(FMA attention), the Gaussian variant (ridge solve, RBF design, erf histogram, sorted re-sampling, Gaussian attention)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from infinite_video_b200.batched import BatchedGaussLTM, BatchedRectLTM
+
+dev = torch.device("cuda:0")
+Bv, L, T, E, Q, N = 32, 256, 32, 768, 32, 256
+torch.manual_seed(0)
+key, val = torch.nn.Linear(E, 768), torch.nn.Linear(E, 768)
+w = (key.weight.detach(), key.bias.detach(), val.weight.detach(), val.bias.detach())
+g = torch.Generator(device=dev).manual_seed(1)
+k = [torch.randn(Bv, L * T, E, device=dev, generator=g) for _ in range(3)]
+q = [torch.randn(Bv, Q, 768, device=dev, generator=g) for _ in range(3)]
+u = [torch.rand(Bv, 512, device=dev, dtype=torch.float64, generator=g) for _ in range(3)]
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+if which in ("all", "rect"):
+    for prec in ("tf32", "tf32x3"):
+        eng = BatchedRectLTM(N, .75, *w, device=dev, precision=prec, keep_scores=(prec == "tf32x3"))
+        for c in range(3):
+            eng.step(k[c], q[c], u[c] if c else None, new_doc=(c == 0))
+        if prec == "tf32x3":
+            eng.density()
+    eng = BatchedRectLTM(512, .75, *w, device=dev)            # num_basis 512
+    for c in range(2):
+        eng.step(k[c], q[c], u[c] if c else None, new_doc=(c == 0))
+if which in ("all", "gauss"):
+    eng = BatchedGaussLTM(N, .75, *w, device=dev)
+    kg = [x.view(Bv, L, T, E)[:, :, 0].contiguous() for x in k]
+    for c in range(3):
+        eng.step(kg[c], q[c], u[c] if c else None, new_doc=(c == 0))
+torch.cuda.synchronize()
+print("ok")

@@ -25,8 +25,10 @@ with open(f'profiles/{tag}_launches_summary.txt', 'w') as f:
     f.write('\nlaunch list (first 120):\n')
     for o in order[:120]: f.write(' '.join(map(str, o)) + '\n')
 PY
-for k in pool gemm attn; do
-  [ -f gpurun_out/prof_$k.ncu-rep ] && ncu -i gpurun_out/prof_$k.ncu-rep --page raw --csv 2>/dev/null | python -c "
+for rep in gpurun_out/prof_*.ncu-rep; do
+  [ -f "$rep" ] || continue
+  k=$(basename $rep .ncu-rep); k=${k#prof_}
+  ncu -i $rep --page raw --csv 2>/dev/null | python -c "
 import csv,sys
 r=list(csv.reader(sys.stdin)); h=r[0]
 keep=['Kernel Name','gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum','gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed','dram__cycles_active.avg','lts__throughput.avg.pct_of_peak_sustained_elapsed','l1tex__throughput.avg.pct_of_peak_sustained_elapsed','sm__throughput.avg.pct_of_peak_sustained_elapsed','sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active','sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active','sm__warps_active.avg.pct_of_peak_sustained_active','launch__registers_per_thread','launch__grid_size','launch__block_size','launch__shared_mem_per_block_dynamic','launch__occupancy_limit_registers','launch__occupancy_limit_shared_mem','smsp__inst_executed.sum','l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']
@@ -36,6 +38,6 @@ for row in r[2:]:
         if w in d: print(f'{w:75s} {d[w]:>18s} {r[1][h.index(w)]}')
     print()
 " > profiles/${TAG}_ncu_$k.txt
-  [ -f gpurun_out/prof_$k.ncu-rep ] && ncu -i gpurun_out/prof_$k.ncu-rep --page source --csv 2>/dev/null | python scripts/ncu_stalls.py 20 >> profiles/${TAG}_ncu_$k.txt
+  ncu -i $rep --page source --csv 2>/dev/null | python scripts/ncu_stalls.py 20 >> profiles/${TAG}_ncu_$k.txt
 done
 ls -la profiles | tail -20
