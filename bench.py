@@ -251,7 +251,7 @@ def _cpu_info():
     return {"nproc": os.cpu_count(), "cpu_model": model, "threads": torch.get_num_threads(), "torch": torch.__version__}
 
 
-def parity_check(dev, chunks, videos=4, precision="tf32"):
+def parity_check(dev, chunks, videos=4, precision="tf32", shape=None):
     """`videos` videos of the bench shape through the CUDA path and through the oracle on the same inputs and the
     same uniforms, NO guard band (the oracle is the checker, not the thing measured).  `flips` counts sampled bins
     that differ from the oracle's own draws: the sampling kernel is bit-exact given (p, u), but end to end p carries
@@ -260,6 +260,7 @@ def parity_check(dev, chunks, videos=4, precision="tf32"):
     chunks are still compared like for like (tolerance 1e-3, max-abs / max-abs)."""
     from oracle import ltm_oracle as O
     from infinite_video_b200.batched import BatchedRectLTM
+    L, T, E, Q, NB = shape or (globals()["L"], globals()["T"], globals()["E"], globals()["Q"], globals()["NB"])
     torch.manual_seed(0)
     key, val = torch.nn.Linear(E, D), torch.nn.Linear(E, D)
     w = (key.weight.detach(), key.bias.detach(), val.weight.detach(), val.bias.detach())
@@ -375,7 +376,8 @@ def run_b200(args):
     key, val = torch.nn.Linear(E, D), torch.nn.Linear(E, D)
     eng = BatchedRectLTM(NB, TAU, key.weight.detach(), key.bias.detach(), val.weight.detach(), val.bias.detach(),
                          tokens_per_frame=T, sticky=True, precision=args.precision, device=dev,
-                         proj_operands=args.proj_operands)
+                         proj_operands=args.proj_operands, kv_state=not args.no_kv_state,
+                         proj_precision=args.proj_precision)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     ks = [torch.randn(Bv, L * T, E, device=dev, generator=g) for _ in range(C)]
     qs = [torch.randn(Bv, Q, D, device=dev, generator=g) for _ in range(C)]
@@ -524,6 +526,35 @@ def run_b200(args):
     ms, stage_avg, clocks, host_enqueue_ms = min(reps, key=lambda t: t[0])
     calls_total = Bv * C * args.steps * world
     value_eager = calls_total / (ms * 1e-3)
+
+    # sustained view: the same steps back to back for >= --sustain-s seconds in ONE timed region (the K-step region
+    # above lasts ~30 ms and ends before the power cap settles the clocks)
+    sustained = None
+    if args.sustain_s > 0:
+        sampler = make_sampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        n_steps = max(args.steps, int(args.sustain_s / (ms * 1e-3 / args.steps)) + 1)
+        D_.barrier(dev)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        if sampler:
+            sampler.mark()
+        s0.record(stream)
+        for _ in range(n_steps):
+            for c in range(C):
+                if overlap:
+                    eng.step_overlapped(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0), k_next=ks[(c + 1) % C])
+                else:
+                    eng.step(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0))
+        s1.record(stream)
+        torch.cuda.synchronize(dev)
+        D_.barrier(dev)
+        clk_s = sampler.stop() if sampler else None
+        ms_s = D_.max_over_ranks(s0.elapsed_time(s1), dev)
+        sustained = {"value": Bv * C * n_steps * world / (ms_s * 1e-3), "unit": "chunks/s", "steps": n_steps,
+                     "seconds": ms_s * 1e-3, "ms_per_step": ms_s / n_steps, "clocks": clk_s}
+        eng.reset()
     ms_graph = None
     if overlap and args.graph:
         ms_graph, clk_graph = graph_pass()
@@ -563,6 +594,15 @@ def run_b200(args):
             single = run_single_video(dev)
         except Exception as ex:
             single = {"error": f"{type(ex).__name__}: {ex}"}
+
+    other = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        other = {}
+        for name, cfg in OTHER_CONFIGS.items():
+            try:
+                other[name] = run_config_arm(dev, name, cfg, with_parity=not args.no_cpu_baseline)
+            except Exception as ex:
+                other[name] = {"error": f"{type(ex).__name__}: {ex}"}
 
     caller = None
     if rank == 0 and world == 1 and not args.no_gauss:
@@ -631,7 +671,9 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (tf32 tensor-core products for the K/V projection and the two attention contractions, fp32 accumulate)"
             if args.precision == "tf32" else "f32 (split-tf32 x3 tensor-core projection, fp32 FMA attention)",
-            "data": "synthetic", "config": workload_config(Bv, C, "gibbs", overlap),
+            "data": "synthetic", "config": dict(workload_config(Bv, C, "gibbs", overlap),
+                                                projected_memory_state=bool(eng.kv_state),
+                                                proj_precision=args.proj_precision or args.precision),
             "frame_blocks_per_s": value * L,
             "roofline": {"bound": "hbm", "kernel": "pool_mean_kernel", "achieved": pool_gbs, "peak": peak,
                          "unit": "GB/s", "frac": pool_gbs / peak, "traffic": pool_traffic, "peak_source": peak_src,
@@ -640,6 +682,7 @@ def run_b200(args):
                                         "kernel on its launching stream)",
                          "achieved_while_overlapped": pool_gbs_ov,
                          "traffic_source": "profiles/r1l_ncu_pool.txt (ncu --set full at 32 videos, per video)"},
+            "value_sustained": sustained,
             "value_without_overlap": calls_total / (ms_serial * 1e-3),
             "value_eager_launch": value_eager, "host_enqueue_ms_per_step_eager": host_enqueue_ms,
             "repeats": {"n": len(reps), "reported": "fastest", "ms_per_step": [r[0] / args.steps for r in reps],
@@ -651,12 +694,72 @@ def run_b200(args):
                               "frac": step_gbs / peak, "algorithmic_bytes_per_step": step_bytes},
             "stage_ms_per_chunk_step": stage_avg,
             "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "variant_gaussian": gauss, "single_video": single, "caller_cross_attention": caller,
+            "variant_gaussian": gauss, "single_video": single, "caller_cross_attention": caller, "configs": other,
         }
         emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0
+
+
+OTHER_CONFIGS = {
+    # BASELINE.json configs[0], [2], [3]: parity-test shapes, timed here so that every named shape has a measured
+    # fraction of its own byte roofline.  (videos per GPU, N, L, T, e, Q)
+    "cfg1": dict(videos=1024, N=64, L=8, T=32, e=768, Q=32,
+                 note="configs[0] shape (8 frames x 32 x 768, num_basis 64), batched: 1024 videos x 8 chunks"),
+    "cfg3": dict(videos=64, N=64, L=16, T=196, e=1024, Q=96,
+                 note="configs[2] VideoChat2 shape (16 frames x 196 x 1024, 96 queries, num_basis 64), one layer"),
+    "cfg4": dict(videos=64, N=512, L=256, T=32, e=768, Q=32,
+                 note="configs[3] long-video stress: num_basis 512, 64 videos, 2048 frame-blocks per video as "
+                      "8 chunks x 256 frames, sticky re-sampling on every chunk"),
+}
+
+
+def run_config_arm(dev, name, cfg, C=8, steps=3, with_parity=True):
+    """One of the other BASELINE shapes through the same overlapped chunk loop as the headline: chunks/s, fraction of
+    the shape's algorithmic-byte roofline, and a parity object at the full shape (oracle on 2 videos x 3 chunks)."""
+    from infinite_video_b200.batched import BatchedRectLTM
+    Bv, N, Lc, Tc, e, Qc = cfg["videos"], cfg["N"], cfg["L"], cfg["T"], cfg["e"], cfg["Q"]
+    torch.manual_seed(0)
+    key, val = torch.nn.Linear(e, D), torch.nn.Linear(e, D)
+    eng = BatchedRectLTM(N, TAU, key.weight.detach(), key.bias.detach(), val.weight.detach(), val.bias.detach(),
+                         tokens_per_frame=Tc, sticky=True, device=dev)
+    g = torch.Generator(device=dev).manual_seed(77)
+    ks = [torch.randn(Bv, Lc * Tc, e, device=dev, generator=g) for _ in range(C)]
+    qs = [torch.randn(Bv, Qc, D, device=dev, generator=g) for _ in range(C)]
+    us = [torch.rand(Bv, S, device=dev, dtype=torch.float64, generator=g) for _ in range(C)]
+
+    def one_step():
+        for c in range(C):
+            eng.step_overlapped(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0), k_next=ks[(c + 1) % C])
+    for _ in range(3):
+        one_step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(steps):
+        one_step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    peak, _src = measured_peaks()
+    step_bytes = algorithmic_bytes_per_call(Lc, Tc, e, Qc, N) * Bv * C + 4 * 2 * (e * D + D)
+    gbs = step_bytes / (ms * 1e-3) / 1e9
+    out = {"value": Bv * C / (ms * 1e-3), "unit": "chunks/s", "videos": Bv, "chunks": C, "ms_per_step": ms,
+           "num_basis": N, "frames_per_chunk_L": Lc, "tokens_per_frame_T": Tc, "encoder_width_e": e, "queries_Q": Qc,
+           "tensor_core_attention": bool(eng.tc_attn), "projected_memory_state": bool(eng.kv_state),
+           "resident_input_bytes": sum(k.numel() for k in ks) * 4,
+           "roofline_step": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                             "algorithmic_bytes_per_step": step_bytes},
+           "note": cfg["note"]}
+    del eng, ks, qs, us
+    torch.cuda.empty_cache()
+    if with_parity:
+        try:
+            out["parity"] = parity_check(dev, 3, videos=2, shape=(Lc, Tc, e, Qc, N))
+        except Exception as ex:
+            out["parity"] = {"error": f"{type(ex).__name__}: {ex}"}
+    return out
 
 
 def run_gauss_arm(dev, Bv, C, Lk, steps=3):
@@ -819,6 +922,10 @@ def main():
     ap.add_argument("--pool-ctas-per-sm", type=int, default=0, help="grid bound of the prefetch pooling kernel")
     ap.add_argument("--proj-operands", choices=["fp32", "fp16"], default="fp32",
                     help="operands of the K/V projection on the tensor-core path (fp16: kind::f16 UMMAs, opt-in)")
+    ap.add_argument("--no-kv-state", action="store_true",
+                    help="project all N coefficient rows every call instead of carrying K|V of the old bins along")
+    ap.add_argument("--proj-precision", default=None, choices=["tf32", "tf32x3"],
+                    help="precision of the K/V projection GEMM alone (default: --precision)")
     ap.add_argument("--repeats", type=int, default=3, help="timed regions of K steps each; the fastest is reported")
     ap.add_argument("--graph", action="store_true",
                     help="also time the K steps replayed from one CUDA graph per step (measured: 160 k vs 175 k eager -- "
@@ -826,6 +933,9 @@ def main():
     ap.add_argument("--hi-prio", action="store_true", help="run the main stream at high priority")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gauss", action="store_true", help="skip the secondary Gaussian-variant measurement")
+    ap.add_argument("--sustain-s", type=float, default=2.0,
+                    help="length of the additional sustained timed region in seconds (0 = skip)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE shapes (cfg1 / cfg3 / cfg4)")
     ap.add_argument("--gauss-videos", type=int, default=128)
     ap.add_argument("--gauss-frames", type=int, default=256, help="Lk of the Gaussian arm (k is consumed un-pooled)")
     args = ap.parse_args()

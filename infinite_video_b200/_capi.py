@@ -27,6 +27,7 @@ class GemmArgs(C.Structure):
         ("CT", C.c_void_p), ("ct_cols", C.c_int), ("ct_group", C.c_int),
         ("c_group", C.c_int), ("c_group_stride", C.c_int64), ("bias_stride", C.c_int64),
         ("round_tf32", C.c_int), ("ab_fp16", C.c_int),
+        ("a_group", C.c_int), ("a_group_stride", C.c_int64),
     ]
 
 
@@ -51,6 +52,7 @@ class RectStepArgs(C.Structure):
         ("prof_events", C.c_void_p * 10),
         ("X", C.c_void_p), ("c_none", C.c_float),
         ("B_half", C.c_void_p), ("Wkv_half", C.c_void_p),
+        ("KV_past", C.c_void_p), ("jf", C.c_int), ("proj_precision", C.c_int),
     ]
 
 
@@ -77,6 +79,8 @@ _SIGS = {
     "ltm_resample": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _P]),
     "ltm_consolidate_rect": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ltm_consolidate_rect_h": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "ltm_consolidate_rect_kv": (C.c_int, [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I,
+                                          _I, _I, _I, _I, _I, _I, _P]),
     "ltm_gemm": (C.c_int, [C.POINTER(GemmArgs), _P]),
     "ltm_project_kv": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_project_kv_t": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),

@@ -102,7 +102,7 @@ class BatchedRectLTM(_BatchedBase):
     def __init__(self, num_basis, tau, w_key, b_key, w_value, b_value, *, n_heads=12, head_size=64,
                  tokens_per_frame=32, sticky=True, nb_samples=tables.NB_SAMPLES, precision="tf32",
                  gemm_impl="tcgen05", device="cuda", keep_scores=False, fast_attn=True, tc_attn=True,
-                 proj_operands="fp32"):
+                 proj_operands="fp32", kv_state=True, proj_precision=None):
         super().__init__(num_basis, tau, w_key, b_key, w_value, b_value, n_heads, head_size, sticky, nb_samples,
                          precision, gemm_impl, device)
         self.T = int(tokens_per_frame)
@@ -119,6 +119,13 @@ class BatchedRectLTM(_BatchedBase):
         if proj_operands not in ("fp16", "fp32"):
             raise ValueError("proj_operands must be 'fp16' or 'fp32'")
         self.half_ops = self.tc_attn and proj_operands == "fp16" and self.e % 8 == 0
+        # projected-memory state (csrc/consolidate.cu): K|V = B W^T + b is affine in B and the memory contraction is
+        # linear, so K|V of the bins that hold only re-sampled memory are the same segmented mean taken over the
+        # previous K|V; only the bins that receive new frames (a quarter at tau = 0.75) go through the projection GEMM.
+        # Needs the row-major K|V layout (tensor-core or generic attention) and one new_doc flag for the whole batch.
+        self.kv_state = bool(kv_state) and not self.half_ops and (self.tc_attn or not self.fast_attn)
+        # precision of the K/V projection GEMM alone (None = `precision`); "tf32x3" makes the stored K|V fp32-grade
+        self.proj_precision = proj_precision
         self._Wkv_h = None
         self.prof_events = None       # optional list of 10 cudaEvent_t handles (bench.py stage timing)
         self._side = None             # side stream for pooling the next chunk ahead of time
@@ -146,7 +153,8 @@ class BatchedRectLTM(_BatchedBase):
                 splits=splits,
                 xparts=[torch.empty(Bv, L, splits, self.e, **f32), torch.empty(Bv, L, splits, self.e, **f32)],
                 xi=0,
-                KV=torch.empty(Bv, self.N, 2 * self.D, **f32) if (self.tc_attn or not self.fast_attn) else None,
+                KVs=[torch.empty(Bv, self.N, 2 * self.D, **f32) for _ in range(2 if self.kv_state else 1)]
+                if (self.tc_attn or not self.fast_attn) else None,
                 Kt=torch.empty(Bv, self.H, self.d, self.N, **f32) if (self.fast_attn and not self.tc_attn) else None,
                 V=torch.empty(Bv, self.N, self.D, **f32) if (self.fast_attn and not self.tc_attn) else None,
                 b_draw=torch.empty(Bv, self.S, **i32), idx=torch.empty(Bv, self.S, **i32),
@@ -218,6 +226,9 @@ class BatchedRectLTM(_BatchedBase):
         a.B_past = self._B[self._cur].data_ptr() if self.has_state else None
         a.B_new = self._B[1 - self._cur].data_ptr()
         a.xpart = ws["xparts"][ws["xi"]].data_ptr()
+        if ws["KVs"] is not None and len(ws["KVs"]) == 2:      # K|V ping-pong, in phase with the coefficient buffers
+            a.KV = ws["KVs"][1 - self._cur].data_ptr()
+            a.KV_past = ws["KVs"][self._cur].data_ptr() if (self.has_state and ws.get("kv_valid")) else None
         if self.prof_events is not None:
             for i, ev in enumerate(self.prof_events):
                 a.prof_events[i] = ev
@@ -250,7 +261,10 @@ class BatchedRectLTM(_BatchedBase):
         a.B_new = self._B[1 - self._cur].data_ptr()
         a.hist_part = self._hist.data_ptr()
         a.xpart = ws["xparts"][ws["xi"]].data_ptr()
-        a.KV = ws["KV"].data_ptr() if ws["KV"] is not None else None
+        a.KV = ws["KVs"][0].data_ptr() if ws["KVs"] is not None else None
+        a.KV_past = None
+        a.jf = tab.jf
+        a.proj_precision = ops.PRECISION[self.proj_precision] if self.proj_precision else 0
         a.Kt = ws["Kt"].data_ptr() if ws["Kt"] is not None else None
         a.V = ws["V"].data_ptr() if ws["V"] is not None else None
         a.b_draw, a.idx, a.ts, a.p = (ws["b_draw"].data_ptr(), ws["idx"].data_ptr(), ws["ts"].data_ptr(),
@@ -284,11 +298,12 @@ class BatchedRectLTM(_BatchedBase):
         self._cur = 1 - self._cur
         self.has_state = True
         self._last_L = ws["xparts"][0].shape[1]
-        last = ws.get("_last")
-        if last is None:
-            V = ws["V"] if ws["V"] is not None else ws["KV"][:, :, self.D:]
-            last = ws["_last"] = dict(b=ws["b_draw"], ts=ws["ts"], idx=ws["idx"], p=ws["p"], scores=ws["scores"], V=V)
-        self.last = last
+        kv = None
+        if ws["KVs"] is not None:
+            ws["kv_valid"] = True                       # the buffer just written is the next call's KV_past
+            kv = ws["KVs"][self._cur if len(ws["KVs"]) == 2 else 0]
+        V = ws["V"] if ws["V"] is not None else kv[:, :, self.D:]
+        self.last = dict(b=ws["b_draw"], ts=ws["ts"], idx=ws["idx"], p=ws["p"], scores=ws["scores"], V=V, KV=kv)
 
     @_on_device
     def prefetch(self, k_next, Q, events=None):

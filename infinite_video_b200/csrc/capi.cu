@@ -63,7 +63,8 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
     LTM_PROF(1);
   }
   const float* B_past = a->B_past;
-  const int32_t* idx = a->idx_uniform;     // non-sticky: fixed table shared by all videos
+  const int32_t* idx = a->idx_uniform;     // non-sticky: fixed table shared by all videos (index stride 0)
+  long long idx_stride = 0;
   if (B_past != nullptr && a->sticky) {
     LTM_REQUIRE(u != nullptr, "rect_step: sticky re-sampling needs the uniform draws");
     LTM_PROF(2);
@@ -72,27 +73,42 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
     if (rc) return rc;
     LTM_PROF(3);
     idx = a->idx;
-  } else if (B_past != nullptr) {
-    // broadcast the uniform table: consolidate reads idx[v*S + p]; give every video the same row
-    LTM_REQUIRE(a->idx != nullptr, "rect_step: idx workspace missing");
-    for (int v = 0; v < a->Bv; ++v)
-      LTM_CUDA(cudaMemcpyAsync(a->idx + (size_t)v * a->S, a->idx_uniform, sizeof(int32_t) * a->S,
-                               cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-    idx = a->idx;
+    idx_stride = a->S;
   }
   LTM_PROF(4);
   // tensor-core attention: row-major tf32-rounded K|V from the projection, both attention contractions as UMMAs
   const bool tcp = a->X != nullptr && a->KV != nullptr && a->precision == 1 && a->gemm_impl == 0 &&
                    ltm_attn_tc_supported(a->N, a->d);
   const bool half_ops = tcp && a->B_half != nullptr && a->Wkv_half != nullptr && a->e % 8 == 0;
-  rc = ltm_consolidate_rect_h(B_past, a->xpart, idx, new_doc, a->seg_ptr0, a->seg_mem0, a->g0, a->seg_ptr1,
-                              a->seg_mem1, a->g1, a->B_new, half_ops ? a->B_half : nullptr, a->Bv, a->N, a->e, a->L,
-                              a->splits, a->S, stream);
+  const bool fast = !tcp && a->Kt != nullptr && a->V != nullptr && ltm_attn_fast_supported(a->N, a->d);
+  // projected-memory state: every video updates, K|V of the previous call are at hand, and the rows that receive new
+  // frames tile the 128-row GEMM tiles evenly -> only those rows are projected (row-major K|V layouts only)
+  const int n_new = a->N - a->jf;
+  const bool kvstate = a->KV_past != nullptr && a->KV != nullptr && !fast && !half_ops && B_past != nullptr &&
+                       new_doc == nullptr && a->jf > 0 && n_new > 0 && (128 % n_new == 0 || n_new % 128 == 0) &&
+                       a->e % 4 == 0;
+  const int pprec = a->proj_precision ? a->proj_precision : a->precision;
+  rc = ltm_consolidate_rect_kv(B_past, a->xpart, idx, idx_stride, new_doc, a->seg_ptr0, a->seg_mem0, a->g0,
+                               a->seg_ptr1, a->seg_mem1, a->g1, a->B_new, half_ops ? a->B_half : nullptr,
+                               kvstate ? a->KV_past : nullptr, a->KV, a->bkv, 2 * D, a->jf, tcp ? 1 : 0,
+                               a->Bv, a->N, a->e, a->L, a->splits, a->S, stream);
   if (rc) return rc;
   LTM_PROF(5);
   LTM_PROF(6);
-  const bool fast = !tcp && a->Kt != nullptr && a->V != nullptr && ltm_attn_fast_supported(a->N, a->d);
-  if (half_ops) {
+  if (kvstate) {
+    // rows [jf, N) of every video as one flat problem: A = B_new + jf * e grouped per video, C = KV + jf * 2D
+    ltm_gemm_args ga;
+    memset(&ga, 0, sizeof(ga));
+    ga.A = a->B_new + (size_t)a->jf * a->e; ga.lda = a->e; ga.a_kmajor = 1;
+    ga.a_group = n_new; ga.a_group_stride = (int64_t)a->N * a->e;
+    ga.B = a->Wkv; ga.ldb = a->e; ga.b_kmajor = 1;
+    ga.K1 = a->e; ga.bias = a->bkv;
+    ga.C = a->KV + (size_t)a->jf * 2 * D; ga.ldc = 2 * D;
+    ga.c_group = n_new; ga.c_group_stride = (int64_t)a->N * 2 * D;
+    ga.M = a->Bv * n_new; ga.Nc = 2 * D; ga.K = a->e; ga.batch = 1;
+    ga.precision = pprec; ga.impl = a->gemm_impl; ga.round_tf32 = tcp ? 1 : 0;
+    rc = ltm_gemm(&ga, stream);
+  } else if (half_ops) {
     ltm_gemm_args ga;
     memset(&ga, 0, sizeof(ga));
     ga.A = reinterpret_cast<const float*>(a->B_half); ga.lda = a->e; ga.a_kmajor = 1;
@@ -103,7 +119,7 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
     ga.precision = 1; ga.impl = 0; ga.round_tf32 = 1; ga.ab_fp16 = 1;
     rc = ltm_gemm(&ga, stream);
   } else if (tcp)
-    rc = ltm_project_kv_r(a->B_new, a->Wkv, a->bkv, a->KV, a->Bv * a->N, a->e, 2 * D, a->precision, a->gemm_impl,
+    rc = ltm_project_kv_r(a->B_new, a->Wkv, a->bkv, a->KV, a->Bv * a->N, a->e, 2 * D, pprec, a->gemm_impl,
                           stream);
   else if (fast)
     rc = ltm_project_kv_t(a->B_new, a->Wkv, a->bkv, a->Kt, a->V, a->Bv * a->N, a->e, D, a->N, a->precision,

@@ -31,7 +31,10 @@ gemm_simt_kernel(const ltm_gemm_args g) {
       if (g.a_kmajor) { mm = f / SK; kk = f - mm * SK; } else { kk = f / ST; mm = f - kk * ST; }
       const int m = m0 + mm, k = k0 + kk;
       float val = 0.f;
-      if (m < g.M && k < g.K) val = g.a_kmajor ? A[(size_t)m * g.lda + k] : A[(size_t)k * g.lda + m];
+      if (m < g.M && k < g.K) {
+        if (g.a_group > 0) val = A[(size_t)(m / g.a_group) * g.a_group_stride + (size_t)(m % g.a_group) * g.lda + k];
+        else val = g.a_kmajor ? A[(size_t)m * g.lda + k] : A[(size_t)k * g.lda + m];
+      }
       As[kk][mm] = val;
     }
     for (int f = threadIdx.x; f < SK * ST; f += 256) {

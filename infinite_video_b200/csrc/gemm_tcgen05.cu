@@ -49,6 +49,7 @@ struct GemmDev {
   int ab_half;                              // operands are fp16 (kind::f16, 64 K-elements per 128-byte row)
   int round_tf32;                           // round stored row-major results to the tf32 grid
   int c_vec;                                // row-major stores may be 128-bit (alignment checked on the host)
+  int a_group;                              // two-level row mapping of A (0 = off): tile rows span 128 / a_group groups
   int dbg;                                  // bring-up builds only (-DLTM_BRINGUP): 1 = no global stores, 2 = no TMA loads
 };
 // The bring-up switches exist only in builds made with -DLTM_BRINGUP (scripts/*_probe.py); the product library
@@ -326,7 +327,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           const uint32_t sa = smem_base + s * C_::STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
           const int k0 = kb * bke;
-          if (g.a_kmajor) {
+          if (g.a_group > 0) {
+            // grouped rows: the tensor map is {K, a_group rows, groups}; one box covers 128 flat rows
+            tma_load_3d(&mapA, sa, full_bar(s), k0, g.a_group > BM ? m0 % g.a_group : 0, m0 / g.a_group);
+          } else if (g.a_kmajor) {
             tma_load_3d(&mapA, sa, full_bar(s), k0, m0, za);
           } else {
 #pragma unroll
@@ -926,8 +930,23 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   const int bn = (a.Nc > 128 && tiles256 >= 74) ? 256 : 128;
   const int K1 = two ? a.K1 : a.K;
   CUtensorMap mA, mB, mB2;
-  if (encode_operand(&mA, a.A, a.M, a.K, a.lda, a.strideA, a.batch, a.a_kmajor, BM, "A", half)) return -1;
-  const bool pair = (g_pair > 0 || (g_pair < 0 && !split)) && a.M > BM;        // CTA pairs need two row tiles
+  if (a.a_group > 0) {
+    // A rows in groups: dims {K, a_group, M / a_group}, box {32, min(a_group, 128), 128 / a_group (>= 1)}
+    LTM_REQUIRE(a.a_kmajor && a.batch == 1 && !half, "gemm: grouped A rows need K-major fp32 A and batch == 1");
+    LTM_REQUIRE((BM % a.a_group == 0 || a.a_group % BM == 0) && a.M % a.a_group == 0,
+                "gemm: a_group=%d must divide %d or be a multiple of it, and divide M=%d", a.a_group, BM, a.M);
+    LTM_REQUIRE(aligned16(a.A) && a.lda % 4 == 0 && a.lda >= a.K && a.a_group_stride % 4 == 0 &&
+                a.a_group_stride >= (long long)a.a_group * a.lda, "gemm: grouped A pitches");
+    cuuint64_t dims[3] = {(cuuint64_t)a.K, (cuuint64_t)a.a_group, (cuuint64_t)(a.M / a.a_group)};
+    cuuint64_t strides[2] = {(cuuint64_t)a.lda * 4ull, (cuuint64_t)a.a_group_stride * 4ull};
+    cuuint32_t box[3] = {32u, (cuuint32_t)(a.a_group < BM ? a.a_group : BM), (cuuint32_t)(a.a_group < BM ? BM / a.a_group : 1)};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = g_encode(&mA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a.A), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LTM_REQUIRE(r == CUDA_SUCCESS, "gemm: cuTensorMapEncodeTiled(grouped A) failed with CUresult %d", (int)r);
+  } else if (encode_operand(&mA, a.A, a.M, a.K, a.lda, a.strideA, a.batch, a.a_kmajor, BM, "A", half)) return -1;
+  const bool pair = (g_pair > 0 || (g_pair < 0 && !split)) && a.M > BM && a.a_group == 0;   // CTA pairs need two row tiles
   const bool mc_pre = !pair && g_cluster >= 2 && a.b_kmajor && !two && a.M > BM;
   const int b_box = (pair || mc_pre) ? bn / 2 : bn;             // B rows fetched per TMA box
   if (encode_operand(&mB, a.B, a.Nc, K1, a.ldb, a.strideB, a.batch, a.b_kmajor, b_box, "B", half)) return -1;
@@ -948,6 +967,7 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   d.ab_half = half;
   d.c_vec = (a.ldc % 4 == 0 && a.strideC % 4 == 0 && a.c_group_stride % 4 == 0 && aligned16(a.C) &&
              (a.CT == nullptr || a.ct_cols % 4 == 0)) ? 1 : 0;
+  d.a_group = a.a_group;
   d.a_batched = a.strideA != 0; d.b_batched = a.strideB != 0; d.b2_batched = a.strideB2 != 0; d.has_b2 = two ? 1 : 0;
 #ifdef LTM_BRINGUP
   if (pair) {

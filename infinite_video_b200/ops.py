@@ -44,6 +44,25 @@ def pool_mean(k, splits=1):
     return out
 
 
+def consolidate_rect_kv(B_past, xpart, idx, tab, S, KV_past, bkv, jf, round_tf32=False, new_doc=None):
+    """`consolidate_rect` that also carries the projected memory K|V along: rows j < jf of KV_new are the segmented
+    mean of KV_past rows (+ bias term); rows >= jf are left untouched for the projection GEMM.  idx: [Bv,S] or [S]
+    (one row shared by all videos).  Returns (B_new, KV_new)."""
+    require_cuda(B_past, xpart, idx, KV_past, bkv, new_doc)
+    Bv, L, splits, e = xpart.shape
+    N = tab["g0"].numel()
+    ldkv = KV_past.shape[-1]
+    B_new = torch.empty(Bv, N, e, device=xpart.device, dtype=torch.float32)
+    KV_new = torch.zeros(Bv, N, ldkv, device=xpart.device, dtype=torch.float32)
+    check(lib().ltm_consolidate_rect_kv(ptr(B_past), ptr(xpart), ptr(idx), S if idx.dim() == 2 else 0, ptr(new_doc),
+                                        ptr(tab["seg_ptr0"]), ptr(tab["seg_mem0"]), ptr(tab["g0"]),
+                                        ptr(tab["seg_ptr1"]), ptr(tab["seg_mem1"]), ptr(tab["g1"]),
+                                        ptr(B_new), None, ptr(KV_past), ptr(KV_new), ptr(bkv), ldkv, jf,
+                                        int(bool(round_tf32)), Bv, N, e, L, splits, S, stream_ptr(xpart.device)),
+          "consolidate_rect_kv")
+    return B_new, KV_new
+
+
 def sticky_hist_rect(scores, jb, tb):
     """scores[Bv,H,Q,N] -> hist_part[Bv,H,127].  gibbs:196-203."""
     require_cuda(scores, jb, tb)
@@ -173,7 +192,7 @@ def gemm(A, B, *, a_kmajor=True, b_kmajor=True, B2=None, bias=None, out=None, pr
 
 def gemm_raw(A, lda, strideA, a_kmajor, B, ldb, strideB, b_kmajor, C_, ldc, strideC, M, Nc, K, batch, *, bias=None,
              bias_stride=0, c_group=0, c_group_stride=0, precision="tf32", impl="tcgen05", a_offset=0, b_offset=0,
-             c_offset=0, round_tf32=False):
+             c_offset=0, round_tf32=False, a_group=0, a_group_stride=0):
     """ltm_gemm with every pitch / batch stride spelled out (elements).  A, B, C_ are the base tensors; *_offset
     shifts the start (elements).  Used where operands are strided views that tensor shapes cannot express
     (per-head column blocks, per-head / per-video output layouts)."""
@@ -190,6 +209,7 @@ def gemm_raw(A, lda, strideA, a_kmajor, B, ldb, strideB, b_kmajor, C_, ldc, stri
     g.CT, g.ct_cols, g.ct_group = None, 0, 0
     g.c_group, g.c_group_stride = c_group, c_group_stride
     g.round_tf32 = int(bool(round_tf32))
+    g.a_group, g.a_group_stride = a_group, a_group_stride
     check(lib().ltm_gemm(C.byref(g), stream_ptr(A.device)), "gemm")
     return C_
 

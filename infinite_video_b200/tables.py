@@ -116,6 +116,8 @@ class RectTables:
     seg_ptr1: np.ndarray = None      # int32 [N+1]
     seg_mem1: np.ndarray = None      # int32 [nnz1]  p < S: sample p ; p >= S: frame p-S
     g1: np.ndarray = None            # fp32  [N]
+    jf: int = 0                      # first bin of the update tables that holds a new frame (bins below it hold
+                                     # re-sampled memory only: their K|V follow from the previous K|V, consolidate.cu)
     # sticky histogram (129 nudged edges) and sampling
     tb: np.ndarray = None            # fp32 [129] evaluation edges
     jb: np.ndarray = None            # int32 [129] basis index at each edge (-1 none)
@@ -181,6 +183,8 @@ def rect_tables(L: int, N: int, tau: float, S: int = NB_SAMPLES, num_quad: int =
     core1 = b1[trim1:trim1 + S + L]
     t.seg_ptr1, t.seg_mem1 = _csr(core1, N)
     t.g1 = (1.0 / (torch.from_numpy(cnt1).float() + ridge)).numpy()
+    fb = core1[S:]
+    t.jf = int(fb[fb >= 0].min()) if (fb >= 0).any() else N
 
     # --- sticky edges (gibbs:163,:197-199,:207-208)
     bins, nudged = sticky_edges()

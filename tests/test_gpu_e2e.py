@@ -86,6 +86,31 @@ def test_generic_attention_path_still_matches(dev, kw):
     assert w["B"] < 1e-5 and w["ctx"] < TOL_CTX, w
 
 
+def test_projected_memory_state_equals_full_projection(dev):
+    """kv_state (K|V of the old bins carried from the previous call, only the new-frame rows projected) against the
+    engine that projects all N rows every call, over enough chunks for a rounding drift to show: coefficients are
+    bit-identical (that path is unchanged), contexts agree well inside the tolerance to the oracle."""
+    from infinite_video_b200.batched import BatchedRectLTM
+    for N, L, kw in ((256, 64, {}), (512, 32, {}), (64, 8, {}), (256, 64, dict(proj_precision="tf32x3")),
+                     (256, 32, dict(fast_attn=False, precision="tf32x3"))):
+        key, val = make_proj(33, 768)
+        a = BatchedRectLTM(N, .75, *proj_tensors(key, val), device=dev, kv_state=True, **kw)
+        b = BatchedRectLTM(N, .75, *proj_tensors(key, val), device=dev, kv_state=False, **kw)
+        assert a.kv_state and not b.kv_state
+        ks, qs, us = make_inputs(34, 10, 3, L * 32, 768, 32)
+        worst = 0.0
+        for c in range(10):
+            k, q, u = ks[c].to(dev), qs[c].to(dev), us[c].to(dev)
+            x = a.step(k, q, u if c else None, new_doc=(c == 0))
+            y = b.step(k, q, u if c else None, new_doc=(c == 0))
+            if c and not torch.equal(a.last["b"], b.last["b"]):
+                assert c >= 4, (N, c)          # a draw on a CDF edge went the other way: nothing left to compare
+                break
+            assert torch.equal(a.B_past, b.B_past), (N, c)
+            worst = max(worst, relerr(x, y), relerr(a.last["KV"], b.last["KV"]))
+        assert worst < (5e-4 if kw.get("precision") != "tf32x3" else 1e-5), (N, kw, worst)
+
+
 def test_rect_split_tf32_is_fp32_grade(dev):
     w = _run_rect(dev, N=256, L=32, C=3, Bv=2, precision="tf32x3")
     assert w["B"] < 1e-5 and w["ctx"] < 2e-5, w

@@ -200,6 +200,68 @@ def test_consolidate_rect(dev, N, L, tau, splits):
     assert torch.equal(got2[1], got0[1].cpu()) and torch.equal(got2[0], got1[0].cpu())
 
 
+@pytest.mark.parametrize("N,L,tau,shared_idx", [(256, 64, .75, False), (64, 8, .75, False), (512, 32, .75, False),
+                                                (100, 30, .5, False), (64, 8, .75, True)])
+def test_consolidate_rect_carries_projected_memory(dev, N, L, tau, shared_idx):
+    """Projected-memory state: K|V of the bins below `jf` from the previous K|V == projection of the new coefficients
+    (the projection is affine, the contraction linear); rows >= jf are not touched."""
+    ops, T = _ops(), _tables()
+    g = torch.Generator().manual_seed(3 * N + L)
+    Bv, e, D2 = 3, 768, 1536
+    x = torch.randn(Bv, L, 1, e, generator=g)
+    B_past = torch.randn(Bv, N, e, generator=g)
+    W = torch.randn(D2, e, generator=g) / 28
+    bias = torch.randn(D2, generator=g)
+    KV_past = (B_past.double() @ W.double().t() + bias.double()).float()
+    tab = T.rect_tables(L, N, tau)
+    td = tab.to(dev)
+    jf = tab.jf
+    assert 0 < jf < N
+    if shared_idx:
+        idx = torch.from_numpy(tab.idx_uniform).int()
+    else:
+        b = torch.randint(0, 127, (Bv, 512), generator=g)
+        idx = torch.from_numpy(tab.bin2basis)[b].int()
+    B_new, KV_new = ops.consolidate_rect_kv(B_past.to(dev), x.to(dev), idx.to(dev), td, 512, KV_past.to(dev),
+                                            bias.to(dev), jf)
+    want_B = ops.consolidate_rect(B_past.to(dev), x.to(dev),
+                                  (idx if idx.dim() == 2 else idx.expand(Bv, 512).contiguous()).to(dev), None, td, 512)
+    assert torch.equal(B_new, want_B)
+    want_KV = (B_new.double().cpu() @ W.double().t() + bias.double()).float()
+    assert relerr(KV_new[:, :jf], want_KV[:, :jf]) < 2e-6
+    assert float(KV_new[:, jf:].abs().max()) == 0.0
+    # rounded store: every value on the tf32 grid, within half a tf32 ulp of the exact one
+    _, KV_r = ops.consolidate_rect_kv(B_past.to(dev), x.to(dev), idx.to(dev), td, 512, KV_past.to(dev), bias.to(dev),
+                                      jf, round_tf32=True)
+    assert int((KV_r.view(torch.int32) & 0x1FFF).abs().max()) == 0
+    assert relerr(KV_r[:, :jf], want_KV[:, :jf]) < 5e-4           # half a tf32 ulp = 2^-11 relative
+
+
+@pytest.mark.parametrize("group,groups,N_rows", [(64, 6, 256), (16, 20, 64), (128, 3, 512), (256, 2, 1024), (32, 5, 40)])
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
+def test_gemm_grouped_rows(dev, group, groups, N_rows, precision):
+    """A rows addressed in groups (rows [jf, N) of every video as one flat problem, one TMA box spanning several
+    videos) and C written through the matching two-level mapping; checked against the SIMT kernel."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(group + groups)
+    K, Nc = 96, 160
+    A = torch.randn(groups, N_rows, K, generator=g).to(dev)
+    Bm = torch.randn(Nc, K, generator=g).to(dev)
+    bias = torch.randn(Nc, generator=g).to(dev)
+    j0 = N_rows - group
+    outs = []
+    for impl in ("tcgen05", "simt"):
+        Cm = torch.zeros(groups, N_rows, Nc, device=dev)
+        ops.gemm_raw(A, K, 0, True, Bm, K, 0, True, Cm, Nc, 0, groups * group, Nc, K, 1, bias=bias,
+                     a_offset=j0 * K, a_group=group, a_group_stride=N_rows * K, c_offset=j0 * Nc,
+                     c_group=group, c_group_stride=N_rows * Nc, precision=precision, impl=impl)
+        outs.append(Cm)
+    want = A[:, j0:].double() @ Bm.double().t() + bias.double()
+    assert float(outs[0][:, :j0].abs().max()) == 0.0
+    assert relerr(outs[1][:, j0:], want) < 1e-5
+    assert relerr(outs[0][:, j0:], want) < (2e-3 if precision == "tf32" else 2e-5)
+
+
 # ---------------------------------------------------------------------------------------- GEMM (tcgen05)
 GEMM_CASES = [
     # M, N, K, batch, a_kmajor, b_kmajor, two_segment, bias
