@@ -371,7 +371,13 @@ def run_b200(args):
     torch.cuda.set_device(dev)
     lib = _capi.lib()
     _capi.check(lib.ltm_device_check(), "device_check")
+    numa = D_.bind_to_gpu_numa_node(local) if world > 1 else None     # before any pinned allocation
     Bv, C = args.videos, args.chunks
+    if args.scaling == "strong":
+        # BASELINE configs[4] literally: a fixed total of independent videos (1024) sharded over the ranks
+        if args.total_videos % world:
+            raise SystemExit("--total-videos must be divisible by the number of GPUs")
+        Bv = args.total_videos // world
     torch.manual_seed(0)
     key, val = torch.nn.Linear(E, D), torch.nn.Linear(E, D)
     eng = BatchedRectLTM(NB, TAU, key.weight.detach(), key.bias.detach(), val.weight.detach(), val.bias.detach(),
@@ -379,7 +385,14 @@ def run_b200(args):
                          proj_operands=args.proj_operands, kv_state=not args.no_kv_state,
                          proj_precision=args.proj_precision)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    ks = [torch.randn(Bv, L * T, E, device=dev, generator=g) for _ in range(C)]
+    # the chunks of all videos stay resident when they fit (128 videos x 8 chunks = 25.8 GB); a large shard (1024
+    # videos on one GPU: 25.8 GB per chunk) streams through a ring of 3 chunk buffers instead -- still far more
+    # than the L2 between two uses of a buffer
+    class _Ring(list):
+        def __getitem__(self, i):
+            return list.__getitem__(self, i % len(self))
+    ring = C if Bv * C * L * T * E * 4 < 90e9 else 3
+    ks = _Ring(torch.randn(Bv, L * T, E, device=dev, generator=g) for _ in range(ring))
     qs = [torch.randn(Bv, Q, D, device=dev, generator=g) for _ in range(C)]
     us = [torch.rand(Bv, S, device=dev, dtype=torch.float64, generator=g) for _ in range(C)]
     stream = torch.cuda.current_stream(dev)
@@ -613,7 +626,10 @@ def run_b200(args):
 
     # ---------------- end to end through the host entry point (pinned host buffers, ring of 2 chunk slots)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and Bv * L * T * E * 4 * 2 > 16e9:
+        e2e = {"skipped": f"{Bv} videos per GPU need {Bv * L * T * E * 8 / 1e9:.0f} GB of pinned host staging; "
+                          "the end-to-end view is measured on the 128-videos-per-GPU workload"}
+    elif not args.no_e2e:
         hk = [torch.randn(Bv, L * T, E).pin_memory() for _ in range(2)]
         hq = [torch.randn(Bv, Q, D).pin_memory() for _ in range(2)]
         hu = [torch.rand(Bv, S, dtype=torch.float64).pin_memory() for _ in range(2)]
@@ -626,6 +642,16 @@ def run_b200(args):
             return float(hout[(C - 1) & 1][0, 0, 0])        # the result is read on the host
 
         host_step()
+        # what the copies alone can deliver: every rank streams one chunk's k from its pinned buffer to its GPU at the
+        # same time (no kernels) -- the ceiling of any end-to-end number on this box (PCIe per GPU; with several GPUs
+        # behind one socket, that socket's DRAM bandwidth)
+        D_.barrier(dev)
+        t0 = time.perf_counter()
+        for i in range(4):
+            eng._ws[next(iter(eng._ws))]["k_dev"].copy_(hk[i & 1], non_blocking=True)
+        torch.cuda.synchronize(dev)
+        dt_copy = D_.max_over_ranks(time.perf_counter() - t0, dev)
+        copy_gbs = 4 * hk[0].numel() * 4 / dt_copy / 1e9
         D_.barrier(dev)
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
@@ -635,6 +661,11 @@ def run_b200(args):
         d2h = C * hout[0].numel() * 4
         e2e = {"value": Bv * C * args.e2e_steps * world / dt, "unit": "chunks/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+               "h2d_copy_ceiling": {"gbs_per_gpu_with_all_ranks_copying": copy_gbs,
+                                    "chunks_per_s": world * Bv / (hk[0].numel() * 4 / (copy_gbs * 1e9)),
+                                    "note": "plain cudaMemcpyAsync of the same pinned chunk buffers on every rank at "
+                                            "once, no kernels: the upper bound of e2e on this host"},
+               "numa_binding": numa,
                "note": "BatchedRectLTM.step_host -> ltm_rect_step_host (C-ABI): pinned host k,q,u -> device, "
                        "kernels, ctx -> pinned host, per chunk; PCIe-bound"}
 
@@ -668,7 +699,7 @@ def run_b200(args):
         launches = args.steps * (C * 5 - 1)
         line = {
             "metric": METRIC, "value": value, "unit": "chunks/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32 (tf32 tensor-core products for the K/V projection and the two attention contractions, fp32 accumulate)"
             if args.precision == "tf32" else "f32 (split-tf32 x3 tensor-core projection, fp32 FMA attention)",
             "data": "synthetic", "config": dict(workload_config(Bv, C, "gibbs", overlap),
@@ -913,7 +944,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--videos", type=int, default=128, help="videos per GPU")
+    ap.add_argument("--videos", type=int, default=128, help="videos per GPU (weak scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --videos per GPU; strong: --total-videos sharded over the GPUs (BASELINE configs[4])")
+    ap.add_argument("--total-videos", type=int, default=1024)
     ap.add_argument("--chunks", type=int, default=8, help="sequential chunks per video")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32x3"])
     ap.add_argument("--e2e-steps", type=int, default=2)

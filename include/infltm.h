@@ -179,6 +179,10 @@ int ltm_cont_attn_gauss(const float* q, const float* KV, const float* basis_mu, 
                         float* ctx, float* scores_out, float* mu_out, float* sd_out,
                         int Bv, int Q, int N, int H, int d, void* stream);
 
+/* ---- G4 optional output: KL(N(mu, sd^2) || N(mu_0, sigma_0^2)) per row, long_term_attention.py:296-304 (including
+ * its quirk: the mean term is dropped when mu_0 > 0).  mu, sd, out: [n]. */
+int ltm_kl_gauss(const float* mu, const float* sd, float mu_0, float sigma_0, float* out, int64_t n, void* stream);
+
 /* ---- fast path of both attention variants for num_basis in {64,128,256}, head_size 64: keys transposed
  * (Kt[Bv,H,64,N], from ltm_project_kv_t), values V[Bv,N,ldv].  Same outputs as the two functions above. */
 int ltm_attn_fast_supported(int N, int d);

@@ -92,6 +92,7 @@ _SIGS = {
     "ltm_cont_attn_gauss_t": (C.c_int, [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_cont_attn_rect": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_cont_attn_gauss": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "ltm_kl_gauss": (C.c_int, [_P, _P, _F, _F, _P, _L, _P]),
     "ltm_rbf_eval": (C.c_int, [_P, _P, _P, _P, _P, _L, _I, _I, _P]),
     "ltm_ridge_workspace_doubles": (C.c_int64, [_I, _I]),
     "ltm_ridge_solve": (C.c_int, [_P, _I, _I, _I, _P, _P, _I, C.c_double, _P, _P, _L, _P, _P]),

@@ -102,10 +102,11 @@ class BatchedRectLTM(_BatchedBase):
     def __init__(self, num_basis, tau, w_key, b_key, w_value, b_value, *, n_heads=12, head_size=64,
                  tokens_per_frame=32, sticky=True, nb_samples=tables.NB_SAMPLES, precision="tf32",
                  gemm_impl="tcgen05", device="cuda", keep_scores=False, fast_attn=True, tc_attn=True,
-                 proj_operands="fp32", kv_state=True, proj_precision=None):
+                 proj_operands="fp32", kv_state=True, proj_precision=None, spacing="linear"):
         super().__init__(num_basis, tau, w_key, b_key, w_value, b_value, n_heads, head_size, sticky, nb_samples,
                          precision, gemm_impl, device)
         self.T = int(tokens_per_frame)
+        self.spacing = spacing        # first-chunk frame positions: 'linear' | 'log' (gibbs:101-127)
         self.keep_scores = keep_scores
         # transposed-key attention path (num_basis 64/128/256, head size 64); `fast_attn=False` forces the generic one
         self.fast_attn = bool(fast_attn) and ops.attn_fast_supported(self.N, self.d)
@@ -291,10 +292,12 @@ class BatchedRectLTM(_BatchedBase):
             self.has_state = False
         elif flags is not None and not self.has_state:
             flags = None                     # nothing to keep anyway: everything is a first chunk
-        tab = tables.rect_tables(L, self.N, self.tau, self.S)
+        tab = tables.rect_tables(L, self.N, self.tau, self.S, spacing=self.spacing)
         return Bv, L, Q, tab, tab.to(self.device), flags
 
-    def _finish(self, ws):
+    def _finish(self, ws, xp=None):
+        self._last_xpart = xp if xp is not None else ws["xparts"][ws["xi"]]
+        self._last_updated = self.has_state          # False: the call just made was a first chunk
         self._cur = 1 - self._cur
         self.has_state = True
         self._last_L = ws["xparts"][0].shape[1]
@@ -357,6 +360,20 @@ class BatchedRectLTM(_BatchedBase):
         return self._evs
 
     @_on_device
+    def x_past(self):
+        """[Bv, e, S+L] ([Bv, e, L] after a first chunk): what the reference keeps as `x_past` (gibbs:215,221) -- the
+        re-sampled rows of the previous coefficients followed by the pooled frames of the most recent call."""
+        xp = self._last_xpart
+        x = xp.sum(2) if xp.shape[2] > 1 else xp[:, :, 0]                                              # [Bv,L,e]
+        if not self._last_updated:
+            return x.transpose(1, 2)
+        idx = self.last["idx"] if self.sticky else \
+            tables.rect_tables(self._last_L, self.N, self.tau, self.S, spacing=self.spacing).to(self.device)[
+                "idx_uniform"].unsqueeze(0).expand(x.shape[0], -1).contiguous()
+        xm = ops.gather_rows(self._B[1 - self._cur], idx)                   # previous coefficients: other buffer
+        return torch.cat([xm, x], 1).transpose(1, 2)
+
+    @_on_device
     def density(self):
         """alphas[Q,Bv,H,768] of the most recent call: the density side-output the Video-LLaMA copy pickles to
         ./alphas_uniform on every forward (gibbs:320-343).  Needs `keep_scores=True`."""
@@ -364,7 +381,7 @@ class BatchedRectLTM(_BatchedBase):
         if sc is None:
             raise RuntimeError("density() needs the scores of the last call: construct with keep_scores=True")
         L = self._last_L
-        td = tables.rect_tables(L, self.N, self.tau, self.S).to(self.device)
+        td = tables.rect_tables(L, self.N, self.tau, self.S, spacing=self.spacing).to(self.device)
         return ops.density_rect(sc, td["jd"], td["wd"])
 
     @_on_device
@@ -406,7 +423,7 @@ class BatchedRectLTM(_BatchedBase):
             a.xpart, a.splits = pooled.data_ptr(), pooled.shape[2]
             check(lib().ltm_rect_step(C.byref(a), None, ptr(q), ptr(u), ptr(flags), ptr(ctx),
                                       stream_ptr(self.device)), "rect_step")
-            self._finish(ws)
+            self._finish(ws, pooled)
             return ctx
         if self.has_state and self.sticky:
             if u is None or u.dtype != torch.float64 or tuple(u.shape) != (Bv, self.S):
@@ -529,7 +546,8 @@ class BatchedGaussLTM(_BatchedBase):
 
     def __init__(self, num_basis, tau, w_key, b_key, w_value, b_value, *, sigmas=(0.005, 0.01), n_heads=12,
                  head_size=64, sticky=True, nb_samples=tables.NB_SAMPLES, precision="tf32x3",
-                 proj_precision=None, gemm_impl="tcgen05", device="cuda", ridge=tables.RIDGE_PENALTY):
+                 proj_precision=None, gemm_impl="tcgen05", device="cuda", ridge=tables.RIDGE_PENALTY,
+                 spacing="linear"):
         ns = len(sigmas)
         n = int(num_basis)
         if n % ns:
@@ -537,6 +555,7 @@ class BatchedGaussLTM(_BatchedBase):
         super().__init__(n, tau, w_key, b_key, w_value, b_value, n_heads, head_size, sticky, nb_samples,
                          precision, gemm_impl, device)
         self.sigmas = tuple(float(s) for s in sigmas)
+        self.spacing = spacing
         self.proj_precision = proj_precision or precision
         self.ridge = float(ridge)
         self._ops = {}
@@ -547,9 +566,9 @@ class BatchedGaussLTM(_BatchedBase):
     @_on_device
     def operators(self, L):
         """Device tables + ridge operators for chunk length L (solved once, fp64, on the device)."""
-        op = self._ops.get(L)
+        op = self._ops.get((L, self.spacing))
         if op is None:
-            t = tables.gauss_tables(L, self.N, self.tau, self.sigmas, self.S)
+            t = tables.gauss_tables(L, self.N, self.tau, self.sigmas, self.S, spacing=self.spacing)
             dev = self.device
             f = lambda a: torch.from_numpy(a).to(dev)
             op = dict(t=t, mu=f(t.basis_mu), sigma=f(t.basis_sigma), tb=f(t.tb), bins=f(t.bins))
@@ -560,7 +579,7 @@ class BatchedGaussLTM(_BatchedBase):
             # design of the 128 possible sticky sample positions (bins[b], b=0..127): rows of Psi
             op["Psi_tab"] = ops.rbf_eval(op["bins"][:128].contiguous(), op["mu"], op["sigma"])   # [128, N]
             op["Psi_uniform"] = ops.rbf_eval(f(t.old_over_tau), op["mu"], op["sigma"])           # [S, N]
-            self._ops[L] = op
+            self._ops[(L, self.spacing)] = op
         return op
 
     @_on_device
@@ -587,13 +606,12 @@ class BatchedGaussLTM(_BatchedBase):
         Bv, L, e = k.shape
         if e != self.e:
             raise ValueError(f"k has width {e}, projections expect {self.e}")
-        if isinstance(new_doc, (bool, int)):
-            if new_doc:
-                self.has_state = False
-        else:
-            raise ValueError("variant G takes one new_doc flag for the whole batch")
         if self.Bv != Bv:
             self.Bv, self.has_state = Bv, False
+        if not isinstance(new_doc, (bool, int)):
+            return self._step_mixed(k, q, u, new_doc)
+        if new_doc:
+            self.has_state = False
         op = self.operators(L)
         info = {}
         if not self.has_state:
@@ -631,6 +649,54 @@ class BatchedGaussLTM(_BatchedBase):
         info.update(mu=mu, sd=sd)
         self.last = info
         return ctx
+
+
+def _gauss_step_mixed(self, k, q, u, new_doc):
+    """Per-video new_doc flags (host booleans): the videos that start a new document and those that continue run
+    through the two branches as two sub-batches; the per-video state is split and merged around them."""
+    flags = torch.as_tensor(new_doc).to("cpu", torch.bool).reshape(-1)
+    Bv = k.shape[0]
+    if flags.numel() != Bv:
+        raise ValueError("new_doc must be a bool or one flag per video")
+    if not self.has_state or bool(flags.all()):
+        return self.step(k, q, u, new_doc=True)
+    if not bool(flags.any()):
+        return self.step(k, q, u, new_doc=False)
+    dev = self.device
+    fi = flags.nonzero().flatten().to(dev)
+    ci = (~flags).nonzero().flatten().to(dev)
+    state = (self._B, self._mu, self._sd)
+    ctx = torch.empty(Bv, q.shape[1], self.D, device=dev, dtype=torch.float32)
+    outs = {}
+    for sel, first in ((ci, False), (fi, True)):
+        self.Bv = int(sel.numel())
+        self.has_state = not first
+        if not first:
+            self._B, self._mu, self._sd = state[0][sel].contiguous(), state[1][sel].contiguous(), state[2][sel].contiguous()
+        ctx[sel] = self.step(k[sel].contiguous(), q[sel].contiguous(), None if (first or u is None) else u[sel].contiguous(),
+                             new_doc=first)
+        outs[first] = (self._B, self._mu, self._sd)
+    B = torch.empty_like(state[0]); mu = torch.empty_like(state[1]); sd = torch.empty_like(state[2])
+    for sel, first in ((ci, False), (fi, True)):
+        B[sel], mu[sel], sd[sel] = outs[first]
+    self._B, self._mu, self._sd = B, mu, sd
+    self.Bv, self.has_state = Bv, True
+    self.last = dict(mu=mu, sd=sd)
+    return ctx
+
+
+def _gauss_kl(self, mu_0, sigma_0):
+    """KL regulariser of the most recent call, [Bv, H*Q] (long_term_attention.py:296-304)."""
+    return ops.kl_gauss(self._mu, self._sd, mu_0, sigma_0)
+
+
+def _gauss_x_past(self):
+    return None
+
+
+BatchedGaussLTM._step_mixed = _gauss_step_mixed
+BatchedGaussLTM.kl = _on_device(_gauss_kl)
+BatchedGaussLTM.x_past = _gauss_x_past
 
 
 def BatchedLTM(variant="gibbs", **kw):

@@ -239,7 +239,34 @@ density_rect_kernel(const float* __restrict__ scores, const int32_t* __restrict_
   for (int i = 0; i < DENS_PTS / 32; ++i) dst[i * 32 + lane] = e[i] / tot;
 }
 
+// KL regulariser of the Gaussian variant (long_term_attention.py:296-304): per (video, head, query) row
+//   kl = 1/2 (var/s0^2 - log(var/s0^2) - 1 [+ (mu - mu0)^2 / s0^2  -- only when mu0 <= 0, as upstream tests `mu_0 > 0`])
+__global__ void kl_gauss_kernel(const float* __restrict__ mu, const float* __restrict__ sd, float mu0, float s0sq,
+                                int with_mean, float* __restrict__ out, long long n) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float var = sd[i] * sd[i];
+  const float r = __fdiv_rn(var, s0sq);
+  float kl = r - logf(r) - 1.f;
+  if (with_mean) {
+    const float dm = mu[i] - mu0;
+    kl += __fdiv_rn(dm * dm, s0sq);
+  }
+  out[i] = 0.5f * kl;
+}
+
 }  // namespace ltm
+
+extern "C" int ltm_kl_gauss(const float* mu, const float* sd, float mu_0, float sigma_0, float* out, int64_t n,
+                            void* stream) {
+  using namespace ltm;
+  LTM_REQUIRE(mu && sd && out && n > 0, "kl_gauss: null pointer / empty");
+  LTM_REQUIRE(sigma_0 > 0.f, "kl_gauss: sigma_0 must be positive");
+  kl_gauss_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mu, sd, mu_0, sigma_0 * sigma_0,
+                                                                               mu_0 > 0.f ? 0 : 1, out, (long long)n);
+  LTM_CHECK_LAUNCH("kl_gauss");
+  return 0;
+}
 
 extern "C" int ltm_density_rect(const float* scores, const int32_t* jd, const float* wd, float* out, int Bv, int H,
                                 int Q, int N, void* stream) {

@@ -70,3 +70,35 @@ def barrier(device=None):
             dist.barrier(device_ids=[torch.device(device).index or 0])
         else:
             dist.barrier()
+
+
+def bind_to_gpu_numa_node(device_index: int):
+    """Pin this process to the CPU cores of the NUMA node its GPU hangs off (sysfs), so that pinned host buffers
+    allocated afterwards are first-touched on that node and H2D copies do not cross the socket interconnect.
+    Returns a small report dict; a no-op (with the reason) where sysfs does not say."""
+    rep = {"numa_node": None, "cpus": None}
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        with open(path) as f:
+            node = int(f.read().strip())
+        rep["numa_node"] = node
+        if node < 0:
+            rep["note"] = "sysfs reports no NUMA affinity for this GPU"
+            return rep
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            rep["cpus"] = len(allowed)
+    except Exception as ex:                      # containers without sysfs access, exotic topologies
+        rep["note"] = f"{type(ex).__name__}: {ex}"
+    return rep
+

@@ -39,7 +39,7 @@ class LongTermAttention(nn.Module):
                  affines: bool, mask: bool, mask_type: str, kl_regularizer: bool, proj_key, proj_value,
                  sigma_0, mu_0, sticky_memories, sigmas, tau, variant: str = "gibbs",
                  tokens_per_frame: int = 32, precision: str = None, gemm_impl: str = "tcgen05",
-                 share_pooling: bool = True, output_density: bool = False, **kwargs):
+                 share_pooling: bool = True, output_density: bool = False, dump_path: str = None, **kwargs):
         super().__init__()
         if not continuous:
             raise NotImplementedError("only the continuous-attention memory is on the LTM path (continuous=True)")
@@ -47,10 +47,12 @@ class LongTermAttention(nn.Module):
             raise NotImplementedError("infinite_memory=False is never used by the Q-formers (Qformer.py:141)")
         if attn_func != "softmax":
             raise NotImplementedError("attn_func must be 'softmax' (Qformer.py:140)")
-        if kl_regularizer:
-            raise NotImplementedError("kl_regularizer is never enabled by the callers (Qformer.py:149)")
         if variant not in ("gibbs", "gaussian"):
             raise ValueError("variant must be 'gibbs' (live module) or 'gaussian'")
+        if kl_regularizer and variant != "gaussian":
+            raise NotImplementedError("kl_regularizer exists in the Gaussian variant only (long_term_attention.py:296-304)")
+        if kl_regularizer and (sigma_0 is None or mu_0 is None):
+            raise ValueError("kl_regularizer needs sigma_0 and mu_0")
         # same attribute surface as the reference (gibbs:32-65)
         self.device = "cuda"
         self.length = length
@@ -75,7 +77,6 @@ class LongTermAttention(nn.Module):
         self.nb_samples = tables.NB_SAMPLES
         self.tau = tau
         self.count = 0
-        self.x_past = None
         self.ridge_penalty = tables.RIDGE_PENALTY
         self.padding = True
         self.spacing = "linear"
@@ -86,8 +87,12 @@ class LongTermAttention(nn.Module):
         self.share_pooling = share_pooling
         # Video-LLaMA copy: density side-output of every call (gibbs:320-343).  Off by default; when on, the
         # result is kept on the device in `self.alphas` ([Q,B,H,768]) instead of being pickled to the cwd.
-        self.output_density = output_density
+        # `dump_path` (e.g. "./alphas_uniform", what the Video-LLaMA copy hard-codes at gibbs:344-345): additionally
+        # pickle the CPU copy of that tensor on every call, the file relevant_frames.py:11-12 reads.
+        self.output_density = bool(output_density) or dump_path is not None
+        self.dump_path = dump_path
         self.alphas = None
+        self.kl_reg = None
         self._engine = None
         self._wver = None
 
@@ -106,16 +111,33 @@ class LongTermAttention(nn.Module):
             if self.variant == "gibbs":
                 self._engine = BatchedRectLTM(tokens_per_frame=self.tokens_per_frame,
                                               precision=self.precision or "tf32",
-                                              keep_scores=self.output_density, **common)
+                                              keep_scores=self.output_density, spacing=self.spacing, **common)
             else:
                 sig = self.sigmas if self.sigmas is not None else (0.005, 0.01)
-                self._engine = BatchedGaussLTM(sigmas=tuple(sig), precision=self.precision or "tf32x3", **common)
+                self._engine = BatchedGaussLTM(sigmas=tuple(sig), precision=self.precision or "tf32x3",
+                                               spacing=self.spacing, **common)
             self._wver = ver
         elif ver != self._wver:
             self._engine.set_projections(self.proj_key.weight, self.proj_key.bias, self.proj_value.weight,
                                          self.proj_value.bias)
             self._wver = ver
+        if self._engine.spacing != self.spacing:        # plain attribute upstream (gibbs:64): honoured when changed
+            self._engine.spacing = self.spacing
+            self._engine.reset()
         return self._engine
+
+    @property
+    def x_past(self):
+        """[B, e, S+L] regression input of the most recent call, as the reference keeps it (gibbs:221): the 512
+        contracted re-samples of the old memory followed by the pooled frames ([B, e, L] after a first chunk).
+        Assembled on demand; None before the first call and for the Gaussian variant fed with 16-bit chunks."""
+        eng = self._engine
+        return None if eng is None or not eng.has_state else eng.x_past()
+
+    @x_past.setter
+    def x_past(self, value):
+        if value is not None:
+            raise AttributeError("x_past can only be cleared (set to None)")
 
     @property
     def B_past(self):
@@ -180,6 +202,13 @@ class LongTermAttention(nn.Module):
             eng.step(k32, q32, u=u, new_doc=False)
         if self.output_density and self.variant == "gibbs":
             self.alphas = eng.density()
+            if self.dump_path is not None:
+                import pickle
+                with open(self.dump_path, "wb") as f:                      # gibbs:344-345
+                    pickle.dump(self.alphas.cpu(), f)
+        if self.kl_regularizer:                                            # gauss:296-304, :389-390
+            self.kl_reg = eng.kl(self.mu_0, self.sigma_0)
+            return ctx.to(out_dtype), self.kl_reg
         return ctx.to(out_dtype)
 
     def extra_repr(self):

@@ -63,6 +63,16 @@ def consolidate_rect_kv(B_past, xpart, idx, tab, S, KV_past, bkv, jf, round_tf32
     return B_new, KV_new
 
 
+def kl_gauss(mu, sd, mu_0, sigma_0):
+    """KL regulariser of the Gaussian variant per (video, head*query) row (long_term_attention.py:296-304)."""
+    require_cuda(mu, sd)
+    mu, sd = _f32c(mu), _f32c(sd)
+    out = torch.empty_like(mu)
+    check(lib().ltm_kl_gauss(ptr(mu), ptr(sd), float(mu_0), float(sigma_0), ptr(out), mu.numel(),
+                             stream_ptr(mu.device)), "kl_gauss")
+    return out
+
+
 def sticky_hist_rect(scores, jb, tb):
     """scores[Bv,H,Q,N] -> hist_part[Bv,H,127].  gibbs:196-203."""
     require_cuda(scores, jb, tb)

@@ -51,13 +51,22 @@ def rect_bin_of(t, n):
     return torch.where(nhit > 0, idx, torch.full_like(idx, -1)).to(torch.int32)
 
 
-def first_chunk_positions(l):
-    """Padded frame positions of a first chunk (gibbs:103-110)."""
+def first_chunk_positions(l, spacing="linear"):
+    """Padded frame positions of a first chunk (gibbs:103-110; `spacing='log'` :114-127: the L frame positions
+    become e^{ln 2 * i / L} - 1, i = 1..L, between the same pads -- evaluated with the reference's own numpy / torch
+    expression because bin membership is decided by its rounding)."""
     if l % 2:
         s = 1 / float(l)
-        return torch.linspace(-.5 + s, 1.5 - s, 2 * l - 1), (l - 1) // 2
-    s = 1 / float(2 * l)
-    return torch.linspace(-.5 + s, 1.5 - s, 2 * l), l // 2
+        pos, trim = torch.linspace(-.5 + s, 1.5 - s, 2 * l - 1), (l - 1) // 2
+    else:
+        s = 1 / float(2 * l)
+        pos, trim = torch.linspace(-.5 + s, 1.5 - s, 2 * l), l // 2
+    if spacing == "log":
+        mid = np.e ** (np.log(1 + 1) * torch.arange(1, l + 1) / l) - 1
+        pos = torch.cat([pos[:int(l / 2)], mid.to(pos.dtype), pos[-int(l / 2):]])
+    elif spacing != "linear":
+        raise ValueError("spacing must be 'linear' or 'log'")
+    return pos, trim
 
 
 def update_positions(l, tau, nb_samples=NB_SAMPLES):
@@ -161,14 +170,15 @@ class RectTables:
 
 
 @lru_cache(maxsize=64)
-def rect_tables(L: int, N: int, tau: float, S: int = NB_SAMPLES, num_quad: int = NUM_QUAD_POINTS) -> RectTables:
+def rect_tables(L: int, N: int, tau: float, S: int = NB_SAMPLES, num_quad: int = NUM_QUAD_POINTS,
+                spacing: str = "linear") -> RectTables:
     if L < 2:
         raise ValueError("chunks of a single frame are not supported (the reference fails on L=1)")
     t = RectTables(L=L, N=N, tau=float(tau), S=S)
     ridge = torch.tensor(RIDGE_PENALTY)
 
     # --- first chunk (gibbs:99-131 + compute_G :68-84)
-    pos0, trim0 = first_chunk_positions(L)
+    pos0, trim0 = first_chunk_positions(L, spacing)
     b0 = rect_bin_of(pos0, N).numpy()
     cnt0 = np.bincount(b0[b0 >= 0], minlength=N)                      # counts include pad positions
     frames0 = b0[trim0:trim0 + L]
@@ -269,14 +279,15 @@ class GaussTables:
 
 
 @lru_cache(maxsize=64)
-def gauss_tables(L: int, N: int, tau: float, sigmas=(0.005, 0.01), S: int = NB_SAMPLES) -> GaussTables:
+def gauss_tables(L: int, N: int, tau: float, sigmas=(0.005, 0.01), S: int = NB_SAMPLES,
+                 spacing: str = "linear") -> GaussTables:
     if L % 2:
         raise ValueError("variant G: odd chunk lengths are broken upstream (long_term_attention.py:162-168)")
     ns = len(sigmas)
     if N % ns:
         N += ns - N % ns                                              # (:107-108)
     mu, sg = torch.meshgrid(torch.linspace(0, 1, N // ns), torch.Tensor(list(sigmas)), indexing="ij")
-    pos0, trim0 = first_chunk_positions(L)
+    pos0, trim0 = first_chunk_positions(L, spacing)
     pos1, trim1, old = update_positions(L, tau, S)
     bins, nudged = sticky_edges()
     return GaussTables(L=L, N=N, tau=float(tau), S=S, sigmas=tuple(sigmas),

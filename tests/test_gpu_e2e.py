@@ -30,8 +30,8 @@ def _run_rect(dev, N, L, C, Bv, T=32, e=768, Q=32, tau=.75, sticky=True, q_scale
     key, val = make_proj(seed, e)
     eng = BatchedRectLTM(N, tau, *proj_tensors(key, val), tokens_per_frame=T, sticky=sticky, precision=precision,
                          device=dev, keep_scores=True, fast_attn=fast_attn, proj_operands=proj_operands, **eng_kw)
-    orcs = [O.RectLTM(N, tau, *proj_tensors(key, val), tokens_per_frame=T, sticky=sticky, rebuild_tables=False)
-            for _ in range(Bv)]
+    orcs = [O.RectLTM(N, tau, *proj_tensors(key, val), tokens_per_frame=T, sticky=sticky, rebuild_tables=False,
+                      spacing=eng_kw.get("spacing", "linear")) for _ in range(Bv)]
     ks, qs, us = make_inputs(seed + 1, C, Bv, L * T, e, Q, q_scale)
     worst = dict(B=0.0, ctx=0.0, flips=0, draws=0)
     with torch.no_grad():
@@ -69,6 +69,8 @@ def _run_rect(dev, N, L, C, Bv, T=32, e=768, Q=32, tau=.75, sticky=True, q_scale
     ("odd", dict(N=64, L=7, C=3, Bv=1)),
     ("nonpow2", dict(N=100, L=30, C=3, Bv=2, tau=.5)),                      # positions that fall in no bin
     ("uniform", dict(N=64, L=8, C=3, Bv=2, sticky=False)),                  # non-sticky re-sampling
+    ("log", dict(N=64, L=8, C=3, Bv=2, spacing="log")),                     # N4: log-spaced first-chunk positions
+    ("log256", dict(N=256, L=32, C=2, Bv=1, spacing="log")),
 ])
 def test_rect_matches_oracle_over_chunks(dev, name, kw):
     w = _run_rect(dev, tag=name, **kw)
@@ -530,6 +532,43 @@ def test_layers_share_one_pooling_pass(dev):
     assert calls["n"] == 3          # one pooling pass per chunk for the two sharing layers (solo ones pool in-step)
 
 
+def test_consolidate_video_chunk_loop(dev):
+    """N2, second half: the model-level chunk loop -- all LTM layers of a Q-former, a batch of videos, the frames of
+    each chunk pooled once (ahead of time, on a side stream) and shared by the layers -- gives the same bits as one
+    engine per layer stepped on its own, with C pooling passes instead of layers x C."""
+    from infinite_video_b200 import ops
+    from infinite_video_b200.batched import BatchedRectLTM
+    from infinite_video_b200.video import consolidate_video
+    nl, C, Bv, L = 3, 4, 3, 16
+    layers = [BatchedRectLTM(64, .75, *proj_tensors(*make_proj(70 + i, 768)), device=dev) for i in range(nl)]
+    solo = [BatchedRectLTM(64, .75, *proj_tensors(*make_proj(70 + i, 768)), device=dev) for i in range(nl)]
+    ks, _, _ = make_inputs(75, C, Bv, L * 32, 768, 32)
+    ks = [k.to(dev) for k in ks]
+    g = torch.Generator().manual_seed(76)
+    qs = [[torch.randn(Bv, 32, 768, generator=g).to(dev) for _ in range(C)] for _ in range(nl)]
+    us = [[torch.rand(Bv, 512, dtype=torch.float64, generator=g).to(dev) for _ in range(C)] for _ in range(nl)]
+    calls = {"n": 0}
+    real = ops.pool_mean
+
+    def counting(*a, **kw):
+        calls["n"] += 1
+        return real(*a, **kw)
+    ops.pool_mean = counting
+    try:
+        got = consolidate_video(layers, ks, qs, us)
+    finally:
+        ops.pool_mean = real
+    assert calls["n"] == C
+    for li in range(nl):
+        for c in range(C):
+            want = solo[li].step(ks[c], qs[li][c], us[li][c] if c else None, new_doc=(c == 0))
+            assert torch.equal(got[li][c], want), (li, c)
+    # running mean over the chunks (what the eval scripts keep), queries produced layer by layer through a callable
+    mean = consolidate_video(layers, ks, lambda li, c, prev: qs[li][c], us, reduce="mean")
+    for li in range(nl):
+        assert relerr(mean[li], torch.stack(got[li]).mean(0)) < 1e-6
+
+
 def test_density_side_output(dev):
     """N3: `output_density=True` reproduces the alphas tensor of the Video-LLaMA copy (gibbs:320-343)."""
     from infinite_video_b200 import LongTermAttention
@@ -548,6 +587,79 @@ def test_density_side_output(dev):
                 assert m.alphas.shape == (32, 1, 12, 768)
                 assert relerr(m.alphas, want) < 1e-3
                 assert abs(float(m.alphas[3, 0, 5].sum()) - 1.0) < 1e-5
+
+
+def test_dump_hook_and_x_past(dev, tmp_path):
+    """Boundary leftovers of the Video-LLaMA copy: `dump_path` writes the pickle relevant_frames.py:11-12 reads
+    (gibbs:344-345: a CPU tensor [Q,B,H,768]), and `x_past` is the regression input the reference keeps (:221)."""
+    import pickle
+    from infinite_video_b200 import LongTermAttention
+    from oracle.ref_loader import caller_kwargs
+    key, val = make_proj(97, 768)
+    kd, vd = make_proj(97, 768)
+    path = str(tmp_path / "alphas_uniform")
+    m = LongTermAttention(**caller_kwargs(64, .75, True, kd.to(dev), vd.to(dev)), dump_path=path)
+    orc = O.RectLTM(64, .75, *proj_tensors(key, val), rebuild_tables=False)
+    ks, qs, us = make_inputs(98, 3, 1, 8 * 32, 768, 32)
+    assert m.x_past is None
+    with torch.no_grad():
+        for c in range(3):
+            m(ks[c].to(dev), qs[c].to(dev), new_doc=(c == 0), layer_n=0, u=us[c])
+            orc.forward(ks[c], qs[c], c == 0, us[c])
+            with open(path, "rb") as f:
+                dumped = pickle.load(f)
+            assert not dumped.is_cuda and dumped.shape == (32, 1, 12, 768)
+            assert torch.equal(dumped, m.alphas.cpu())
+            assert relerr(dumped, O.rect_density_alphas(orc, orc.tables(8))) < 1e-3
+            assert m.x_past.shape == orc.x_past.shape
+            assert relerr(m.x_past, orc.x_past) < 1e-5, f"x_past, chunk {c}"
+    m.x_past = None
+    with pytest.raises(AttributeError):
+        m.x_past = torch.zeros(1)
+
+
+def test_gauss_kl_regularizer_and_per_video_new_doc(dev):
+    """N4 / boundary leftovers of variant G: `(ctx, kl_reg)` when kl_regularizer is on (gauss:296-304,389-390), and
+    per-video new_doc flags in the batched engine (a video may start while others continue)."""
+    from infinite_video_b200 import LongTermAttention
+    from infinite_video_b200.batched import BatchedGaussLTM
+    from oracle.ref_loader import caller_kwargs
+    N, L = 64, 8
+    key, val = make_proj(45, 768)
+    kd, vd = make_proj(45, 768)
+    for mu_0 in (0.5, -1.0):
+        kw = caller_kwargs(N, .75, True, kd.to(dev), vd.to(dev), sigmas=[0.005, 0.01])
+        kw.update(kl_regularizer=True, sigma_0=0.3, mu_0=mu_0)
+        m = LongTermAttention(**kw, variant="gaussian")
+        orc = O.GaussLTM(N, .75, *proj_tensors(key, val), rebuild_tables=False, kl_regularizer=True, sigma_0=0.3,
+                         mu_0=mu_0)
+        m._get_engine(dev).set_operators(L, G0=orc.tables(L)["G0"], G_inf=orc.tables(L)["G_inf"])
+        ks, qs, us = make_inputs(46, 2, 2, L, 768, 32)
+        with torch.no_grad():
+            for c in range(2):
+                u = guard_band(us[c], orc.sticky_hist(orc.tables(L))) if c else us[c]
+                ctx, kl = m(ks[c].to(dev), qs[c].to(dev), new_doc=(c == 0), layer_n=0, u=u)
+                want = orc.forward(ks[c], qs[c], c == 0, u)
+                assert relerr(ctx, want) < 5e-3
+                assert kl.shape == orc.kl_reg.shape and relerr(kl, orc.kl_reg) < 2e-3, (mu_0, c)
+    # per-video flags: video 1 restarts at chunk 1 while video 0 continues
+    eng = BatchedGaussLTM(N, .75, *proj_tensors(key, val), device=dev)
+    orcs = [O.GaussLTM(N, .75, *proj_tensors(key, val), rebuild_tables=False) for _ in range(2)]
+    tb = orcs[0].tables(L)
+    eng.set_operators(L, G0=tb["G0"], G_inf=tb["G_inf"])
+    ks, qs, us = make_inputs(47, 3, 2, L, 768, 32)
+    flags = [[True, True], [False, True], [False, False]]
+    with torch.no_grad():
+        for c in range(3):
+            u = us[c].clone()
+            for v in range(2):
+                if not flags[c][v]:
+                    u[v:v + 1] = guard_band(u[v:v + 1], orcs[v].sticky_hist(tb))
+            got = eng.step(ks[c].to(dev), qs[c].to(dev), u.to(dev), new_doc=flags[c])
+            for v in range(2):
+                want = orcs[v].forward(ks[c][v:v + 1], qs[c][v:v + 1], flags[c][v], u[v:v + 1])
+                assert relerr(eng.B_past[v], orcs[v].B_past[0]) < TOL_B, (c, v)
+                assert relerr(got[v], want[0]) < 5e-3, (c, v)
 
 
 def test_fp16_chunk_through_the_drop_in(dev):

@@ -71,6 +71,55 @@ def test_gauss_oracle_is_bit_identical(N, L, C, Bv):
             assert torch.equal(got, want), f"ctx differs at chunk {c}"
 
 
+@pytest.mark.parametrize("N,L", [(64, 8), (256, 32), (64, 7)])
+def test_rect_oracle_log_spacing_and_x_past(N, L, tmp_path):
+    """N4: `spacing='log'` (a plain attribute upstream, gibbs:64,114-127) and the `x_past` state (:221)."""
+    mod = RL.load_gibbs_vl()
+    key, val = make_proj(8, 768)
+    ref = mod.LongTermAttention(**RL.caller_kwargs(N, 0.75, True, key, val))
+    ref.spacing = "log"
+    orc = O.RectLTM(N, 0.75, *proj_tensors(key, val), spacing="log")
+    ks, qs, _ = make_inputs(9, 3, 1, L * 32, 768, 32)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        with torch.no_grad():
+            for c in range(3):
+                torch.manual_seed(300 + c)
+                want = ref(ks[c], qs[c], new_doc=(c == 0), layer_n=0)
+                torch.manual_seed(300 + c)
+                u = torch.rand(1, 512, dtype=torch.float64)
+                got = orc.forward(ks[c], qs[c], c == 0, u)
+                assert torch.equal(orc.B_past, ref.B_past) and torch.equal(got, want), f"chunk {c}"
+                assert torch.equal(orc.x_past, ref.x_past), f"x_past, chunk {c}"
+    finally:
+        os.chdir(cwd)
+
+
+@pytest.mark.parametrize("mu_0", [0.5, -1.0])
+def test_gauss_oracle_kl_regularizer(mu_0):
+    """N4: kl_regularizer (long_term_attention.py:296-304,389-390), both branches of its `mu_0 > 0` test."""
+    N, L = 64, 8
+    mod = RL.load_gaussian_vl()
+    key, val = make_proj(5, 768)
+    kw = RL.caller_kwargs(N, 0.75, True, key, val, sigmas=[0.005, 0.01])
+    kw.update(kl_regularizer=True, sigma_0=0.3, mu_0=mu_0)
+    ref = mod.LongTermAttention(**kw)
+    ref.device = "cpu"
+    orc = O.GaussLTM(N, 0.75, *proj_tensors(key, val), kl_regularizer=True, sigma_0=0.3, mu_0=mu_0)
+    ks, qs, _ = make_inputs(6, 2, 2, L, 768, 32)
+    with torch.no_grad():
+        for c in range(2):
+            ref.length = ref.target_len = L
+            torch.manual_seed(200 + c)
+            want, kl = ref(ks[c], qs[c], new_doc=(c == 0), layer_n=0)
+            torch.manual_seed(200 + c)
+            nn.Linear(N, 1, bias=False); nn.Linear(N, 1, bias=False)
+            u = torch.rand(2, 512, dtype=torch.float64)
+            got = orc.forward(ks[c], qs[c], c == 0, u)
+            assert torch.equal(got, want) and torch.equal(orc.kl_reg, kl), f"chunk {c}"
+
+
 def test_kat_from_survey():
     """Known-answer recipe recorded in SURVEY.md section 8c."""
     mod = RL.load_gibbs_vl()

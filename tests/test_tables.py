@@ -94,3 +94,13 @@ def test_tensor_core_attention_operand_rows(N, L):
     got = float(((t.X[:, 1].astype(np.float64) + t.X[:, 2]) * e).sum() + t.c_none * np.exp(-m))
     assert abs(got - want) < 1e-6 * want
     assert abs(float((t.X[:, 0] * e).sum()) - float(e.sum())) < 1e-12
+
+
+def test_log_spacing_tables_equal_the_dense_operator():
+    """spacing='log' moves the first-chunk frame positions (gibbs:114-127): CSR tables == dense ridge operator."""
+    for N, L in ((64, 8), (256, 32), (64, 7), (100, 30)):
+        t = T.rect_tables(L, N, .75, spacing="log")
+        psi = O.RectBasis(N)
+        G0 = O.ridge_operator(psi, O.first_chunk_positions(L, "log"), L).numpy()
+        assert np.array_equal(t.dense_G0(), G0), (N, L)
+        assert not np.array_equal(t.dense_G0(), T.rect_tables(L, N, .75).dense_G0())
