@@ -51,6 +51,11 @@ int ltm_pool_mean_16(const void* k, int is_bf16, float* xpart, int Bv, int L, in
 int ltm_sticky_hist_rect(const float* scores, const int32_t* jb, const float* tb, float* hist_part,
                          int Bv, int H, int Q, int N, void* stream);
 
+/* same, one partial histogram per (head, query tile of 32): hist_part[Bv, H*ceil(Q/32), 127] -- the layout the fused
+ * attention kernels write */
+int ltm_sticky_hist_rect_tiles(const float* scores, const int32_t* jb, const float* tb, float* hist_part,
+                               int Bv, int H, int Q, int N, void* stream);
+
 /* ---- R12 side output (Video-LLaMA copy only, gibbs:320-343 -> ./alphas_uniform -> relevant_frames.py):
  * scores[Bv,H,Q,N] -> out[Q,Bv,H,768]: Gibbs density on linspace(0,.25,256) | (.25,.5,256) | (.5,1,256), each segment
  * normalised by its trapezoid integral (weights wd[768]), the concatenation normalised to sum 1.  jd[768] = basis
@@ -203,6 +208,16 @@ int ltm_cont_attn_rect_tc(const float* q, const float* K, const float* V, int64_
                           const float* W, float W_out, float c_none, const int32_t* jb, const float* tb,
                           float* ctx, float* scores_out, float* hist_part,
                           int Bv, int Q, int N, int H, int d, void* stream);
+/* num_basis 512 on the same kernel: every (query tile, head, video) is split into two work items over the halves of
+ * the basis range, merged by a small combine kernel (online-softmax rescaling); the next call's sticky histogram is
+ * computed from the stored scores.  scores_ws[Bv,H,Q,N] and part_ws[ltm_attn_tc_split_workspace_floats(Bv,Q,H)] are
+ * caller-provided workspaces (scores_ws doubles as the optional scores output). */
+int ltm_attn_tc_split_supported(int N, int d);
+int64_t ltm_attn_tc_split_workspace_floats(int Bv, int Q, int H);
+int ltm_cont_attn_rect_tc_split(const float* q, const float* K, const float* V, int64_t ldkv, const float* X,
+                                const float* W, float W_out, const int32_t* jb, const float* tb,
+                                float* ctx, float* scores_ws, float* part_ws, float* hist_part,
+                                int Bv, int Q, int N, int H, int d, void* stream);
 /* ltm_project_kv with the stored K and V rounded to tf32 */
 int ltm_project_kv_r(const float* Bcoef, const float* Wkv, const float* bkv, float* KV,
                      int M, int e, int D2, int precision, int impl, void* stream);
@@ -265,6 +280,13 @@ typedef struct {
    * jf > 0, every video takes the update branch (B_past != NULL, new_doc == NULL) and N - jf tiles 128 rows evenly;
    * otherwise all N rows are projected.  proj_precision: precision of the K/V projection GEMM (0 = `precision`). */
   const float* KV_past; int jf; int proj_precision;
+  /* > 0: consolidate / project / attend in blocks of this many videos, so that what a block writes (K|V, coefficient
+   * rows) is read back from L2; 0 or >= Bv: every kernel covers all videos.  In blocked mode only prof_events[4]
+   * (before the first block) and [9] (after the last) are recorded besides the pooling / re-sampling pairs. */
+  int video_block;
+  /* workspace of the two-half tensor-core attention (num_basis 512): ltm_attn_tc_split_workspace_floats(Bv,Q,H)
+   * floats; with it (and `scores`) set, num_basis 512 takes ltm_cont_attn_rect_tc_split */
+  float* attn_part;
 } ltm_rect_step_args;
 int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const float* q, const double* u,
                   const uint8_t* new_doc, float* ctx, void* stream);

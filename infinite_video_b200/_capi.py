@@ -52,7 +52,8 @@ class RectStepArgs(C.Structure):
         ("prof_events", C.c_void_p * 10),
         ("X", C.c_void_p), ("c_none", C.c_float),
         ("B_half", C.c_void_p), ("Wkv_half", C.c_void_p),
-        ("KV_past", C.c_void_p), ("jf", C.c_int), ("proj_precision", C.c_int),
+        ("KV_past", C.c_void_p), ("jf", C.c_int), ("proj_precision", C.c_int), ("video_block", C.c_int),
+        ("attn_part", C.c_void_p),
     ]
 
 
@@ -74,6 +75,7 @@ _SIGS = {
     "ltm_pool_mean_16": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_pool_mean_grid": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ltm_sticky_hist_rect": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "ltm_sticky_hist_rect_tiles": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ltm_density_rect": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ltm_sticky_hist_gauss": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "ltm_resample": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _P]),
@@ -88,6 +90,10 @@ _SIGS = {
     "ltm_attn_fast_supported": (C.c_int, [_I, _I]),
     "ltm_attn_tc_supported": (C.c_int, [_I, _I]),
     "ltm_cont_attn_rect_tc": (C.c_int, [_P, _P, _P, _L, _P, _P, _F, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "ltm_attn_tc_split_supported": (C.c_int, [_I, _I]),
+    "ltm_attn_tc_split_workspace_floats": (C.c_int64, [_I, _I, _I]),
+    "ltm_cont_attn_rect_tc_split": (C.c_int, [_P, _P, _P, _L, _P, _P, _F, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I,
+                                              _P]),
     "ltm_cont_attn_rect_t": (C.c_int, [_P, _P, _P, _L, _P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_cont_attn_gauss_t": (C.c_int, [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_cont_attn_rect": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),

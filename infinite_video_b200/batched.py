@@ -111,8 +111,11 @@ class BatchedRectLTM(_BatchedBase):
         # transposed-key attention path (num_basis 64/128/256, head size 64); `fast_attn=False` forces the generic one
         self.fast_attn = bool(fast_attn) and ops.attn_fast_supported(self.N, self.d)
         # tensor-core attention (csrc/attn_tc.cu): num_basis 64/128/256, head size 64, single-pass tf32 projection
+        # (num_basis 512: the same kernel over the two halves of the basis range + a combine kernel)
+        self.tc_split = ops.attn_tc_split_supported(self.N, self.d)
         self.tc_attn = (bool(tc_attn) and bool(fast_attn) and precision == "tf32" and gemm_impl == "tcgen05"
-                        and ops.attn_tc_supported(self.N, self.d))
+                        and (ops.attn_tc_supported(self.N, self.d) or self.tc_split))
+        self.tc_split = self.tc_split and self.tc_attn
         # operands of the K/V projection on the tensor-core path: "fp32" (default: tf32 UMMAs straight from the fp32
         # tensors) or "fp16" (coefficients and weights rounded to fp16: tf32's 11-bit significand at half the bytes
         # and twice the MMA rate -- projection 0.134 -> 0.108 ms, serial step +3 %, overlapped step +0.7 % at 128
@@ -127,6 +130,8 @@ class BatchedRectLTM(_BatchedBase):
         self.kv_state = bool(kv_state) and not self.half_ops and (self.tc_attn or not self.fast_attn)
         # precision of the K/V projection GEMM alone (None = `precision`); "tf32x3" makes the stored K|V fp32-grade
         self.proj_precision = proj_precision
+        # consolidate / project / attend in blocks of this many videos (L2 reuse of what a block writes); 0 = off
+        self.video_block = 0
         self._Wkv_h = None
         self.prof_events = None       # optional list of 10 cudaEvent_t handles (bench.py stage timing)
         self._side = None             # side stream for pooling the next chunk ahead of time
@@ -160,7 +165,9 @@ class BatchedRectLTM(_BatchedBase):
                 V=torch.empty(Bv, self.N, self.D, **f32) if (self.fast_attn and not self.tc_attn) else None,
                 b_draw=torch.empty(Bv, self.S, **i32), idx=torch.empty(Bv, self.S, **i32),
                 ts=torch.empty(Bv, self.S, **f32), p=torch.empty(Bv, 127, **f32),
-                scores=torch.empty(Bv, self.H, Q, self.N, **f32) if self.keep_scores else None,
+                scores=torch.empty(Bv, self.H, Q, self.N, **f32) if (self.keep_scores or self.tc_split) else None,
+                attn_part=torch.empty(int(lib().ltm_attn_tc_split_workspace_floats(Bv, Q, self.H)), **f32)
+                if self.tc_split else None,
                 B_half=torch.empty(Bv, self.N, self.e, device=dev, dtype=torch.float16) if self.half_ops else None,
                 k_dev=None, q_dev=None, u_dev=None, nd_dev=None, ctx_dev=None,
             )
@@ -224,6 +231,7 @@ class BatchedRectLTM(_BatchedBase):
             ws["_args"], ws["_args_sig"], ws["_args_prof"] = a, sig, False
             ws["_args_keep"] = (tdev, self.Wkv, self.bkv, self._hist)     # the block holds raw pointers into these
         a.splits = ws["splits"]
+        a.video_block = int(self.video_block)
         a.B_past = self._B[self._cur].data_ptr() if self.has_state else None
         a.B_new = self._B[1 - self._cur].data_ptr()
         a.xpart = ws["xparts"][ws["xi"]].data_ptr()
@@ -271,6 +279,7 @@ class BatchedRectLTM(_BatchedBase):
         a.b_draw, a.idx, a.ts, a.p = (ws["b_draw"].data_ptr(), ws["idx"].data_ptr(), ws["ts"].data_ptr(),
                                       ws["p"].data_ptr())
         a.scores = ws["scores"].data_ptr() if ws["scores"] is not None else None
+        a.attn_part = ws["attn_part"].data_ptr() if ws["attn_part"] is not None else None
         for f, n in (("k_dev", "k_dev"), ("q_dev", "q_dev"), ("u_dev", "u_dev"), ("new_doc_dev", "nd_dev"),
                      ("ctx_dev", "ctx_dev")):
             setattr(a, f, ws[n].data_ptr() if ws[n] is not None else None)
@@ -547,7 +556,7 @@ class BatchedGaussLTM(_BatchedBase):
     def __init__(self, num_basis, tau, w_key, b_key, w_value, b_value, *, sigmas=(0.005, 0.01), n_heads=12,
                  head_size=64, sticky=True, nb_samples=tables.NB_SAMPLES, precision="tf32x3",
                  proj_precision=None, gemm_impl="tcgen05", device="cuda", ridge=tables.RIDGE_PENALTY,
-                 spacing="linear"):
+                 spacing="linear", value_precision=None):
         ns = len(sigmas)
         n = int(num_basis)
         if n % ns:
@@ -557,6 +566,11 @@ class BatchedGaussLTM(_BatchedBase):
         self.sigmas = tuple(float(s) for s in sigmas)
         self.spacing = spacing
         self.proj_precision = proj_precision or precision
+        # optional lower precision for the value half of the projection ("tf32": values only enter the final
+        # contraction r.V, the keys feed softmax(20 S) and stay split-TF32).  Measured: 128.7 k -> 161.3 k chunks/s at
+        # 128 videos, but the tensor core TRUNCATES the fp32 operands, a systematic ~1e-3 shrink of V that the
+        # 1e-3 context tolerance does not leave room for -- so the default stays split-TF32 for both halves.
+        self.value_precision = value_precision
         self.ridge = float(ridge)
         self._ops = {}
         self._B = None
@@ -638,7 +652,7 @@ class BatchedGaussLTM(_BatchedBase):
         self._B = B
         if ops.attn_fast_supported(self.N, self.d):
             Kt, V = ops.project_kv_t(B, self.Wkv, self.bkv, self.N, precision=self.proj_precision,
-                                     impl=self.gemm_impl)
+                                     impl=self.gemm_impl, precision_v=self.value_precision)
             ctx, scores, mu, sd = ops.cont_attn_gauss_t(q, Kt, V, op["mu"], op["sigma"])
         else:
             KV = ops.project_kv(B, self.Wkv, self.bkv, precision=self.proj_precision, impl=self.gemm_impl)

@@ -45,8 +45,15 @@ struct Params {
   float* scores_out;     // optional [Bv,H,Q,NB]
   float* hist_part;      // optional [Bv, H*q_tiles, 127]
   int Q, H;
+  // num_basis = halves * NB: with halves == 2 (num_basis 512) every (query tile, head, video) is two work items, one
+  // per half of the basis range; each writes its un-normalised accumulator rows, the normaliser sums and its shift
+  // m_q to `part` ([item][68][32]: rows 0..63 D[d][q], 64 sum_j e, 65 / 66 the histogram integral hi / lo, 67 m_q)
+  // and attn_tc_combine_kernel merges the two halves (exp(m_half - m) rescaling, as in a two-block online softmax).
+  int halves, NT;
+  float* part;
   unsigned long long* trace;   // bring-up: CTA 0 writes globaltimer stamps [item][16] (NULL = off)
 };
+constexpr int PART_ROWS = 68;
 
 template <int NB>
 struct Lay {
@@ -142,12 +149,16 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
   const uint32_t sK = sbase + L_::K_OFF, sV = sbase + L_::V_OFF, sR = sbase + L_::R_OFF, sQ = sbase + L_::Q_OFF;
   // videos are walked last-to-first: the projection kernel that ran just before wrote K|V first-to-last, so the
   // most recently written rows are the ones still resident in L2
-  const int nvid = total / (H * q_tiles);
+  const int halves = p.halves, NT = p.NT;
+  const int nvid = total / (H * q_tiles * halves);
+  // (qt, h, v) of a work item; the basis half is w % halves and enters through `jrow` = first K|V row of the item
   auto decode = [&](int w, int& qt, int& h, int& v) {
-    h = w % H;
-    qt = (w / H) % q_tiles;
-    v = nvid - 1 - w / (H * q_tiles);
+    const int w2 = w / halves;
+    h = w2 % H;
+    qt = (w2 / H) % q_tiles;
+    v = nvid - 1 - w2 / (H * q_tiles);
   };
+  auto jrow = [&](int w, int v) { return v * NT + (w % halves) * NB; };
   const int w0 = blockIdx.x, wstride = gridDim.x;
 
   if (warp == 8) {
@@ -165,12 +176,12 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
       int qt, h, v;
       decode(w0, qt, h, v);
       mbar_arrive_expect_tx(bar_k, 2 * L_::SLAB);
-      tma_load_2d(&mapK, sK, bar_k, h * DH, v * NB);
-      tma_load_2d(&mapK, sK + L_::SLAB, bar_k, h * DH + 32, v * NB);
+      tma_load_2d(&mapK, sK, bar_k, h * DH, jrow(w0, v));
+      tma_load_2d(&mapK, sK + L_::SLAB, bar_k, h * DH + 32, jrow(w0, v));
       mbar_arrive_expect_tx(bar_v, 3 * L_::SLAB);
-      tma_load_2d(&mapV, sV, bar_v, h * DH, v * NB);
-      tma_load_2d(&mapV, sV + L_::SLAB, bar_v, h * DH + 32, v * NB);
-      tma_load_2d(&mapX, sV + 2 * L_::SLAB, bar_v, 0, 0);
+      tma_load_2d(&mapV, sV, bar_v, h * DH, jrow(w0, v));
+      tma_load_2d(&mapV, sV + L_::SLAB, bar_v, h * DH + 32, jrow(w0, v));
+      tma_load_2d(&mapX, sV + 2 * L_::SLAB, bar_v, 0, (w0 % halves) * NB);
     }
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -223,8 +234,8 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
         stamp(p.trace, it, 0);
         if (wn < total) {
           mbar_arrive_expect_tx(bar_k, 2 * L_::SLAB);
-          tma_load_2d(&mapK, sK, bar_k, hn * DH, vn * NB);
-          tma_load_2d(&mapK, sK + L_::SLAB, bar_k, hn * DH + 32, vn * NB);
+          tma_load_2d(&mapK, sK, bar_k, hn * DH, jrow(wn, vn));
+          tma_load_2d(&mapK, sK + L_::SLAB, bar_k, hn * DH + 32, jrow(wn, vn));
         }
         mbar_wait(bar_r, ph);                          // e^T written, D free
         stamp(p.trace, it, 1);
@@ -246,9 +257,11 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
         mbar_wait(bar_pv, ph);                         // the V buffer (and e^T) have been read
         stamp(p.trace, it, 4);
         if (wn < total) {
-          mbar_arrive_expect_tx(bar_v, 2 * L_::SLAB);
-          tma_load_2d(&mapV, sV, bar_v, hn * DH, vn * NB);
-          tma_load_2d(&mapV, sV + L_::SLAB, bar_v, hn * DH + 32, vn * NB);
+          // (the per-basis operand rows X change with the basis half: re-fetched with V when there are two)
+          mbar_arrive_expect_tx(bar_v, (halves > 1 ? 3 : 2) * L_::SLAB);
+          tma_load_2d(&mapV, sV, bar_v, hn * DH, jrow(wn, vn));
+          tma_load_2d(&mapV, sV + L_::SLAB, bar_v, hn * DH + 32, jrow(wn, vn));
+          if (halves > 1) tma_load_2d(&mapX, sV + 2 * L_::SLAB, bar_v, 0, (wn % halves) * NB);
         }
       }
     }
@@ -278,8 +291,8 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
     const bool active = warp < JWARPS;
     const int j = (warp >> 2) * 128 + (warp & 3) * 32 + lane;      // this thread's basis in the weight phase
     const int quarter = warp & 3, chalf = warp >> 2;
-    const float Wj = active ? __ldg(p.W + j) : 0.f;
-    const float rWj = active ? 1.0f / Wj : 0.f;
+    float Wj = active ? __ldg(p.W + (w0 % halves) * NB + j) : 0.f;
+    float rWj = active ? 1.0f / Wj : 0.f;
     // histogram bin of this thread (tid < 127): p_i = dt_{i+1}/2 (G[jb_{i+1}] + G[jb_{i+2}])
     int hja = NB, hjb = NB;
     float hdt = 0.f;
@@ -313,6 +326,11 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
       const int rows = min(QT, Q - q0);
       float e[32];
       const int wn = w + wstride;
+      const int jhalf = (w % halves) * NB;               // first basis of this item's half
+      if (halves > 1 && active) {
+        Wj = __ldg(p.W + jhalf + j);
+        rWj = 1.0f / Wj;
+      }
       mbar_wait(bar_s, ph);
       if (tid == 0) stamp(p.trace, it, 8);
       tcgen05_fence_after();
@@ -347,10 +365,10 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
         }
         wmax[warp * 32 + lane] = __uint_as_float(mine);
         if (p.scores_out) {
-          float* dst = p.scores_out + (((size_t)v * H + h) * Q + q0) * NB + j;
+          float* dst = p.scores_out + (((size_t)v * H + h) * Q + q0) * NT + jhalf + j;
 #pragma unroll
           for (int c = 0; c < 32; ++c)
-            if (c < rows) dst[(size_t)c * NB] = e[c];
+            if (c < rows) dst[(size_t)c * NT] = e[c];
         }
       }
       cw_sync();                                                                           // column maxima
@@ -406,6 +424,19 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int i = 0; i < 16; ++i) dv[i] = __uint_as_float(r[i]) + __uint_as_float(r2[i]);
+      }
+      if (p.part != nullptr) {
+        // one half of a two-half item: hand the raw accumulator rows, the normaliser sums and the shift to the combine
+        // kernel (TMEM lane = row m: quarters 0, 1 hold D[d][q], lanes 0..2 of quarter 2 the three sums)
+        float* pw = p.part + (size_t)w * (PART_ROWS * QT);
+        const int prow = quarter * 32 + lane;
+        if (quarter < 2 || (quarter == 2 && lane < 3)) {
+          float4* dst = reinterpret_cast<float4*>(pw + prow * QT + chalf * 16);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = make_float4(dv[4 * i], dv[4 * i + 1], dv[4 * i + 2], dv[4 * i + 3]);
+        }
+        if (quarter == 3 && lane < 16) pw[67 * QT + chalf * 16 + lane] = mcol[chalf * 16 + lane];
+        continue;    // (mcol is rewritten behind the next item's first cw_sync, which every thread must reach first)
       }
       if (quarter == 2) {
         // lanes 0,1,2 hold rows 64 (sum_j e), 65, 66 (sum_j c_j/W_j e, hi + lo) of this warp's 16 columns: through
@@ -464,6 +495,34 @@ cont_attn_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
   }
 }
 
+// Merge of the two basis halves of num_basis = 512: ctx = (D_0 s_0 + D_1 s_1) / (Z_0 s_0 + Z_1 s_1 + W_out e^{-m}),
+// m = max(m_0, m_1), s_i = e^{m_i - m}.  One CTA per (query tile, head, video); thread -> (q, d) with d fastest.
+__global__ void __launch_bounds__(256)
+attn_tc_combine_kernel(const float* __restrict__ part, float* __restrict__ ctx, float W_out, int Q, int H,
+                       int q_tiles, int nvid) {
+  const int w2 = blockIdx.x;
+  const int h = w2 % H, qt = (w2 / H) % q_tiles, v = nvid - 1 - w2 / (H * q_tiles);
+  const float* p0 = part + (size_t)(2 * w2) * (PART_ROWS * QT);
+  const float* p1 = p0 + PART_ROWS * QT;
+  __shared__ float s0[QT], s1[QT], rz[QT];
+  if (threadIdx.x < QT) {
+    const int q = threadIdx.x;
+    const float m0 = p0[67 * QT + q], m1 = p1[67 * QT + q];
+    const float m = fmaxf(m0, m1);
+    const float a = expf(m0 - m), b = expf(m1 - m);
+    s0[q] = a;
+    s1[q] = b;
+    rz[q] = 1.0f / (p0[64 * QT + q] * a + p1[64 * QT + q] * b + W_out * expf(-m));
+  }
+  __syncthreads();
+  const int q0 = qt * QT, rows = min(QT, Q - q0), D = H * DH;
+  for (int i = threadIdx.x; i < QT * DH; i += 256) {
+    const int d = i & (DH - 1), q = i >> 6;
+    if (q < rows)
+      ctx[((size_t)v * Q + q0 + q) * D + h * DH + d] = (p0[d * QT + q] * s0[q] + p1[d * QT + q] * s1[q]) * rz[q];
+  }
+}
+
 template <int NB>
 static int launch(const CUtensorMap& mK, const CUtensorMap& mV, const CUtensorMap& mX, const Params& p, int Bv,
                   cudaStream_t stream) {
@@ -471,11 +530,15 @@ static int launch(const CUtensorMap& mK, const CUtensorMap& mV, const CUtensorMa
   int num_sms = 0;
   if (int rc = kernel_setup(cont_attn_tc_kernel<NB>, (size_t)Lay<NB>::BYTES, pd, &num_sms)) return rc;
   const int q_tiles = (p.Q + QT - 1) / QT;
-  const long long total = (long long)q_tiles * p.H * Bv;
+  const long long total = (long long)q_tiles * p.H * Bv * p.halves;
   LTM_REQUIRE(total < (1ll << 31), "cont_attn_rect_tc: too many work items");
   const unsigned grid = (unsigned)(total < num_sms ? total : num_sms);
   cont_attn_tc_kernel<NB><<<grid, THREADS, Lay<NB>::BYTES, stream>>>(mK, mV, mX, p, q_tiles, (int)total);
   LTM_CHECK_LAUNCH("cont_attn_rect_tc");
+  if (p.halves > 1) {
+    attn_tc_combine_kernel<<<(unsigned)(total / 2), 256, 0, stream>>>(p.part, p.ctx, p.W_out, p.Q, p.H, q_tiles, Bv);
+    LTM_CHECK_LAUNCH("attn_tc_combine");
+  }
   return 0;
 }
 
@@ -487,30 +550,64 @@ extern "C" void ltm_debug_set_attn_trace(void* p) { ltm::tc::g_trace = (unsigned
 #endif
 
 extern "C" int ltm_attn_tc_supported(int N, int d) { return (d == 64 && (N == 64 || N == 128 || N == 256)) ? 1 : 0; }
+extern "C" int ltm_attn_tc_split_supported(int N, int d) { return (d == 64 && N == 512) ? 1 : 0; }
+extern "C" int64_t ltm_attn_tc_split_workspace_floats(int Bv, int Q, int H) {
+  return (int64_t)Bv * H * ((Q + ltm::tc::QT - 1) / ltm::tc::QT) * 2 * ltm::tc::PART_ROWS * ltm::tc::QT;
+}
+
+static int cont_attn_rect_tc_impl(const float* q, const float* K, const float* V, int64_t ldkv, const float* X,
+                                  const float* W, float W_out, float c_none, const int32_t* jb, const float* tb,
+                                  float* ctx, float* scores_out, float* hist_part, float* part, int Bv, int Q, int N,
+                                  int H, int d, void* stream) {
+  using namespace ltm;
+  const int halves = part != nullptr ? 2 : 1;
+  const int NBk = N / halves;                        // basis functions per work item
+  LTM_REQUIRE(q && K && V && X && W && ctx, "cont_attn_rect_tc: null pointer");
+  LTM_REQUIRE(hist_part == nullptr || (jb && tb), "cont_attn_rect_tc: histogram requested without edge tables");
+  LTM_REQUIRE(Bv > 0 && Bv <= 65535 && Q > 0 && H > 0 && H <= 65535 && ldkv % 4 == 0 && ldkv >= (int64_t)H * d,
+              "cont_attn_rect_tc: bad shape");
+  LTM_REQUIRE(aligned16(q) && aligned16(ctx) && aligned16(part), "cont_attn_rect_tc: 16-byte alignment");
+  CUtensorMap mK, mV, mX;
+  const unsigned long long rows = (unsigned long long)Bv * N;
+  if (tma_encode_2d(&mK, K, (unsigned long long)H * d, rows, (unsigned long long)ldkv, 32, (unsigned)NBk, 0, "attn K"))
+    return -1;
+  if (tma_encode_2d(&mV, V, (unsigned long long)H * d, rows, (unsigned long long)ldkv, 32, (unsigned)NBk, 1, "attn V"))
+    return -1;
+  if (tma_encode_2d(&mX, X, 32, (unsigned long long)N, 32, 32, (unsigned)NBk, 1, "attn X")) return -1;
+  tc::Params p{};
+  p.q = q; p.W = W; p.tb = tb; p.jb = jb; p.W_out = W_out; p.c_none = c_none; p.ctx = ctx;
+  p.scores_out = scores_out; p.hist_part = hist_part; p.Q = Q; p.H = H;
+  p.halves = halves; p.NT = N; p.part = part;
+  p.trace = tc::g_trace;
+  if (NBk == 256) return tc::launch<256>(mK, mV, mX, p, Bv, (cudaStream_t)stream);
+  if (NBk == 128) return tc::launch<128>(mK, mV, mX, p, Bv, (cudaStream_t)stream);
+  return tc::launch<64>(mK, mV, mX, p, Bv, (cudaStream_t)stream);
+}
 
 extern "C" int ltm_cont_attn_rect_tc(const float* q, const float* K, const float* V, int64_t ldkv, const float* X,
                                      const float* W, float W_out, float c_none, const int32_t* jb, const float* tb,
                                      float* ctx, float* scores_out, float* hist_part, int Bv, int Q, int N, int H,
                                      int d, void* stream) {
   using namespace ltm;
-  LTM_REQUIRE(q && K && V && X && W && ctx, "cont_attn_rect_tc: null pointer");
-  LTM_REQUIRE(hist_part == nullptr || (jb && tb), "cont_attn_rect_tc: histogram requested without edge tables");
   LTM_REQUIRE(ltm_attn_tc_supported(N, d), "cont_attn_rect_tc: unsupported num_basis=%d / head_size=%d", N, d);
-  LTM_REQUIRE(Bv > 0 && Bv <= 65535 && Q > 0 && H > 0 && H <= 65535 && ldkv % 4 == 0 && ldkv >= (int64_t)H * d,
-              "cont_attn_rect_tc: bad shape");
-  LTM_REQUIRE(aligned16(q) && aligned16(ctx), "cont_attn_rect_tc: 16-byte alignment");
-  CUtensorMap mK, mV, mX;
-  const unsigned long long rows = (unsigned long long)Bv * N;
-  if (tma_encode_2d(&mK, K, (unsigned long long)H * d, rows, (unsigned long long)ldkv, 32, (unsigned)N, 0, "attn K"))
-    return -1;
-  if (tma_encode_2d(&mV, V, (unsigned long long)H * d, rows, (unsigned long long)ldkv, 32, (unsigned)N, 1, "attn V"))
-    return -1;
-  if (tma_encode_2d(&mX, X, 32, (unsigned long long)N, 32, 32, (unsigned)N, 1, "attn X")) return -1;
-  tc::Params p{};
-  p.q = q; p.W = W; p.tb = tb; p.jb = jb; p.W_out = W_out; p.c_none = c_none; p.ctx = ctx;
-  p.scores_out = scores_out; p.hist_part = hist_part; p.Q = Q; p.H = H;
-  p.trace = tc::g_trace;
-  if (N == 256) return tc::launch<256>(mK, mV, mX, p, Bv, (cudaStream_t)stream);
-  if (N == 128) return tc::launch<128>(mK, mV, mX, p, Bv, (cudaStream_t)stream);
-  return tc::launch<64>(mK, mV, mX, p, Bv, (cudaStream_t)stream);
+  return cont_attn_rect_tc_impl(q, K, V, ldkv, X, W, W_out, c_none, jb, tb, ctx, scores_out, hist_part, nullptr, Bv, Q,
+                                N, H, d, stream);
+}
+
+// num_basis 512: two work items per (query tile, head, video), merged by attn_tc_combine_kernel; the sticky
+// histogram of the next call then comes from the stored scores (ltm_sticky_hist_rect_tiles), because the density of a
+// basis needs the normaliser over BOTH halves.  scores_ws[Bv,H,Q,N] and part_ws (ltm_attn_tc_split_workspace_floats)
+// are caller-provided workspaces.
+extern "C" int ltm_cont_attn_rect_tc_split(const float* q, const float* K, const float* V, int64_t ldkv,
+                                           const float* X, const float* W, float W_out, const int32_t* jb,
+                                           const float* tb, float* ctx, float* scores_ws, float* part_ws,
+                                           float* hist_part, int Bv, int Q, int N, int H, int d, void* stream) {
+  using namespace ltm;
+  LTM_REQUIRE(ltm_attn_tc_split_supported(N, d), "cont_attn_rect_tc_split: unsupported num_basis=%d / head_size=%d", N, d);
+  LTM_REQUIRE(part_ws != nullptr && (hist_part == nullptr || scores_ws != nullptr),
+              "cont_attn_rect_tc_split: workspaces missing");
+  int rc = cont_attn_rect_tc_impl(q, K, V, ldkv, X, W, W_out, 0.f, jb, tb, ctx, scores_ws, nullptr, part_ws, Bv, Q, N,
+                                  H, d, stream);
+  if (rc || hist_part == nullptr) return rc;
+  return ltm_sticky_hist_rect_tiles(scores_ws, jb, tb, hist_part, Bv, H, Q, N, stream);
 }

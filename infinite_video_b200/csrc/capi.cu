@@ -75,10 +75,10 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
     idx = a->idx;
     idx_stride = a->S;
   }
-  LTM_PROF(4);
   // tensor-core attention: row-major tf32-rounded K|V from the projection, both attention contractions as UMMAs
+  const bool tc512 = a->attn_part != nullptr && a->scores != nullptr && ltm_attn_tc_split_supported(a->N, a->d);
   const bool tcp = a->X != nullptr && a->KV != nullptr && a->precision == 1 && a->gemm_impl == 0 &&
-                   ltm_attn_tc_supported(a->N, a->d);
+                   (ltm_attn_tc_supported(a->N, a->d) || tc512);
   const bool half_ops = tcp && a->B_half != nullptr && a->Wkv_half != nullptr && a->e % 8 == 0;
   const bool fast = !tcp && a->Kt != nullptr && a->V != nullptr && ltm_attn_fast_supported(a->N, a->d);
   // projected-memory state: every video updates, K|V of the previous call are at hand, and the rows that receive new
@@ -88,58 +88,79 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
                        new_doc == nullptr && a->jf > 0 && n_new > 0 && (128 % n_new == 0 || n_new % 128 == 0) &&
                        a->e % 4 == 0;
   const int pprec = a->proj_precision ? a->proj_precision : a->precision;
-  rc = ltm_consolidate_rect_kv(B_past, a->xpart, idx, idx_stride, new_doc, a->seg_ptr0, a->seg_mem0, a->g0,
-                               a->seg_ptr1, a->seg_mem1, a->g1, a->B_new, half_ops ? a->B_half : nullptr,
-                               kvstate ? a->KV_past : nullptr, a->KV, a->bkv, 2 * D, a->jf, tcp ? 1 : 0,
-                               a->Bv, a->N, a->e, a->L, a->splits, a->S, stream);
-  if (rc) return rc;
-  LTM_PROF(5);
-  LTM_PROF(6);
-  if (kvstate) {
-    // rows [jf, N) of every video as one flat problem: A = B_new + jf * e grouped per video, C = KV + jf * 2D
-    ltm_gemm_args ga;
-    memset(&ga, 0, sizeof(ga));
-    ga.A = a->B_new + (size_t)a->jf * a->e; ga.lda = a->e; ga.a_kmajor = 1;
-    ga.a_group = n_new; ga.a_group_stride = (int64_t)a->N * a->e;
-    ga.B = a->Wkv; ga.ldb = a->e; ga.b_kmajor = 1;
-    ga.K1 = a->e; ga.bias = a->bkv;
-    ga.C = a->KV + (size_t)a->jf * 2 * D; ga.ldc = 2 * D;
-    ga.c_group = n_new; ga.c_group_stride = (int64_t)a->N * 2 * D;
-    ga.M = a->Bv * n_new; ga.Nc = 2 * D; ga.K = a->e; ga.batch = 1;
-    ga.precision = pprec; ga.impl = a->gemm_impl; ga.round_tf32 = tcp ? 1 : 0;
-    rc = ltm_gemm(&ga, stream);
-  } else if (half_ops) {
-    ltm_gemm_args ga;
-    memset(&ga, 0, sizeof(ga));
-    ga.A = reinterpret_cast<const float*>(a->B_half); ga.lda = a->e; ga.a_kmajor = 1;
-    ga.B = reinterpret_cast<const float*>(a->Wkv_half); ga.ldb = a->e; ga.b_kmajor = 1;
-    ga.K1 = a->e; ga.bias = a->bkv;
-    ga.C = a->KV; ga.ldc = 2 * D;
-    ga.M = a->Bv * a->N; ga.Nc = 2 * D; ga.K = a->e; ga.batch = 1;
-    ga.precision = 1; ga.impl = 0; ga.round_tf32 = 1; ga.ab_fp16 = 1;
-    rc = ltm_gemm(&ga, stream);
-  } else if (tcp)
-    rc = ltm_project_kv_r(a->B_new, a->Wkv, a->bkv, a->KV, a->Bv * a->N, a->e, 2 * D, pprec, a->gemm_impl,
-                          stream);
-  else if (fast)
-    rc = ltm_project_kv_t(a->B_new, a->Wkv, a->bkv, a->Kt, a->V, a->Bv * a->N, a->e, D, a->N, a->precision,
-                          a->gemm_impl, stream);
-  else
-    rc = ltm_project_kv(a->B_new, a->Wkv, a->bkv, a->KV, a->Bv * a->N, a->e, 2 * D, a->precision, a->gemm_impl,
-                        stream);
-  if (rc) return rc;
-  LTM_PROF(7);
-  LTM_PROF(8);
-  if (tcp)
-    rc = ltm_cont_attn_rect_tc(q, a->KV, a->KV + D, 2 * D, a->X, a->W, a->W_out, a->c_none, a->jb, a->tb, ctx,
-                               a->scores, a->sticky ? a->hist_part : nullptr, a->Bv, a->Q, a->N, a->H, a->d, stream);
-  else if (fast)
-    rc = ltm_cont_attn_rect_t(q, a->Kt, a->V, D, a->W, a->W_out, a->jb, a->tb, ctx, a->scores,
-                              a->sticky ? a->hist_part : nullptr, a->Bv, a->Q, a->N, a->H, a->d, stream);
-  else
-    rc = ltm_cont_attn_rect(q, a->KV, a->W, a->W_out, a->jb, a->tb, ctx, a->scores,
-                            a->sticky ? a->hist_part : nullptr, a->Bv, a->Q, a->N, a->H, a->d, stream);
-  LTM_PROF(9);
+  // Blocks of videos run consolidate -> project -> attention back to back, so that the K|V (and coefficient) rows a
+  // block has just written are still in L2 when its attention (projection) reads them: with all videos per kernel
+  // the 201 MB of K|V at 128 videos go out to HBM and come back.  video_block: 0 = all videos in one block.
+  int vblock = (a->video_block > 0 && a->video_block < a->Bv && !fast) ? a->video_block : a->Bv;
+  const size_t sB = (size_t)a->N * a->e, sKV = (size_t)a->N * 2 * D, sX = (size_t)a->L * a->splits * a->e;
+  const bool blocked = vblock < a->Bv;
+  if (blocked) LTM_PROF(4);
+  for (int v0 = 0; v0 < a->Bv; v0 += vblock) {
+    const int nv = (a->Bv - v0 < vblock) ? a->Bv - v0 : vblock;
+    const float* Bp = B_past ? B_past + v0 * sB : nullptr;
+    float* Bn = a->B_new + v0 * sB;
+    float* KVn = a->KV ? a->KV + v0 * sKV : nullptr;
+    const float* KVp = kvstate ? a->KV_past + v0 * sKV : nullptr;
+    void* Bh = half_ops ? (void*)((uint16_t*)a->B_half + v0 * sB) : nullptr;
+    if (!blocked) LTM_PROF(4);
+    rc = ltm_consolidate_rect_kv(Bp, a->xpart + v0 * sX, idx_stride ? idx + (size_t)v0 * idx_stride : idx, idx_stride,
+                                 new_doc ? new_doc + v0 : nullptr, a->seg_ptr0, a->seg_mem0, a->g0, a->seg_ptr1,
+                                 a->seg_mem1, a->g1, Bn, Bh, KVp, KVn, a->bkv, 2 * D, a->jf, tcp ? 1 : 0, nv, a->N,
+                                 a->e, a->L, a->splits, a->S, stream);
+    if (rc) return rc;
+    if (!blocked) { LTM_PROF(5); LTM_PROF(6); }
+    if (kvstate) {
+      // rows [jf, N) of every video as one flat problem: A = B_new + jf * e grouped per video, C = KV + jf * 2D
+      ltm_gemm_args ga;
+      memset(&ga, 0, sizeof(ga));
+      ga.A = Bn + (size_t)a->jf * a->e; ga.lda = a->e; ga.a_kmajor = 1;
+      ga.a_group = n_new; ga.a_group_stride = (int64_t)a->N * a->e;
+      ga.B = a->Wkv; ga.ldb = a->e; ga.b_kmajor = 1;
+      ga.K1 = a->e; ga.bias = a->bkv;
+      ga.C = KVn + (size_t)a->jf * 2 * D; ga.ldc = 2 * D;
+      ga.c_group = n_new; ga.c_group_stride = (int64_t)a->N * 2 * D;
+      ga.M = nv * n_new; ga.Nc = 2 * D; ga.K = a->e; ga.batch = 1;
+      ga.precision = pprec; ga.impl = a->gemm_impl; ga.round_tf32 = tcp ? 1 : 0;
+      rc = ltm_gemm(&ga, stream);
+    } else if (half_ops) {
+      ltm_gemm_args ga;
+      memset(&ga, 0, sizeof(ga));
+      ga.A = reinterpret_cast<const float*>(Bh); ga.lda = a->e; ga.a_kmajor = 1;
+      ga.B = reinterpret_cast<const float*>(a->Wkv_half); ga.ldb = a->e; ga.b_kmajor = 1;
+      ga.K1 = a->e; ga.bias = a->bkv;
+      ga.C = KVn; ga.ldc = 2 * D;
+      ga.M = nv * a->N; ga.Nc = 2 * D; ga.K = a->e; ga.batch = 1;
+      ga.precision = 1; ga.impl = 0; ga.round_tf32 = 1; ga.ab_fp16 = 1;
+      rc = ltm_gemm(&ga, stream);
+    } else if (tcp)
+      rc = ltm_project_kv_r(Bn, a->Wkv, a->bkv, KVn, nv * a->N, a->e, 2 * D, pprec, a->gemm_impl, stream);
+    else if (fast)
+      rc = ltm_project_kv_t(Bn, a->Wkv, a->bkv, a->Kt, a->V, nv * a->N, a->e, D, a->N, a->precision, a->gemm_impl,
+                            stream);
+    else
+      rc = ltm_project_kv(Bn, a->Wkv, a->bkv, KVn, nv * a->N, a->e, 2 * D, a->precision, a->gemm_impl, stream);
+    if (rc) return rc;
+    if (!blocked) { LTM_PROF(7); LTM_PROF(8); }
+    const float* qb = q + (size_t)v0 * a->Q * D;
+    float* cb = ctx + (size_t)v0 * a->Q * D;
+    float* sc = a->scores ? a->scores + (size_t)v0 * a->H * a->Q * a->N : nullptr;
+    float* hp = a->sticky ? a->hist_part + (size_t)v0 * a->H * qtiles * (LTM_STICKY_EDGES - 2) : nullptr;
+    if (tcp && tc512)
+      rc = ltm_cont_attn_rect_tc_split(qb, KVn, KVn + D, 2 * D, a->X, a->W, a->W_out, a->jb, a->tb, cb, sc,
+                                       a->attn_part + ltm_attn_tc_split_workspace_floats(v0, a->Q, a->H), hp, nv, a->Q,
+                                       a->N, a->H, a->d, stream);
+    else if (tcp)
+      rc = ltm_cont_attn_rect_tc(qb, KVn, KVn + D, 2 * D, a->X, a->W, a->W_out, a->c_none, a->jb, a->tb, cb, sc, hp,
+                                 nv, a->Q, a->N, a->H, a->d, stream);
+    else if (fast)
+      rc = ltm_cont_attn_rect_t(qb, a->Kt, a->V, D, a->W, a->W_out, a->jb, a->tb, cb, sc, hp, nv, a->Q, a->N, a->H,
+                                a->d, stream);
+    else
+      rc = ltm_cont_attn_rect(qb, KVn, a->W, a->W_out, a->jb, a->tb, cb, sc, hp, nv, a->Q, a->N, a->H, a->d, stream);
+    if (rc) return rc;
+    if (!blocked) LTM_PROF(9);
+  }
+  if (blocked) LTM_PROF(9);
 #undef LTM_PROF
   return rc;
 }

@@ -5,12 +5,17 @@
 
 namespace ltm {
 
-// Standalone op: scores[Bv,H,Q,N] -> hist_part[Bv,H,127]; one CTA per (head, video).
+// Standalone op: scores[Bv,H,Q,N] -> hist_part[Bv,H,127]; one CTA per (head, video).  q_tiles > 0: one CTA per
+// (head, query tile of 32, video) writing hist_part[Bv, H*q_tiles, 127] -- the layout the fused attention kernels
+// produce -- used for num_basis 512, whose tensor-core attention works on two basis halves.
 __global__ void __launch_bounds__(256)
 sticky_hist_rect_kernel(const float* __restrict__ scores, const int32_t* __restrict__ jb,
-                        const float* __restrict__ tb, float* __restrict__ hist_part, int H, int Q, int N) {
+                        const float* __restrict__ tb, float* __restrict__ hist_part, int H, int Q, int N,
+                        int q_tiles) {
   extern __shared__ float smem[];
-  const int h = blockIdx.x, v = blockIdx.y;
+  const int h = q_tiles > 0 ? blockIdx.x / q_tiles : blockIdx.x, v = blockIdx.y;
+  const int q_lo = q_tiles > 0 ? (blockIdx.x % q_tiles) * 32 : 0;
+  const int q_hi = q_tiles > 0 ? min(Q, q_lo + 32) : Q;
   const float* S = scores + ((size_t)(v * H + h) * Q) * N;
   constexpr int RT = 32;
   float* Eb = smem;                       // [RT][130]
@@ -19,8 +24,8 @@ sticky_hist_rect_kernel(const float* __restrict__ scores, const int32_t* __restr
   float* part = mr + RT;                  // [128]
   float* accum = part + 128;              // [128]
   for (int i = threadIdx.x; i < 128; i += blockDim.x) accum[i] = 0.f;
-  for (int q0 = 0; q0 < Q; q0 += RT) {
-    const int rows = min(RT, Q - q0);
+  for (int q0 = q_lo; q0 < q_hi; q0 += RT) {
+    const int rows = min(RT, q_hi - q0);
     __syncthreads();
     // per-row shift m = max(0, max_i z_i) keeps exp() finite; it cancels in E/Z
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -40,7 +45,7 @@ sticky_hist_rect_kernel(const float* __restrict__ scores, const int32_t* __restr
   }
   __syncthreads();
   for (int i = threadIdx.x; i < EDGES - 2; i += blockDim.x)
-    hist_part[((size_t)v * H + h) * (EDGES - 2) + i] = accum[i];
+    hist_part[((size_t)v * gridDim.x + blockIdx.x) * (EDGES - 2) + i] = accum[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -287,8 +292,21 @@ extern "C" int ltm_sticky_hist_rect(const float* scores, const int32_t* jb, cons
   LTM_REQUIRE(Bv > 0 && Bv <= 65535 && H > 0 && Q > 0 && N > 0, "sticky_hist_rect: bad shape");
   const size_t smem = sizeof(float) * (32 * (EDGES + 1) + 32 + 32 + 128 + 128);
   dim3 grid(H, Bv);
-  sticky_hist_rect_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(scores, jb, tb, hist_part, H, Q, N);
+  sticky_hist_rect_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(scores, jb, tb, hist_part, H, Q, N, 0);
   LTM_CHECK_LAUNCH("sticky_hist_rect");
+  return 0;
+}
+
+extern "C" int ltm_sticky_hist_rect_tiles(const float* scores, const int32_t* jb, const float* tb, float* hist_part,
+                                          int Bv, int H, int Q, int N, void* stream) {
+  using namespace ltm;
+  LTM_REQUIRE(scores && jb && tb && hist_part, "sticky_hist_rect_tiles: null pointer");
+  LTM_REQUIRE(Bv > 0 && Bv <= 65535 && H > 0 && Q > 0 && N > 0, "sticky_hist_rect_tiles: bad shape");
+  const size_t smem = sizeof(float) * (32 * (EDGES + 1) + 32 + 32 + 128 + 128);
+  const int q_tiles = (Q + 31) / 32;
+  dim3 grid(H * q_tiles, Bv);
+  sticky_hist_rect_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(scores, jb, tb, hist_part, H, Q, N, q_tiles);
+  LTM_CHECK_LAUNCH("sticky_hist_rect_tiles");
   return 0;
 }
 

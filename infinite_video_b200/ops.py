@@ -202,7 +202,7 @@ def gemm(A, B, *, a_kmajor=True, b_kmajor=True, B2=None, bias=None, out=None, pr
 
 def gemm_raw(A, lda, strideA, a_kmajor, B, ldb, strideB, b_kmajor, C_, ldc, strideC, M, Nc, K, batch, *, bias=None,
              bias_stride=0, c_group=0, c_group_stride=0, precision="tf32", impl="tcgen05", a_offset=0, b_offset=0,
-             c_offset=0, round_tf32=False, a_group=0, a_group_stride=0):
+             c_offset=0, round_tf32=False, a_group=0, a_group_stride=0, bias_offset=0):
     """ltm_gemm with every pitch / batch stride spelled out (elements).  A, B, C_ are the base tensors; *_offset
     shifts the start (elements).  Used where operands are strided views that tensor shapes cannot express
     (per-head column blocks, per-head / per-video output layouts)."""
@@ -211,7 +211,7 @@ def gemm_raw(A, lda, strideA, a_kmajor, B, ldb, strideB, b_kmajor, C_, ldc, stri
     g.A, g.lda, g.strideA, g.a_kmajor = A.data_ptr() + 4 * a_offset, lda, strideA, int(a_kmajor)
     g.B, g.ldb, g.strideB, g.b_kmajor = B.data_ptr() + 4 * b_offset, ldb, strideB, int(b_kmajor)
     g.B2, g.ldb2, g.strideB2, g.K1 = None, 0, 0, K
-    g.bias = bias.data_ptr() if bias is not None else None
+    g.bias = bias.data_ptr() + 4 * bias_offset if bias is not None else None
     g.bias_stride = bias_stride
     g.C, g.ldc, g.strideC = C_.data_ptr() + 4 * c_offset, ldc, strideC
     g.M, g.Nc, g.K, g.batch = M, Nc, K, batch
@@ -289,6 +289,11 @@ def attn_tc_supported(N, d=64):
     return bool(lib().ltm_attn_tc_supported(int(N), int(d)))
 
 
+def attn_tc_split_supported(N, d=64):
+    """num_basis 512: the tensor-core attention in two basis halves + combine (ltm_cont_attn_rect_tc_split)."""
+    return bool(lib().ltm_attn_tc_split_supported(int(N), int(d)))
+
+
 def project_kv_r(Bcoef, Wkv, bkv, precision="tf32", out=None):
     """`project_kv` with the stored K|V rounded to the tf32 grid (operands of the tensor-core attention)."""
     require_cuda(Bcoef, Wkv, bkv)
@@ -314,14 +319,26 @@ def cont_attn_rect_tc(q, KV, X, W, W_out, c_none, jb=None, tb=None, want_scores=
     hist = (torch.empty(Bv, H * ((Q + 31) // 32), STICKY_EDGES - 2, device=q.device, dtype=torch.float32)
             if want_hist else None)
     kv = KV.reshape(Bv * N, 2 * D)
+    if attn_tc_split_supported(N, d):          # num_basis 512: two basis halves + combine, histogram from the scores
+        if scores is None and want_hist:
+            scores = torch.empty(Bv, H, Q, N, device=q.device, dtype=torch.float32)
+        part = torch.empty(int(lib().ltm_attn_tc_split_workspace_floats(Bv, Q, H)), device=q.device,
+                           dtype=torch.float32)
+        check(lib().ltm_cont_attn_rect_tc_split(ptr(q), ptr(kv), C.c_void_p(kv.data_ptr() + 4 * D), 2 * D, ptr(X),
+                                                ptr(W), float(W_out), ptr(jb), ptr(tb), ptr(ctx), ptr(scores),
+                                                ptr(part), ptr(hist), Bv, Q, N, H, d, stream_ptr(q.device)),
+              "cont_attn_rect_tc_split")
+        return ctx, (scores if want_scores else None), hist
     check(lib().ltm_cont_attn_rect_tc(ptr(q), ptr(kv), C.c_void_p(kv.data_ptr() + 4 * D), 2 * D, ptr(X), ptr(W),
                                       float(W_out), float(c_none), ptr(jb), ptr(tb), ptr(ctx), ptr(scores), ptr(hist),
                                       Bv, Q, N, H, d, stream_ptr(q.device)), "cont_attn_rect_tc")
     return ctx, scores, hist
 
 
-def project_kv_t(Bcoef, Wkv, bkv, N, precision="tf32", impl="tcgen05"):
-    """Same projection with the keys stored transposed per head: -> (Kt[Bv,H,64,N], V[Bv,N,D])."""
+def project_kv_t(Bcoef, Wkv, bkv, N, precision="tf32", impl="tcgen05", precision_v=None):
+    """Same projection with the keys stored transposed per head: -> (Kt[Bv,H,64,N], V[Bv,N,D]).
+    `precision_v` (None = `precision`): a different precision for the value half -- the Gaussian variant needs
+    fp32-grade keys (softmax(20 S) amplifies score errors 20x) but its values only enter the final contraction."""
     require_cuda(Bcoef, Wkv, bkv)
     Bc = _f32c(Bcoef).reshape(-1, Bcoef.shape[-1])
     M, e = Bc.shape
@@ -329,6 +346,19 @@ def project_kv_t(Bcoef, Wkv, bkv, N, precision="tf32", impl="tcgen05"):
     Bv = M // N
     Kt = torch.empty(Bv, D // 64, 64, N, device=Bc.device, dtype=torch.float32)
     V = torch.empty(Bv, N, D, device=Bc.device, dtype=torch.float32)
+    if precision_v is not None and PRECISION[precision_v] != PRECISION[precision]:
+        g = GemmArgs()                                   # keys: all D columns through the transposed store
+        g.A, g.lda, g.a_kmajor = Bc.data_ptr(), e, 1
+        g.B, g.ldb, g.b_kmajor = Wkv.data_ptr(), e, 1
+        g.K1, g.bias = e, bkv.data_ptr()
+        g.C, g.ldc = V.data_ptr(), D                     # (no column takes the row-major path)
+        g.CT, g.ct_cols, g.ct_group = Kt.data_ptr(), D, N
+        g.M, g.Nc, g.K, g.batch = M, D, e, 1
+        g.precision, g.impl = PRECISION[precision], GEMM_IMPL[impl]
+        check(lib().ltm_gemm(C.byref(g), stream_ptr(Bc.device)), "project_k_t")
+        gemm_raw(Bc, e, 0, True, Wkv, e, 0, True, V, D, 0, M, D, e, 1, bias=bkv, precision=precision_v, impl=impl,
+                 b_offset=D * e, bias_offset=D)
+        return Kt, V
     check(lib().ltm_project_kv_t(ptr(Bc), ptr(Wkv), ptr(bkv), ptr(Kt), ptr(V), M, e, D, N, PRECISION[precision],
                                  GEMM_IMPL[impl], stream_ptr(Bc.device)), "project_kv_t")
     return Kt, V

@@ -99,11 +99,13 @@ def load_gaussian_vl():
     return mod
 
 
-def load_qformer_vl():
+def load_qformer_vl(ltm_module=None, pkg="_ref_vl"):
     """Reference caller: ``Qformer.py`` of Video-LLaMA (``BertSelfAttention`` :115-310 constructs, triggers and
     blends the LTM).  Written for transformers 4.x; three helpers it imports from ``transformers.modeling_utils``
     moved / disappeared in 5.x and are aliased or stubbed (they are only used by ``prune_heads``), and its absolute
-    import of the LTM module (:50) is pointed at the isolated copy loaded above."""
+    import of the LTM module (:50) is pointed at the isolated copy loaded above -- or, for the import-swap test, at
+    `ltm_module` (any module exposing ``LongTermAttention``), in which case the file is loaded a second time under
+    the package name `pkg` so that both flavours can live side by side."""
     import transformers.modeling_utils as MU
     import transformers.pytorch_utils as PU
 
@@ -114,11 +116,17 @@ def load_qformer_vl():
     for n in ("apply_chunking_to_forward", "find_pruneable_heads_and_indices", "prune_linear_layer"):
         if not hasattr(MU, n):
             setattr(MU, n, getattr(PU, n, None) or _missing(n))
-    ltm = load_gibbs_vl()
+    ltm = load_gibbs_vl() if ltm_module is None else ltm_module
     for name in ("InfVideoLLaMA", "InfVideoLLaMA.models"):
         sys.modules.setdefault(name, types.ModuleType(name))
-    sys.modules["InfVideoLLaMA.models.long_term_attention_gibbs"] = ltm
-    return _load_pkg("_ref_vl", _VL, ["Qformer"])["Qformer"]
+    alias = "InfVideoLLaMA.models.long_term_attention_gibbs"
+    saved = sys.modules.get(alias)
+    sys.modules[alias] = ltm
+    try:
+        return _load_pkg(pkg, _VL, ["Qformer"])["Qformer"]
+    finally:
+        if saved is not None:
+            sys.modules[alias] = saved
 
 
 def bert_config(num_basis, tau, alpha, sticky=True, encoder_width=768):

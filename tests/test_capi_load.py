@@ -50,7 +50,8 @@ def test_version_and_error_convention(lib):
                                    1, 32, 256, 12, 64, None)
     assert rc < 0 and b"cont_attn_rect_tc" in lib.ltm_last_error()
     assert lib.ltm_attn_tc_supported(256, 64) == 1 and lib.ltm_attn_tc_supported(64, 64) == 1
-    assert lib.ltm_attn_tc_supported(512, 64) == 0
+    assert lib.ltm_attn_tc_supported(512, 64) == 0 and lib.ltm_attn_tc_split_supported(512, 64) == 1
+    assert lib.ltm_attn_tc_split_supported(256, 64) == 0 and lib.ltm_attn_tc_split_workspace_floats(2, 40, 12) == 2 * 12 * 2 * 2 * 68 * 32
     assert lib.ltm_attn_tc_supported(256, 128) == 0
     a, o = _capi.RectStepArgs(), _capi.Overlap()
     rc = lib.ltm_rect_step_overlap(C.byref(a), C.byref(o), None, None, None, None)

@@ -711,3 +711,50 @@ def test_caller_cross_attention_with_ltm_blend_on_gpu(dev, alpha, N, L, B):
             stm = m.short_term(torch.nn.functional.linear(hidden, lq.weight, lq.bias).to(dev), enc.to(dev))
             assert relerr(stm, torch.cat([o.last_stm for o in orcs])) < TOL_CTX, f"short-term, chunk {c}"
             assert relerr(got, want) < TOL_CTX, f"blend, chunk {c}"
+
+
+def test_import_swap_through_the_real_qformer(dev, tmp_path):
+    """the UNMODIFIED `Qformer.BertSelfAttention` (baseline/_ref on the GPU box, oracle/install_ref.py)
+    with its one import line (Qformer.py:50) resolved to `infinite_video_b200` instead of the reference module: two
+    cross-attention layers, alpha = 0.5, three chunks, against the same caller running the real reference LTM on the
+    CPU.  Uniforms come from torch's global CPU generator in both (same seed before every call)."""
+    import copy
+    import os
+    import infinite_video_b200
+    from oracle import ref_loader as RL
+    if not RL.reference_available():
+        pytest.skip("reference files absent (neither /root/reference nor baseline/_ref)")
+    Qref = RL.load_qformer_vl()
+    Qswap = RL.load_qformer_vl(ltm_module=infinite_video_b200, pkg="_swap_vl")
+    assert Qswap.LongTermAttention is infinite_video_b200.LongTermAttention
+    cfg = RL.bert_config(64, 0.75, 0.5)
+    torch.manual_seed(11)
+    ref_layers = [Qref.BertSelfAttention(cfg, is_cross_attention=True).eval() for _ in range(2)]
+    swap_layers = []
+    for r in ref_layers:
+        m = Qswap.BertSelfAttention(cfg, is_cross_attention=True).eval()
+        m.load_state_dict(copy.deepcopy(r.state_dict()), strict=False)
+        swap_layers.append(m.to(dev))
+        assert isinstance(m.long_term_attention, infinite_video_b200.LongTermAttention)
+    g = torch.Generator().manual_seed(12)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)                       # the reference LTM pickles ./alphas_uniform on every call
+    try:
+        with torch.no_grad():
+            for c in range(3):
+                enc = torch.randn(1, 8 * 32, 768, generator=g)
+                enc_d = enc.to(dev)
+                for li in range(2):
+                    hidden = torch.randn(1, 32, 768, generator=g)
+                    torch.manual_seed(700 + 10 * c + li)
+                    want = ref_layers[li](hidden, position_embedding_ext=torch.zeros(1), layer=li,
+                                          encoder_hidden_states=enc, new_video=(c == 0))[0]
+                    torch.manual_seed(700 + 10 * c + li)
+                    got = swap_layers[li](hidden.to(dev), position_embedding_ext=torch.zeros(1, device=dev), layer=li,
+                                          encoder_hidden_states=enc_d, new_video=(c == 0))[0]
+                    assert got.is_cuda and got.shape == want.shape
+                    assert relerr(got, want) < TOL_CTX, (c, li)
+                    assert relerr(swap_layers[li].long_term_attention.B_past,
+                                  ref_layers[li].long_term_attention.B_past) < 1e-5, (c, li)
+    finally:
+        os.chdir(cwd)

@@ -115,7 +115,7 @@ def _tf32_rna(x):
 
 @pytest.mark.parametrize("N,L,Q,q_scale", [(64, 8, 32, 1.0), (256, 16, 32, 8.0), (512, 16, 32, 4.0),
                                            (64, 8, 96, 2.0), (100, 30, 40, 2.0), (128, 16, 32, 2.0),
-                                           (256, 8, 40, 1.0)])
+                                           (256, 8, 40, 1.0), (512, 32, 72, 1.0)])
 def test_cont_attn_rect_and_fused_histogram(dev, N, L, Q, q_scale):
     ops, T = _ops(), _tables()
     key, val, k, q, outs = _rect_case(N, L, Q, 7, q_scale)
@@ -155,7 +155,7 @@ def test_cont_attn_rect_and_fused_histogram(dev, N, L, Q, q_scale):
         assert torch.equal(ctx4, ctx3)
     # tensor-core path: both contractions as tf32 UMMAs over tf32-rounded K|V (tolerances are tf32's: operands carry
     # 2^-12 relative rounding; the scores enter an exponential, so ctx / p are held to 1e-3 like the e2e tests)
-    if ops.attn_tc_supported(N):
+    if ops.attn_tc_supported(N) or ops.attn_tc_split_supported(N):     # (512: two basis halves + combine)
         KVr = _tf32_rna(KV).to(dev)
         ctx5, scores5, hist5 = ops.cont_attn_rect_tc(q.to(dev), KVr, td["X"], td["W"], tab.W_out, tab.c_none,
                                                      td["jb"], td["tb"], want_scores=True, want_hist=True)
