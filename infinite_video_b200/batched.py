@@ -131,6 +131,7 @@ class BatchedRectLTM(_BatchedBase):
         # precision of the K/V projection GEMM alone (None = `precision`); "tf32x3" makes the stored K|V fp32-grade
         self.proj_precision = proj_precision
         # consolidate / project / attend in blocks of this many videos (L2 reuse of what a block writes); 0 = off
+        # (measured at 128 videos: 16 / 32 / 43 / 64-video blocks all lose 4-14 % to the smaller kernels' tails)
         self.video_block = 0
         self._Wkv_h = None
         self.prof_events = None       # optional list of 10 cudaEvent_t handles (bench.py stage timing)
@@ -175,7 +176,12 @@ class BatchedRectLTM(_BatchedBase):
         return ws
 
     def _splits(self, units):
-        return 1 if units >= 2 * self.sm_count else max(1, min(self.T, -(-self.sm_count * 8 // units)))
+        """Token-splits of the frame pooling: one CTA per frame when that already gives the GPU four waves of CTAs
+        (8 resident per SM), otherwise each frame's tokens are split so that it does -- a grid of barely more than one
+        wave leaves the second one almost empty (VideoChat2 shape, 64 videos x 16 frames = 1024 CTAs for 1184 slots:
+        146 us for 822 MB)."""
+        want = 4 * 8 * self.sm_count
+        return 1 if units >= want else max(1, min(self.T, -(-want // units)))
 
     def reset(self):
         """Forget every video (new_doc for all) and every pending prefetch."""

@@ -532,7 +532,12 @@ static int launch(const CUtensorMap& mK, const CUtensorMap& mV, const CUtensorMa
   const int q_tiles = (p.Q + QT - 1) / QT;
   const long long total = (long long)q_tiles * p.H * Bv * p.halves;
   LTM_REQUIRE(total < (1ll << 31), "cont_attn_rect_tc: too many work items");
-  const unsigned grid = (unsigned)(total < num_sms ? total : num_sms);
+  // persistent CTAs: one per SM for num_basis 256 (209 KB of shared memory), two for 64 / 128 (60 / 106 KB; 2 x 320
+  // threads x 96 registers and 2 x 128 TMEM columns fit): an item costs ~3 us of mostly latency whatever its size, so
+  // the small shapes (cfg1, cfg3: 12 k / 2.3 k items of 64 bases) gain from a second CTA filling the bubbles
+  constexpr int PER_SM = (2 * Lay<NB>::BYTES <= 227 * 1024) ? 2 : 1;
+  const long long slots = (long long)num_sms * PER_SM;
+  const unsigned grid = (unsigned)(total < slots ? total : slots);
   cont_attn_tc_kernel<NB><<<grid, THREADS, Lay<NB>::BYTES, stream>>>(mK, mV, mX, p, q_tiles, (int)total);
   LTM_CHECK_LAUNCH("cont_attn_rect_tc");
   if (p.halves > 1) {

@@ -83,10 +83,19 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
   const bool fast = !tcp && a->Kt != nullptr && a->V != nullptr && ltm_attn_fast_supported(a->N, a->d);
   // projected-memory state: every video updates, K|V of the previous call are at hand, and the rows that receive new
   // frames tile the 128-row GEMM tiles evenly -> only those rows are projected (row-major K|V layouts only)
-  const int n_new = a->N - a->jf;
+  // (the projected rows start at jg <= jf, chosen so that N - jg divides -- or is a multiple of -- the 128-row GEMM
+  // tile: bins in [jg, jf) hold re-sampled memory only and could go either way)
+  int n_new = a->N - a->jf;
+  if (n_new > 0 && n_new <= 128) {
+    int p2 = 1;
+    while (p2 < n_new) p2 <<= 1;
+    n_new = p2;
+  } else if (n_new > 128) {
+    n_new = (n_new + 127) / 128 * 128;
+  }
+  const int jg = a->N - n_new;
   const bool kvstate = a->KV_past != nullptr && a->KV != nullptr && !fast && !half_ops && B_past != nullptr &&
-                       new_doc == nullptr && a->jf > 0 && n_new > 0 && (128 % n_new == 0 || n_new % 128 == 0) &&
-                       a->e % 4 == 0;
+                       new_doc == nullptr && a->jf > 0 && n_new > 0 && jg > 0 && a->e % 4 == 0;
   const int pprec = a->proj_precision ? a->proj_precision : a->precision;
   // Blocks of videos run consolidate -> project -> attention back to back, so that the K|V (and coefficient) rows a
   // block has just written are still in L2 when its attention (projection) reads them: with all videos per kernel
@@ -105,7 +114,7 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
     if (!blocked) LTM_PROF(4);
     rc = ltm_consolidate_rect_kv(Bp, a->xpart + v0 * sX, idx_stride ? idx + (size_t)v0 * idx_stride : idx, idx_stride,
                                  new_doc ? new_doc + v0 : nullptr, a->seg_ptr0, a->seg_mem0, a->g0, a->seg_ptr1,
-                                 a->seg_mem1, a->g1, Bn, Bh, KVp, KVn, a->bkv, 2 * D, a->jf, tcp ? 1 : 0, nv, a->N,
+                                 a->seg_mem1, a->g1, Bn, Bh, KVp, KVn, a->bkv, 2 * D, jg, tcp ? 1 : 0, nv, a->N,
                                  a->e, a->L, a->splits, a->S, stream);
     if (rc) return rc;
     if (!blocked) { LTM_PROF(5); LTM_PROF(6); }
@@ -113,11 +122,11 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
       // rows [jf, N) of every video as one flat problem: A = B_new + jf * e grouped per video, C = KV + jf * 2D
       ltm_gemm_args ga;
       memset(&ga, 0, sizeof(ga));
-      ga.A = Bn + (size_t)a->jf * a->e; ga.lda = a->e; ga.a_kmajor = 1;
+      ga.A = Bn + (size_t)jg * a->e; ga.lda = a->e; ga.a_kmajor = 1;
       ga.a_group = n_new; ga.a_group_stride = (int64_t)a->N * a->e;
       ga.B = a->Wkv; ga.ldb = a->e; ga.b_kmajor = 1;
       ga.K1 = a->e; ga.bias = a->bkv;
-      ga.C = KVn + (size_t)a->jf * 2 * D; ga.ldc = 2 * D;
+      ga.C = KVn + (size_t)jg * 2 * D; ga.ldc = 2 * D;
       ga.c_group = n_new; ga.c_group_stride = (int64_t)a->N * 2 * D;
       ga.M = nv * n_new; ga.Nc = 2 * D; ga.K = a->e; ga.batch = 1;
       ga.precision = pprec; ga.impl = a->gemm_impl; ga.round_tf32 = tcp ? 1 : 0;

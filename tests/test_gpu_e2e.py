@@ -323,7 +323,9 @@ def test_full_size_properties(dev):
     half = BatchedRectLTM(N, .75, *proj_tensors(key, val), device=dev)
     h0 = half.step(k0[2:6], q[2:6], None, new_doc=True)
     h1 = half.step(k1[2:6], q[2:6], u[2:6], new_doc=False)
-    assert torch.equal(h0, c0[2:6]) and torch.equal(h1, c1[2:6])
+    # (a smaller batch pools with more token-splits per frame to fill the GPU: same value up to summation order; 1e-7
+    # differences in B can cross a tf32 rounding boundary of K, V or the attention weights, 2^-12 relative each)
+    assert relerr(h0, c0[2:6]) < 1e-4 and relerr(h1, c1[2:6]) < 1e-4
     solo = BatchedRectLTM(N, .75, *proj_tensors(key, val), device=dev)
     s0 = solo.step(k0[3:4], q[3:4], None, new_doc=True)
     s1 = solo.step(k1[3:4], q[3:4], u[3:4], new_doc=False)
