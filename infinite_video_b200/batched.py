@@ -181,7 +181,8 @@ class BatchedRectLTM(_BatchedBase):
         wave leaves the second one almost empty (VideoChat2 shape, 64 videos x 16 frames = 1024 CTAs for 1184 slots:
         146 us for 822 MB)."""
         want = 4 * 8 * self.sm_count
-        return 1 if units >= want else max(1, min(self.T, -(-want // units)))
+        # (at most T/8 splits: the partial sums are written and read back, T/splits rows of input per row of output)
+        return 1 if units >= want else max(1, min(max(1, self.T // 8), -(-want // units)))
 
     def reset(self):
         """Forget every video (new_doc for all) and every pending prefetch."""
