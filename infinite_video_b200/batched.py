@@ -302,8 +302,13 @@ class BatchedRectLTM(_BatchedBase):
         Q = qshape[1]
         if qshape[0] != Bv or qshape[2] != self.D:
             raise ValueError(f"q must be [{Bv}, Q, {self.D}]")
-        self._state(Bv, Q)
         all_new, flags = _as_flags(new_doc, Bv, self.device)
+        if (self.has_state and not all_new and self._B is not None and self.Bv == Bv
+                and self._hist.shape[1] != self.H * ((Q + 31) // 32)):
+            # the sticky histogram of the previous call is kept per (head, tile of 32 queries): a different number
+            # of query tiles inside a video would silently restart the memory
+            raise ValueError(f"the number of queries changed inside a video ({Q} now): pass new_doc=True or keep Q")
+        self._state(Bv, Q)
         if all_new:
             self.has_state = False
         elif flags is not None and not self.has_state:

@@ -88,6 +88,36 @@ def test_generic_attention_path_still_matches(dev, kw):
     assert w["B"] < 1e-5 and w["ctx"] < TOL_CTX, w
 
 
+def test_ragged_video_chunk_lengths(dev):
+    """A video whose chunks differ in length (the last chunk of a real video is shorter; the reference rebuilds its
+    tables for whatever `k.size(1)` it is handed): the memory state carries over between chunk lengths, the carried
+    K|V are simply re-projected once after a change of shape.  Also: a change of the query count inside a video is
+    refused instead of silently restarting the memory."""
+    from infinite_video_b200.batched import BatchedRectLTM
+    key, val = make_proj(37, 768)
+    N, Bv = 64, 2
+    eng = BatchedRectLTM(N, .75, *proj_tensors(key, val), device=dev)
+    orcs = [O.RectLTM(N, .75, *proj_tensors(key, val), rebuild_tables=False) for _ in range(Bv)]
+    g = torch.Generator().manual_seed(38)
+    for c, L in enumerate((16, 16, 8, 8, 5, 16)):
+        k = torch.randn(Bv, L * 32, 768, generator=g)
+        q = torch.randn(Bv, 32, 768, generator=g)
+        u = torch.rand(Bv, 512, dtype=torch.float64, generator=g)
+        with torch.no_grad():
+            got = eng.step(k.to(dev), q.to(dev), u.to(dev) if c else None, new_doc=(c == 0))
+            b_got = eng.last["b"].cpu().long() if c else None
+            want = torch.cat([orcs[v].forward(k[v:v + 1], q[v:v + 1], c == 0, u[v:v + 1],
+                                              b_override=b_got[v:v + 1] if c else None) for v in range(Bv)])
+        if c:
+            compare_draws(b_got, torch.cat([o.last["b_own"] for o in orcs]), u, torch.cat([o.last["p"] for o in orcs]),
+                          TIE["tf32"])
+        assert relerr(eng.B_past, torch.cat([o.B_past for o in orcs])) < 1e-5, (c, L)
+        assert relerr(got, want) < TOL_CTX, (c, L)
+    with pytest.raises(ValueError):
+        eng.step(torch.randn(Bv, 16 * 32, 768, device=dev), torch.randn(Bv, 40, 768, device=dev),
+                 torch.rand(Bv, 512, dtype=torch.float64, device=dev))
+
+
 def test_projected_memory_state_equals_full_projection(dev):
     """kv_state (K|V of the old bins carried from the previous call, only the new-frame rows projected) against the
     engine that projects all N rows every call, over enough chunks for a rounding drift to show: coefficients are
@@ -257,12 +287,17 @@ def test_gauss_matches_oracle_with_shared_operators(dev, N, L, Bv, C):
                 assert torch.equal(eng.last["b"].cpu().long(), orc.last["b"]), f"bins differ at chunk {c}"
                 assert torch.equal(eng.last["ts"].cpu(), orc.last["ts"])
             assert relerr(eng.B_past, orc.B_past) < TOL_B, f"B, chunk {c}"
-            # ctx: 1e-3 in general.  Where softmax(20 S) is peaky the reference's own variance
-            # sigma^2 = E[t^2] - mu^2 (long_term_attention.py:291, fp32) cancels down to ~1e-3 relative noise and
-            # r_j amplifies it; there the CUDA path must be at least as close to exact (fp64) arithmetic as the
-            # reference is, and within 5e-3 of it.
+            # ctx: 1e-3 wherever the reference's own result is well conditioned.  Its variance
+            # sigma^2 = E[t^2] - mu^2 (long_term_attention.py:291) is a cancelling subtraction of two ~0.5-sized fp32
+            # numbers; when softmax(20 S) is so peaky that sigma^2 drops below 5e-5, four of fp32's seven digits are
+            # gone and the reference's own context is several 1e-3 away from exact arithmetic (measured here: reference
+            # vs fp64 3.3e-3, CUDA path vs fp64 1.0e-3 at min sigma^2 = 2.5e-5; <= 1.1e-4 to the reference in every other
+            # case).  There -- decided by the CONDITIONING of the reference, not by the error -- the CUDA path must be
+            # at least as close to exact arithmetic as the reference is, and within 5e-3 of it.
             err = relerr(got, want)
-            if err >= TOL_CTX:
+            if float(orc.last["var"].min()) >= 5e-5:
+                assert err < TOL_CTX, (c, err)
+            else:
                 ours = relerr(got, _gauss_ctx_fp64(eng.B_past, qs[c], key, val, tb["psi"]))
                 theirs = relerr(want, _gauss_ctx_fp64(orc.B_past, qs[c], key, val, tb["psi"]))
                 assert err < 5e-3 and ours <= 1.5 * max(theirs, 1e-4), (c, err, ours, theirs)
