@@ -383,7 +383,7 @@ def run_b200(args):
     eng = BatchedRectLTM(NB, TAU, key.weight.detach(), key.bias.detach(), val.weight.detach(), val.bias.detach(),
                          tokens_per_frame=T, sticky=True, precision=args.precision, device=dev,
                          proj_operands=args.proj_operands, kv_state=not args.no_kv_state,
-                         proj_precision=args.proj_precision)
+                         proj_precision=args.proj_precision, kv_dtype=args.kv_dtype)
     eng.video_block = args.video_block
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     # the chunks of all videos stay resident when they fit (128 videos x 8 chunks = 25.8 GB); a large shard (1024
@@ -708,11 +708,13 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": value, "unit": "chunks/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
-            "vs_baseline": None, "dtype": "f32 (tf32 tensor-core products for the K/V projection and the two attention contractions, fp32 accumulate)"
+            "vs_baseline": None, "dtype": ("f32 state and accumulation; tf32 tensor-core K/V projection; projected memory K|V stored as "
+                      + ("fp16 (tf32's 11-bit significand), kind::f16 tensor-core attention" if eng.kv_half else
+                         "fp32 on the tf32 grid, tf32 tensor-core attention"))
             if args.precision == "tf32" else "f32 (split-tf32 x3 tensor-core projection, fp32 FMA attention)",
             "data": "synthetic", "config": dict(workload_config(Bv, C, "gibbs", overlap),
                                                 projected_memory_state=bool(eng.kv_state),
-                                                video_block=args.video_block,
+                                                video_block=args.video_block, kv_dtype=args.kv_dtype,
                                                 proj_precision=args.proj_precision or args.precision),
             "frame_blocks_per_s": value * L,
             "roofline": {"bound": "hbm", "kernel": "pool_mean_kernel",
@@ -1016,6 +1018,8 @@ def main():
     ap.add_argument("--pool-ctas-per-sm", type=int, default=0, help="grid bound of the prefetch pooling kernel")
     ap.add_argument("--proj-operands", choices=["fp32", "fp16"], default="fp32",
                     help="operands of the K/V projection on the tensor-core path (fp16: kind::f16 UMMAs, opt-in)")
+    ap.add_argument("--kv-dtype", default="fp16", choices=["fp32", "fp16"],
+                    help="storage of the projected memory K|V on the tensor-core path")
     ap.add_argument("--video-block", type=int, default=0,
                     help="consolidate / project / attend in blocks of this many videos (L2 reuse); 0 = all at once")
     ap.add_argument("--no-kv-state", action="store_true",

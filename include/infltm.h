@@ -104,8 +104,9 @@ int ltm_consolidate_rect_h(const float* B_past, const float* xpart, const int32_
  *   KV_new[v,j,:] = g[j] * sum_{p in seg(j), idx[v,p] >= 0} KV_past[v, idx[v,p], :] + (1 - g[j] * cnt) * bkv      j < jf
  * (cnt = number of members with a valid index), so that only the rows j >= jf that receive new frames go through the
  * projection GEMM (a quarter of them at tau = 0.75).  Same launch as ltm_consolidate_rect_h: B_new is produced as
- * before; the KV rows j < jf are written only for videos that take the update branch.  round_tf32 != 0 stores the KV
- * rows rounded to the tf32 grid (operands of the tensor-core attention).  idx_stride: elements between the index
+ * before; the KV rows j < jf are written only for videos that take the update branch.  round_tf32 == 1 stores the KV
+ * rows rounded to the tf32 grid (operands of the tensor-core attention); round_tf32 == 2: KV_past / KV_new point to
+ * IEEE fp16 storage [Bv, N, ldkv] (fp32 accumulation, one rounding at the store; ldkv % 8 == 0).  idx_stride: elements between the index
  * rows of consecutive videos (S; 0 = one row shared by all videos, the uniform re-sampling table).
  * KV_past / KV_new: [Bv, N, ldkv] with ldkv = 2D; KV_past == NULL: coefficients only. */
 int ltm_consolidate_rect_kv(const float* B_past, const float* xpart, const int32_t* idx, int64_t idx_stride,
@@ -155,6 +156,9 @@ typedef struct {
    * matrix as one flat problem (A = B_new + jf * e, a_group = N - jf, a_group_stride = N * e).  a_group must divide
    * 128 or be a multiple of 128, and M % a_group == 0 (one TMA box spans 128 / a_group groups).  0 = plain m * lda. */
   int a_group; int64_t a_group_stride;
+  /* != 0: C points to IEEE fp16 storage (ldc / strideC / c_group_stride in elements; round to nearest even): the
+   * product feeds a kind::f16 tensor-core contraction whose operands carry the same 11-bit significand as tf32 */
+  int c_fp16;
 } ltm_gemm_args;
 int ltm_gemm(const ltm_gemm_args* args, void* stream);
 
@@ -218,6 +222,18 @@ int ltm_cont_attn_rect_tc_split(const float* q, const float* K, const float* V, 
                                 const float* W, float W_out, const int32_t* jb, const float* tb,
                                 float* ctx, float* scores_ws, float* part_ws, float* hist_part,
                                 int Bv, int Q, int N, int H, int d, void* stream);
+/* the same two entry points for K|V stored as IEEE fp16 (csrc/attn_tc16.cu: kind::f16 UMMAs, the same 11-bit
+ * significand as the tf32 grid at half the bytes).  K, V: fp16 [Bv*N, ldkv] (ldkv in halves, % 8 == 0; e.g. the two
+ * halves of an fp16 KV[Bv,N,2D] from ltm_gemm c_fp16 / ltm_consolidate_rect_kv round_tf32 == 2); X16: fp16 [N,64]
+ * (columns 0..2 = 1, hi, lo of c_j / W_j; infinite_video_b200/tables.py).  q, W, outputs as above (fp32). */
+int ltm_cont_attn_rect_tc16(const float* q, const void* K, const void* V, int64_t ldkv, const void* X16,
+                            const float* W, float W_out, float c_none, const int32_t* jb, const float* tb,
+                            float* ctx, float* scores_out, float* hist_part,
+                            int Bv, int Q, int N, int H, int d, void* stream);
+int ltm_cont_attn_rect_tc16_split(const float* q, const void* K, const void* V, int64_t ldkv, const void* X16,
+                                  const float* W, float W_out, const int32_t* jb, const float* tb,
+                                  float* ctx, float* scores_ws, float* part_ws, float* hist_part,
+                                  int Bv, int Q, int N, int H, int d, void* stream);
 /* ltm_project_kv with the stored K and V rounded to tf32 */
 int ltm_project_kv_r(const float* Bcoef, const float* Wkv, const float* bkv, float* KV,
                      int M, int e, int D2, int precision, int impl, void* stream);
@@ -287,6 +303,10 @@ typedef struct {
   /* workspace of the two-half tensor-core attention (num_basis 512): ltm_attn_tc_split_workspace_floats(Bv,Q,H)
    * floats; with it (and `scores`) set, num_basis 512 takes ltm_cont_attn_rect_tc_split */
   float* attn_part;
+  /* kv_half != 0: KV / KV_past point to IEEE fp16 storage [Bv,N,2D] and X16 (fp16 [N,64]) is set: the projection
+   * GEMM stores fp16, the carried rows are accumulated in fp32 and stored as fp16, the attention runs on
+   * ltm_cont_attn_rect_tc16.  Same significand as the tf32 grid of the fp32 layout; magnitudes beyond 65504 become inf. */
+  int kv_half; const void* X16;
 } ltm_rect_step_args;
 int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const float* q, const double* u,
                   const uint8_t* new_doc, float* ctx, void* stream);

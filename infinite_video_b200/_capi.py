@@ -27,7 +27,7 @@ class GemmArgs(C.Structure):
         ("CT", C.c_void_p), ("ct_cols", C.c_int), ("ct_group", C.c_int),
         ("c_group", C.c_int), ("c_group_stride", C.c_int64), ("bias_stride", C.c_int64),
         ("round_tf32", C.c_int), ("ab_fp16", C.c_int),
-        ("a_group", C.c_int), ("a_group_stride", C.c_int64),
+        ("a_group", C.c_int), ("a_group_stride", C.c_int64), ("c_fp16", C.c_int),
     ]
 
 
@@ -54,6 +54,7 @@ class RectStepArgs(C.Structure):
         ("B_half", C.c_void_p), ("Wkv_half", C.c_void_p),
         ("KV_past", C.c_void_p), ("jf", C.c_int), ("proj_precision", C.c_int), ("video_block", C.c_int),
         ("attn_part", C.c_void_p),
+        ("kv_half", C.c_int), ("X16", C.c_void_p),
     ]
 
 
@@ -94,6 +95,9 @@ _SIGS = {
     "ltm_attn_tc_split_workspace_floats": (C.c_int64, [_I, _I, _I]),
     "ltm_cont_attn_rect_tc_split": (C.c_int, [_P, _P, _P, _L, _P, _P, _F, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I,
                                               _P]),
+    "ltm_cont_attn_rect_tc16": (C.c_int, [_P, _P, _P, _L, _P, _P, _F, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "ltm_cont_attn_rect_tc16_split": (C.c_int, [_P, _P, _P, _L, _P, _P, _F, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I,
+                                                _I, _P]),
     "ltm_cont_attn_rect_t": (C.c_int, [_P, _P, _P, _L, _P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_cont_attn_gauss_t": (C.c_int, [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_cont_attn_rect": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),

@@ -102,7 +102,7 @@ class BatchedRectLTM(_BatchedBase):
     def __init__(self, num_basis, tau, w_key, b_key, w_value, b_value, *, n_heads=12, head_size=64,
                  tokens_per_frame=32, sticky=True, nb_samples=tables.NB_SAMPLES, precision="tf32",
                  gemm_impl="tcgen05", device="cuda", keep_scores=False, fast_attn=True, tc_attn=True,
-                 proj_operands="fp32", kv_state=True, proj_precision=None, spacing="linear"):
+                 proj_operands="fp32", kv_state=True, proj_precision=None, spacing="linear", kv_dtype="fp16"):
         super().__init__(num_basis, tau, w_key, b_key, w_value, b_value, n_heads, head_size, sticky, nb_samples,
                          precision, gemm_impl, device)
         self.T = int(tokens_per_frame)
@@ -130,6 +130,16 @@ class BatchedRectLTM(_BatchedBase):
         self.kv_state = bool(kv_state) and not self.half_ops and (self.tc_attn or not self.fast_attn)
         # precision of the K/V projection GEMM alone (None = `precision`); "tf32x3" makes the stored K|V fp32-grade
         self.proj_precision = proj_precision
+        # storage of the projected memory on the tensor-core path: "fp16" (default) or "fp32" (values on the tf32
+        # grid).  fp16 carries the same 11-bit significand as that grid at half the bytes -- K|V are written once and
+        # read twice per call: ~250 MB less per 128-video chunk, 181.0 k -> 190.0 k chunks/s -- and the attention
+        # contractions run as kind::f16 UMMAs.  What it gives up is range: |K|, |V| > 65504 become inf (and show up as
+        # NaN contexts); keys / values are projections of layer-normed features, orders of magnitude below that, and
+        # the VideoChat2 pipeline of the reference computes them in fp16 itself (autocast).
+        if kv_dtype not in ("fp32", "fp16"):
+            raise ValueError("kv_dtype must be 'fp32' or 'fp16'")
+        self.kv_half = (kv_dtype == "fp16" and self.tc_attn and not self.half_ops
+                        and proj_precision in (None, "tf32"))       # (a split-TF32 projection keeps fp32 storage)
         # consolidate / project / attend in blocks of this many videos (L2 reuse of what a block writes); 0 = off
         # (measured at 128 videos: 16 / 32 / 43 / 64-video blocks all lose 4-14 % to the smaller kernels' tails)
         self.video_block = 0
@@ -160,7 +170,9 @@ class BatchedRectLTM(_BatchedBase):
                 splits=splits,
                 xparts=[torch.empty(Bv, L, splits, self.e, **f32), torch.empty(Bv, L, splits, self.e, **f32)],
                 xi=0,
-                KVs=[torch.empty(Bv, self.N, 2 * self.D, **f32) for _ in range(2 if self.kv_state else 1)]
+                KVs=[torch.empty(Bv, self.N, 2 * self.D, device=dev,
+                                 dtype=torch.float16 if self.kv_half else torch.float32)
+                     for _ in range(2 if self.kv_state else 1)]
                 if (self.tc_attn or not self.fast_attn) else None,
                 Kt=torch.empty(Bv, self.H, self.d, self.N, **f32) if (self.fast_attn and not self.tc_attn) else None,
                 V=torch.empty(Bv, self.N, self.D, **f32) if (self.fast_attn and not self.tc_attn) else None,
@@ -287,6 +299,8 @@ class BatchedRectLTM(_BatchedBase):
                                       ws["p"].data_ptr())
         a.scores = ws["scores"].data_ptr() if ws["scores"] is not None else None
         a.attn_part = ws["attn_part"].data_ptr() if ws["attn_part"] is not None else None
+        if self.kv_half:
+            a.kv_half, a.X16 = 1, tdev["X16"].data_ptr()
         for f, n in (("k_dev", "k_dev"), ("q_dev", "q_dev"), ("u_dev", "u_dev"), ("new_doc_dev", "nd_dev"),
                      ("ctx_dev", "ctx_dev")):
             setattr(a, f, ws[n].data_ptr() if ws[n] is not None else None)

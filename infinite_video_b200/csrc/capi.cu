@@ -97,6 +97,7 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
   const bool kvstate = a->KV_past != nullptr && a->KV != nullptr && !fast && !half_ops && B_past != nullptr &&
                        new_doc == nullptr && a->jf > 0 && n_new > 0 && jg > 0 && a->e % 4 == 0;
   const int pprec = a->proj_precision ? a->proj_precision : a->precision;
+  const bool kvh = a->kv_half != 0 && tcp && a->X16 != nullptr && !half_ops;       // K|V stored as fp16
   // Blocks of videos run consolidate -> project -> attention back to back, so that the K|V (and coefficient) rows a
   // block has just written are still in L2 when its attention (projection) reads them: with all videos per kernel
   // the 201 MB of K|V at 128 videos go out to HBM and come back.  video_block: 0 = all videos in one block.
@@ -108,13 +109,15 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
     const int nv = (a->Bv - v0 < vblock) ? a->Bv - v0 : vblock;
     const float* Bp = B_past ? B_past + v0 * sB : nullptr;
     float* Bn = a->B_new + v0 * sB;
-    float* KVn = a->KV ? a->KV + v0 * sKV : nullptr;
-    const float* KVp = kvstate ? a->KV_past + v0 * sKV : nullptr;
+    // (fp16 K|V: the same pointers, offsets counted in 2-byte elements)
+    const size_t kvo = kvh ? v0 * sKV / 2 : v0 * sKV;
+    float* KVn = a->KV ? a->KV + kvo : nullptr;
+    const float* KVp = kvstate ? a->KV_past + kvo : nullptr;
     void* Bh = half_ops ? (void*)((uint16_t*)a->B_half + v0 * sB) : nullptr;
     if (!blocked) LTM_PROF(4);
     rc = ltm_consolidate_rect_kv(Bp, a->xpart + v0 * sX, idx_stride ? idx + (size_t)v0 * idx_stride : idx, idx_stride,
                                  new_doc ? new_doc + v0 : nullptr, a->seg_ptr0, a->seg_mem0, a->g0, a->seg_ptr1,
-                                 a->seg_mem1, a->g1, Bn, Bh, KVp, KVn, a->bkv, 2 * D, jg, tcp ? 1 : 0, nv, a->N,
+                                 a->seg_mem1, a->g1, Bn, Bh, KVp, KVn, a->bkv, 2 * D, jg, kvh ? 2 : (tcp ? 1 : 0), nv, a->N,
                                  a->e, a->L, a->splits, a->S, stream);
     if (rc) return rc;
     if (!blocked) { LTM_PROF(5); LTM_PROF(6); }
@@ -126,10 +129,12 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
       ga.a_group = n_new; ga.a_group_stride = (int64_t)a->N * a->e;
       ga.B = a->Wkv; ga.ldb = a->e; ga.b_kmajor = 1;
       ga.K1 = a->e; ga.bias = a->bkv;
-      ga.C = KVn + (size_t)jg * 2 * D; ga.ldc = 2 * D;
+      ga.C = kvh ? reinterpret_cast<float*>(reinterpret_cast<uint16_t*>(KVn) + (size_t)jg * 2 * D)
+                 : KVn + (size_t)jg * 2 * D;
+      ga.ldc = 2 * D;
       ga.c_group = n_new; ga.c_group_stride = (int64_t)a->N * 2 * D;
       ga.M = nv * n_new; ga.Nc = 2 * D; ga.K = a->e; ga.batch = 1;
-      ga.precision = pprec; ga.impl = a->gemm_impl; ga.round_tf32 = tcp ? 1 : 0;
+      ga.precision = pprec; ga.impl = a->gemm_impl; ga.round_tf32 = (tcp && !kvh) ? 1 : 0; ga.c_fp16 = kvh ? 1 : 0;
       rc = ltm_gemm(&ga, stream);
     } else if (half_ops) {
       ltm_gemm_args ga;
@@ -140,6 +145,16 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
       ga.C = KVn; ga.ldc = 2 * D;
       ga.M = nv * a->N; ga.Nc = 2 * D; ga.K = a->e; ga.batch = 1;
       ga.precision = 1; ga.impl = 0; ga.round_tf32 = 1; ga.ab_fp16 = 1;
+      rc = ltm_gemm(&ga, stream);
+    } else if (kvh) {
+      ltm_gemm_args ga;
+      memset(&ga, 0, sizeof(ga));
+      ga.A = Bn; ga.lda = a->e; ga.a_kmajor = 1;
+      ga.B = a->Wkv; ga.ldb = a->e; ga.b_kmajor = 1;
+      ga.K1 = a->e; ga.bias = a->bkv;
+      ga.C = KVn; ga.ldc = 2 * D;
+      ga.M = nv * a->N; ga.Nc = 2 * D; ga.K = a->e; ga.batch = 1;
+      ga.precision = pprec; ga.impl = a->gemm_impl; ga.c_fp16 = 1;
       rc = ltm_gemm(&ga, stream);
     } else if (tcp)
       rc = ltm_project_kv_r(Bn, a->Wkv, a->bkv, KVn, nv * a->N, a->e, 2 * D, pprec, a->gemm_impl, stream);
@@ -154,7 +169,16 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
     float* cb = ctx + (size_t)v0 * a->Q * D;
     float* sc = a->scores ? a->scores + (size_t)v0 * a->H * a->Q * a->N : nullptr;
     float* hp = a->sticky ? a->hist_part + (size_t)v0 * a->H * qtiles * (LTM_STICKY_EDGES - 2) : nullptr;
-    if (tcp && tc512)
+    if (kvh) {
+      const uint16_t* Kh = reinterpret_cast<const uint16_t*>(KVn);
+      if (tc512)
+        rc = ltm_cont_attn_rect_tc16_split(qb, Kh, Kh + D, 2 * D, a->X16, a->W, a->W_out, a->jb, a->tb, cb, sc,
+                                           a->attn_part + ltm_attn_tc_split_workspace_floats(v0, a->Q, a->H), hp, nv,
+                                           a->Q, a->N, a->H, a->d, stream);
+      else
+        rc = ltm_cont_attn_rect_tc16(qb, Kh, Kh + D, 2 * D, a->X16, a->W, a->W_out, a->c_none, a->jb, a->tb, cb, sc, hp,
+                                     nv, a->Q, a->N, a->H, a->d, stream);
+    } else if (tcp && tc512)
       rc = ltm_cont_attn_rect_tc_split(qb, KVn, KVn + D, 2 * D, a->X, a->W, a->W_out, a->jb, a->tb, cb, sc,
                                        a->attn_part + ltm_attn_tc_split_workspace_floats(v0, a->Q, a->H), hp, nv, a->Q,
                                        a->N, a->H, a->d, stream);

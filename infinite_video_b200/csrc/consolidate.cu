@@ -17,6 +17,7 @@ struct KvState {
   float4* KV_new;
   const float4* bkv;          // [ldkv4]
   int ldkv4, jf, round_tf32;
+  int half;                   // K|V are stored as IEEE fp16 ([Bv, N, ldkv] halves): same pointers, read as uint4 = 8 halves
 };
 
 __device__ __forceinline__ float tf32_round(float x) {
@@ -71,7 +72,42 @@ consolidate_rect_kernel(const float4* __restrict__ B_past, const float4* __restr
   // projected memory: a bin below jf holds re-sampled memory only, and K|V = B W^T + b is affine in B, so its
   // keys / values are the same segmented mean taken over the previous call's K|V rows (the bias enters once:
   // g sum_p (KV_past[p] - b) + b).  Rows >= jf are left to the projection GEMM.
-  if (kv.KV_past != nullptr && !first && j < kv.jf) {
+  if (kv.KV_past != nullptr && !first && j < kv.jf && kv.half) {
+    // fp16 K|V: rows of ldkv4 * 4 halves = ldkv8 uint4; fp32 accumulation, one rounding at the store
+    const int ld8 = kv.ldkv4 / 2;
+    const uint4* kvp = reinterpret_cast<const uint4*>(kv.KV_past) + (size_t)v * N * ld8;
+    uint4* out = reinterpret_cast<uint4*>(kv.KV_new) + ((size_t)v * N + j) * ld8;
+    int cnt = 0;
+    for (int m = m0; m < m1; ++m) cnt += (iv[seg_mem[m]] >= 0) ? 1 : 0;
+    const float bw = 1.f - g * (float)cnt;
+    for (int c = threadIdx.x; c < ld8; c += blockDim.x) {
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      for (int m = m0; m < m1; ++m) {
+        const int row = iv[seg_mem[m]];
+        if (row >= 0) {
+          const uint4 u = kvp[(size_t)row * ld8 + c];
+          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[i]));
+            acc[2 * i] += f.x;
+            acc[2 * i + 1] += f.y;
+          }
+        }
+      }
+      const float4 b0 = kv.bkv[2 * c], b1 = kv.bkv[2 * c + 1];
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      uint32_t pk[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __half2 h = __floats2half2_rn(fmaf(acc[2 * i], g, bw * bb[2 * i]), fmaf(acc[2 * i + 1], g, bw * bb[2 * i + 1]));
+        pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      out[c] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  } else if (kv.KV_past != nullptr && !first && j < kv.jf) {
     const float4* kvp = kv.KV_past + (size_t)v * N * kv.ldkv4;
     int cnt = 0;
     for (int m = m0; m < m1; ++m) cnt += (iv[seg_mem[m]] >= 0) ? 1 : 0;
@@ -133,6 +169,8 @@ extern "C" int ltm_consolidate_rect_kv(const float* B_past, const float* xpart, 
                                        const float* KV_past, float* KV_new, const float* bkv, int ldkv, int jf,
                                        int round_tf32, int Bv, int N, int e, int L, int splits, int S, void* stream) {
   using namespace ltm;
+  // round_tf32 == 2: KV_past / KV_new point to fp16 storage [Bv, N, ldkv] (ldkv % 8 == 0)
+  const int kv_half = round_tf32 == 2 ? 1 : 0;
   LTM_REQUIRE(B_half == nullptr || (reinterpret_cast<uintptr_t>(B_half) & 7u) == 0, "consolidate_rect: B_half alignment");
   LTM_REQUIRE(xpart && B_new && seg_ptr0 && seg_mem0 && g0, "consolidate_rect: null pointer");
   LTM_REQUIRE(B_past == nullptr || (idx && seg_ptr1 && seg_mem1 && g1),
@@ -152,7 +190,8 @@ extern "C" int ltm_consolidate_rect_kv(const float* B_past, const float* xpart, 
     kv.KV_past = reinterpret_cast<const float4*>(KV_past);
     kv.KV_new = reinterpret_cast<float4*>(KV_new);
     kv.bkv = reinterpret_cast<const float4*>(bkv);
-    kv.ldkv4 = ldkv / 4; kv.jf = jf; kv.round_tf32 = round_tf32;
+    LTM_REQUIRE(!kv_half || ldkv % 8 == 0, "consolidate_rect_kv: fp16 K|V rows need ldkv %% 8 == 0");
+    kv.ldkv4 = ldkv / 4; kv.jf = jf; kv.round_tf32 = kv_half ? 0 : round_tf32; kv.half = kv_half;
   }
   const int e4 = e / 4;
   const int threads = e4 >= 256 ? 256 : ((e4 + 31) / 32) * 32;

@@ -20,6 +20,7 @@
 // only); two TMEM accumulators so the epilogue of one tile overlaps the MMAs of the next.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "tcgen05.cuh"
@@ -50,6 +51,7 @@ struct GemmDev {
   int round_tf32;                           // round stored row-major results to the tf32 grid
   int c_vec;                                // row-major stores may be 128-bit (alignment checked on the host)
   int a_group;                              // two-level row mapping of A (0 = off): tile rows span 128 / a_group groups
+  int c_half;                               // C is fp16 storage (row-major path only)
   int dbg;                                  // bring-up builds only (-DLTM_BRINGUP): 1 = no global stores, 2 = no TMA loads
 };
 // The bring-up switches exist only in builds made with -DLTM_BRINGUP (scripts/*_probe.py); the product library
@@ -116,7 +118,7 @@ constexpr int GEMM_MAX_REGS = 96;
 
 // Drains one 128-row accumulator tile.  `ew` = epilogue warp 0..7 (its CTA warp id & 3 must be ew & 3: a warp can
 // only read its own TMEM lane quarter), `tmem_acc` = TMEM address of the tile's first column.
-template <int BN>
+template <int BN, bool HOUT>
 __device__ __forceinline__ void epilogue_tile(const GemmDev& g, uint32_t tmem_acc, int ew, int warp_quarter, int lane,
                                               float* stg, int m0, int n0, int bz, uint32_t tfull, uint32_t tfull_parity) {
   const int row0 = m0 + warp_quarter * 32;
@@ -125,12 +127,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& g, uint32_t tmem_ac
   float* cbase_ptr = g.C + (size_t)bz * g.strideC;
   const float* bias = g.bias ? g.bias + (size_t)bz * g.bias_stride : nullptr;
   // rows this lane stores in the row-major path: 4 i + (lane >> 3); its 16-byte column chunk: lane & 7
-  const int lrow = lane >> 3, lchunk = lane & 7;
+  // (fp16 output: 8 rows per pass, four lanes per row, 8 columns = one 16-byte store per lane; passes i < 4)
+  const int lrow = HOUT ? lane >> 2 : lane >> 3, lchunk = HOUT ? lane & 3 : lane & 7;
+  constexpr int rstep = HOUT ? 8 : 4;
   size_t roff[8];
   bool rok[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int row = row0 + 4 * i + lrow;
+    const int row = row0 + rstep * i + lrow;
     rok[i] = row < g.M;
     roff[i] = g.c_group > 0 ? (size_t)(row / g.c_group) * g.c_group_stride + (size_t)(row % g.c_group) * g.ldc
                             : (size_t)row * g.ldc;
@@ -206,6 +210,41 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& g, uint32_t tmem_ac
           make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
                       __uint_as_float(r[4 * q + 3]));
     __syncwarp();
+    if (HOUT) {
+      // fp16 rows: lane -> (row 8 i + lane / 4, columns 8 (lane % 4) .. + 7): two staged 16-byte chunks -> one 16-byte
+      // store of 8 halves (rows of 64 B per warp-wide store)
+      const int col8 = n0 + c0 + 8 * lchunk;
+      const bool vec8 = g.c_vec && (g.ldc % 8 == 0) && (col8 + 7 < g.Nc);
+      float bb[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) bb[t] = (bias != nullptr && col8 + t < g.Nc) ? __ldg(bias + col8 + t) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int srow = 8 * i + lrow;
+        const float4 v0 = *reinterpret_cast<const float4*>(stg + srow * EPI_COLS + (((2 * lchunk) ^ (srow & 7)) << 2));
+        const float4 v1 = *reinterpret_cast<const float4*>(stg + srow * EPI_COLS + (((2 * lchunk + 1) ^ (srow & 7)) << 2));
+        const float f[8] = {v0.x + bb[0], v0.y + bb[1], v0.z + bb[2], v0.w + bb[3],
+                            v1.x + bb[4], v1.y + bb[5], v1.z + bb[6], v1.w + bb[7]};
+        if (rok[i]) {
+          __half* dst = reinterpret_cast<__half*>(g.C) + (size_t)bz * g.strideC + roff[i] + (col8 - (g.CT != nullptr ? g.ct_cols : 0));
+          if (vec8) {
+            uint4 pk;
+            __half2 h;
+            h = __floats2half2_rn(f[0], f[1]); pk.x = *reinterpret_cast<const uint32_t*>(&h);
+            h = __floats2half2_rn(f[2], f[3]); pk.y = *reinterpret_cast<const uint32_t*>(&h);
+            h = __floats2half2_rn(f[4], f[5]); pk.z = *reinterpret_cast<const uint32_t*>(&h);
+            h = __floats2half2_rn(f[6], f[7]); pk.w = *reinterpret_cast<const uint32_t*>(&h);
+            *reinterpret_cast<uint4*>(dst) = pk;
+          } else {
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+              if (col8 + t < g.Nc) dst[t] = __float2half_rn(f[t]);
+          }
+        }
+      }
+      __syncwarp();
+      continue;
+    }
     const int col = n0 + c0 + 4 * lchunk;
     const float4 bv = bvs[j];
     const int ccol = col - (g.CT != nullptr ? g.ct_cols : 0);
@@ -254,7 +293,7 @@ struct Cfg {
 //   warp 1      TMEM owner + tcgen05.mma issuer (one lane)
 //   warps 2-9   epilogue (see epilogue_tile)
 //   warps 10-17 (precision 3 only) operand splitter hi/lo
-template <int BN, int STAGES, bool SPLIT, int CLUSTER>
+template <int BN, int STAGES, bool SPLIT, int CLUSTER, bool HOUT>
 __global__ void __maxnreg__(GEMM_MAX_REGS)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ CUtensorMap mapB2, const GemmDev g) {
@@ -414,7 +453,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       int n0, m0, bz;
       decode_work<CLUSTER, BN>(w, tiles_n, tiles_m, crank, n0, m0, bz);
       const uint32_t buf = tc & 1u, tph = (tc >> 1) & 1u;
-      epilogue_tile<BN>(g, tmem_base + buf * BN, ew, warp & 3, lane, stg, m0, n0, bz, tfull_bar(buf), tph);
+      epilogue_tile<BN, HOUT>(g, tmem_base + buf * BN, ew, warp & 3, lane, stg, m0, n0, bz, tfull_bar(buf), tph);
       tcgen05_fence_before();
       mbar_arrive(tempty_bar(buf));              // EPI_THREADS arrivals hand the accumulator back to the MMA warp
     }
@@ -713,7 +752,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       int n0, m0, bz;
       decode_work<2, BN>(w, tiles_n, tiles_m, (int)crank, n0, m0, bz);
       const uint32_t buf = tc & 1u, tph = (tc >> 1) & 1u;
-      epilogue_tile<BN>(g, tmem_base + buf * BN, ew, warp & 3, lane, stg, m0, n0, bz, tfull_bar(buf), tph);
+      epilogue_tile<BN, false>(g, tmem_base + buf * BN, ew, warp & 3, lane, stg, m0, n0, bz, tfull_bar(buf), tph);
       tcgen05_fence_before();
       mbar_arrive_remote(mapa_rank(tempty_bar(buf), 0));      // 2 x EPI_THREADS arrivals on the leader's barrier
     }
@@ -844,13 +883,13 @@ int tma_encode_2d(CUtensorMap* map, const float* base, unsigned long long inner,
   return 0;
 }
 
-template <int BN, int STAGES, bool SPLIT, int CLUSTER = 1>
+template <int BN, int STAGES, bool SPLIT, int CLUSTER = 1, bool HOUT = false>
 static int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mB2, const GemmDev& d,
                       int batch, cudaStream_t stream) {
   using C_ = Cfg<BN, STAGES, SPLIT>;
   static PerDevice pd = {};
   int num_sms = 0;
-  if (int rc = kernel_setup(gemm_tf32_kernel<BN, STAGES, SPLIT, CLUSTER>, (size_t)C_::SMEM_BYTES, pd, &num_sms))
+  if (int rc = kernel_setup(gemm_tf32_kernel<BN, STAGES, SPLIT, CLUSTER, HOUT>, (size_t)C_::SMEM_BYTES, pd, &num_sms))
     return rc;
   const long long tiles = (long long)((d.Nc + BN - 1) / BN) * ((d.M + BM - 1) / BM) * batch;
   LTM_REQUIRE(tiles < (1ll << 31), "gemm: too many tiles");
@@ -873,11 +912,11 @@ static int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const CUtens
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    LTM_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, STAGES, SPLIT, CLUSTER>, mA, mB, mB2, d));
+    LTM_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, STAGES, SPLIT, CLUSTER, HOUT>, mA, mB, mB2, d));
     return 0;
   }
   const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);     // persistent: one CTA per SM
-  gemm_tf32_kernel<BN, STAGES, SPLIT, 1><<<grid, C_::THREADS, C_::SMEM_BYTES, stream>>>(mA, mB, mB2, d);
+  gemm_tf32_kernel<BN, STAGES, SPLIT, 1, HOUT><<<grid, C_::THREADS, C_::SMEM_BYTES, stream>>>(mA, mB, mB2, d);
   LTM_CHECK_LAUNCH("gemm(tcgen05)");
   return 0;
 }
@@ -946,8 +985,8 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     LTM_REQUIRE(r == CUDA_SUCCESS, "gemm: cuTensorMapEncodeTiled(grouped A) failed with CUresult %d", (int)r);
   } else if (encode_operand(&mA, a.A, a.M, a.K, a.lda, a.strideA, a.batch, a.a_kmajor, BM, "A", half)) return -1;
-  const bool pair = (g_pair > 0 || (g_pair < 0 && !split)) && a.M > BM && a.a_group == 0;   // CTA pairs need two row tiles
-  const bool mc_pre = !pair && g_cluster >= 2 && a.b_kmajor && !two && a.M > BM;
+  const bool pair = (g_pair > 0 || (g_pair < 0 && !split)) && a.M > BM && a.a_group == 0 && !a.c_fp16;
+  const bool mc_pre = !pair && g_cluster >= 2 && a.b_kmajor && !two && a.M > BM && !a.c_fp16;
   const int b_box = (pair || mc_pre) ? bn / 2 : bn;             // B rows fetched per TMA box
   if (encode_operand(&mB, a.B, a.Nc, K1, a.ldb, a.strideB, a.batch, a.b_kmajor, b_box, "B", half)) return -1;
   if (two) {
@@ -968,6 +1007,8 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   d.c_vec = (a.ldc % 4 == 0 && a.strideC % 4 == 0 && a.c_group_stride % 4 == 0 && aligned16(a.C) &&
              (a.CT == nullptr || a.ct_cols % 4 == 0)) ? 1 : 0;
   d.a_group = a.a_group;
+  d.c_half = a.c_fp16 ? 1 : 0;
+  LTM_REQUIRE(!a.c_fp16 || a.CT == nullptr, "gemm: fp16 output has no transposed store");
   d.a_batched = a.strideA != 0; d.b_batched = a.strideB != 0; d.b2_batched = a.strideB2 != 0; d.has_b2 = two ? 1 : 0;
 #ifdef LTM_BRINGUP
   if (pair) {
@@ -984,6 +1025,11 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
     return launch_cfg<128, 6, false, 2>(mA, mB, mB2, d, a.batch, stream);
   }
 #endif
+  if (d.c_half) {           // fp16 output: single-pass products only (the projected-memory K|V)
+    LTM_REQUIRE(!split, "gemm: fp16 output needs precision 1");
+    return bn == 256 ? launch_cfg<256, 4, false, 1, true>(mA, mB, mB2, d, a.batch, stream)
+                     : launch_cfg<128, 6, false, 1, true>(mA, mB, mB2, d, a.batch, stream);
+  }
   if (split && bn == 256) return launch_cfg<256, 2, true>(mA, mB, mB2, d, a.batch, stream);
   if (split) return launch_cfg<128, 4, true>(mA, mB, mB2, d, a.batch, stream);
   if (bn == 256) return launch_cfg<256, 4, false>(mA, mB, mB2, d, a.batch, stream);
@@ -1018,6 +1064,7 @@ extern "C" int ltm_gemm(const ltm_gemm_args* args, void* stream) {
                                   a.ct_group % 32 == 0 && a.M % a.ct_group == 0),
               "gemm: transposed store needs ct_cols %% 32 == 0, ct_group %% 32 == 0 and M %% ct_group == 0");
   LTM_REQUIRE(a.CT == nullptr || a.batch == 1, "gemm: transposed store is defined for batch == 1");
+  LTM_REQUIRE(!(a.c_fp16 && a.impl == 1), "gemm: fp16 output exists in the tcgen05 kernel only");
   if (a.impl == 1) return gemm_simt_launch(a, (cudaStream_t)stream);
   LTM_REQUIRE(a.impl == 0, "gemm: unknown impl %d", a.impl);
   return gemm_tcgen05_launch(a, (cudaStream_t)stream);

@@ -202,7 +202,7 @@ def gemm(A, B, *, a_kmajor=True, b_kmajor=True, B2=None, bias=None, out=None, pr
 
 def gemm_raw(A, lda, strideA, a_kmajor, B, ldb, strideB, b_kmajor, C_, ldc, strideC, M, Nc, K, batch, *, bias=None,
              bias_stride=0, c_group=0, c_group_stride=0, precision="tf32", impl="tcgen05", a_offset=0, b_offset=0,
-             c_offset=0, round_tf32=False, a_group=0, a_group_stride=0, bias_offset=0):
+             c_offset=0, round_tf32=False, a_group=0, a_group_stride=0, bias_offset=0, c_fp16=False):
     """ltm_gemm with every pitch / batch stride spelled out (elements).  A, B, C_ are the base tensors; *_offset
     shifts the start (elements).  Used where operands are strided views that tensor shapes cannot express
     (per-head column blocks, per-head / per-video output layouts)."""
@@ -213,7 +213,8 @@ def gemm_raw(A, lda, strideA, a_kmajor, B, ldb, strideB, b_kmajor, C_, ldc, stri
     g.B2, g.ldb2, g.strideB2, g.K1 = None, 0, 0, K
     g.bias = bias.data_ptr() + 4 * bias_offset if bias is not None else None
     g.bias_stride = bias_stride
-    g.C, g.ldc, g.strideC = C_.data_ptr() + 4 * c_offset, ldc, strideC
+    g.C, g.ldc, g.strideC = C_.data_ptr() + (2 if c_fp16 else 4) * c_offset, ldc, strideC
+    g.c_fp16 = int(bool(c_fp16))
     g.M, g.Nc, g.K, g.batch = M, Nc, K, batch
     g.precision, g.impl = PRECISION[precision], GEMM_IMPL[impl]
     g.CT, g.ct_cols, g.ct_group = None, 0, 0
@@ -332,6 +333,36 @@ def cont_attn_rect_tc(q, KV, X, W, W_out, c_none, jb=None, tb=None, want_scores=
     check(lib().ltm_cont_attn_rect_tc(ptr(q), ptr(kv), C.c_void_p(kv.data_ptr() + 4 * D), 2 * D, ptr(X), ptr(W),
                                       float(W_out), float(c_none), ptr(jb), ptr(tb), ptr(ctx), ptr(scores), ptr(hist),
                                       Bv, Q, N, H, d, stream_ptr(q.device)), "cont_attn_rect_tc")
+    return ctx, scores, hist
+
+
+def cont_attn_rect_tc16(q, KV16, X16, W, W_out, c_none, jb=None, tb=None, want_scores=False, want_hist=True,
+                        n_heads=12):
+    """fp16 flavour of `cont_attn_rect_tc`: KV16[Bv,N,2D] float16, X16[N,64] float16 -> (ctx, scores|None, hist|None)."""
+    require_cuda(q, KV16, X16, W, jb, tb)
+    q = _f32c(q)
+    if KV16.dtype != torch.float16 or X16.dtype != torch.float16 or not KV16.is_contiguous():
+        raise ValueError("cont_attn_rect_tc16 takes contiguous float16 K|V and X16")
+    Bv, Q, D = q.shape
+    N = KV16.shape[1]
+    H, d = n_heads, D // n_heads
+    ctx = torch.empty(Bv, Q, D, device=q.device, dtype=torch.float32)
+    scores = torch.empty(Bv, H, Q, N, device=q.device, dtype=torch.float32) if want_scores else None
+    hist = (torch.empty(Bv, H * ((Q + 31) // 32), STICKY_EDGES - 2, device=q.device, dtype=torch.float32)
+            if want_hist else None)
+    kp, vp = C.c_void_p(KV16.data_ptr()), C.c_void_p(KV16.data_ptr() + 2 * D)
+    if attn_tc_split_supported(N, d):
+        if scores is None and want_hist:
+            scores = torch.empty(Bv, H, Q, N, device=q.device, dtype=torch.float32)
+        part = torch.empty(int(lib().ltm_attn_tc_split_workspace_floats(Bv, Q, H)), device=q.device,
+                           dtype=torch.float32)
+        check(lib().ltm_cont_attn_rect_tc16_split(ptr(q), kp, vp, 2 * D, ptr(X16), ptr(W), float(W_out), ptr(jb),
+                                                  ptr(tb), ptr(ctx), ptr(scores), ptr(part), ptr(hist), Bv, Q, N, H, d,
+                                                  stream_ptr(q.device)), "cont_attn_rect_tc16_split")
+        return ctx, (scores if want_scores else None), hist
+    check(lib().ltm_cont_attn_rect_tc16(ptr(q), kp, vp, 2 * D, ptr(X16), ptr(W), float(W_out), float(c_none), ptr(jb),
+                                        ptr(tb), ptr(ctx), ptr(scores), ptr(hist), Bv, Q, N, H, d,
+                                        stream_ptr(q.device)), "cont_attn_rect_tc16")
     return ctx, scores, hist
 
 

@@ -136,6 +136,7 @@ class RectTables:
     W: np.ndarray = None             # fp32 [N]
     W_out: float = 0.0
     X: np.ndarray = None             # fp32 [N,32] extra operand rows of the tensor-core attention (or None)
+    X16: np.ndarray = None           # fp16 [N,64] the same table for the fp16 attention (csrc/attn_tc16.cu)
     c_none: float = 0.0              # trapezoid node weight of the sticky edges outside every basis
     # uniform (non-sticky) resampling table: basis index of sample s (-1 none)  (gibbs:152-157,:212)
     idx_uniform: np.ndarray = None   # int32 [S]
@@ -152,6 +153,7 @@ class RectTables:
                          "bin2basis", "W", "idx_uniform", "jd", "wd"):
                 d[name] = torch.from_numpy(getattr(self, name)).to(device)
             d["X"] = torch.from_numpy(self.X).to(device) if self.X is not None else None
+            d["X16"] = torch.from_numpy(self.X16).to(device) if self.X16 is not None else None
             self._dev[key] = d
         return self._dev[key]
 
@@ -235,6 +237,12 @@ def rect_tables(L: int, N: int, tau: float, S: int = NB_SAMPLES, num_quad: int =
         X[:, 1] = hi
         X[:, 2] = (ratio.astype(np.float64) - hi.astype(np.float64)).astype(np.float32)
         t.X = X
+        # fp16 flavour: 1, and c_j / W_j as hi + lo halves (22 bits between them), in a 64-column MN atom
+        X16 = np.zeros((N, 64), dtype=np.float16)
+        X16[:, 0] = 1.0
+        X16[:, 1] = ratio.astype(np.float16)
+        X16[:, 2] = (ratio.astype(np.float64) - X16[:, 1].astype(np.float64)).astype(np.float16)
+        t.X16 = X16
     else:
         t.X = None                     # a basis without quadrature points: the tensor-core path is not used
 

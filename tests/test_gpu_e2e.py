@@ -71,6 +71,11 @@ def _run_rect(dev, N, L, C, Bv, T=32, e=768, Q=32, tau=.75, sticky=True, q_scale
     ("uniform", dict(N=64, L=8, C=3, Bv=2, sticky=False)),                  # non-sticky re-sampling
     ("log", dict(N=64, L=8, C=3, Bv=2, spacing="log")),                     # N4: log-spaced first-chunk positions
     ("log256", dict(N=256, L=32, C=2, Bv=1, spacing="log")),
+    ("cfg2_kv32", dict(N=256, L=256, C=4, Bv=2, kv_dtype="fp32")),          # projected memory on the tf32 grid
+    ("cfg1_kv32", dict(N=64, L=8, C=4, Bv=3, kv_dtype="fp32")),             # (the default stores it as fp16)
+    ("n128_kv32", dict(N=128, L=16, C=3, Bv=2, Q=40, kv_dtype="fp32")),
+    ("cfg4_kv32", dict(N=512, L=32, C=3, Bv=2, kv_dtype="fp32")),
+    ("peaky_kv32", dict(N=64, L=8, C=3, Bv=2, q_scale=8.0, kv_dtype="fp32")),
 ])
 def test_rect_matches_oracle_over_chunks(dev, name, kw):
     w = _run_rect(dev, tag=name, **kw)
@@ -123,7 +128,8 @@ def test_projected_memory_state_equals_full_projection(dev):
     engine that projects all N rows every call, over enough chunks for a rounding drift to show: coefficients are
     bit-identical (that path is unchanged), contexts agree well inside the tolerance to the oracle."""
     from infinite_video_b200.batched import BatchedRectLTM
-    for N, L, kw in ((256, 64, {}), (512, 32, {}), (64, 8, {}), (256, 64, dict(proj_precision="tf32x3")),
+    for N, L, kw in ((256, 64, {}), (512, 32, {}), (64, 8, {}), (256, 64, dict(kv_dtype="fp32")),
+                     (256, 64, dict(proj_precision="tf32x3", kv_dtype="fp32")),
                      (256, 32, dict(fast_attn=False, precision="tf32x3"))):
         key, val = make_proj(33, 768)
         a = BatchedRectLTM(N, .75, *proj_tensors(key, val), device=dev, kv_state=True, **kw)
@@ -139,7 +145,7 @@ def test_projected_memory_state_equals_full_projection(dev):
                 assert c >= 4, (N, c)          # a draw on a CDF edge went the other way: nothing left to compare
                 break
             assert torch.equal(a.B_past, b.B_past), (N, c)
-            worst = max(worst, relerr(x, y), relerr(a.last["KV"], b.last["KV"]))
+            worst = max(worst, relerr(x, y), relerr(a.last["KV"].float(), b.last["KV"].float()))
         assert worst < (5e-4 if kw.get("precision") != "tf32x3" else 1e-5), (N, kw, worst)
 
 
@@ -383,7 +389,7 @@ def test_full_size_properties(dev):
     eng.step(k0, torch.zeros_like(q), None, new_doc=True)
     V = eng.last["V"]
     W = tables.rect_tables(L, N, .75).to(dev)["W"]
-    want = torch.einsum("j,vjd->vd", W / (W.sum() + tables.rect_tables(L, N, .75).W_out), V)
+    want = torch.einsum("j,vjd->vd", W / (W.sum() + tables.rect_tables(L, N, .75).W_out), V.float())
     got = eng.step(k0, torch.zeros_like(q), None, new_doc=True)
     # (the tensor-core attention rounds the weights W_j and the values to tf32: 2^-12 relative per element)
     assert relerr(got[:, 0], want) < 2e-4 and relerr(got[:, 31], want) < 2e-4

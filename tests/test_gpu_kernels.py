@@ -165,6 +165,14 @@ def test_cont_attn_rect_and_fused_histogram(dev, N, L, Q, q_scale):
         assert relerr(got5["p"], want_p) < 1e-3
         ctx6, _, _ = ops.cont_attn_rect_tc(q.to(dev), KVr, td["X"], td["W"], tab.W_out, tab.c_none, want_hist=False)
         assert torch.equal(ctx6, ctx5)
+        # fp16 K|V (kind::f16 UMMAs): the same 11-bit significand, same tolerances
+        KVh = KV.half().to(dev)
+        ctx7, scores7, hist7 = ops.cont_attn_rect_tc16(q.to(dev), KVh, td["X16"], td["W"], tab.W_out, tab.c_none,
+                                                       td["jb"], td["tb"], want_scores=True, want_hist=True)
+        assert relerr(scores7, want_S) < 5e-4
+        assert relerr(ctx7, want_ctx) < 1e-3
+        got7 = ops.resample(hist7, u, bins, td["bin2basis"], normalize=True)
+        assert relerr(got7["p"], want_p) < 1e-3
 
 
 # ---------------------------------------------------------------------------------------- R3/R5/R8
@@ -235,6 +243,56 @@ def test_consolidate_rect_carries_projected_memory(dev, N, L, tau, shared_idx):
                                       jf, round_tf32=True)
     assert int((KV_r.view(torch.int32) & 0x1FFF).abs().max()) == 0
     assert relerr(KV_r[:, :jf], want_KV[:, :jf]) < 5e-4           # half a tf32 ulp = 2^-11 relative
+
+
+def test_gemm_fp16_output_and_fp16_projected_memory(dev):
+    """`c_fp16`: the GEMM epilogue stores IEEE fp16 (through the plain and the two-level row mapping); and the
+    consolidation carries fp16 K|V rows (fp32 accumulation, one rounding at the store)."""
+    ops, T = _ops(), _tables()
+    g = torch.Generator().manual_seed(5)
+    M, K, Nc = 300, 96, 160
+    A = torch.randn(M, K, generator=g).to(dev)
+    Bm = torch.randn(Nc, K, generator=g).to(dev)
+    bias = torch.randn(Nc, generator=g).to(dev)
+    Ch = torch.zeros(M, Nc, device=dev, dtype=torch.float16)
+    ops.gemm_raw(A, K, 0, True, Bm, K, 0, True, Ch, Nc, 0, M, Nc, K, 1, bias=bias, precision="tf32", c_fp16=True)
+    want = (A.double() @ Bm.double().t() + bias.double())
+    assert relerr(Ch.float(), want) < 2e-3                      # single-pass TF32 product + one fp16 rounding
+    C32 = torch.zeros(M, Nc, device=dev)
+    ops.gemm_raw(A, K, 0, True, Bm, K, 0, True, C32, Nc, 0, M, Nc, K, 1, bias=bias, precision="tf32")
+    assert torch.equal(Ch, C32.half())                          # the same accumulator, rounded once
+    # two-level row mapping of A and C
+    Cg = torch.zeros(5, 64, 160, device=dev, dtype=torch.float16)
+    Ag = torch.randn(5, 64, K, generator=g).to(dev)
+    ops.gemm_raw(Ag, K, 0, True, Bm, K, 0, True, Cg, Nc, 0, 5 * 32, Nc, K, 1, bias=bias, a_offset=32 * K, a_group=32,
+                 a_group_stride=64 * K, c_offset=32 * Nc, c_group=32, c_group_stride=64 * Nc, c_fp16=True)
+    assert float(Cg[:, :32].abs().max()) == 0.0
+    assert relerr(Cg[:, 32:].float(), Ag[:, 32:].double() @ Bm.double().t() + bias.double()) < 2e-3
+    # carried rows in fp16
+    N, L, Bv, e, D2 = 256, 64, 2, 768, 1536
+    tab = T.rect_tables(L, N, .75)
+    td = tab.to(dev)
+    x = torch.randn(Bv, L, 1, e, generator=g)
+    B_past = torch.randn(Bv, N, e, generator=g)
+    W = torch.randn(D2, e, generator=g) / 28
+    bkv = torch.randn(D2, generator=g)
+    KV_past = (B_past.double() @ W.double().t() + bkv.double()).half()
+    idx = torch.from_numpy(tab.bin2basis)[torch.randint(0, 127, (Bv, 512), generator=g)].int()
+    import ctypes as C
+    from infinite_video_b200 import _capi
+    B_new = torch.empty(Bv, N, e, device=dev)
+    KV_new = torch.zeros(Bv, N, D2, device=dev, dtype=torch.float16)
+    Bp, xp, ix, kvp, bk = B_past.to(dev), x.to(dev), idx.to(dev), KV_past.to(dev), bkv.to(dev)
+    _capi.check(_capi.lib().ltm_consolidate_rect_kv(
+        _capi.ptr(Bp), _capi.ptr(xp), _capi.ptr(ix), 512, None, _capi.ptr(td["seg_ptr0"]), _capi.ptr(td["seg_mem0"]),
+        _capi.ptr(td["g0"]), _capi.ptr(td["seg_ptr1"]), _capi.ptr(td["seg_mem1"]), _capi.ptr(td["g1"]),
+        _capi.ptr(B_new), None, _capi.ptr(kvp), _capi.ptr(KV_new), _capi.ptr(bk), D2, tab.jf, 2, Bv, N, e, L, 1, 512,
+        _capi.stream_ptr(dev)), "consolidate_rect_kv")
+    # reference: the same segmented mean over the fp16 rows in exact arithmetic
+    Bn64, KVn = ops.consolidate_rect_kv(Bp, xp, ix, td, 512, kvp.float(), bk, tab.jf)
+    assert torch.equal(B_new, Bn64)
+    assert relerr(KV_new[:, :tab.jf].float(), KVn[:, :tab.jf]) < 6e-4
+    assert float(KV_new[:, tab.jf:].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("group,groups,N_rows", [(64, 6, 256), (16, 20, 64), (128, 3, 512), (256, 2, 1024), (32, 5, 40)])
