@@ -39,7 +39,8 @@ class LongTermAttention(nn.Module):
                  affines: bool, mask: bool, mask_type: str, kl_regularizer: bool, proj_key, proj_value,
                  sigma_0, mu_0, sticky_memories, sigmas, tau, variant: str = "gibbs",
                  tokens_per_frame: int = 32, precision: str = None, gemm_impl: str = "tcgen05",
-                 share_pooling: bool = True, output_density: bool = False, dump_path: str = None, **kwargs):
+                 share_pooling: bool = True, output_density: bool = False, dump_path: str = None,
+                 kv_dtype: str = "fp16", **kwargs):
         super().__init__()
         if not continuous:
             raise NotImplementedError("only the continuous-attention memory is on the LTM path (continuous=True)")
@@ -85,6 +86,9 @@ class LongTermAttention(nn.Module):
         self.precision = precision
         self.gemm_impl = gemm_impl
         self.share_pooling = share_pooling
+        # storage of the projected keys / values between calls: "fp16" (default; same 11-bit significand as the tf32
+        # grid, half the bytes, |K|,|V| <= 65504) or "fp32"
+        self.kv_dtype = kv_dtype
         # Video-LLaMA copy: density side-output of every call (gibbs:320-343).  Off by default; when on, the
         # result is kept on the device in `self.alphas` ([Q,B,H,768]) instead of being pickled to the cwd.
         # `dump_path` (e.g. "./alphas_uniform", what the Video-LLaMA copy hard-codes at gibbs:344-345): additionally
@@ -111,7 +115,8 @@ class LongTermAttention(nn.Module):
             if self.variant == "gibbs":
                 self._engine = BatchedRectLTM(tokens_per_frame=self.tokens_per_frame,
                                               precision=self.precision or "tf32",
-                                              keep_scores=self.output_density, spacing=self.spacing, **common)
+                                              keep_scores=self.output_density, spacing=self.spacing,
+                                              kv_dtype=self.kv_dtype, **common)
             else:
                 sig = self.sigmas if self.sigmas is not None else (0.005, 0.01)
                 self._engine = BatchedGaussLTM(sigmas=tuple(sig), precision=self.precision or "tf32x3",

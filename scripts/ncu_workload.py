@@ -17,12 +17,15 @@ q = [torch.randn(Bv, Q, 768, device=dev, generator=g) for _ in range(3)]
 u = [torch.rand(Bv, 512, device=dev, dtype=torch.float64, generator=g) for _ in range(3)]
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 if which in ("all", "rect"):
-    for prec in ("tf32", "tf32x3"):
-        eng = BatchedRectLTM(N, .75, *w, device=dev, precision=prec, keep_scores=(prec == "tf32x3"))
+    for prec, kvd in (("tf32", "fp16"), ("tf32", "fp32"), ("tf32x3", "fp32")):
+        eng = BatchedRectLTM(N, .75, *w, device=dev, precision=prec, keep_scores=(prec == "tf32x3"), kv_dtype=kvd)
         for c in range(3):
             eng.step(k[c], q[c], u[c] if c else None, new_doc=(c == 0))
         if prec == "tf32x3":
             eng.density()
+    eng = BatchedRectLTM(512, .75, *w, device=dev, kv_dtype="fp32")            # num_basis 512 (fp32 K|V)
+    for c in range(2):
+        eng.step(k[c], q[c], u[c] if c else None, new_doc=(c == 0))
     eng = BatchedRectLTM(512, .75, *w, device=dev)            # num_basis 512
     for c in range(2):
         eng.step(k[c], q[c], u[c] if c else None, new_doc=(c == 0))
