@@ -58,7 +58,7 @@ def _pad_rows(m):
 
 class _BatchedBase:
     def __init__(self, num_basis, tau, w_key, b_key, w_value, b_value, n_heads, head_size, sticky, nb_samples,
-                 precision, gemm_impl, device):
+                 precision, device):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ValueError("the LTM consolidation path runs on CUDA devices only (no CPU fallback)")
@@ -72,7 +72,7 @@ class _BatchedBase:
         self.sticky = bool(sticky)
         self.S = int(nb_samples)
         self.precision = precision
-        self.gemm_impl = gemm_impl
+        self.gemm_impl = "tcgen05"      # one backend: the SIMT GEMM is a kernel-level test cross-check (ops.gemm impl=)
         self.set_projections(w_key, b_key, w_value, b_value)
         self.Bv = None
         self.has_state = False
@@ -101,10 +101,10 @@ class BatchedRectLTM(_BatchedBase):
 
     def __init__(self, num_basis, tau, w_key, b_key, w_value, b_value, *, n_heads=12, head_size=64,
                  tokens_per_frame=32, sticky=True, nb_samples=tables.NB_SAMPLES, precision="tf32",
-                 gemm_impl="tcgen05", device="cuda", keep_scores=False, fast_attn=True, tc_attn=True,
+                 device="cuda", keep_scores=False, fast_attn=True, tc_attn=True,
                  proj_operands="fp32", kv_state=True, proj_precision=None, spacing="linear", kv_dtype="fp16"):
         super().__init__(num_basis, tau, w_key, b_key, w_value, b_value, n_heads, head_size, sticky, nb_samples,
-                         precision, gemm_impl, device)
+                         precision, device)
         self.T = int(tokens_per_frame)
         self.spacing = spacing        # first-chunk frame positions: 'linear' | 'log' (gibbs:101-127)
         self.keep_scores = keep_scores
@@ -113,7 +113,7 @@ class BatchedRectLTM(_BatchedBase):
         # tensor-core attention (csrc/attn_tc.cu): num_basis 64/128/256, head size 64, single-pass tf32 projection
         # (num_basis 512: the same kernel over the two halves of the basis range + a combine kernel)
         self.tc_split = ops.attn_tc_split_supported(self.N, self.d)
-        self.tc_attn = (bool(tc_attn) and bool(fast_attn) and precision == "tf32" and gemm_impl == "tcgen05"
+        self.tc_attn = (bool(tc_attn) and bool(fast_attn) and precision == "tf32"
                         and (ops.attn_tc_supported(self.N, self.d) or self.tc_split))
         self.tc_split = self.tc_split and self.tc_attn
         # operands of the K/V projection on the tensor-core path: "fp32" (default: tf32 UMMAs straight from the fp32
@@ -581,14 +581,14 @@ class BatchedGaussLTM(_BatchedBase):
 
     def __init__(self, num_basis, tau, w_key, b_key, w_value, b_value, *, sigmas=(0.005, 0.01), n_heads=12,
                  head_size=64, sticky=True, nb_samples=tables.NB_SAMPLES, precision="tf32x3",
-                 proj_precision=None, gemm_impl="tcgen05", device="cuda", ridge=tables.RIDGE_PENALTY,
+                 proj_precision=None, device="cuda", ridge=tables.RIDGE_PENALTY,
                  spacing="linear", value_precision=None):
         ns = len(sigmas)
         n = int(num_basis)
         if n % ns:
             n += ns - n % ns
         super().__init__(n, tau, w_key, b_key, w_value, b_value, n_heads, head_size, sticky, nb_samples,
-                         precision, gemm_impl, device)
+                         precision, device)
         self.sigmas = tuple(float(s) for s in sigmas)
         self.spacing = spacing
         self.proj_precision = proj_precision or precision

@@ -43,7 +43,9 @@ __device__ __forceinline__ void pool_unit(const float4* __restrict__ k, float4* 
 #pragma unroll
     for (int i = 1; i < POOL_ACC; ++i) f4_add(acc[0], acc[i]);
     float4 o = acc[0];
-    // torch.mean == sum / T (true division, so T = 196 rounds like the reference)
+    // torch.mean == sum / T (true division, so T = 196 rounds like the reference).  With splits > 1 (small batches
+    // only) every partial sum is divided -- and rounded -- on its own and the consumer adds the partial means: the
+    // pooled frame then differs from sum / T by up to `splits` ulp (1e-7 relative; the coefficient tolerance is 1e-5).
     o.x = __fdiv_rn(o.x, Tf); o.y = __fdiv_rn(o.y, Tf); o.z = __fdiv_rn(o.z, Tf); o.w = __fdiv_rn(o.w, Tf);
     xpart[((size_t)unit * splits + sp) * e4 + c] = o;
   }

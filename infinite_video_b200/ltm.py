@@ -38,7 +38,7 @@ class LongTermAttention(nn.Module):
                  continuous: bool, attn_drop: float, infinite_memory: bool, n_layers: int, n_heads: int,
                  affines: bool, mask: bool, mask_type: str, kl_regularizer: bool, proj_key, proj_value,
                  sigma_0, mu_0, sticky_memories, sigmas, tau, variant: str = "gibbs",
-                 tokens_per_frame: int = 32, precision: str = None, gemm_impl: str = "tcgen05",
+                 tokens_per_frame: int = 32, precision: str = None,
                  share_pooling: bool = True, output_density: bool = False, dump_path: str = None,
                  kv_dtype: str = "fp16", **kwargs):
         super().__init__()
@@ -84,7 +84,6 @@ class LongTermAttention(nn.Module):
         self.variant = variant
         self.tokens_per_frame = tokens_per_frame
         self.precision = precision
-        self.gemm_impl = gemm_impl
         self.share_pooling = share_pooling
         # storage of the projected keys / values between calls: "fp16" (default; same 11-bit significand as the tf32
         # grid, half the bytes, |K|,|V| <= 65504) or "fp32"
@@ -111,7 +110,7 @@ class LongTermAttention(nn.Module):
             common = dict(num_basis=self.attn_num_basis, tau=self.tau, w_key=self.proj_key.weight,
                           b_key=self.proj_key.bias, w_value=self.proj_value.weight, b_value=self.proj_value.bias,
                           n_heads=self.n_head, head_size=self.head_size, sticky=bool(self.sticky_memories),
-                          nb_samples=self.nb_samples, gemm_impl=self.gemm_impl, device=device)
+                          nb_samples=self.nb_samples, device=device)
             if self.variant == "gibbs":
                 self._engine = BatchedRectLTM(tokens_per_frame=self.tokens_per_frame,
                                               precision=self.precision or "tf32",
