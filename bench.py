@@ -860,7 +860,7 @@ def run_gauss_arm(dev, Bv, C, Lk, steps=3):
                          "issues 3 MMAs per product; peak = 1/2 of the measured bf16 GEMM"}}
 
 
-def run_caller_arm(dev, Bv=16, C=3, steps=3):
+def run_caller_arm(dev, Bv=32, C=3, steps=3):
     """the whole cross-attention branch of the Q-former's BertSelfAttention
     (query projection, short-term attention over the L*T chunk tokens, LTM, alpha blend) per video chunk."""
     from infinite_video_b200.cross_attention import CrossAttentionLTM
@@ -892,7 +892,8 @@ def run_caller_arm(dev, Bv=16, C=3, steps=3):
     return {"value": calls / (ms * 1e-3), "unit": "chunks/s", "videos": Bv, "chunks": C, "ms_per_step": ms,
             "finite": bool(torch.isfinite(out).all()), "short_term_tflops": tfl,
             "note": "Qformer.py:197-310 eval path: q = query(h); LTM(enc, q); softmax(q K^T) V over L*T = 8192 "
-                    "tokens without forming K, V (scores TF32 on a rounded operand, values split-TF32); alpha blend"}
+                    "tokens without forming K, V; chunk tokens converted once to fp16 (round to nearest), scores and "
+                    "values as kind::f16 tensor-core GEMMs with fp32 accumulation; alpha blend"}
 
 
 def run_gemm_arm(dev, reps=30):

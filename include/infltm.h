@@ -148,8 +148,9 @@ typedef struct {
    * tf32 tensor-core contraction (the tensor core itself would truncate, which biases sums of products) */
   int round_tf32;
   /* != 0: A, B (and B2) point to IEEE fp16 data (leading dimensions / strides in elements, multiples of 8), both
-   * K-major; the products run as kind::f16 UMMAs with fp32 accumulation -- the same 11-bit significand as tf32 at
-   * half the operand bytes and twice the MMA rate, for operands whose range fits fp16 (precision must be 1) */
+   * A K-major, B K-major or MN-major; the products run as kind::f16 UMMAs with fp32 accumulation -- the same 11-bit
+   * significand as tf32 at half the operand bytes and twice the MMA rate, for operands whose range fits fp16
+   * (precision must be 1) */
   int ab_fp16;
   /* optional two-level row mapping of A (K-major A, batch == 1): row m lives at
    * A + (m / a_group) * a_group_stride + (m % a_group) * lda  -- e.g. the rows [jf, N) of every video's coefficient
@@ -335,6 +336,11 @@ int ltm_rect_step_overlap(const ltm_rect_step_args* a, const ltm_overlap* o, con
  * out = alpha * a + (1 - alpha) * b over n elements. */
 int ltm_softmax_rows(float* S, const float* mask, int rows, int n, int rows_per_mask, float scale, void* stream);
 int ltm_blend(const float* a, const float* b, float alpha, float* out, int64_t n, void* stream);
+/* the same softmax with the probabilities written as IEEE fp16 to P16[rows, n] (S is scratch afterwards), and the
+ * fp32 -> fp16 conversion (round to nearest even) of the chunk tokens: operands of the kind::f16 short-term GEMMs */
+int ltm_softmax_rows_h(float* S, const float* mask, void* P16, int rows, int n, int rows_per_mask, float scale,
+                       void* stream);
+int ltm_to_half(const float* src, void* dst, int64_t n, void* stream);
 
 /* ---- CUDA-event helpers so a ctypes host can time stages on the launching stream */
 int ltm_event_create(void** ev);

@@ -108,6 +108,8 @@ _SIGS = {
     "ltm_ridge_solve": (C.c_int, [_P, _I, _I, _I, _P, _P, _I, C.c_double, _P, _P, _L, _P, _P]),
     "ltm_gather_rows": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "ltm_softmax_rows": (C.c_int, [_P, _P, _I, _I, _I, _F, _P]),
+    "ltm_softmax_rows_h": (C.c_int, [_P, _P, _P, _I, _I, _I, _F, _P]),
+    "ltm_to_half": (C.c_int, [_P, _P, _L, _P]),
     "ltm_blend": (C.c_int, [_P, _P, _F, _P, _L, _P]),
     "ltm_event_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "ltm_event_create_sync": (C.c_int, [C.POINTER(C.c_void_p)]),

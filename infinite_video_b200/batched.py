@@ -138,8 +138,7 @@ class BatchedRectLTM(_BatchedBase):
         # the VideoChat2 pipeline of the reference computes them in fp16 itself (autocast).
         if kv_dtype not in ("fp32", "fp16"):
             raise ValueError("kv_dtype must be 'fp32' or 'fp16'")
-        self.kv_half = (kv_dtype == "fp16" and self.tc_attn and not self.half_ops
-                        and proj_precision in (None, "tf32"))       # (a split-TF32 projection keeps fp32 storage)
+        self.kv_half = kv_dtype == "fp16" and self.tc_attn and not self.half_ops
         # consolidate / project / attend in blocks of this many videos (L2 reuse of what a block writes); 0 = off
         # (measured at 128 videos: 16 / 32 / 43 / 64-video blocks all lose 4-14 % to the smaller kernels' tails)
         self.video_block = 0

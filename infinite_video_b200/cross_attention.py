@@ -30,14 +30,17 @@ class CrossAttentionLTM(nn.Module):
     mask).  Construct from the caller's own `query` / `key` / `value` `nn.Linear`s and its config values."""
 
     def __init__(self, query: nn.Linear, key: nn.Linear, value: nn.Linear, alpha: float, num_basis: int, tau: float,
-                 sticky: bool = True, n_heads: int = 12, tokens_per_frame: int = 32, videos_per_pass: int = 8,
-                 precision: str = "tf32", score_precision: str = None, value_precision: str = None, **ltm_kwargs):
+                 sticky: bool = True, n_heads: int = 12, tokens_per_frame: int = 32, videos_per_pass: int = 32,
+                 precision: str = "tf32", score_precision: str = None, value_precision: str = None,
+                 operands: str = "fp16", **ltm_kwargs):
         super().__init__()
         self.query, self.key, self.value = query, key, value
         self.alpha = float(alpha)
         self.H = n_heads
         self.d = query.out_features // n_heads
-        self.videos_per_pass = videos_per_pass        # bounds the [videos, H*Q, L*T] score buffer
+        # bounds the [videos, H*Q, L*T] score buffer (12.6 MB per video at L*T = 8192); large passes amortise the
+        # host side of the five GEMM launches, which is what bounds small batches
+        self.videos_per_pass = videos_per_pass
         self.precision = precision
         # the two large contractions (scores = Qt enc^T, Y = probs enc); the three small ones always run split-TF32.
         # Measured (scripts/stm_probe.py, error vs fp64 at L*T = 8192 / 256, time at 16 videos):
@@ -48,6 +51,14 @@ class CrossAttentionLTM(nn.Module):
         # (the value contraction reads the raw chunk, which the tensor core truncates: its bias is the larger error)
         self.score_precision = score_precision or precision
         self.value_precision = value_precision or "tf32x3"
+        # operands of the two large contractions.  "fp16" (default): the chunk tokens are converted ONCE per chunk to
+        # fp16 with round-to-nearest (one streaming pass, 25 -> 12.6 MB per video), `Qt` and the probabilities are
+        # produced as fp16, and both contractions run as kind::f16 UMMAs (twice the TF32 rate, half the operand bytes;
+        # the values need no split: rounding is unbiased where the tensor core's truncation of fp32 was not).
+        # "fp32": the TF32 / split-TF32 path described above.
+        if operands not in ("fp16", "fp32"):
+            raise ValueError("operands must be 'fp16' or 'fp32'")
+        self.operands = operands
         self.long_term_attention = LongTermAttention(
             head_size=self.d, length=key.in_features, target_len=key.in_features, attn_func="softmax",
             attn_num_basis=num_basis, continuous=True, attn_drop=0.1, infinite_memory=True, n_layers=2,
@@ -80,6 +91,27 @@ class CrossAttentionLTM(nn.Module):
             nb = min(self.videos_per_pass, B - v0)
             qv = q[v0:v0 + nb].contiguous()
             ev = enc[v0:v0 + nb].contiguous()
+            if self.operands == "fp16" and e % 8 == 0 and LT % 8 == 0:
+                e16 = ops.to_half(ev)                                            # [nb, LT, e] fp16, rounded
+                # (1) Qt as fp16, straight out of the (split-TF32) GEMM epilogue
+                Qt = torch.empty(nb, H, Q, e, device=dev, dtype=torch.float16)
+                ops.gemm_raw(qv, D, d, True, wk, e, d * e, False, Qt, e, Q * e, nb * Q, e, d, H,
+                             c_group=Q, c_group_stride=H * Q * e, precision="tf32x3", c_fp16=True)
+                # (2) scores[v] = Qt[v] enc[v]^T : both operands fp16, K-major
+                S = torch.empty(nb, H * Q, LT, device=dev, dtype=torch.float32)
+                ops.gemm_raw(Qt, e, H * Q * e, True, e16, e, LT * e, True, S, LT, H * Q * LT, H * Q, LT, e, nb,
+                             precision="tf32", ab_fp16=True)
+                # (3) probabilities as fp16
+                m = None if mask is None else mask[v0:v0 + nb].float().contiguous()
+                P = ops.softmax_rows_half(S, 1.0 / math.sqrt(d), m, H * Q)
+                # (4) Yh[h][v][q][:] = probs enc[v] : A fp16 K-major, B = enc16[v] read as [K = LT][N = e] (MN-major)
+                Yh = torch.empty(H, nb, Q, e, device=dev, dtype=torch.float32)
+                ops.gemm_raw(P, LT, H * Q * LT, True, e16, e, LT * e, False, Yh, e, Q * e, H * Q, e, LT, nb,
+                             c_group=Q, c_group_stride=nb * Q * e, precision="tf32", ab_fp16=True)
+                # (5) as below
+                ops.gemm_raw(Yh, e, nb * Q * e, True, wv, e, d * e, True, out, D, d, nb * Q, d, e, H,
+                             bias=bv, bias_stride=d, precision="tf32x3", c_offset=v0 * Q * D)
+                continue
             # (1) Qt[v][h][q][:] = q_h W_k,h : batch over heads, A = column block h of q, B = row block h of W_k
             #     read as [K = d][N = e] (MN-major); rows m = (v, q) land at (v*H + h)*Q + q
             Qt = torch.empty(nb, H, Q, e, device=dev, dtype=torch.float32)

@@ -388,6 +388,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                            (uint16_t)((1u << CLUSTER) - 1u));
           } else if (g.b_kmajor) {
             tma_load_3d(mb, sb, full_bar(s), kk, n0, zb);
+          } else if (g.ab_half) {
+            // 16-bit MN-major: slabs of [64 k rows][64 n halves = 128 B], one per 64 columns of the tile
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_3d(mb, sb + i * (64 * 128), full_bar(s), n0 + 64 * i, kk, zb);
           } else {
 #pragma unroll
             for (int i = 0; i < BN / 32; ++i)
@@ -831,14 +836,15 @@ static int resolve_encode() {
 static int encode_operand(CUtensorMap* map, const float* base, int rows, int K, long long ld, long long bstride,
                           int batch, int kmajor, int box_rows, const char* what, int half = 0) {
   if (half) {
-    // fp16 operand, K-major only: memory [rows][K] halves -> dims {K, rows, batch}, box {64, box_rows, 1}
-    LTM_REQUIRE(kmajor, "gemm: fp16 operands must be K-major (%s)", what);
-    LTM_REQUIRE(aligned16(base) && ld % 8 == 0 && ld >= K && bstride % 8 == 0,
+    // fp16 operand.  K-major: memory [rows][K] halves -> dims {K, rows, batch}, box {64, box_rows, 1};
+    // MN-major (B only): memory [K][rows] halves -> dims {rows, K, batch}, box {64, 64, 1} (one 8 KB slab per load)
+    const long long inner = kmajor ? K : rows, outer = kmajor ? rows : K;
+    LTM_REQUIRE(aligned16(base) && ld % 8 == 0 && ld >= inner && bstride % 8 == 0,
                 "gemm: fp16 %s needs a 16-byte aligned base and pitches that are multiples of 8 elements", what);
     const int nbh = (bstride == 0) ? 1 : batch;
-    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)nbh};
-    cuuint64_t strides[2] = {(cuuint64_t)ld * 2ull, (cuuint64_t)((bstride == 0 ? ld * (long long)rows : bstride) * 2ll)};
-    cuuint32_t box[3] = {64u, (cuuint32_t)box_rows, 1u};
+    cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)nbh};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2ull, (cuuint64_t)((bstride == 0 ? ld * outer : bstride) * 2ll)};
+    cuuint32_t box[3] = {64u, (cuuint32_t)(kmajor ? box_rows : 64), 1u};
     cuuint32_t estr[3] = {1u, 1u, 1u};
     CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<float*>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -959,8 +965,7 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   const int half = a.ab_fp16 ? 1 : 0;
   const int bke = half ? 2 * BK : BK;
   LTM_REQUIRE(!two || (a.K1 > 0 && a.K1 % bke == 0), "gemm: K1=%d must be a positive multiple of %d", a.K1, bke);
-  LTM_REQUIRE(!half || (a.precision == 1 && a.a_kmajor && a.b_kmajor),
-              "gemm: fp16 operands need precision 1 and K-major A and B");
+  LTM_REQUIRE(!half || (a.precision == 1 && a.a_kmajor), "gemm: fp16 operands need precision 1 and a K-major A");
   LTM_REQUIRE(a.precision == 1 || a.precision == 3, "gemm: precision must be 1 (tf32) or 3 (split tf32)");
   const bool split = a.precision == 3;
   // 256-wide tiles (128 x 256 x 8 atoms) unless the problem is too small to give every SM a tile: then 128-wide
@@ -1001,6 +1006,11 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   d.CT = a.CT; d.ct_cols = a.ct_cols; d.ct_group = a.ct_group;
   d.c_group = a.c_group; d.c_group_stride = a.c_group_stride; d.bias_stride = a.bias_stride;
   d.mn_layout = g_mn_desc[0]; d.mn_lbo = g_mn_desc[1]; d.mn_sbo = g_mn_desc[2]; d.mn_kadv = g_mn_desc[3];
+  if (half) {
+    // 16-bit MN-major SWIZZLE_128B: atoms of [8 k][64 mn], MN atoms one 8 KB slab apart (LBO), 8-row k groups 1024 B
+    // apart (SBO); one MMA (K = 16) advances two groups
+    d.mn_layout = 2u; d.mn_lbo = 64u * 128u; d.mn_sbo = 1024u; d.mn_kadv = 2048u;
+  }
   d.dbg = g_dbg;
   d.round_tf32 = a.round_tf32;
   d.ab_half = half;
@@ -1025,8 +1035,9 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
     return launch_cfg<128, 6, false, 2>(mA, mB, mB2, d, a.batch, stream);
   }
 #endif
-  if (d.c_half) {           // fp16 output: single-pass products only (the projected-memory K|V)
-    LTM_REQUIRE(!split, "gemm: fp16 output needs precision 1");
+  if (d.c_half) {           // fp16 output (the projected-memory K|V; Qt of the short-term attention)
+    if (split) return bn == 256 ? launch_cfg<256, 2, true, 1, true>(mA, mB, mB2, d, a.batch, stream)
+                                : launch_cfg<128, 4, true, 1, true>(mA, mB, mB2, d, a.batch, stream);
     return bn == 256 ? launch_cfg<256, 4, false, 1, true>(mA, mB, mB2, d, a.batch, stream)
                      : launch_cfg<128, 6, false, 1, true>(mA, mB, mB2, d, a.batch, stream);
   }

@@ -4,12 +4,32 @@
 //   ctx_h  = (P_h enc) W_v,h^T + b_v,h         (rows of P sum to 1)
 //   out    = alpha ctx + (1 - alpha) a_long    <- ltm_blend (this file)
 // so that neither K nor V of the 8192 short-term tokens is ever materialised.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace ltm {
 
+// fp32 -> fp16 (round to nearest even), 8 elements per thread and step: the chunk tokens as operands of the kind::f16
+// short-term attention GEMMs (rounded, where the tensor core would truncate fp32 read as tf32)
 __global__ void __launch_bounds__(256)
-softmax_rows_kernel(float* __restrict__ S, const float* __restrict__ mask, int n, int rows_per_mask, float scale) {
+to_half_kernel(const float4* __restrict__ src, uint4* __restrict__ dst, long long n8) {
+  const uint64_t pol = policy_evict_first();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = ldg_stream(src + 2 * i, pol), b = ldg_stream(src + 2 * i + 1, pol);
+    __half2 h;
+    uint4 o;
+    h = __floats2half2_rn(a.x, a.y); o.x = *reinterpret_cast<const uint32_t*>(&h);
+    h = __floats2half2_rn(a.z, a.w); o.y = *reinterpret_cast<const uint32_t*>(&h);
+    h = __floats2half2_rn(b.x, b.y); o.z = *reinterpret_cast<const uint32_t*>(&h);
+    h = __floats2half2_rn(b.z, b.w); o.w = *reinterpret_cast<const uint32_t*>(&h);
+    dst[i] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(float* __restrict__ S, const float* __restrict__ mask, int n, int rows_per_mask, float scale,
+                    __half* __restrict__ P16) {
   __shared__ float red[8];
   const int row = blockIdx.x;
   float4* s4 = reinterpret_cast<float4*>(S + (size_t)row * n);
@@ -45,10 +65,19 @@ softmax_rows_kernel(float* __restrict__ S, const float* __restrict__ mask, int n
   __syncthreads();
   sum = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
   const float inv = 1.0f / sum;
+  uint2* p2 = P16 ? reinterpret_cast<uint2*>(P16 + (size_t)row * n) : nullptr;
   for (int i = tid; i < n4; i += 256) {
     float4 v = s4[i];
     v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
-    s4[i] = v;
+    if (p2 != nullptr) {                 // probabilities as fp16 (the A operand of the kind::f16 value GEMM)
+      const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+      p2[i] = pk;
+    } else {
+      s4[i] = v;
+    }
   }
 }
 
@@ -71,8 +100,34 @@ extern "C" int ltm_softmax_rows(float* S, const float* mask, int rows, int n, in
   LTM_REQUIRE(rows > 0 && n > 0 && n % 4 == 0, "softmax_rows: bad shape rows=%d n=%d (n %% 4 == 0)", rows, n);
   LTM_REQUIRE(mask == nullptr || rows_per_mask > 0, "softmax_rows: rows_per_mask must be positive");
   LTM_REQUIRE(aligned16(S) && aligned16(mask), "softmax_rows: 16-byte alignment");
-  softmax_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(S, mask, n, rows_per_mask > 0 ? rows_per_mask : 1, scale);
+  softmax_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(S, mask, n, rows_per_mask > 0 ? rows_per_mask : 1, scale,
+                                                              nullptr);
   LTM_CHECK_LAUNCH("softmax_rows");
+  return 0;
+}
+
+extern "C" int ltm_softmax_rows_h(float* S, const float* mask, void* P16, int rows, int n, int rows_per_mask,
+                                  float scale, void* stream) {
+  using namespace ltm;
+  LTM_REQUIRE(S != nullptr && P16 != nullptr, "softmax_rows_h: null pointer");
+  LTM_REQUIRE(rows > 0 && n > 0 && n % 4 == 0, "softmax_rows_h: bad shape rows=%d n=%d (n %% 4 == 0)", rows, n);
+  LTM_REQUIRE(mask == nullptr || rows_per_mask > 0, "softmax_rows_h: rows_per_mask must be positive");
+  LTM_REQUIRE(aligned16(S) && aligned16(mask) && (reinterpret_cast<uintptr_t>(P16) & 7u) == 0, "softmax_rows_h: alignment");
+  softmax_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(S, mask, n, rows_per_mask > 0 ? rows_per_mask : 1, scale,
+                                                              reinterpret_cast<__half*>(P16));
+  LTM_CHECK_LAUNCH("softmax_rows_h");
+  return 0;
+}
+
+extern "C" int ltm_to_half(const float* src, void* dst, int64_t n, void* stream) {
+  using namespace ltm;
+  LTM_REQUIRE(src && dst, "to_half: null pointer");
+  LTM_REQUIRE(n > 0 && n % 8 == 0 && aligned16(src) && aligned16(dst), "to_half: n %% 8 == 0 and 16-byte alignment");
+  const long long n8 = n / 8;
+  const int blocks = (int)((n8 + 255) / 256 < 148 * 16 ? (n8 + 255) / 256 : 148 * 16);
+  to_half_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(src),
+                                                           reinterpret_cast<uint4*>(dst), n8);
+  LTM_CHECK_LAUNCH("to_half");
   return 0;
 }
 

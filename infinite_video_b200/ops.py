@@ -202,14 +202,16 @@ def gemm(A, B, *, a_kmajor=True, b_kmajor=True, B2=None, bias=None, out=None, pr
 
 def gemm_raw(A, lda, strideA, a_kmajor, B, ldb, strideB, b_kmajor, C_, ldc, strideC, M, Nc, K, batch, *, bias=None,
              bias_stride=0, c_group=0, c_group_stride=0, precision="tf32", impl="tcgen05", a_offset=0, b_offset=0,
-             c_offset=0, round_tf32=False, a_group=0, a_group_stride=0, bias_offset=0, c_fp16=False):
+             c_offset=0, round_tf32=False, a_group=0, a_group_stride=0, bias_offset=0, c_fp16=False, ab_fp16=False):
     """ltm_gemm with every pitch / batch stride spelled out (elements).  A, B, C_ are the base tensors; *_offset
     shifts the start (elements).  Used where operands are strided views that tensor shapes cannot express
     (per-head column blocks, per-head / per-video output layouts)."""
     require_cuda(A, B, C_, bias)
     g = GemmArgs()
-    g.A, g.lda, g.strideA, g.a_kmajor = A.data_ptr() + 4 * a_offset, lda, strideA, int(a_kmajor)
-    g.B, g.ldb, g.strideB, g.b_kmajor = B.data_ptr() + 4 * b_offset, ldb, strideB, int(b_kmajor)
+    esz = 2 if ab_fp16 else 4                     # (ab_fp16: A and B are float16 tensors, offsets in elements)
+    g.A, g.lda, g.strideA, g.a_kmajor = A.data_ptr() + esz * a_offset, lda, strideA, int(a_kmajor)
+    g.B, g.ldb, g.strideB, g.b_kmajor = B.data_ptr() + esz * b_offset, ldb, strideB, int(b_kmajor)
+    g.ab_fp16 = int(bool(ab_fp16))
     g.B2, g.ldb2, g.strideB2, g.K1 = None, 0, 0, K
     g.bias = bias.data_ptr() + 4 * bias_offset if bias is not None else None
     g.bias_stride = bias_stride
@@ -257,6 +259,28 @@ def softmax_rows(S, scale=1.0, mask=None, rows_per_mask=1):
     check(lib().ltm_softmax_rows(ptr(S), ptr(mask), rows, n, rows_per_mask, float(scale), stream_ptr(S.device)),
           "softmax_rows")
     return S
+
+
+def softmax_rows_half(S, scale=1.0, mask=None, rows_per_mask=1):
+    """softmax(S * scale + mask) with the probabilities returned as float16 (S is scratch afterwards)."""
+    require_cuda(S, mask)
+    if not S.is_contiguous() or S.dtype != torch.float32:
+        raise ValueError("softmax_rows_half needs a contiguous float32 tensor")
+    n = S.shape[-1]
+    rows = S.numel() // n
+    P = torch.empty(S.shape, device=S.device, dtype=torch.float16)
+    check(lib().ltm_softmax_rows_h(ptr(S), ptr(mask), ptr(P), rows, n, rows_per_mask, float(scale),
+                                   stream_ptr(S.device)), "softmax_rows_h")
+    return P
+
+
+def to_half(x):
+    """fp32 -> fp16 copy (round to nearest even) by the library's streaming kernel."""
+    require_cuda(x)
+    x = _f32c(x)
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    check(lib().ltm_to_half(ptr(x), ptr(out), x.numel(), stream_ptr(x.device)), "to_half")
+    return out
 
 
 def blend(a, b, alpha, out=None):

@@ -725,8 +725,9 @@ def test_fp16_chunk_through_the_drop_in(dev):
             assert relerr(got.float(), want) < 2e-3          # output rounded to fp16 (2^-11) on top of TOL_CTX
 
 
-@pytest.mark.parametrize("alpha,N,L,B", [(0.5, 64, 8, 2), (0.9, 256, 64, 1)])
-def test_caller_cross_attention_with_ltm_blend_on_gpu(dev, alpha, N, L, B):
+@pytest.mark.parametrize("operands", ["fp16", "fp32"])
+@pytest.mark.parametrize("alpha,N,L,B", [(0.5, 64, 8, 2), (0.9, 256, 64, 1), (0.7, 256, 256, 2)])
+def test_caller_cross_attention_with_ltm_blend_on_gpu(dev, alpha, N, L, B, operands):
     """N1: short-term softmax attention over the chunk + (1-alpha) LTM, against the oracle of the caller
     (bit-identical to the real BertSelfAttention, tests/test_oracle_vs_reference.py)."""
     from infinite_video_b200.cross_attention import CrossAttentionLTM
@@ -737,7 +738,7 @@ def test_caller_cross_attention_with_ltm_blend_on_gpu(dev, alpha, N, L, B):
             for _ in range(B)]
     import copy
     m = CrossAttentionLTM(copy.deepcopy(lq).to(dev), copy.deepcopy(lk).to(dev), copy.deepcopy(lv).to(dev), alpha, N,
-                          .75)
+                          .75, operands=operands)
     g = torch.Generator().manual_seed(22)
     with torch.no_grad():
         for c in range(3):

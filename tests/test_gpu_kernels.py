@@ -440,6 +440,40 @@ def test_gemm_fp16_operands(dev, gemm_cluster, M, N, K):
     assert relerr(got, want.float()) < 2e-6
 
 
+@pytest.mark.parametrize("M,N,K,batch", [(384, 768, 8192, 2), (128, 256, 64, 1), (300, 200, 136, 3), (96, 1024, 512, 1)])
+def test_gemm_fp16_mn_major_b(dev, M, N, K, batch):
+    """kind::f16 GEMM with the B operand MN-major (memory [K][N], 16-bit SWIZZLE_128B atoms of 8 k x 64 n): the value
+    contraction of the short-term attention reads the fp16 chunk tokens this way (P[H*Q, LT] @ enc16[LT, e])."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.rand(batch, M, K, generator=g) / K * 4).half().to(dev)             # probability-like rows
+    B = torch.randn(batch, K, N, generator=g).half().to(dev)
+    C = torch.zeros(batch, M, N, device=dev)
+    ops.gemm_raw(A, K, M * K, True, B, N, K * N, False, C, N, M * N, M, N, K, batch, precision="tf32", ab_fp16=True)
+    want = A.double() @ B.double()
+    assert relerr(C, want) < 2e-5                        # exact fp16 products, fp32 accumulation over up to 8192 terms
+    # K-major B through the same raw entry, and an fp16 result
+    Bt = B.transpose(1, 2).contiguous()
+    C2 = torch.zeros(batch, M, N, device=dev, dtype=torch.float16)
+    ops.gemm_raw(A, K, M * K, True, Bt, K, N * K, True, C2, N, M * N, M, N, K, batch, precision="tf32", ab_fp16=True,
+                 c_fp16=True)
+    assert relerr(C2.float(), want) < 6e-4
+
+
+def test_to_half_and_half_softmax(dev):
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(3, 1000, 768, generator=g).to(dev)
+    assert torch.equal(ops.to_half(x), x.half())
+    S = (torch.randn(2, 40, 512, generator=g) * 3).to(dev)
+    mask = torch.zeros(2, 512)
+    mask[1, 400:] = -10000.0
+    want = torch.softmax(S.cpu().double() * 0.125 + mask.double().unsqueeze(1), -1)
+    P = ops.softmax_rows_half(S.clone(), 0.125, mask.to(dev), 40)
+    assert P.dtype == torch.float16 and relerr(P.float(), want) < 6e-4
+    assert float((P.float().sum(-1) - 1).abs().max()) < 2e-3
+
+
 def test_project_kv_rounded_to_tf32(dev):
     """`ltm_project_kv_r`: the same product as `ltm_project_kv`, stored on the tf32 grid (round to nearest)."""
     ops = _ops()
