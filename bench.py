@@ -708,13 +708,15 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": value, "unit": "chunks/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
-            "vs_baseline": None, "dtype": ("f32 state and accumulation; tf32 tensor-core K/V projection; projected memory K|V stored as "
+            "vs_baseline": None, "dtype": ("f32 state and accumulation; K/V projection on "
+                      + ("kind::f16" if eng.half_ops else "tf32") + " tensor cores; projected memory K|V stored as "
                       + ("fp16 (tf32's 11-bit significand), kind::f16 tensor-core attention" if eng.kv_half else
                          "fp32 on the tf32 grid, tf32 tensor-core attention"))
             if args.precision == "tf32" else "f32 (split-tf32 x3 tensor-core projection, fp32 FMA attention)",
             "data": "synthetic", "config": dict(workload_config(Bv, C, "gibbs", overlap),
                                                 projected_memory_state=bool(eng.kv_state),
                                                 video_block=args.video_block, kv_dtype=args.kv_dtype,
+                                                proj_operands=args.proj_operands,
                                                 proj_precision=args.proj_precision or args.precision),
             "frame_blocks_per_s": value * L,
             "roofline": {"bound": "hbm", "kernel": "pool_mean_kernel",
@@ -1017,7 +1019,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="do not pool chunk c+1 under chunk c's compute")
     ap.add_argument("--pool-ctas-per-sm", type=int, default=0, help="grid bound of the prefetch pooling kernel")
-    ap.add_argument("--proj-operands", choices=["fp32", "fp16"], default="fp32",
+    ap.add_argument("--proj-operands", choices=["fp32", "fp16"], default="fp16",
                     help="operands of the K/V projection on the tensor-core path (fp16: kind::f16 UMMAs, opt-in)")
     ap.add_argument("--kv-dtype", default="fp16", choices=["fp32", "fp16"],
                     help="storage of the projected memory K|V on the tensor-core path")

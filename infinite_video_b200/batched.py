@@ -102,7 +102,7 @@ class BatchedRectLTM(_BatchedBase):
     def __init__(self, num_basis, tau, w_key, b_key, w_value, b_value, *, n_heads=12, head_size=64,
                  tokens_per_frame=32, sticky=True, nb_samples=tables.NB_SAMPLES, precision="tf32",
                  device="cuda", keep_scores=False, fast_attn=True, tc_attn=True,
-                 proj_operands="fp32", kv_state=True, proj_precision=None, spacing="linear", kv_dtype="fp16"):
+                 proj_operands="fp16", kv_state=True, proj_precision=None, spacing="linear", kv_dtype="fp16"):
         super().__init__(num_basis, tau, w_key, b_key, w_value, b_value, n_heads, head_size, sticky, nb_samples,
                          precision, device)
         self.T = int(tokens_per_frame)
@@ -116,10 +116,11 @@ class BatchedRectLTM(_BatchedBase):
         self.tc_attn = (bool(tc_attn) and bool(fast_attn) and precision == "tf32"
                         and (ops.attn_tc_supported(self.N, self.d) or self.tc_split))
         self.tc_split = self.tc_split and self.tc_attn
-        # operands of the K/V projection on the tensor-core path: "fp32" (default: tf32 UMMAs straight from the fp32
-        # tensors) or "fp16" (coefficients and weights rounded to fp16: tf32's 11-bit significand at half the bytes
-        # and twice the MMA rate -- projection 0.134 -> 0.108 ms, serial step +3 %, overlapped step +0.7 % at 128
-        # videos -- but coefficients beyond 65504 turn into inf, which is why it is opt-in)
+        # operands of the K/V projection on the tensor-core path: "fp16" (default) -- the consolidation also writes the
+        # coefficient rows the projection will read as fp16 (round to nearest: unbiased, where the tensor core
+        # TRUNCATES fp32 operands read as tf32) and the weights are kept as fp16: kind::f16 UMMAs at twice the TF32
+        # rate and half the operand bytes (projection 0.064 -> 0.040 ms per 128-video chunk, 190.3 k -> 193.5 k
+        # chunks/s) -- or "fp32" (tf32 UMMAs straight from the fp32 tensors).  fp16's range applies: |B|, |W| <= 65504.
         if proj_operands not in ("fp16", "fp32"):
             raise ValueError("proj_operands must be 'fp16' or 'fp32'")
         self.half_ops = self.tc_attn and proj_operands == "fp16" and self.e % 8 == 0
@@ -127,7 +128,7 @@ class BatchedRectLTM(_BatchedBase):
         # linear, so K|V of the bins that hold only re-sampled memory are the same segmented mean taken over the
         # previous K|V; only the bins that receive new frames (a quarter at tau = 0.75) go through the projection GEMM.
         # Needs the row-major K|V layout (tensor-core or generic attention) and one new_doc flag for the whole batch.
-        self.kv_state = bool(kv_state) and not self.half_ops and (self.tc_attn or not self.fast_attn)
+        self.kv_state = bool(kv_state) and (self.tc_attn or not self.fast_attn)
         # precision of the K/V projection GEMM alone (None = `precision`); "tf32x3" makes the stored K|V fp32-grade
         self.proj_precision = proj_precision
         # storage of the projected memory on the tensor-core path: "fp16" (default) or "fp32" (values on the tf32
@@ -138,7 +139,7 @@ class BatchedRectLTM(_BatchedBase):
         # the VideoChat2 pipeline of the reference computes them in fp16 itself (autocast).
         if kv_dtype not in ("fp32", "fp16"):
             raise ValueError("kv_dtype must be 'fp32' or 'fp16'")
-        self.kv_half = kv_dtype == "fp16" and self.tc_attn and not self.half_ops
+        self.kv_half = kv_dtype == "fp16" and self.tc_attn
         # consolidate / project / attend in blocks of this many videos (L2 reuse of what a block writes); 0 = off
         # (measured at 128 videos: 16 / 32 / 43 / 64-video blocks all lose 4-14 % to the smaller kernels' tails)
         self.video_block = 0

@@ -94,10 +94,10 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
     n_new = (n_new + 127) / 128 * 128;
   }
   const int jg = a->N - n_new;
-  const bool kvstate = a->KV_past != nullptr && a->KV != nullptr && !fast && !half_ops && B_past != nullptr &&
+  const bool kvstate = a->KV_past != nullptr && a->KV != nullptr && !fast && B_past != nullptr &&
                        new_doc == nullptr && a->jf > 0 && n_new > 0 && jg > 0 && a->e % 4 == 0;
   const int pprec = a->proj_precision ? a->proj_precision : a->precision;
-  const bool kvh = a->kv_half != 0 && tcp && a->X16 != nullptr && !half_ops;       // K|V stored as fp16
+  const bool kvh = a->kv_half != 0 && tcp && a->X16 != nullptr;                    // K|V stored as fp16
   // Blocks of videos run consolidate -> project -> attention back to back, so that the K|V (and coefficient) rows a
   // block has just written are still in L2 when its attention (projection) reads them: with all videos per kernel
   // the 201 MB of K|V at 128 videos go out to HBM and come back.  video_block: 0 = all videos in one block.
@@ -125,16 +125,21 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
       // rows [jf, N) of every video as one flat problem: A = B_new + jf * e grouped per video, C = KV + jf * 2D
       ltm_gemm_args ga;
       memset(&ga, 0, sizeof(ga));
-      ga.A = Bn + (size_t)jg * a->e; ga.lda = a->e; ga.a_kmajor = 1;
+      // (fp16 operands: the fp16 copy of the new coefficient rows and of the weights, kind::f16 UMMAs)
+      ga.A = half_ops ? reinterpret_cast<const float*>(reinterpret_cast<const uint16_t*>(Bh) + (size_t)jg * a->e)
+                      : Bn + (size_t)jg * a->e;
+      ga.lda = a->e; ga.a_kmajor = 1;
       ga.a_group = n_new; ga.a_group_stride = (int64_t)a->N * a->e;
-      ga.B = a->Wkv; ga.ldb = a->e; ga.b_kmajor = 1;
+      ga.B = half_ops ? reinterpret_cast<const float*>(a->Wkv_half) : a->Wkv; ga.ldb = a->e; ga.b_kmajor = 1;
+      ga.ab_fp16 = half_ops ? 1 : 0;
       ga.K1 = a->e; ga.bias = a->bkv;
       ga.C = kvh ? reinterpret_cast<float*>(reinterpret_cast<uint16_t*>(KVn) + (size_t)jg * 2 * D)
                  : KVn + (size_t)jg * 2 * D;
       ga.ldc = 2 * D;
       ga.c_group = n_new; ga.c_group_stride = (int64_t)a->N * 2 * D;
       ga.M = nv * n_new; ga.Nc = 2 * D; ga.K = a->e; ga.batch = 1;
-      ga.precision = pprec; ga.impl = a->gemm_impl; ga.round_tf32 = (tcp && !kvh) ? 1 : 0; ga.c_fp16 = kvh ? 1 : 0;
+      ga.precision = half_ops ? 1 : pprec; ga.impl = a->gemm_impl; ga.round_tf32 = (tcp && !kvh) ? 1 : 0;
+      ga.c_fp16 = kvh ? 1 : 0;
       rc = ltm_gemm(&ga, stream);
     } else if (half_ops) {
       ltm_gemm_args ga;
@@ -144,7 +149,7 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
       ga.K1 = a->e; ga.bias = a->bkv;
       ga.C = KVn; ga.ldc = 2 * D;
       ga.M = nv * a->N; ga.Nc = 2 * D; ga.K = a->e; ga.batch = 1;
-      ga.precision = 1; ga.impl = 0; ga.round_tf32 = 1; ga.ab_fp16 = 1;
+      ga.precision = 1; ga.impl = 0; ga.round_tf32 = kvh ? 0 : 1; ga.ab_fp16 = 1; ga.c_fp16 = kvh ? 1 : 0;
       rc = ltm_gemm(&ga, stream);
     } else if (kvh) {
       ltm_gemm_args ga;

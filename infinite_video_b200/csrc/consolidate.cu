@@ -61,7 +61,8 @@ consolidate_rect_kernel(const float4* __restrict__ B_past, const float4* __restr
     }
     acc.x *= g; acc.y *= g; acc.z *= g; acc.w *= g;
     B_new[((size_t)v * N + j) * e4 + c] = acc;
-    if (B_half != nullptr) {                    // fp16 copy: operand of the K/V projection (kind::f16 UMMAs)
+    // fp16 copy: operand of the K/V projection (kind::f16 UMMAs) -- only the rows the projection will read
+    if (B_half != nullptr && (kv.KV_past == nullptr || first || j >= kv.jf)) {
       const __half2 lo = __floats2half2_rn(acc.x, acc.y), hi = __floats2half2_rn(acc.z, acc.w);
       uint2 pk;
       pk.x = *reinterpret_cast<const uint32_t*>(&lo);

@@ -976,17 +976,21 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   CUtensorMap mA, mB, mB2;
   if (a.a_group > 0) {
     // A rows in groups: dims {K, a_group, M / a_group}, box {32, min(a_group, 128), 128 / a_group (>= 1)}
-    LTM_REQUIRE(a.a_kmajor && a.batch == 1 && !half, "gemm: grouped A rows need K-major fp32 A and batch == 1");
+    LTM_REQUIRE(a.a_kmajor && a.batch == 1, "gemm: grouped A rows need a K-major A and batch == 1");
     LTM_REQUIRE((BM % a.a_group == 0 || a.a_group % BM == 0) && a.M % a.a_group == 0,
                 "gemm: a_group=%d must divide %d or be a multiple of it, and divide M=%d", a.a_group, BM, a.M);
-    LTM_REQUIRE(aligned16(a.A) && a.lda % 4 == 0 && a.lda >= a.K && a.a_group_stride % 4 == 0 &&
+    const int al = half ? 8 : 4;                       // pitch granularity in elements (16 bytes)
+    LTM_REQUIRE(aligned16(a.A) && a.lda % al == 0 && a.lda >= a.K && a.a_group_stride % al == 0 &&
                 a.a_group_stride >= (long long)a.a_group * a.lda, "gemm: grouped A pitches");
+    const unsigned long long esz = half ? 2ull : 4ull;
     cuuint64_t dims[3] = {(cuuint64_t)a.K, (cuuint64_t)a.a_group, (cuuint64_t)(a.M / a.a_group)};
-    cuuint64_t strides[2] = {(cuuint64_t)a.lda * 4ull, (cuuint64_t)a.a_group_stride * 4ull};
-    cuuint32_t box[3] = {32u, (cuuint32_t)(a.a_group < BM ? a.a_group : BM), (cuuint32_t)(a.a_group < BM ? BM / a.a_group : 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)a.lda * esz, (cuuint64_t)a.a_group_stride * esz};
+    cuuint32_t box[3] = {half ? 64u : 32u, (cuuint32_t)(a.a_group < BM ? a.a_group : BM),
+                         (cuuint32_t)(a.a_group < BM ? BM / a.a_group : 1)};
     cuuint32_t estr[3] = {1u, 1u, 1u};
-    CUresult r = g_encode(&mA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a.A), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = g_encode(&mA, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                          const_cast<float*>(a.A), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     LTM_REQUIRE(r == CUDA_SUCCESS, "gemm: cuTensorMapEncodeTiled(grouped A) failed with CUresult %d", (int)r);
   } else if (encode_operand(&mA, a.A, a.M, a.K, a.lda, a.strideA, a.batch, a.a_kmajor, BM, "A", half)) return -1;

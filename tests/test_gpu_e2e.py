@@ -25,7 +25,7 @@ FLIPS = {}          # test id -> (flips, draws): printed in the summary line of 
 
 
 def _run_rect(dev, N, L, C, Bv, T=32, e=768, Q=32, tau=.75, sticky=True, q_scale=1.0, seed=31, precision="tf32",
-              fast_attn=True, proj_operands="fp32", tag=None, **eng_kw):
+              fast_attn=True, proj_operands="fp16", tag=None, **eng_kw):
     from infinite_video_b200.batched import BatchedRectLTM
     key, val = make_proj(seed, e)
     eng = BatchedRectLTM(N, tau, *proj_tensors(key, val), tokens_per_frame=T, sticky=sticky, precision=precision,
@@ -76,6 +76,9 @@ def _run_rect(dev, N, L, C, Bv, T=32, e=768, Q=32, tau=.75, sticky=True, q_scale
     ("n128_kv32", dict(N=128, L=16, C=3, Bv=2, Q=40, kv_dtype="fp32")),
     ("cfg4_kv32", dict(N=512, L=32, C=3, Bv=2, kv_dtype="fp32")),
     ("peaky_kv32", dict(N=64, L=8, C=3, Bv=2, q_scale=8.0, kv_dtype="fp32")),
+    ("cfg2_p32", dict(N=256, L=256, C=3, Bv=2, proj_operands="fp32")),      # tf32 projection from the fp32 coefficients
+    ("cfg2_p32_kv32", dict(N=256, L=64, C=3, Bv=2, proj_operands="fp32", kv_dtype="fp32")),   # the round-1 numerics
+    ("cfg4_p32", dict(N=512, L=32, C=3, Bv=2, proj_operands="fp32")),
 ])
 def test_rect_matches_oracle_over_chunks(dev, name, kw):
     w = _run_rect(dev, tag=name, **kw)
@@ -491,11 +494,11 @@ def test_overlapped_step_is_bit_identical(dev):
     torch.cuda.synchronize()
 
 
-def test_fp16_projection_operands(dev):
-    """`proj_operands="fp16"`: coefficients and weights enter the K/V projection as fp16 (kind::f16 UMMAs, fp32
-    accumulation).  Same tolerances as the default path; the coefficients themselves stay fp32."""
+def test_fp32_projection_operands(dev):
+    """`proj_operands="fp32"`: tf32 UMMAs straight from the fp32 coefficients and weights (the default converts both to
+    fp16 first).  Same tolerances; the coefficients themselves are fp32 either way."""
     for kw in (dict(N=256, L=64, C=3, Bv=2), dict(N=128, L=16, C=3, Bv=2, Q=40)):
-        w = _run_rect(dev, proj_operands="fp16", **kw)
+        w = _run_rect(dev, proj_operands="fp32", **kw)
         assert w["B"] < 1e-5 and w["ctx"] < TOL_CTX, w
 
 
