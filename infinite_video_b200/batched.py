@@ -592,10 +592,11 @@ class BatchedGaussLTM(_BatchedBase):
         self.sigmas = tuple(float(s) for s in sigmas)
         self.spacing = spacing
         self.proj_precision = proj_precision or precision
-        # optional lower precision for the value half of the projection ("tf32": values only enter the final
-        # contraction r.V, the keys feed softmax(20 S) and stay split-TF32).  Measured: 128.7 k -> 161.3 k chunks/s at
-        # 128 videos, but the tensor core TRUNCATES the fp32 operands, a systematic ~1e-3 shrink of V that the
-        # 1e-3 context tolerance does not leave room for -- so the default stays split-TF32 for both halves.
+        # precision of the value half of the projection: None (default) = split-TF32 like the keys.  Both cheaper
+        # options were measured and miss the 1e-3 context tolerance: "tf32" (single pass on the fp32 operands; the
+        # tensor core TRUNCATES them, a systematic ~1e-3 shrink of V; 128.7 k -> 161.3 k chunks/s) and "fp16" (operands
+        # rounded to fp16 first: unbiased, but the Gaussian weights r_j reach ~80 with mixed signs downstream of the
+        # ridge operators and amplify the 2^-12 rounding to 1.15e-3; 143 k -> 161.8 k).
         self.value_precision = value_precision
         self.ridge = float(ridge)
         self._ops = {}

@@ -401,7 +401,7 @@ def project_kv_t(Bcoef, Wkv, bkv, N, precision="tf32", impl="tcgen05", precision
     Bv = M // N
     Kt = torch.empty(Bv, D // 64, 64, N, device=Bc.device, dtype=torch.float32)
     V = torch.empty(Bv, N, D, device=Bc.device, dtype=torch.float32)
-    if precision_v is not None and PRECISION[precision_v] != PRECISION[precision]:
+    if precision_v is not None and (precision_v == "fp16" or PRECISION[precision_v] != PRECISION[precision]):
         g = GemmArgs()                                   # keys: all D columns through the transposed store
         g.A, g.lda, g.a_kmajor = Bc.data_ptr(), e, 1
         g.B, g.ldb, g.b_kmajor = Wkv.data_ptr(), e, 1
@@ -411,8 +411,14 @@ def project_kv_t(Bcoef, Wkv, bkv, N, precision="tf32", impl="tcgen05", precision
         g.M, g.Nc, g.K, g.batch = M, D, e, 1
         g.precision, g.impl = PRECISION[precision], GEMM_IMPL[impl]
         check(lib().ltm_gemm(C.byref(g), stream_ptr(Bc.device)), "project_k_t")
-        gemm_raw(Bc, e, 0, True, Wkv, e, 0, True, V, D, 0, M, D, e, 1, bias=bkv, precision=precision_v, impl=impl,
-                 b_offset=D * e, bias_offset=D)
+        if precision_v == "fp16":
+            # values through kind::f16 UMMAs: coefficients and weights ROUNDED to fp16 first (unbiased; the tensor
+            # core would truncate fp32 operands read as tf32, a systematic shrink of V)
+            gemm_raw(to_half(Bc), e, 0, True, to_half(Wkv[D:].contiguous()), e, 0, True, V, D, 0, M, D, e, 1,
+                     bias=bkv, bias_offset=D, ab_fp16=True, precision="tf32")
+        else:
+            gemm_raw(Bc, e, 0, True, Wkv, e, 0, True, V, D, 0, M, D, e, 1, bias=bkv, precision=precision_v, impl=impl,
+                     b_offset=D * e, bias_offset=D)
         return Kt, V
     check(lib().ltm_project_kv_t(ptr(Bc), ptr(Wkv), ptr(bkv), ptr(Kt), ptr(V), M, e, D, N, PRECISION[precision],
                                  GEMM_IMPL[impl], stream_ptr(Bc.device)), "project_kv_t")
