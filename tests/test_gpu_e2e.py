@@ -96,6 +96,42 @@ def test_generic_attention_path_still_matches(dev, kw):
     assert w["B"] < 1e-5 and w["ctx"] < TOL_CTX, w
 
 
+def test_no_drift_over_a_long_video(dev):
+    """The projected memory K|V is carried from call to call (rounded to fp16 at every store) instead of being
+    re-projected from the coefficients: 48 sequential chunks against the oracle, which projects afresh every call --
+    the context error must stay where it starts (the rounding noise of a carried row is averaged and shrunk by
+    g_j * cnt_j < 1 each call), not accumulate."""
+    from infinite_video_b200.batched import BatchedRectLTM
+    key, val = make_proj(39, 768)
+    N, L, Bv, C = 64, 8, 2, 48
+    eng = BatchedRectLTM(N, .75, *proj_tensors(key, val), device=dev)
+    assert eng.kv_state and eng.kv_half
+    orcs = [O.RectLTM(N, .75, *proj_tensors(key, val), rebuild_tables=False, faithful_quadrature=False)
+            for _ in range(Bv)]
+    g = torch.Generator().manual_seed(40)
+    errs, flips = [], 0
+    with torch.no_grad():
+        for c in range(C):
+            k = torch.randn(Bv, L * 32, 768, generator=g)
+            q = torch.randn(Bv, 32, 768, generator=g)
+            u = torch.rand(Bv, 512, dtype=torch.float64, generator=g)
+            got = eng.step(k.to(dev), q.to(dev), u.to(dev) if c else None, new_doc=(c == 0))
+            b_got = eng.last["b"].cpu().long() if c else None
+            want = torch.cat([orcs[v].forward(k[v:v + 1], q[v:v + 1], c == 0, u[v:v + 1],
+                                              b_override=b_got[v:v + 1] if c else None) for v in range(Bv)])
+            if c:
+                f, _ = compare_draws(b_got, torch.cat([o.last["b_own"] for o in orcs]), u,
+                                     torch.cat([o.last["p"] for o in orcs]), TIE["tf32"])
+                flips += f
+            assert relerr(eng.B_past, torch.cat([o.B_past for o in orcs])) < 1e-5, c
+            errs.append(relerr(got, want))
+    assert max(errs) < TOL_CTX, max(errs)
+    first, last = sum(errs[1:9]) / 8, sum(errs[-8:]) / 8
+    print(f"[drift] ctx error, mean of chunks 1-8: {first:.2e}, of the last 8: {last:.2e}; flips {flips} of {(C - 1) * Bv * 512}")
+    assert last < 2 * first + 1e-4
+    assert flips <= 0.002 * (C - 1) * Bv * 512
+
+
 def test_ragged_video_chunk_lengths(dev):
     """A video whose chunks differ in length (the last chunk of a real video is shorter; the reference rebuilds its
     tables for whatever `k.size(1)` it is handed): the memory state carries over between chunk lengths, the carried
