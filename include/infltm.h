@@ -40,6 +40,11 @@ int ltm_pool_mean(const float* k, float* xpart, int Bv, int L, int T, int e, int
 int ltm_pool_mean_grid(const float* k, float* xpart, int Bv, int L, int T, int e, int splits, int max_ctas,
                        void* stream);
 
+/* frame pooling that also writes the chunk as IEEE fp16 (round to nearest even) to k16[Bv,L,T,e]: one pass over the
+ * chunk serves the LTM and the kind::f16 short-term attention of the caller */
+int ltm_pool_mean_convert(const float* k, float* xpart, void* k16, int Bv, int L, int T, int e, int splits,
+                          void* stream);
+
 /* same for a 16-bit chunk (fp16 when is_bf16 == 0, else bfloat16; the VideoChat2 Q-former runs under fp16
  * autocast): 128-bit loads of 8 elements, fp32 accumulation, fp32 output.  e % 8 == 0. */
 int ltm_pool_mean_16(const void* k, int is_bf16, float* xpart, int Bv, int L, int T, int e, int splits,

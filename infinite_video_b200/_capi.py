@@ -73,6 +73,7 @@ _SIGS = {
     "ltm_last_error": (C.c_char_p, []),
     "ltm_device_check": (C.c_int, []),
     "ltm_pool_mean": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "ltm_pool_mean_convert": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_pool_mean_16": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_pool_mean_grid": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ltm_sticky_hist_rect": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),

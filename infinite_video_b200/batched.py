@@ -420,17 +420,22 @@ class BatchedRectLTM(_BatchedBase):
         return ops.density_rect(sc, td["jd"], td["wd"])
 
     @_on_device
-    def pool(self, k):
+    def pool(self, k, with_half=False):
         """Frame pooling alone (gibbs:304): k[Bv, L*T, e] -> pooled frames [Bv, L, splits, e].  The result can be
         handed to `step(..., pooled=...)` of SEVERAL engines: every LTM layer of a Q-former receives the same
         `encoder_hidden_states` per chunk (2 layers in Video-LLaMA, 6 in VideoChat2), so the
-        25 MB/video chunk needs to be streamed from HBM once, not once per layer."""
+        25 MB/video chunk needs to be streamed from HBM once, not once per layer.
+        `with_half=True` (fp32 chunks): the same pass also writes the chunk as float16 and returns
+        (pooled, k16[Bv, L*T, e]) -- the operand of the caller's short-term attention."""
         require_cuda(k)
         k = k.contiguous()
         Bv, LT, e = k.shape
         if e != self.e or LT % self.T:
             raise ValueError(f"k must be [Bv, L*{self.T}, {self.e}]")
         L = LT // self.T
+        if with_half:
+            x, k16 = ops.pool_mean_convert(k.view(Bv, L, self.T, e), self._splits(Bv * L))
+            return x, k16.view(Bv, LT, e)
         return ops.pool_mean(k.view(Bv, L, self.T, e), self._splits(Bv * L))
 
     @_on_device

@@ -76,9 +76,10 @@ class CrossAttentionLTM(nn.Module):
                             bias=b, precision=precision)
 
     @torch.no_grad()
-    def short_term(self, q, enc, mask=None):
+    def short_term(self, q, enc, mask=None, enc16=None):
         """softmax(q_h K_h^T / sqrt(d) + mask) V_h for all heads.  q[B,Q,D] (already projected), enc[B,LT,e] fp32,
-        mask: additive [B, LT] or None.  Returns [B,Q,D]."""
+        mask: additive [B, LT] or None; enc16: the chunk as float16 when the caller already has it (the pooling pass of
+        the LTM writes it, `LongTermAttention.pool_for_caller`).  Returns [B,Q,D]."""
         B, Q, D = q.shape
         LT, e = enc.shape[1], enc.shape[2]
         H, d = self.H, self.d
@@ -92,7 +93,8 @@ class CrossAttentionLTM(nn.Module):
             qv = q[v0:v0 + nb].contiguous()
             ev = enc[v0:v0 + nb].contiguous()
             if self.operands == "fp16" and e % 8 == 0 and LT % 8 == 0:
-                e16 = ops.to_half(ev)                                            # [nb, LT, e] fp16, rounded
+                # [nb, LT, e] fp16, rounded: from the LTM's pooling pass, or converted here
+                e16 = enc16[v0:v0 + nb].contiguous() if enc16 is not None else ops.to_half(ev)
                 # (1) Qt as fp16, straight out of the (split-TF32) GEMM epilogue
                 Qt = torch.empty(nb, H, Q, e, device=dev, dtype=torch.float16)
                 ops.gemm_raw(qv, D, d, True, wk, e, d * e, False, Qt, e, Q * e, nb * Q, e, d, H,
@@ -147,7 +149,15 @@ class CrossAttentionLTM(nn.Module):
         mask = None
         if encoder_attention_mask is not None:                       # HF additive mask [B,1,1,LT] -> [B,LT]
             mask = encoder_attention_mask.reshape(B, -1)
-        ctx = self.short_term(q, enc, mask)
+        ltm = self.long_term_attention
+        enc16 = None
+        if (self.alpha != 1.0 and self.operands == "fp16" and ltm.variant == "gibbs" and ltm.share_pooling
+                and enc.dtype == torch.float32 and enc.is_contiguous() and enc.shape[2] % 8 == 0 and enc.shape[1] % 8 == 0
+                and enc.shape[1] % ltm.tokens_per_frame == 0):
+            # one pass over the chunk: pooled frames for the LTM (parked in its shared-pooling slot) + the fp16 copy
+            # the short-term GEMMs read
+            enc16 = ltm.pool_for_caller(enc)
+        ctx = self.short_term(q, enc, mask, enc16=enc16)
         if self.alpha == 1.0:
             return ctx.to(hidden_states.dtype)
         a_long = self.long_term_attention(enc, q, new_doc=new_video, layer_n=layer, u=u)

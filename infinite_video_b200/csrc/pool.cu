@@ -51,6 +51,56 @@ __device__ __forceinline__ void pool_unit(const float4* __restrict__ k, float4* 
   }
 }
 
+// Frame pooling that also leaves an fp16 copy of the chunk behind (round to nearest even): the short-term attention of
+// the caller (Qformer.py:224-304) reads the same tokens as kind::f16 tensor-core operands, so the chunk is streamed
+// from HBM once for both ("sharing the pass with frame pooling").  Same summation order as pool_unit.
+__global__ void __launch_bounds__(256)
+pool_mean_convert_kernel(const float4* __restrict__ k, float4* __restrict__ xpart, uint2* __restrict__ k16, int T,
+                         int e4, int splits, float Tf) {
+  const uint64_t pol = policy_evict_first();
+  const unsigned work = blockIdx.x;
+  const int unit = work / splits;
+  const int sp = work - unit * splits;
+  const int r0 = (int)(((long long)T * sp) / splits);
+  const int r1 = (int)(((long long)T * (sp + 1)) / splits);
+  const float4* base = k + (size_t)unit * T * e4;
+  uint2* base16 = k16 + (size_t)unit * T * e4;
+  for (int c = threadIdx.x; c < e4; c += blockDim.x) {
+    float4 acc[POOL_ACC];
+#pragma unroll
+    for (int i = 0; i < POOL_ACC; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int r = r0;
+    for (; r + POOL_UNROLL <= r1; r += POOL_UNROLL) {
+      float4 v[POOL_UNROLL];
+#pragma unroll
+      for (int i = 0; i < POOL_UNROLL; ++i) v[i] = ldg_stream(base + (size_t)(r + i) * e4 + c, pol);
+#pragma unroll
+      for (int i = 0; i < POOL_UNROLL; ++i) {
+        f4_add(acc[i % POOL_ACC], v[i]);
+        const __half2 lo = __floats2half2_rn(v[i].x, v[i].y), hi = __floats2half2_rn(v[i].z, v[i].w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        base16[(size_t)(r + i) * e4 + c] = pk;
+      }
+    }
+    for (; r < r1; ++r) {
+      const float4 v = ldg_stream(base + (size_t)r * e4 + c, pol);
+      f4_add(acc[0], v);
+      const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+      base16[(size_t)r * e4 + c] = pk;
+    }
+#pragma unroll
+    for (int i = 1; i < POOL_ACC; ++i) f4_add(acc[0], acc[i]);
+    float4 o = acc[0];
+    o.x = __fdiv_rn(o.x, Tf); o.y = __fdiv_rn(o.y, Tf); o.z = __fdiv_rn(o.z, Tf); o.w = __fdiv_rn(o.w, Tf);
+    xpart[((size_t)unit * splits + sp) * e4 + c] = o;
+  }
+}
+
 // one CTA per (frame, split)
 __global__ void __launch_bounds__(256)
 pool_mean_kernel(const float4* __restrict__ k, float4* __restrict__ xpart, int T, int e4, int splits, float Tf) {
@@ -183,3 +233,24 @@ extern "C" int ltm_pool_mean_grid(const float* k, float* xpart, int Bv, int L, i
   LTM_CHECK_LAUNCH("pool_mean");
   return 0;
 }
+
+extern "C" int ltm_pool_mean_convert(const float* k, float* xpart, void* k16, int Bv, int L, int T, int e, int splits,
+                                     void* stream) {
+  using namespace ltm;
+  LTM_REQUIRE(k && xpart && k16, "pool_mean_convert: null pointer");
+  LTM_REQUIRE(Bv > 0 && L > 0 && T > 0 && e > 0 && e % 4 == 0, "pool_mean_convert: bad shape Bv=%d L=%d T=%d e=%d", Bv, L,
+              T, e);
+  LTM_REQUIRE(splits >= 1 && splits <= T, "pool_mean_convert: splits=%d out of range [1,%d]", splits, T);
+  LTM_REQUIRE(aligned16(k) && aligned16(xpart) && (reinterpret_cast<uintptr_t>(k16) & 7u) == 0,
+              "pool_mean_convert: pointer alignment");
+  const long long units = (long long)Bv * L * splits;
+  LTM_REQUIRE(units < (1ll << 31), "pool_mean_convert: too many frames");
+  const int e4 = e / 4;
+  const int threads = e4 >= 256 ? 256 : ((e4 + 31) / 32) * 32;
+  pool_mean_convert_kernel<<<(unsigned)units, threads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(k), reinterpret_cast<float4*>(xpart), reinterpret_cast<uint2*>(k16), T, e4, splits,
+      (float)T);
+  LTM_CHECK_LAUNCH("pool_mean_convert");
+  return 0;
+}
+

@@ -215,6 +215,17 @@ class LongTermAttention(nn.Module):
             return ctx.to(out_dtype), self.kl_reg
         return ctx.to(out_dtype)
 
+    def pool_for_caller(self, k):
+        """One pass over an fp32 chunk for both halves of the caller's cross-attention branch: pools the frames for
+        this (and every other) LTM layer -- the result is parked in the shared-pooling slot, so the following
+        `forward(k, ...)` does not stream the chunk again -- and returns the chunk as float16 for the short-term
+        attention GEMMs (cross_attention.py)."""
+        eng = self._get_engine(k.device)
+        kc = k.contiguous()
+        pooled, k16 = eng.pool(kc, with_half=True)
+        LongTermAttention._shared_pool.update(key=(weakref.ref(k), k._version, self.tokens_per_frame), x=pooled)
+        return k16
+
     def extra_repr(self):
         return (f"variant={self.variant}, num_basis={self.attn_num_basis}, tau={self.tau}, "
                 f"sticky={self.sticky_memories}, nb_samples={self.nb_samples}")

@@ -44,6 +44,18 @@ def pool_mean(k, splits=1):
     return out
 
 
+def pool_mean_convert(k, splits=1):
+    """`pool_mean` that also returns the chunk as float16: k[Bv,L,T,e] fp32 -> (xpart[Bv,L,splits,e], k16[Bv,L,T,e])."""
+    require_cuda(k)
+    k = _f32c(k)
+    Bv, L, T, e = k.shape
+    out = torch.empty(Bv, L, splits, e, device=k.device, dtype=torch.float32)
+    k16 = torch.empty(Bv, L, T, e, device=k.device, dtype=torch.float16)
+    check(lib().ltm_pool_mean_convert(ptr(k), ptr(out), ptr(k16), Bv, L, T, e, splits, stream_ptr(k.device)),
+          "pool_mean_convert")
+    return out, k16
+
+
 def consolidate_rect_kv(B_past, xpart, idx, tab, S, KV_past, bkv, jf, round_tf32=False, new_doc=None):
     """`consolidate_rect` that also carries the projected memory K|V along: rows j < jf of KV_new are the segmented
     mean of KV_past rows (+ bias term); rows >= jf are left untouched for the projection GEMM.  idx: [Bv,S] or [S]

@@ -49,6 +49,17 @@ def test_pool_mean_16bit_inputs(dev, dtype, Bv, L, T, e, splits):
     assert relerr(got, want) < 1e-6
 
 
+@pytest.mark.parametrize("Bv,L,T,e,splits", [(2, 8, 32, 768, 1), (2, 8, 32, 768, 4), (1, 16, 196, 1024, 7),
+                                             (3, 5, 9, 776, 2)])
+def test_pool_mean_convert(dev, Bv, L, T, e, splits):
+    """One pass: pooled partial sums bit-identical to `pool_mean`, fp16 copy identical to a round-to-nearest cast."""
+    g = torch.Generator().manual_seed(3)
+    k = (torch.randn(Bv, L, T, e, generator=g) * 3).to(dev)
+    x, k16 = _ops().pool_mean_convert(k, splits)
+    assert torch.equal(x, _ops().pool_mean(k, splits))
+    assert torch.equal(k16, k.half())
+
+
 # ---------------------------------------------------------------------------------------- R7
 @pytest.mark.parametrize("ncat,Bv,zeros,sort", [(127, 1, False, False), (127, 37, True, False),
                                                 (128, 5, False, True), (128, 4, True, True)])
