@@ -341,7 +341,8 @@ int ltm_rect_step_overlap(const ltm_rect_step_args* a, const ltm_overlap* o, con
  * out = alpha * a + (1 - alpha) * b over n elements. */
 int ltm_softmax_rows(float* S, const float* mask, int rows, int n, int rows_per_mask, float scale, void* stream);
 int ltm_blend(const float* a, const float* b, float alpha, float* out, int64_t n, void* stream);
-/* the same softmax with the probabilities written as IEEE fp16 to P16[rows, n] (S is scratch afterwards), and the
+/* the same softmax with the probabilities written as IEEE fp16 to P16[rows, n] (S is scratch afterwards; rows of
+ * n <= 8192 are held in registers: one pass over HBM, S untouched), and the
  * fp32 -> fp16 conversion (round to nearest even) of the chunk tokens: operands of the kind::f16 short-term GEMMs */
 int ltm_softmax_rows_h(float* S, const float* mask, void* P16, int rows, int n, int rows_per_mask, float scale,
                        void* stream);

@@ -81,6 +81,72 @@ softmax_rows_kernel(float* __restrict__ S, const float* __restrict__ mask, int n
   }
 }
 
+// Rows of up to 8192 scores with fp16 output: the row lives in registers (8 x 128 bit per thread), so the scores are
+// read from HBM once and nothing but the fp16 probabilities is written (the general kernel below re-reads the row twice
+// and parks the exponentials in S).  Same arithmetic, same reduction order.
+__global__ void __launch_bounds__(256)
+softmax_rows_reg_kernel(const float* __restrict__ S, const float* __restrict__ mask, int n, int rows_per_mask,
+                        float scale, __half* __restrict__ P16) {
+  constexpr int ITEMS = 8;
+  __shared__ float red[8];
+  const int row = blockIdx.x;
+  const float4* s4 = reinterpret_cast<const float4*>(S + (size_t)row * n);
+  const float4* m4 = mask ? reinterpret_cast<const float4*>(mask + (size_t)(row / rows_per_mask) * n) : nullptr;
+  const int n4 = n >> 2, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float4 v[ITEMS];
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    const int i = tid + 256 * k;
+    v[k] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (i < n4) {
+      asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(v[k].x), "=f"(v[k].y), "=f"(v[k].z), "=f"(v[k].w) : "l"(s4 + i));
+    }
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    const int i = tid + 256 * k;
+    if (i < n4) {
+      v[k].x *= scale; v[k].y *= scale; v[k].z *= scale; v[k].w *= scale;
+      if (m4) { const float4 mm = m4[i]; v[k].x += mm.x; v[k].y += mm.y; v[k].z += mm.z; v[k].w += mm.w; }
+      mx = fmaxf(mx, fmaxf(fmaxf(v[k].x, v[k].y), fmaxf(v[k].z, v[k].w)));
+    }
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    if (tid + 256 * k < n4) {
+      v[k].x = expf(v[k].x - mx); v[k].y = expf(v[k].y - mx); v[k].z = expf(v[k].z - mx); v[k].w = expf(v[k].w - mx);
+      sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
+  const float inv = 1.0f / sum;
+  uint2* p2 = reinterpret_cast<uint2*>(P16 + (size_t)row * n);
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    const int i = tid + 256 * k;
+    if (i < n4) {
+      const __half2 lo = __floats2half2_rn(v[k].x * inv, v[k].y * inv), hi = __floats2half2_rn(v[k].z * inv, v[k].w * inv);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+      p2[i] = pk;
+    }
+  }
+}
+
 __global__ void blend_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float alpha,
                              float4* __restrict__ out, long long n4) {
   const float beta = 1.0f - alpha;
@@ -113,8 +179,12 @@ extern "C" int ltm_softmax_rows_h(float* S, const float* mask, void* P16, int ro
   LTM_REQUIRE(rows > 0 && n > 0 && n % 4 == 0, "softmax_rows_h: bad shape rows=%d n=%d (n %% 4 == 0)", rows, n);
   LTM_REQUIRE(mask == nullptr || rows_per_mask > 0, "softmax_rows_h: rows_per_mask must be positive");
   LTM_REQUIRE(aligned16(S) && aligned16(mask) && (reinterpret_cast<uintptr_t>(P16) & 7u) == 0, "softmax_rows_h: alignment");
-  softmax_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(S, mask, n, rows_per_mask > 0 ? rows_per_mask : 1, scale,
-                                                              reinterpret_cast<__half*>(P16));
+  if (n <= 8192)   // the row fits the registers of one CTA: one pass over HBM (S is left untouched)
+    softmax_rows_reg_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(S, mask, n, rows_per_mask > 0 ? rows_per_mask : 1,
+                                                                    scale, reinterpret_cast<__half*>(P16));
+  else
+    softmax_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(S, mask, n, rows_per_mask > 0 ? rows_per_mask : 1, scale,
+                                                                reinterpret_cast<__half*>(P16));
   LTM_CHECK_LAUNCH("softmax_rows_h");
   return 0;
 }

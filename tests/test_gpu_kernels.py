@@ -483,6 +483,13 @@ def test_to_half_and_half_softmax(dev):
     P = ops.softmax_rows_half(S.clone(), 0.125, mask.to(dev), 40)
     assert P.dtype == torch.float16 and relerr(P.float(), want) < 6e-4
     assert float((P.float().sum(-1) - 1).abs().max()) < 2e-3
+    # full rows of the caller's shape (register-resident kernel, n = 8192), a ragged width, and a row longer than the
+    # registers hold (three-pass kernel)
+    for n in (8192, 8188, 12288):
+        S = (torch.randn(5, n, generator=g) * 4).to(dev)
+        want = torch.softmax(S.cpu().double() * 0.125, -1)
+        P = ops.softmax_rows_half(S.clone(), 0.125)
+        assert relerr(P.float(), want) < 6e-4, n
 
 
 def test_project_kv_rounded_to_tf32(dev):
