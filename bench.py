@@ -266,7 +266,8 @@ def parity_check(dev, chunks, videos=4, precision="tf32", shape=None):
     w = (key.weight.detach(), key.bias.detach(), val.weight.detach(), val.bias.detach())
     orcs = [O.RectLTM(NB, TAU, *w, tokens_per_frame=T, sticky=True, rebuild_tables=False, faithful_quadrature=False)
             for _ in range(videos)]
-    eng = BatchedRectLTM(NB, TAU, *w, tokens_per_frame=T, sticky=True, device=dev, precision=precision)
+    # (bin_pool=True: the per-bin pooling the batched headline uses, which a one-video engine would not pick by itself)
+    eng = BatchedRectLTM(NB, TAU, *w, tokens_per_frame=T, sticky=True, device=dev, precision=precision, bin_pool=True)
     g = torch.Generator().manual_seed(4321)
     worst_ctx, worst_B, flips, draws, worst_tie = 0.0, 0.0, 0, 0, 0.0
     rel = lambda a, b: float((a.double().cpu() - b.double()).abs().max() / b.double().abs().max())
@@ -383,7 +384,8 @@ def run_b200(args):
     eng = BatchedRectLTM(NB, TAU, key.weight.detach(), key.bias.detach(), val.weight.detach(), val.bias.detach(),
                          tokens_per_frame=T, sticky=True, precision=args.precision, device=dev,
                          proj_operands=args.proj_operands, kv_state=not args.no_kv_state,
-                         proj_precision=args.proj_precision, kv_dtype=args.kv_dtype)
+                         proj_precision=args.proj_precision, kv_dtype=args.kv_dtype,
+                         bin_pool=False if args.no_bin_pool else None)
     eng.video_block = args.video_block
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     # the chunks of all videos stay resident when they fit (128 videos x 8 chunks = 25.8 GB); a large shard (1024
@@ -418,7 +420,7 @@ def run_b200(args):
             with torch.cuda.graph(g):
                 for c in range(C):
                     out_g = eng.step_overlapped(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0),
-                                                k_next=ks[(c + 1) % C])
+                                                k_next=ks[(c + 1) % C], next_new_doc=((c + 1) % C == 0))
                 # join the pooling of the next step's first chunk into the capture
                 torch.cuda.current_stream(dev).wait_stream(eng._side)
             for _ in range(2):
@@ -471,7 +473,8 @@ def run_b200(args):
         while done < n_warm or (with_overlap == overlap and time.time() - t_warm < warm_s and done < 200):
             for c in range(C):
                 if with_overlap:
-                    eng.step_overlapped(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0), k_next=ks[(c + 1) % C])
+                    eng.step_overlapped(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0), k_next=ks[(c + 1) % C],
+                                        next_new_doc=((c + 1) % C == 0))
                 else:
                     eng.step(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0))
             torch.cuda.synchronize(dev)
@@ -494,7 +497,7 @@ def run_b200(args):
                     # one library call per chunk: this chunk's kernels + the pooling of the next chunk beside them
                     # (the pool events of set i bracket the pooling of chunk i + 1)
                     out = eng.step_overlapped(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0),
-                                              k_next=ks[(c + 1) % C])
+                                              k_next=ks[(c + 1) % C], next_new_doc=((c + 1) % C == 0))
                 else:
                     out = eng.step(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0))
             if world > 1:
@@ -558,7 +561,8 @@ def run_b200(args):
         for _ in range(n_steps):
             for c in range(C):
                 if overlap:
-                    eng.step_overlapped(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0), k_next=ks[(c + 1) % C])
+                    eng.step_overlapped(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0), k_next=ks[(c + 1) % C],
+                                        next_new_doc=((c + 1) % C == 0))
                 else:
                     eng.step(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0))
         s1.record(stream)
@@ -585,6 +589,8 @@ def run_b200(args):
 
     peak, peak_src = measured_peaks()
     pool_bytes = 4.0 * Bv * L * T * E                       # algorithmic bytes of the dominant kernel per launch
+    from infinite_video_b200 import tables as _tables
+    binned_pool = eng._bin_ok(Bv, L, _tables.rect_tables(L, NB, TAU, S))
     pool_gbs = pool_bytes / (stage_serial["pool"] * 1e-3) / 1e9 if stage_serial["pool"] > 0 else 0.0
     pool_gbs_ov = pool_bytes / (stage_avg["pool"] * 1e-3) / 1e9 if stage_avg["pool"] > 0 else 0.0
     # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/r1l_ncu_pool.txt:
@@ -716,10 +722,12 @@ def run_b200(args):
             "data": "synthetic", "config": dict(workload_config(Bv, C, "gibbs", overlap),
                                                 projected_memory_state=bool(eng.kv_state),
                                                 video_block=args.video_block, kv_dtype=args.kv_dtype,
-                                                proj_operands=args.proj_operands,
+                                                proj_operands=args.proj_operands, pool_per_bin=bool(binned_pool),
                                                 proj_precision=args.proj_precision or args.precision),
             "frame_blocks_per_s": value * L,
-            "roofline": {"bound": "hbm", "kernel": "pool_mean_kernel",
+            "roofline": {"bound": "hbm",
+                         "kernel": "pool_bins_kernel (update chunks: 7 of 8 launches; first chunks: pool_mean_kernel)"
+                         if binned_pool else "pool_mean_kernel",
                          "achieved": pool_gbs_ov if overlap else pool_gbs, "peak": peak, "unit": "GB/s",
                          "frac": (pool_gbs_ov if overlap else pool_gbs) / peak, "traffic": pool_traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": pool_bytes,
@@ -782,7 +790,8 @@ def run_config_arm(dev, name, cfg, C=8, steps=3, with_parity=True):
 
     def one_step():
         for c in range(C):
-            eng.step_overlapped(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0), k_next=ks[(c + 1) % C])
+            eng.step_overlapped(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0), k_next=ks[(c + 1) % C],
+                                        next_new_doc=((c + 1) % C == 0))
     for _ in range(3):
         one_step()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -1023,6 +1032,8 @@ def main():
                     help="operands of the K/V projection on the tensor-core path (fp16: kind::f16 UMMAs, opt-in)")
     ap.add_argument("--kv-dtype", default="fp16", choices=["fp32", "fp16"],
                     help="storage of the projected memory K|V on the tensor-core path")
+    ap.add_argument("--no-bin-pool", action="store_true",
+                    help="pool every frame on its own (round-1 layout) instead of one row per basis bin on update chunks")
     ap.add_argument("--video-block", type=int, default=0,
                     help="consolidate / project / attend in blocks of this many videos (L2 reuse); 0 = all at once")
     ap.add_argument("--no-kv-state", action="store_true",

@@ -45,6 +45,14 @@ int ltm_pool_mean_grid(const float* k, float* xpart, int Bv, int L, int T, int e
 int ltm_pool_mean_convert(const float* k, float* xpart, void* k16, int Bv, int L, int T, int e, int splits,
                           void* stream);
 
+/* Frame pooling folded with the first half of the regression of an UPDATE chunk: fbin_ptr[rows+1] lists, per basis
+ * bin that receives new frames, its (consecutive) frames [fbin_ptr[r], fbin_ptr[r+1]); xbin[Bv,rows,e] receives the
+ * sum of their pooled means (each frame pooled exactly like ltm_pool_mean with splits == 1).  The consolidation then
+ * takes xbin as its frame operand (L = rows, splits = 1) with tables whose frame members are the bins
+ * (ltm_rect_step_args.binned).  long_term_attention_gibbs.py:304 + :217-219. */
+int ltm_pool_bins(const float* k, float* xbin, const int32_t* fbin_ptr, int Bv, int L, int T, int e, int rows,
+                  void* stream);
+
 /* same for a 16-bit chunk (fp16 when is_bf16 == 0, else bfloat16; the VideoChat2 Q-former runs under fp16
  * autocast): 128-bit loads of 8 elements, fp32 accumulation, fp32 output.  e % 8 == 0. */
 int ltm_pool_mean_16(const void* k, int is_bf16, float* xpart, int Bv, int L, int T, int e, int splits,
@@ -313,6 +321,11 @@ typedef struct {
    * GEMM stores fp16, the carried rows are accumulated in fp32 and stored as fp16, the attention runs on
    * ltm_cont_attn_rect_tc16.  Same significand as the tf32 grid of the fp32 layout; magnitudes beyond 65504 become inf. */
   int kv_half; const void* X16;
+  /* binned != 0 (update calls of all videos only: B_past set, new_doc NULL): `xpart` holds / receives the bin sums of
+   * ltm_pool_bins ([Bv, xb_rows, e]) instead of the pooled frames; fbin_ptr[xb_rows+1] is its frame table and
+   * seg_ptr1b / seg_mem1b the update tables with the frames of a bin collapsed into one member S + r. */
+  int binned, xb_rows;
+  const int32_t* fbin_ptr; const int32_t* seg_ptr1b; const int32_t* seg_mem1b;
 } ltm_rect_step_args;
 int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const float* q, const double* u,
                   const uint8_t* new_doc, float* ctx, void* stream);
@@ -332,6 +345,7 @@ typedef struct {
   void *main_stream, *side_stream, *compute_stream;
   void *ev_fork_pool, *ev_pooled_cur, *ev_pooled_next, *ev_fork, *ev_join;
   const float* k_next; float* xpart_next; int pool_ctas;
+  int next_binned;     /* pool k_next with ltm_pool_bins (the call that consumes it must set args.binned) */
 } ltm_overlap;
 int ltm_rect_step_overlap(const ltm_rect_step_args* a, const ltm_overlap* o, const float* q, const double* u,
                           const uint8_t* new_doc, float* ctx);

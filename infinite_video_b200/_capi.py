@@ -55,6 +55,8 @@ class RectStepArgs(C.Structure):
         ("KV_past", C.c_void_p), ("jf", C.c_int), ("proj_precision", C.c_int), ("video_block", C.c_int),
         ("attn_part", C.c_void_p),
         ("kv_half", C.c_int), ("X16", C.c_void_p),
+        ("binned", C.c_int), ("xb_rows", C.c_int),
+        ("fbin_ptr", C.c_void_p), ("seg_ptr1b", C.c_void_p), ("seg_mem1b", C.c_void_p),
     ]
 
 
@@ -64,6 +66,7 @@ class Overlap(C.Structure):
         ("ev_fork_pool", C.c_void_p), ("ev_pooled_cur", C.c_void_p), ("ev_pooled_next", C.c_void_p),
         ("ev_fork", C.c_void_p), ("ev_join", C.c_void_p),
         ("k_next", C.c_void_p), ("xpart_next", C.c_void_p), ("pool_ctas", C.c_int),
+        ("next_binned", C.c_int),
     ]
 
 
@@ -74,6 +77,7 @@ _SIGS = {
     "ltm_device_check": (C.c_int, []),
     "ltm_pool_mean": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_pool_mean_convert": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "ltm_pool_bins": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_pool_mean_16": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_pool_mean_grid": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ltm_sticky_hist_rect": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),

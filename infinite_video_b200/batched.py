@@ -102,10 +102,17 @@ class BatchedRectLTM(_BatchedBase):
     def __init__(self, num_basis, tau, w_key, b_key, w_value, b_value, *, n_heads=12, head_size=64,
                  tokens_per_frame=32, sticky=True, nb_samples=tables.NB_SAMPLES, precision="tf32",
                  device="cuda", keep_scores=False, fast_attn=True, tc_attn=True,
-                 proj_operands="fp16", kv_state=True, proj_precision=None, spacing="linear", kv_dtype="fp16"):
+                 proj_operands="fp16", kv_state=True, proj_precision=None, spacing="linear", kv_dtype="fp16",
+                 bin_pool=None):
         super().__init__(num_basis, tau, w_key, b_key, w_value, b_value, n_heads, head_size, sticky, nb_samples,
                          precision, device)
         self.T = int(tokens_per_frame)
+        # frame pooling folded with the regression of update chunks (csrc/pool.cu: pool_bins_kernel): the pooling
+        # kernel writes one row per basis bin (the sum of the pooled frames that fall into it) instead of one per
+        # frame.  None: when it pays (several frames per bin, enough (video, bin) pairs to fill the GPU); True: whenever
+        # the tables allow it; False: never.  Applies where this engine pools the chunk itself (`step` without
+        # `pooled=`, `prefetch(update=True)`, `step_overlapped`).
+        self.bin_pool = bin_pool
         self.spacing = spacing        # first-chunk frame positions: 'linear' | 'log' (gibbs:101-127)
         self.keep_scores = keep_scores
         # transposed-key attention path (num_basis 64/128/256, head size 64); `fast_attn=False` forces the generic one
@@ -166,9 +173,15 @@ class BatchedRectLTM(_BatchedBase):
             splits = self._splits(units)
             f32 = dict(device=dev, dtype=torch.float32)
             i32 = dict(device=dev, dtype=torch.int32)
+            # pooled-frame buffers: [Bv, L, splits, e] per-frame partial means, or -- same storage -- [Bv, rows, e]
+            # per-bin sums (xtag[i]: what buffer i currently holds)
+            xrows = max(L * splits, self.N)
+            xbufs = [torch.empty(Bv * xrows * self.e, **f32) for _ in range(2)]
             ws = dict(
                 splits=splits,
-                xparts=[torch.empty(Bv, L, splits, self.e, **f32), torch.empty(Bv, L, splits, self.e, **f32)],
+                xbufs=xbufs,
+                xparts=[b[:Bv * L * splits * self.e].view(Bv, L, splits, self.e) for b in xbufs],
+                xtag=[False, False],
                 xi=0,
                 KVs=[torch.empty(Bv, self.N, 2 * self.D, device=dev,
                                  dtype=torch.float16 if self.kv_half else torch.float32)
@@ -195,6 +208,14 @@ class BatchedRectLTM(_BatchedBase):
         want = 4 * 8 * self.sm_count
         # (at most T/8 splits: the partial sums are written and read back, T/splits rows of input per row of output)
         return 1 if units >= want else max(1, min(max(1, self.T // 8), -(-want // units)))
+
+    def _bin_ok(self, Bv, L, tab):
+        """Whether an update chunk of this shape is pooled per bin (see `bin_pool`)."""
+        if self.bin_pool is False or tab.xb_rows <= 0:
+            return False
+        if self.bin_pool:
+            return True
+        return L >= 2 * tab.xb_rows and Bv * tab.xb_rows >= 4 * 8 * self.sm_count
 
     def reset(self):
         """Forget every video (new_doc for all) and every pending prefetch."""
@@ -253,7 +274,8 @@ class BatchedRectLTM(_BatchedBase):
         a.video_block = int(self.video_block)
         a.B_past = self._B[self._cur].data_ptr() if self.has_state else None
         a.B_new = self._B[1 - self._cur].data_ptr()
-        a.xpart = ws["xparts"][ws["xi"]].data_ptr()
+        a.xpart = ws["xbufs"][ws["xi"]].data_ptr()
+        a.binned = 1 if ws["xtag"][ws["xi"]] else 0
         if ws["KVs"] is not None and len(ws["KVs"]) == 2:      # K|V ping-pong, in phase with the coefficient buffers
             a.KV = ws["KVs"][1 - self._cur].data_ptr()
             a.KV_past = ws["KVs"][self._cur].data_ptr() if (self.has_state and ws.get("kv_valid")) else None
@@ -288,7 +310,11 @@ class BatchedRectLTM(_BatchedBase):
         a.B_past = self._B[self._cur].data_ptr() if self.has_state else None
         a.B_new = self._B[1 - self._cur].data_ptr()
         a.hist_part = self._hist.data_ptr()
-        a.xpart = ws["xparts"][ws["xi"]].data_ptr()
+        a.xpart = ws["xbufs"][ws["xi"]].data_ptr()
+        if tab.xb_rows > 0:
+            a.xb_rows = tab.xb_rows
+            a.fbin_ptr, a.seg_ptr1b, a.seg_mem1b = (tdev["fbin_ptr"].data_ptr(), tdev["seg_ptr1b"].data_ptr(),
+                                                    tdev["seg_mem1b"].data_ptr())
         a.KV = ws["KVs"][0].data_ptr() if ws["KVs"] is not None else None
         a.KV_past = None
         a.jf = tab.jf
@@ -330,8 +356,12 @@ class BatchedRectLTM(_BatchedBase):
         tab = tables.rect_tables(L, self.N, self.tau, self.S, spacing=self.spacing)
         return Bv, L, Q, tab, tab.to(self.device), flags
 
-    def _finish(self, ws, xp=None):
-        self._last_xpart = xp if xp is not None else ws["xparts"][ws["xi"]]
+    def _finish(self, ws, xp=None, k=None):
+        # pooled frames of this call (for `x_past`); a call that pooled per bin keeps a weak reference to the chunk
+        # instead and pools it again on demand
+        binned = xp is None and ws["xtag"][ws["xi"]]
+        self._last_xpart = xp if xp is not None else (None if binned else ws["xparts"][ws["xi"]])
+        self._last_k = weakref.ref(k) if (binned and k is not None) else None
         self._last_updated = self.has_state          # False: the call just made was a first chunk
         self._cur = 1 - self._cur
         self.has_state = True
@@ -344,8 +374,10 @@ class BatchedRectLTM(_BatchedBase):
         self.last = dict(b=ws["b_draw"], ts=ws["ts"], idx=ws["idx"], p=ws["p"], scores=ws["scores"], V=V, KV=kv)
 
     @_on_device
-    def prefetch(self, k_next, Q, events=None):
+    def prefetch(self, k_next, Q, events=None, update=False):
         """Pool the frames of the NEXT chunk now, on a side stream, into the alternate buffer.
+        `update=True`: the chunk will continue every video (no new_doc), so it may be pooled per bin (`bin_pool`); a
+        step that turns out to start a new document pools it again.
 
         Frame pooling (gibbs:304) does not depend on the memory state, and it is the HBM-bound 93 % of a
         call's bytes, while regression / projection / attention of the current chunk are compute-bound; issuing
@@ -377,13 +409,19 @@ class BatchedRectLTM(_BatchedBase):
         k_next.record_stream(self._side)
         if events is not None:
             check(lib().ltm_event_record(events[0], sp), "event_record")
-        check(lib().ltm_pool_mean_grid(ptr(k_next), ptr(ws["xparts"][b]), Bv, L, self.T, self.e, ws["splits"],
-                                       int(self.pool_ctas), sp), "pool_mean")
+        tab = tables.rect_tables(L, self.N, self.tau, self.S, spacing=self.spacing)
+        binned = bool(update) and self._bin_ok(Bv, L, tab)
+        if binned:
+            check(lib().ltm_pool_bins(ptr(k_next), ptr(ws["xbufs"][b]), ptr(tab.to(self.device)["fbin_ptr"]), Bv, L,
+                                      self.T, self.e, tab.xb_rows, sp), "pool_bins")
+        else:
+            check(lib().ltm_pool_mean_grid(ptr(k_next), ptr(ws["xbufs"][b]), Bv, L, self.T, self.e, ws["splits"],
+                                           int(self.pool_ctas), sp), "pool_mean")
         if events is not None:
             check(lib().ltm_event_record(events[1], sp), "event_record")
         check(lib().ltm_event_record(ev["pooled"][b], sp), "event_record")
         self._pref.append(dict(ref=weakref.ref(k_next), ver=k_next._version, buf=b, event=ev["pooled"][b],
-                               captured=torch.cuda.is_current_stream_capturing()))
+                               captured=torch.cuda.is_current_stream_capturing(), binned=binned))
 
     def _sync_events(self):
         if self._evs is None:
@@ -399,6 +437,12 @@ class BatchedRectLTM(_BatchedBase):
         """[Bv, e, S+L] ([Bv, e, L] after a first chunk): what the reference keeps as `x_past` (gibbs:215,221) -- the
         re-sampled rows of the previous coefficients followed by the pooled frames of the most recent call."""
         xp = self._last_xpart
+        if xp is None:                      # the last call pooled per bin: pool the chunk again, per frame
+            k = self._last_k() if getattr(self, "_last_k", None) is not None else None
+            if k is None:
+                raise RuntimeError("x_past: the frames of the last chunk were pooled per bin and the chunk tensor is "
+                                   "gone; construct the engine with bin_pool=False to keep them")
+            xp = self.pool(k)
         x = xp.sum(2) if xp.shape[2] > 1 else xp[:, :, 0]                                              # [Bv,L,e]
         if not self._last_updated:
             return x.transpose(1, 2)
@@ -460,7 +504,7 @@ class BatchedRectLTM(_BatchedBase):
                 u = u.contiguous()
             ctx = torch.empty(Bv, Q, self.D, device=self.device, dtype=torch.float32)
             a = self._args(Bv, L, Q, ws, tab, tdev)
-            a.xpart, a.splits = pooled.data_ptr(), pooled.shape[2]
+            a.xpart, a.splits, a.binned = pooled.data_ptr(), pooled.shape[2], 0
             check(lib().ltm_rect_step(C.byref(a), None, ptr(q), ptr(u), ptr(flags), ptr(ctx),
                                       stream_ptr(self.device)), "rect_step")
             self._finish(ws, pooled)
@@ -471,11 +515,15 @@ class BatchedRectLTM(_BatchedBase):
             u = u.contiguous()
         ctx = torch.empty(Bv, Q, self.D, device=self.device, dtype=torch.float32)
         hit = self._pref_take(k)
+        update = self.has_state and flags is None       # every video continues: per-bin pooling is possible
+        if hit is not None and hit["binned"] and not update:
+            hit = None                                   # pooled per bin for an update that did not come: pool again
         pooled = hit is not None
         main = torch.cuda.current_stream(self.device)
         run = main
         if pooled:
             ws["xi"] = hit["buf"]
+            ws["xtag"][hit["buf"]] = hit["binned"]
             run = self._compute                      # fork: high-priority compute stream, joined below
             ev = self._sync_events()
             rp, mp = C.c_void_p(run.cuda_stream), C.c_void_p(main.cuda_stream)
@@ -490,22 +538,24 @@ class BatchedRectLTM(_BatchedBase):
             ws["xi"] = (1 - ws["xi"]) if (1 - ws["xi"]) not in held else ws["xi"]
             if ws["xi"] in held:
                 self._pref[:] = [e for e in self._pref if e["buf"] != ws["xi"]]
+            ws["xtag"][ws["xi"]] = update and self._bin_ok(Bv, L, tab)
         a = self._args(Bv, L, Q, ws, tab, tdev)
         check(lib().ltm_rect_step(C.byref(a), None if pooled else ptr(k), ptr(q), ptr(u), ptr(flags), ptr(ctx),
                                   C.c_void_p(run.cuda_stream)), "rect_step")
         if pooled:
             check(lib().ltm_event_record(ev["join"], rp), "event_record")
             check(lib().ltm_stream_wait_event(mp, ev["join"]), "stream_wait_event")
-        self._finish(ws)
+        self._finish(ws, k=k)
         return ctx
 
     @_on_device
-    def step_overlapped(self, k, q, u=None, new_doc=False, k_next=None):
+    def step_overlapped(self, k, q, u=None, new_doc=False, k_next=None, next_new_doc=False):
         """`step(k, ...)` with the frame pooling of `k_next` issued beside it, in ONE library call
         (`ltm_rect_step_overlap`: side stream pools the next chunk, a high-priority stream runs this chunk's
         regression / projection / attention, the current stream joins both).  `k` must be the tensor handed over as
         `k_next` by the previous call (or to `prefetch`); the first chunk of a stream is pooled here.  Same results as
-        `step`, bit for bit."""
+        `step`, bit for bit.  `next_new_doc=True` says that `k_next` will start new documents (then it is pooled per
+        frame; a chunk expected to continue the videos may be pooled per bin, see `bin_pool`)."""
         require_cuda(k, q, u, k_next)
         if k.dtype != torch.float32 or q.dtype != torch.float32 or (k_next is not None and k_next.dtype != torch.float32):
             raise ValueError("step_overlapped takes float32 tensors")
@@ -517,13 +567,17 @@ class BatchedRectLTM(_BatchedBase):
                 raise ValueError(f"sticky re-sampling needs u: float64 [{Bv},{self.S}]")
             u = u.contiguous()
         hit = self._pref_take(k)
+        update = self.has_state and flags is None
+        if hit is not None and hit["binned"] and not update:
+            hit = None                                   # pooled per bin for an update that did not come: pool again
         if hit is None:
-            self.prefetch(k, Q)
+            self.prefetch(k, Q, update=update)
             hit = self._pref_take(k)
         ev = self._sync_events()
         main = torch.cuda.current_stream(self.device)
         capturing = torch.cuda.is_current_stream_capturing()
         ws["xi"] = hit["buf"]
+        ws["xtag"][hit["buf"]] = hit["binned"]
         o = Overlap()
         o.main_stream, o.side_stream, o.compute_stream = main.cuda_stream, self._side.cuda_stream, self._compute.cuda_stream
         o.ev_fork, o.ev_join = ev["fork"], ev["join"]
@@ -533,16 +587,17 @@ class BatchedRectLTM(_BatchedBase):
             if not k_next.is_contiguous() or tuple(k_next.shape) != tuple(k.shape):
                 raise ValueError("k_next must be contiguous and have the shape of k")
             b = self._pref_buffer(ws)
-            o.k_next, o.xpart_next = k_next.data_ptr(), ws["xparts"][b].data_ptr()
+            nb = (not next_new_doc) and self._bin_ok(Bv, L, tab)
+            o.k_next, o.xpart_next, o.next_binned = k_next.data_ptr(), ws["xbufs"][b].data_ptr(), int(nb)
             o.ev_fork_pool, o.ev_pooled_next = ev["fork_pool"][b], ev["pooled"][b]
             k_next.record_stream(self._side)
             self._pref.append(dict(ref=weakref.ref(k_next), ver=k_next._version, buf=b, event=ev["pooled"][b],
-                                   captured=capturing))
+                                   captured=capturing, binned=nb))
         ctx = torch.empty(Bv, Q, self.D, device=self.device, dtype=torch.float32)   # main joins the compute stream
         a = self._args(Bv, L, Q, ws, tab, tdev)
         check(lib().ltm_rect_step_overlap(C.byref(a), C.byref(o), ptr(q), ptr(u), ptr(flags), ptr(ctx)),
               "rect_step_overlap")
-        self._finish(ws)
+        self._finish(ws, k=k)
         return ctx
 
     @_on_device
@@ -568,6 +623,7 @@ class BatchedRectLTM(_BatchedBase):
             raise ValueError(f"sticky re-sampling needs u_host: float64 [{Bv},{self.S}]")
         if k_host.dtype != torch.float32 or q_host.dtype != torch.float32:
             raise ValueError("step_host takes float32 k and q")
+        ws["xtag"][ws["xi"]] = False          # the host path pools per frame
         a = self._args(Bv, L, Q, ws, tab, tdev)
         nd_host = None
         if flags is not None:

@@ -56,13 +56,23 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
   cudaStream_t st_ = (cudaStream_t)stream;
 #define LTM_PROF(i) do { if (a->prof_events[i]) cudaEventRecord((cudaEvent_t)a->prof_events[i], st_); } while (0)
   int rc = 0;
+  const float* B_past = a->B_past;
+  // binned: a->xpart carries per-bin sums of the pooled frames (ltm_pool_bins) and the update tables list bins
+  const bool binned = a->binned != 0;
+  if (binned) {
+    LTM_REQUIRE(B_past != nullptr && new_doc == nullptr, "rect_step: bin sums only exist for update calls of all videos");
+    LTM_REQUIRE(a->xb_rows > 0 && a->fbin_ptr && a->seg_ptr1b && a->seg_mem1b, "rect_step: binned tables missing");
+  }
   if (k != nullptr) {          // k == NULL: a->xpart was already filled (frame pooling is stateless and may be
     LTM_PROF(0);               // issued ahead of time on another stream, see BatchedRectLTM.prefetch)
-    rc = ltm_pool_mean(k, a->xpart, a->Bv, a->L, a->T, a->e, a->splits, stream);
+    rc = binned ? ltm_pool_bins(k, a->xpart, a->fbin_ptr, a->Bv, a->L, a->T, a->e, a->xb_rows, stream)
+                : ltm_pool_mean(k, a->xpart, a->Bv, a->L, a->T, a->e, a->splits, stream);
     if (rc) return rc;
     LTM_PROF(1);
   }
-  const float* B_past = a->B_past;
+  const int xL = binned ? a->xb_rows : a->L, xsplits = binned ? 1 : a->splits;
+  const int32_t* seg_ptr1 = binned ? a->seg_ptr1b : a->seg_ptr1;
+  const int32_t* seg_mem1 = binned ? a->seg_mem1b : a->seg_mem1;
   const int32_t* idx = a->idx_uniform;     // non-sticky: fixed table shared by all videos (index stride 0)
   long long idx_stride = 0;
   if (B_past != nullptr && a->sticky) {
@@ -102,7 +112,7 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
   // block has just written are still in L2 when its attention (projection) reads them: with all videos per kernel
   // the 201 MB of K|V at 128 videos go out to HBM and come back.  video_block: 0 = all videos in one block.
   int vblock = (a->video_block > 0 && a->video_block < a->Bv && !fast) ? a->video_block : a->Bv;
-  const size_t sB = (size_t)a->N * a->e, sKV = (size_t)a->N * 2 * D, sX = (size_t)a->L * a->splits * a->e;
+  const size_t sB = (size_t)a->N * a->e, sKV = (size_t)a->N * 2 * D, sX = (size_t)xL * xsplits * a->e;
   const bool blocked = vblock < a->Bv;
   if (blocked) LTM_PROF(4);
   for (int v0 = 0; v0 < a->Bv; v0 += vblock) {
@@ -116,9 +126,9 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
     void* Bh = half_ops ? (void*)((uint16_t*)a->B_half + v0 * sB) : nullptr;
     if (!blocked) LTM_PROF(4);
     rc = ltm_consolidate_rect_kv(Bp, a->xpart + v0 * sX, idx_stride ? idx + (size_t)v0 * idx_stride : idx, idx_stride,
-                                 new_doc ? new_doc + v0 : nullptr, a->seg_ptr0, a->seg_mem0, a->g0, a->seg_ptr1,
-                                 a->seg_mem1, a->g1, Bn, Bh, KVp, KVn, a->bkv, 2 * D, jg, kvh ? 2 : (tcp ? 1 : 0), nv, a->N,
-                                 a->e, a->L, a->splits, a->S, stream);
+                                 new_doc ? new_doc + v0 : nullptr, a->seg_ptr0, a->seg_mem0, a->g0, seg_ptr1,
+                                 seg_mem1, a->g1, Bn, Bh, KVp, KVn, a->bkv, 2 * D, jg, kvh ? 2 : (tcp ? 1 : 0), nv, a->N,
+                                 a->e, xL, xsplits, a->S, stream);
     if (rc) return rc;
     if (!blocked) { LTM_PROF(5); LTM_PROF(6); }
     if (kvstate) {
@@ -262,7 +272,9 @@ extern "C" int ltm_rect_step_overlap(const ltm_rect_step_args* a, const ltm_over
     LTM_CUDA(cudaStreamWaitEvent(ss, (cudaEvent_t)o->ev_fork_pool, 0));
     LTM_OV_MARK(0);
     if (a->prof_events[0]) cudaEventRecord((cudaEvent_t)a->prof_events[0], ss);
-    int rc = ltm_pool_mean_grid(o->k_next, o->xpart_next, a->Bv, a->L, a->T, a->e, a->splits, o->pool_ctas, ss);
+    int rc = o->next_binned
+                 ? ltm_pool_bins(o->k_next, o->xpart_next, a->fbin_ptr, a->Bv, a->L, a->T, a->e, a->xb_rows, ss)
+                 : ltm_pool_mean_grid(o->k_next, o->xpart_next, a->Bv, a->L, a->T, a->e, a->splits, o->pool_ctas, ss);
     if (rc) return rc;
     if (a->prof_events[1]) cudaEventRecord((cudaEvent_t)a->prof_events[1], ss);
     LTM_OV_MARK(1);

@@ -17,6 +17,29 @@ namespace ltm {
 constexpr int POOL_UNROLL = 8;
 constexpr int POOL_ACC = 2;
 
+// Sum of the token rows [r0, r1) of one frame for the 128-bit column group c: 8 independent 128-bit loads in flight,
+// folded into two accumulators (the register file is what limits how many of these CTAs fit next to the
+// compute-bound kernels of the other stream: 44 registers -> 7 per SM).  Every pooling kernel goes through this
+// function, so the summation order -- and with it every bit of the pooled frame -- is the same in all of them.
+__device__ __forceinline__ float4 pool_rows(const float4* __restrict__ base, int r0, int r1, int e4, int c,
+                                            uint64_t pol) {
+  float4 acc[POOL_ACC];
+#pragma unroll
+  for (int i = 0; i < POOL_ACC; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int r = r0;
+  for (; r + POOL_UNROLL <= r1; r += POOL_UNROLL) {
+    float4 v[POOL_UNROLL];
+#pragma unroll
+    for (int i = 0; i < POOL_UNROLL; ++i) v[i] = ldg_stream(base + (size_t)(r + i) * e4 + c, pol);
+#pragma unroll
+    for (int i = 0; i < POOL_UNROLL; ++i) f4_add(acc[i % POOL_ACC], v[i]);
+  }
+  for (; r < r1; ++r) f4_add(acc[0], ldg_stream(base + (size_t)r * e4 + c, pol));
+#pragma unroll
+  for (int i = 1; i < POOL_ACC; ++i) f4_add(acc[0], acc[i]);
+  return acc[0];
+}
+
 // One (frame, token-split) work item: the threads of the CTA each own 128-bit column groups.
 __device__ __forceinline__ void pool_unit(const float4* __restrict__ k, float4* __restrict__ xpart, int T, int e4,
                                           int splits, float Tf, unsigned work, uint64_t pol) {
@@ -26,28 +49,39 @@ __device__ __forceinline__ void pool_unit(const float4* __restrict__ k, float4* 
   const int r1 = (int)(((long long)T * (sp + 1)) / splits);
   const float4* base = k + (size_t)unit * T * e4;
   for (int c = threadIdx.x; c < e4; c += blockDim.x) {
-    // 8 independent 128-bit loads in flight, folded into two accumulators: the register file is what limits how
-    // many of these CTAs fit next to the compute-bound kernels of the other stream (44 registers -> 7 per SM)
-    float4 acc[POOL_ACC];
-#pragma unroll
-    for (int i = 0; i < POOL_ACC; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    int r = r0;
-    for (; r + POOL_UNROLL <= r1; r += POOL_UNROLL) {
-      float4 v[POOL_UNROLL];
-#pragma unroll
-      for (int i = 0; i < POOL_UNROLL; ++i) v[i] = ldg_stream(base + (size_t)(r + i) * e4 + c, pol);
-#pragma unroll
-      for (int i = 0; i < POOL_UNROLL; ++i) f4_add(acc[i % POOL_ACC], v[i]);
-    }
-    for (; r < r1; ++r) f4_add(acc[0], ldg_stream(base + (size_t)r * e4 + c, pol));
-#pragma unroll
-    for (int i = 1; i < POOL_ACC; ++i) f4_add(acc[0], acc[i]);
-    float4 o = acc[0];
+    float4 o = pool_rows(base, r0, r1, e4, c, pol);
     // torch.mean == sum / T (true division, so T = 196 rounds like the reference).  With splits > 1 (small batches
     // only) every partial sum is divided -- and rounded -- on its own and the consumer adds the partial means: the
     // pooled frame then differs from sum / T by up to `splits` ulp (1e-7 relative; the coefficient tolerance is 1e-5).
     o.x = __fdiv_rn(o.x, Tf); o.y = __fdiv_rn(o.y, Tf); o.z = __fdiv_rn(o.z, Tf); o.w = __fdiv_rn(o.w, Tf);
     xpart[((size_t)unit * splits + sp) * e4 + c] = o;
+  }
+}
+
+// Frame pooling folded with the first half of the regression ("bin sums instead of xpart"): the frames of
+// an update chunk that fall into the same basis bin are consecutive (tables.py: fbin_ptr), and the consolidation only
+// ever needs their sum, so one CTA per (video, bin) pools its frames one after the other -- each exactly like
+// pool_unit with splits == 1 -- and writes the running sum of the frame means: xbin[v, r, :] = sum_f mean_t k[v,f,t,:].
+// At the NExT-QA shape that is 64 rows per video instead of 256 (0.2 instead of 0.8 MB written and read back).
+// (Measured alternatives: FP = 2..4 frames of a bin side by side in one CTA of FP x 192 threads, frame means staged in
+// shared memory.  Alone on the GPU that is the fastest pooling kernel of all -- 0.4645 ms for 3.2 GB at FP = 4 -- but
+// next to the other stream's kernels its large CTAs lose: 188.6 k chunks/s at FP = 4, 192.9 k at FP = 2, against
+// 194.4 k for this one-frame-at-a-time form, whose CTAs hold 7.7 k registers each and leave room sooner.)
+__global__ void __launch_bounds__(256)
+pool_bins_kernel(const float4* __restrict__ k, float4* __restrict__ xbin, const int32_t* __restrict__ fbin_ptr,
+                 int L, int T, int e4, int rows, float Tf) {
+  const uint64_t pol = policy_evict_first();
+  const int r = blockIdx.x, v = blockIdx.y;
+  const int f0 = fbin_ptr[r], f1 = fbin_ptr[r + 1];
+  const float4* kv = k + (size_t)v * L * T * e4;
+  for (int c = threadIdx.x; c < e4; c += blockDim.x) {
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int f = f0; f < f1; ++f) {
+      float4 o = pool_rows(kv + (size_t)f * T * e4, 0, T, e4, c, pol);
+      o.x = __fdiv_rn(o.x, Tf); o.y = __fdiv_rn(o.y, Tf); o.z = __fdiv_rn(o.z, Tf); o.w = __fdiv_rn(o.w, Tf);
+      f4_add(sum, o);
+    }
+    xbin[((size_t)v * rows + r) * e4 + c] = sum;
   }
 }
 
@@ -231,6 +265,21 @@ extern "C" int ltm_pool_mean_grid(const float* k, float* xpart, int Bv, int L, i
         reinterpret_cast<const float4*>(k), reinterpret_cast<float4*>(xpart), T, e4, splits, (float)T);
   }
   LTM_CHECK_LAUNCH("pool_mean");
+  return 0;
+}
+
+extern "C" int ltm_pool_bins(const float* k, float* xbin, const int32_t* fbin_ptr, int Bv, int L, int T, int e, int rows,
+                             void* stream) {
+  using namespace ltm;
+  LTM_REQUIRE(k && xbin && fbin_ptr, "pool_bins: null pointer");
+  LTM_REQUIRE(Bv > 0 && Bv <= 65535 && L > 0 && T > 0 && e > 0 && e % 4 == 0 && rows > 0,
+              "pool_bins: bad shape Bv=%d L=%d T=%d e=%d rows=%d", Bv, L, T, e, rows);
+  LTM_REQUIRE(aligned16(k) && aligned16(xbin), "pool_bins: pointers must be 16-byte aligned");
+  const int e4 = e / 4;
+  const int threads = e4 >= 256 ? 256 : ((e4 + 31) / 32) * 32;
+  pool_bins_kernel<<<dim3(rows, Bv), threads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(k), reinterpret_cast<float4*>(xbin), fbin_ptr, L, T, e4, rows, (float)T);
+  LTM_CHECK_LAUNCH("pool_bins");
   return 0;
 }
 

@@ -56,6 +56,17 @@ def pool_mean_convert(k, splits=1):
     return out, k16
 
 
+def pool_bins(k, fbin_ptr, rows):
+    """Per-bin pooling of an update chunk: k[Bv,L,T,e] fp32, fbin_ptr int32 [rows+1] -> xbin[Bv,rows,e], the sum of the
+    pooled frames [fbin_ptr[r], fbin_ptr[r+1]) (tables.RectTables.fbin_ptr)."""
+    require_cuda(k, fbin_ptr)
+    k = _f32c(k)
+    Bv, L, T, e = k.shape
+    out = torch.empty(Bv, rows, e, device=k.device, dtype=torch.float32)
+    check(lib().ltm_pool_bins(ptr(k), ptr(out), ptr(fbin_ptr), Bv, L, T, e, rows, stream_ptr(k.device)), "pool_bins")
+    return out
+
+
 def consolidate_rect_kv(B_past, xpart, idx, tab, S, KV_past, bkv, jf, round_tf32=False, new_doc=None):
     """`consolidate_rect` that also carries the projected memory K|V along: rows j < jf of KV_new are the segmented
     mean of KV_past rows (+ bias term); rows >= jf are left untouched for the projection GEMM.  idx: [Bv,S] or [S]

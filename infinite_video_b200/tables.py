@@ -127,6 +127,13 @@ class RectTables:
     g1: np.ndarray = None            # fp32  [N]
     jf: int = 0                      # first bin of the update tables that holds a new frame (bins below it hold
                                      # re-sampled memory only: their K|V follow from the previous K|V, consolidate.cu)
+    # update tables with the new frames folded per bin (csrc/pool.cu: pool_bins_kernel): the frames of bin xb_row0 + r
+    # are the consecutive frames [fbin_ptr[r], fbin_ptr[r+1]) and enter seg_mem1b as ONE member, id S + r
+    xb_row0: int = 0
+    xb_rows: int = 0                 # 0: the frames of some bin are not consecutive -> no folding
+    fbin_ptr: np.ndarray = None      # int32 [xb_rows+1]
+    seg_ptr1b: np.ndarray = None     # int32 [N+1]
+    seg_mem1b: np.ndarray = None     # int32 [nnz1b]  p < S: sample p ; p >= S: bin sum p-S
     # sticky histogram (129 nudged edges) and sampling
     tb: np.ndarray = None            # fp32 [129] evaluation edges
     jb: np.ndarray = None            # int32 [129] basis index at each edge (-1 none)
@@ -152,6 +159,8 @@ class RectTables:
             for name in ("seg_ptr0", "seg_mem0", "g0", "seg_ptr1", "seg_mem1", "g1", "tb", "jb", "bins",
                          "bin2basis", "W", "idx_uniform", "jd", "wd"):
                 d[name] = torch.from_numpy(getattr(self, name)).to(device)
+            for name in ("fbin_ptr", "seg_ptr1b", "seg_mem1b"):
+                d[name] = torch.from_numpy(getattr(self, name)).to(device) if self.xb_rows > 0 else None
             d["X"] = torch.from_numpy(self.X).to(device) if self.X is not None else None
             d["X16"] = torch.from_numpy(self.X16).to(device) if self.X16 is not None else None
             self._dev[key] = d
@@ -169,6 +178,44 @@ class RectTables:
         for j in range(self.N):
             G[self.seg_mem1[self.seg_ptr1[j]:self.seg_ptr1[j + 1]], j] = self.g1[j]
         return G
+
+
+def _fold_frames(t, fb):
+    """Update tables with the new frames folded per bin.  fb[f] = bin of frame f (-1: outside every basis).  Possible
+    when the frames of the bins [jf, N) are consecutive runs that follow each other without a gap (they are whenever the
+    frame positions increase, i.e. for both spacings of the reference); the members of a bin keep their order: samples
+    first, then the bin sum."""
+    S, N = t.S, t.N
+    if t.jf >= N:
+        return
+    rows = N - t.jf
+    ptr = np.zeros(rows + 1, np.int64)
+    seg_ptr, seg_mem = [0], []
+    end = None                                   # one past the last frame folded so far
+    for j in range(N):
+        mem = t.seg_mem1[t.seg_ptr1[j]:t.seg_ptr1[j + 1]]
+        fr = mem[mem >= S] - S
+        seg_mem.extend(int(m) for m in mem[mem < S])
+        if fr.size:
+            if j < t.jf or not np.array_equal(fr, np.arange(fr[0], fr[0] + fr.size)):
+                return
+            if end is None:
+                ptr[:j - t.jf + 1] = int(fr[0])
+            elif int(fr[0]) != end:
+                return                           # a gap (frames outside every basis) between two bins
+            end = int(fr[0]) + fr.size
+            seg_mem.append(S + (j - t.jf))
+        if j >= t.jf and end is not None:
+            ptr[j - t.jf + 1] = end
+        seg_ptr.append(len(seg_mem))
+    covered = np.zeros(fb.shape[0], bool)
+    covered[ptr[0]:ptr[-1]] = True
+    if end is None or not np.array_equal(covered, fb >= 0):
+        return
+    t.xb_row0, t.xb_rows = t.jf, rows
+    t.fbin_ptr = ptr.astype(np.int32)
+    t.seg_ptr1b = np.asarray(seg_ptr, np.int32)
+    t.seg_mem1b = np.asarray(seg_mem, np.int32)
 
 
 @lru_cache(maxsize=64)
@@ -197,6 +244,7 @@ def rect_tables(L: int, N: int, tau: float, S: int = NB_SAMPLES, num_quad: int =
     t.g1 = (1.0 / (torch.from_numpy(cnt1).float() + ridge)).numpy()
     fb = core1[S:]
     t.jf = int(fb[fb >= 0].min()) if (fb >= 0).any() else N
+    _fold_frames(t, fb)
 
     # --- sticky edges (gibbs:163,:197-199,:207-208)
     bins, nudged = sticky_edges()

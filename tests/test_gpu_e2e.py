@@ -455,6 +455,41 @@ def test_prefetched_pooling_is_bit_identical(dev):
         assert torch.equal(a.B_past, b.B_past)
 
 
+@pytest.mark.parametrize("N,L,Bv", [(256, 64, 3), (256, 256, 2), (512, 256, 2), (64, 8, 2)])
+def test_per_bin_pooling_matches_per_frame_pooling(dev, N, L, Bv):
+    """`bin_pool=True` (frames of an update chunk pooled per basis bin, csrc/pool.cu) against `bin_pool=False`: bins
+    with frames only are bit-identical, a bin that mixes re-sampled memory and frames adds them in another order
+    (1 ulp); through `step`, `prefetch(update=True)` + `step`, `step_overlapped`, and a chunk that was pooled per bin
+    but then starts a new document (pooled again per frame)."""
+    from infinite_video_b200.batched import BatchedRectLTM
+    key, val = make_proj(67, 768)
+    mk = lambda bp: BatchedRectLTM(N, .75, *proj_tensors(key, val), device=dev, bin_pool=bp)
+    a, b, c, d = mk(False), mk(True), mk(True), mk(True)
+    C = 5
+    ks, qs, us = make_inputs(68, C, Bv, L * 32, 768, 32)
+    ks = [k.to(dev) for k in ks]
+    qs = [q.to(dev) for q in qs]
+    us = [u.to(dev) for u in us]
+    firsts = [True, False, False, True, False]                        # chunk 3 starts a new document
+    for i in range(C):
+        u = None if firsts[i] else us[i]
+        x = a.step(ks[i], qs[i], u, new_doc=firsts[i])
+        y = b.step(ks[i], qs[i], u, new_doc=firsts[i])
+        if i + 1 < C:
+            c.prefetch(ks[i + 1], 32, update=True)                    # wrong guess for chunk 3: pooled again
+        z = c.step(ks[i], qs[i], u, new_doc=firsts[i])
+        w = d.step_overlapped(ks[i], qs[i], u, new_doc=firsts[i], k_next=ks[i + 1] if i + 1 < C else None,
+                              next_new_doc=(i + 1 < C and firsts[i + 1] and i != 2))   # i == 2: wrong hint on purpose
+        for other in (b, c, d):
+            assert relerr(other.B_past, a.B_past) < 1e-6, i
+            assert firsts[i] or torch.equal(other.last["b"], a.last["b"]), i
+        assert torch.equal(y, z) and torch.equal(y, w), i
+        assert relerr(y, x) < 1e-4, i          # a 1-ulp coefficient can round to the neighbouring fp16 key / value
+        if not firsts[i]:
+            xa, xb = a.x_past(), b.x_past()                           # the frames are pooled again on demand
+            assert torch.equal(xb[:, :, 512:], xa[:, :, 512:]) and relerr(xb, xa) < 1e-6
+
+
 def test_prefetch_bookkeeping_survives_abandoned_and_interleaved_chunks(dev):
     """Pending prefetches are keyed on tensor identity + version, never on the data pointer: an abandoned prefetch,
     a non-prefetched step in between, a recycled address or an in-place rewrite must not make a step consume stale

@@ -60,6 +60,23 @@ def test_pool_mean_convert(dev, Bv, L, T, e, splits):
     assert torch.equal(k16, k.half())
 
 
+@pytest.mark.parametrize("Bv,N,L,T,e", [(3, 256, 256, 32, 768), (2, 512, 256, 32, 768), (2, 64, 16, 196, 1024),
+                                        (2, 64, 8, 32, 768), (1, 100, 64, 9, 772), (2, 128, 256, 4, 768)])
+def test_pool_bins(dev, Bv, N, L, T, e):
+    """Per-bin pooling == summing the per-frame pooling over the frames of each bin, in frame order, bit for bit."""
+    ops, tb = _ops(), _tables()
+    t = tb.rect_tables(L, N, 0.75, 512)
+    g = torch.Generator().manual_seed(4)
+    k = (torch.randn(Bv, L, T, e, generator=g) * 2).to(dev)
+    got = ops.pool_bins(k, t.to(dev)["fbin_ptr"], t.xb_rows)
+    x = ops.pool_mean(k, 1)[:, :, 0]                                   # [Bv, L, e]
+    want = torch.zeros_like(got)
+    for r in range(t.xb_rows):
+        for f in range(int(t.fbin_ptr[r]), int(t.fbin_ptr[r + 1])):
+            want[:, r] += x[:, f]
+    assert torch.equal(got, want)
+
+
 # ---------------------------------------------------------------------------------------- R7
 @pytest.mark.parametrize("ncat,Bv,zeros,sort", [(127, 1, False, False), (127, 37, True, False),
                                                 (128, 5, False, True), (128, 4, True, True)])

@@ -104,3 +104,24 @@ def test_log_spacing_tables_equal_the_dense_operator():
         G0 = O.ridge_operator(psi, O.first_chunk_positions(L, "log"), L).numpy()
         assert np.array_equal(t.dense_G0(), G0), (N, L)
         assert not np.array_equal(t.dense_G0(), T.rect_tables(L, N, .75).dense_G0())
+
+
+@pytest.mark.parametrize("N,L,spacing", [(256, 256, "linear"), (512, 256, "linear"), (64, 8, "linear"), (64, 16, "log"),
+                                         (100, 64, "linear"), (128, 256, "log"), (64, 5, "linear")])
+def test_folded_frame_tables_expand_to_the_per_frame_tables(N, L, spacing):
+    """`fbin_ptr` / `seg_mem1b` (per-bin pooling, csrc/pool.cu) are the update tables with the frames of a bin collapsed
+    into one member: expanding them must give back `seg_mem1` member for member, in order."""
+    t = T.rect_tables(L, N, 0.75, 512, spacing=spacing)
+    assert t.xb_rows == N - t.jf and t.xb_row0 == t.jf
+    assert t.fbin_ptr.shape[0] == t.xb_rows + 1 and (np.diff(t.fbin_ptr) >= 0).all()
+    for j in range(N):
+        want = list(t.seg_mem1[t.seg_ptr1[j]:t.seg_ptr1[j + 1]])
+        got = []
+        for m in t.seg_mem1b[t.seg_ptr1b[j]:t.seg_ptr1b[j + 1]]:
+            if m < t.S:
+                got.append(int(m))
+            else:
+                r = int(m) - t.S
+                assert r == j - t.xb_row0
+                got.extend(t.S + f for f in range(t.fbin_ptr[r], t.fbin_ptr[r + 1]))
+        assert got == want, j
