@@ -591,11 +591,12 @@ def run_b200(args):
     pool_bytes = 4.0 * Bv * L * T * E                       # algorithmic bytes of the dominant kernel per launch
     from infinite_video_b200 import tables as _tables
     binned_pool = eng._bin_ok(Bv, L, _tables.rect_tables(L, NB, TAU, S))
+    # dram read + write of one launch from the `ncu --set full` captures at 32 videos, scaled per video
+    pool_traffic = ((802.18e6 + 14.36e6) if binned_pool else (805.39e6 + 7.50e6)) / 32.0 * Bv
     pool_gbs = pool_bytes / (stage_serial["pool"] * 1e-3) / 1e9 if stage_serial["pool"] > 0 else 0.0
     pool_gbs_ov = pool_bytes / (stage_avg["pool"] * 1e-3) / 1e9 if stage_avg["pool"] > 0 else 0.0
     # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/r1l_ncu_pool.txt:
     # dram__bytes_read.sum 805.32 MB + dram__bytes_write.sum 8.0 MB per launch at 32 videos), scaled per video
-    pool_traffic = (805.39e6 + 7.50e6) / 32.0 * Bv
     step_bytes = algorithmic_bytes_per_call() * Bv * C + 4 * 2 * (E * D + D)   # + weights once per launch
     ms_per_step = ms / args.steps
     step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9
@@ -738,8 +739,10 @@ def run_b200(args):
                          "achieved_isolated": pool_gbs, "frac_isolated": pool_gbs / peak,
                          "avg_launch_ms_isolated": stage_serial["pool"],
                          "isolated_measured_in": "non-overlapped timed pass of the same steps (kernel alone on the GPU)",
-                         "traffic_source": "profiles/r2b_ncu_pool_mean_kernel.txt (ncu --set full at 32 videos: "
-                                           "dram read 805.4 MB + write 7.5 MB, scaled per video)"},
+                         "traffic_source": ("profiles/r2f_ncu_pool_bins_kernel.txt (ncu --set full at 32 videos: dram "
+                                            "read 802.2 MB + write 14.4 MB, scaled per video)") if binned_pool else
+                                           ("profiles/r2b_ncu_pool_mean_kernel.txt (ncu --set full at 32 videos: "
+                                            "dram read 805.4 MB + write 7.5 MB, scaled per video)")},
             "value_sustained": sustained,
             "value_without_overlap": calls_total / (ms_serial * 1e-3),
             "value_eager_launch": value_eager, "host_enqueue_ms_per_step_eager": host_enqueue_ms,

@@ -29,6 +29,18 @@ if which in ("all", "rect"):
     eng = BatchedRectLTM(512, .75, *w, device=dev)            # num_basis 512
     for c in range(2):
         eng.step(k[c], q[c], u[c] if c else None, new_doc=(c == 0))
+if which in ("all", "bins"):
+    # per-bin pooling of update chunks (forced: 32 videos would not pick it by themselves)
+    eng = BatchedRectLTM(N, .75, *w, device=dev, bin_pool=True)
+    for c in range(3):
+        eng.step(k[c], q[c], u[c] if c else None, new_doc=(c == 0))
+if which in ("all", "caller"):
+    # caller branch (N1): pooling + fp16 copy of the chunk in one pass, fp16 GEMMs, register-resident row softmax
+    from infinite_video_b200.cross_attention import CrossAttentionLTM
+    lin = lambda: torch.nn.Linear(E, 768).to(dev)
+    mod = CrossAttentionLTM(lin(), lin(), lin(), alpha=0.9, num_basis=N, tau=.75, sticky=True, n_heads=12)
+    for c in range(2):
+        mod(q[c], k[c], new_video=(c == 0), u=u[c] if c else None)
 if which in ("all", "gauss"):
     eng = BatchedGaussLTM(N, .75, *w, device=dev)
     kg = [x.view(Bv, L, T, E)[:, :, 0].contiguous() for x in k]

@@ -2,11 +2,13 @@
 # Copies the judged evidence of a gpurun call from gpurun_out/ (scratch) into profiles/ (tracked).
 # usage: scripts/save_profiles.sh <tag>      e.g. r1c
 TAG=${1:?tag}
-mkdir -p profiles
-for f in gpurun_out/bench*.json; do [ -s "$f" ] && cp "$f" profiles/${TAG}_$(basename $f); done
-[ -f gpurun_out/launches.csv ] && python - "$TAG" <<'PY'
-import csv, collections, sys
+DEST=${DEST:-profiles}        # DEST=gpurun_out/profiles on the GPU box (only gpurun_out/ travels back, capped at 64 MiB)
+mkdir -p $DEST
+for f in gpurun_out/bench*.json; do [ -s "$f" ] && cp "$f" $DEST/${TAG}_$(basename $f); done
+[ -f gpurun_out/launches.csv ] && DEST=$DEST python - "$TAG" <<'PY'
+import csv, collections, os, sys
 tag = sys.argv[1]
+dest = os.environ.get('DEST', 'profiles')
 rows = list(csv.reader(open('gpurun_out/launches.csv', errors='replace')))
 hdr = None; agg = collections.defaultdict(list); order = []
 for r in rows:
@@ -17,8 +19,8 @@ for r in rows:
             agg[d['Kernel Name']].append(float(d['Metric Value'].replace(',', '')))
             order.append((d['ID'], d['Kernel Name'][:90], d['Metric Value'], d.get('Metric Unit', '')))
 tot = sum(sum(v) for v in agg.values()) or 1
-with open(f'profiles/{tag}_launches_summary.txt', 'w') as f:
-    f.write('ncu --metrics gpu__time_duration.sum --clock-control none -c 400  python bench.py --steps 1 --warmup 3 --videos 32 --no-e2e --no-cpu-baseline\n')
+with open(f'{dest}/{tag}_launches_summary.txt', 'w') as f:
+    f.write('ncu --metrics gpu__time_duration.sum --clock-control none -c 400  python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-gauss --no-configs --sustain-s 0  (128 videos)\n')
     f.write('(cold-cache, serialised launches: compare SHARES, not absolutes; torch randn/fill kernels are input generation outside the timed region)\n\n')
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         f.write(f"{k[:100]:100s} n={len(v):4d} avg_us={sum(v)/len(v)/1e3:9.1f} share={100*sum(v)/tot:5.1f}%\n")
@@ -37,7 +39,7 @@ for row in r[2:]:
     for w in keep:
         if w in d: print(f'{w:75s} {d[w]:>18s} {r[1][h.index(w)]}')
     print()
-" > profiles/${TAG}_ncu_$k.txt
-  ncu -i $rep --page source --csv 2>/dev/null | python scripts/ncu_stalls.py 20 >> profiles/${TAG}_ncu_$k.txt
+" > $DEST/${TAG}_ncu_$k.txt
+  ncu -i $rep --page source --csv 2>/dev/null | python scripts/ncu_stalls.py 20 >> $DEST/${TAG}_ncu_$k.txt
 done
-ls -la profiles | tail -20
+ls -la $DEST | tail -20
