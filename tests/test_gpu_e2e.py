@@ -193,10 +193,11 @@ def test_rect_split_tf32_is_fp32_grade(dev):
     assert w["B"] < 1e-5 and w["ctx"] < 2e-5, w
 
 
+@pytest.mark.parametrize("bin_pool", [False, True])
 @pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
 @pytest.mark.parametrize("name", ["gibbs_vl_cfg1.npz", "gibbs_vl_cfg2.npz", "gibbs_vl_peaky.npz",
                                   "gibbs_vc_cfg3.npz", "gibbs_vl_cfg4.npz"])
-def test_rect_reproduces_reference_goldens(dev, name, precision):
+def test_rect_reproduces_reference_goldens(dev, name, precision, bin_pool):
     """CUDA path vs outputs of the real reference module (tests/golden, generated in the dev container) fed with
     the uniforms the reference itself consumed -- no guard band: the sampled bins must equal the reference's
     (`b`, observed through Categorical.sample by make_golden.py), and with them coefficients and contexts."""
@@ -204,8 +205,9 @@ def test_rect_reproduces_reference_goldens(dev, name, precision):
     g = load_golden(name)
     N, L, C, seed, T, e, Q = (int(x) for x in g["meta"])
     key, val = make_proj(seed, e)
+    # bin_pool: update chunks pooled per frame (what a one-video engine picks) / per basis bin (the batched headline)
     eng = BatchedRectLTM(N, float(g["tau"]), *proj_tensors(key, val), tokens_per_frame=T, device=dev,
-                         precision=precision)
+                         precision=precision, bin_pool=bin_pool)
     ks, qs, _ = make_inputs(seed + 1, C, 1, L * T, e, Q, float(g["q_scale"]))
     for c in range(C):
         u = torch.from_numpy(g["u"][c]).to(dev)
@@ -226,6 +228,8 @@ def test_cfg4_at_full_size(dev):
     from infinite_video_b200.batched import BatchedRectLTM
     key, val = make_proj(15, 768)
     eng = BatchedRectLTM(N, .75, *proj_tensors(key, val), device=dev)
+    from infinite_video_b200 import tables as _T
+    assert eng._bin_ok(Bv, L, _T.rect_tables(L, N, .75, 512))     # this batch pools its update chunks per basis bin
     check = [0, 21, 42, 63]
     orcs = {v: O.RectLTM(N, .75, *proj_tensors(key, val), rebuild_tables=False, faithful_quadrature=False)
             for v in check}
