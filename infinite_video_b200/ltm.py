@@ -32,7 +32,7 @@ class LongTermAttention(nn.Module):
     # Pooled frames of the most recent chunk, shared by every instance in the process: all LTM layers of a
     # Q-former are called with the same `encoder_hidden_states` tensor per chunk (Qformer.py:216-223 inside
     # BertEncoder's layer loop), so only the first layer streams the chunk from HBM.
-    _shared_pool = {"key": None, "x": None}
+    _shared_pool = {"key": None, "x": None, "k16": None}
 
     def __init__(self, head_size: int, length: int, target_len: int, attn_func: str, attn_num_basis: int,
                  continuous: bool, attn_drop: float, infinite_memory: bool, n_layers: int, n_heads: int,
@@ -181,7 +181,7 @@ class LongTermAttention(nn.Module):
             eng.reset()                                                    # gibbs:300-302
             sp = LongTermAttention._shared_pool
             if sp["key"] is None or sp["key"][0]() is not k:               # do not keep the last video's frames alive
-                sp.update(key=None, x=None)
+                sp.update(key=None, x=None, k16=None)
         if eng.Bv is not None and eng.Bv != bsz:
             eng.reset()            # a different batch size starts from scratch: decide that BEFORE touching the RNG
         if eng.has_state and eng.sticky:
@@ -199,7 +199,7 @@ class LongTermAttention(nn.Module):
             hit = (ref is not None and ref[0]() is k and ref[1] == k._version and ref[2] == self.tokens_per_frame
                    and sp["x"] is not None and sp["x"].device == k.device)
             if not hit:
-                sp["x"] = eng.pool(k32)
+                sp["x"], sp["k16"] = eng.pool(k32), None
                 sp["key"] = (weakref.ref(k), k._version, self.tokens_per_frame)
             pooled = sp["x"]
         ctx = eng.step(k32, q32, u=u, new_doc=False, pooled=pooled) if pooled is not None else \
@@ -219,11 +219,16 @@ class LongTermAttention(nn.Module):
         """One pass over an fp32 chunk for both halves of the caller's cross-attention branch: pools the frames for
         this (and every other) LTM layer -- the result is parked in the shared-pooling slot, so the following
         `forward(k, ...)` does not stream the chunk again -- and returns the chunk as float16 for the short-term
-        attention GEMMs (cross_attention.py)."""
+        attention GEMMs (cross_attention.py).  Every cross-attention layer of a Q-former is handed the same chunk: the
+        second and later layers find both results in the slot."""
+        sp = LongTermAttention._shared_pool
+        ref = sp["key"]
+        if (ref is not None and ref[0]() is k and ref[1] == k._version and ref[2] == self.tokens_per_frame
+                and sp["x"] is not None and sp["k16"] is not None and sp["x"].device == k.device):
+            return sp["k16"]
         eng = self._get_engine(k.device)
-        kc = k.contiguous()
-        pooled, k16 = eng.pool(kc, with_half=True)
-        LongTermAttention._shared_pool.update(key=(weakref.ref(k), k._version, self.tokens_per_frame), x=pooled)
+        pooled, k16 = eng.pool(k.contiguous(), with_half=True)
+        sp.update(key=(weakref.ref(k), k._version, self.tokens_per_frame), x=pooled, k16=k16)
         return k16
 
     def extra_repr(self):

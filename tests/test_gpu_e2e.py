@@ -835,6 +835,44 @@ def test_caller_cross_attention_with_ltm_blend_on_gpu(dev, alpha, N, L, B, opera
             assert relerr(got, want) < TOL_CTX, f"blend, chunk {c}"
 
 
+def test_caller_layers_share_the_pooling_and_fp16_pass(dev):
+    """Two cross-attention layers of a Q-former receive the same chunk: the pass that pools its frames and writes its
+    fp16 copy runs once per chunk (the second layer finds both in the shared slot), and each layer equals a module that
+    works alone."""
+    import copy
+    from infinite_video_b200 import LongTermAttention, ops
+    from infinite_video_b200.cross_attention import CrossAttentionLTM
+    torch.manual_seed(31)
+    mods, solo = [], []
+    for i in range(2):
+        lin = [torch.nn.Linear(768, 768).to(dev) for _ in range(3)]
+        mods.append(CrossAttentionLTM(*lin, 0.5, 64, .75))
+        solo.append(CrossAttentionLTM(*copy.deepcopy(lin), 0.5, 64, .75))
+    calls = {"n": 0}
+    real = ops.pool_mean_convert
+
+    def counting(*a, **kw):
+        calls["n"] += 1
+        return real(*a, **kw)
+    g = torch.Generator().manual_seed(32)
+    outs = []
+    ops.pool_mean_convert = counting
+    try:
+        for c in range(3):
+            enc = torch.randn(2, 8 * 32, 768, generator=g).to(dev)
+            hs = [torch.randn(2, 32, 768, generator=g).to(dev) for _ in range(2)]
+            u = torch.rand(2, 512, dtype=torch.float64, generator=g)
+            outs.append((enc, hs, u, [mods[i](hs[i], enc, new_video=(c == 0), layer=i, u=u) for i in range(2)]))
+    finally:
+        ops.pool_mean_convert = real
+    assert calls["n"] == 3
+    for c, (enc, hs, u, got) in enumerate(outs):
+        for i in range(2):
+            LongTermAttention._shared_pool.update(key=None, x=None, k16=None)       # the solo module shares nothing
+            want = solo[i](hs[i], enc, new_video=(c == 0), layer=i, u=u)
+            assert torch.equal(got[i], want), (c, i)
+
+
 def test_import_swap_through_the_real_qformer(dev, tmp_path):
     """the UNMODIFIED `Qformer.BertSelfAttention` (baseline/_ref on the GPU box, oracle/install_ref.py)
     with its one import line (Qformer.py:50) resolved to `infinite_video_b200` instead of the reference module: two
