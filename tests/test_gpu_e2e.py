@@ -228,8 +228,6 @@ def test_cfg4_at_full_size(dev):
     from infinite_video_b200.batched import BatchedRectLTM
     key, val = make_proj(15, 768)
     eng = BatchedRectLTM(N, .75, *proj_tensors(key, val), device=dev)
-    from infinite_video_b200 import tables as _T
-    assert eng._bin_ok(Bv, L, _T.rect_tables(L, N, .75, 512))     # this batch pools its update chunks per basis bin
     check = [0, 21, 42, 63]
     orcs = {v: O.RectLTM(N, .75, *proj_tensors(key, val), rebuild_tables=False, faithful_quadrature=False)
             for v in check}
