@@ -96,15 +96,16 @@ def test_generic_attention_path_still_matches(dev, kw):
     assert w["B"] < 1e-5 and w["ctx"] < TOL_CTX, w
 
 
-def test_no_drift_over_a_long_video(dev):
+@pytest.mark.parametrize("N,L,Bv,C,bin_pool", [(64, 8, 2, 48, None), (256, 16, 1, 256, True)])
+def test_no_drift_over_a_long_video(dev, N, L, Bv, C, bin_pool):
     """The projected memory K|V is carried from call to call (rounded to fp16 at every store) instead of being
-    re-projected from the coefficients: 48 sequential chunks against the oracle, which projects afresh every call --
-    the context error must stay where it starts (the rounding noise of a carried row is averaged and shrunk by
+    re-projected from the coefficients: 48 sequential chunks -- and the 256 chunks of a full NExT-QA video
+    (BASELINE configs[1]: max_int = 256, num_basis 256) -- against the oracle, which projects afresh every call: the
+    context error must stay where it starts (the rounding noise of a carried row is averaged and shrunk by
     g_j * cnt_j < 1 each call), not accumulate."""
     from infinite_video_b200.batched import BatchedRectLTM
     key, val = make_proj(39, 768)
-    N, L, Bv, C = 64, 8, 2, 48
-    eng = BatchedRectLTM(N, .75, *proj_tensors(key, val), device=dev)
+    eng = BatchedRectLTM(N, .75, *proj_tensors(key, val), device=dev, bin_pool=bin_pool)
     assert eng.kv_state and eng.kv_half
     orcs = [O.RectLTM(N, .75, *proj_tensors(key, val), rebuild_tables=False, faithful_quadrature=False)
             for _ in range(Bv)]
