@@ -270,6 +270,13 @@ int ltm_ridge_solve(const float* positions, int P, int trim, int rows,
 int ltm_gather_rows(const float* src, const int32_t* idx, float* out, int Bv, int rows_src, int S, int e,
                     void* stream);
 
+/* ---- variant G, sticky update without materialising the re-sampled rows: b_sorted[Bv,S] are the drawn bins in
+ * ascending order (ltm_resample sort = 1), GT[N, >= S+L] the update operator G_inf^T (row pitch ldg).
+ * out[v, n, b] = sum of GT[n, s] over the draws s with b_sorted[v,s] == b (b < nbins), out[v, n, nbins + l] = GT[n, S+l]:
+ * out[v] [R ; k] == GT [xm ; k] with xm[s] = R[b_s].  long_term_attention.py:239-250. */
+int ltm_fold_sample_columns(const float* GT, int64_t ldg, const int32_t* b_sorted, float* out, int Bv, int N, int S,
+                            int L, int nbins, void* stream);
+
 /* ---- whole per-chunk step of variant R for Bv videos (device buffers), and the same through
  * host buffers (H2D of k,q,u,new_doc and D2H of ctx enqueued on `stream`; caller synchronises).
  * ltm_rect_step with k == NULL skips the frame pooling and consumes a->xpart as already filled by an

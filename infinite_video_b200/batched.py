@@ -644,7 +644,7 @@ class BatchedGaussLTM(_BatchedBase):
     def __init__(self, num_basis, tau, w_key, b_key, w_value, b_value, *, sigmas=(0.005, 0.01), n_heads=12,
                  head_size=64, sticky=True, nb_samples=tables.NB_SAMPLES, precision="tf32x3",
                  proj_precision=None, device="cuda", ridge=tables.RIDGE_PENALTY,
-                 spacing="linear", value_precision=None):
+                 spacing="linear", value_precision=None, fold_samples=True):
         ns = len(sigmas)
         n = int(num_basis)
         if n % ns:
@@ -660,6 +660,9 @@ class BatchedGaussLTM(_BatchedBase):
         # rounded to fp16 first: unbiased, but the Gaussian weights r_j reach ~80 with mixed signs downstream of the
         # ridge operators and amplify the 2^-12 rounding to 1.15e-3; 143 k -> 161.8 k).
         self.value_precision = value_precision
+        # sticky update as A_v [R ; k] with the operator's sample columns folded per drawn bin (ltm_fold_sample_columns)
+        # instead of G_inf^T [gather(R) ; k]: same B, no [Bv,S,e] intermediate, contraction 128 + L instead of S + L
+        self.fold_samples = bool(fold_samples)
         self.ridge = float(ridge)
         self._ops = {}
         self._B = None
@@ -731,13 +734,22 @@ class BatchedGaussLTM(_BatchedBase):
                 # xm[s] = Psi(ts_s) B_past  ==  (Psi_tab B_past)[b_s]
                 R = ops.gemm(op["Psi_tab"], self._B, a_kmajor=True, b_kmajor=False, precision=self.precision,
                              impl=self.gemm_impl)                                          # [Bv,128,e]
-                xm = ops.gather_rows(R, rs["b_used"])                                       # [Bv,S,e]
+                if self.fold_samples:
+                    # G_inf^T [xm ; k] = A_v [R ; k]: the sample columns of the operator summed per drawn bin (the
+                    # draws are sorted), so the 512 gathered rows are never written and the contraction is 128 + L long
+                    A_v = ops.fold_sample_columns(op["GinfT"], rs["b_used"], self.S, L)     # [Bv,N,128+L]
+                    B = ops.gemm(A_v, R, B2=k, a_kmajor=True, b_kmajor=False, precision=self.precision,
+                                 impl=self.gemm_impl)
+                    xm = None
+                else:
+                    xm = ops.gather_rows(R, rs["b_used"])                                   # [Bv,S,e]
             else:
                 xm = ops.gemm(op["Psi_uniform"], self._B, a_kmajor=True, b_kmajor=False, precision=self.precision,
                               impl=self.gemm_impl)
-            # B = G_inf^T [xm ; k]  without materialising the concatenation
-            B = ops.gemm(op["GinfT"], xm, B2=k, a_kmajor=True, b_kmajor=False, precision=self.precision,
-                         impl=self.gemm_impl)
+            if xm is not None:
+                # B = G_inf^T [xm ; k]  without materialising the concatenation
+                B = ops.gemm(op["GinfT"], xm, B2=k, a_kmajor=True, b_kmajor=False, precision=self.precision,
+                             impl=self.gemm_impl)
         self._B = B
         if ops.attn_fast_supported(self.N, self.d):
             Kt, V = ops.project_kv_t(B, self.Wkv, self.bkv, self.N, precision=self.proj_precision,

@@ -128,6 +128,44 @@ consolidate_rect_kernel(const float4* __restrict__ B_past, const float4* __restr
   }
 }
 
+// Variant G, sticky update: the S re-sampled rows xm[s] = R[b_s] (R = Psi_tab B_past, 128 candidate rows) enter the
+// regression as G_inf^T[:, :S] xm = sum_b (sum_{s: b_s = b} G_inf^T[:, s]) R[b]: with the draws sorted by bin the inner
+// sums are runs of consecutive columns of the (constant) operator.  out[v, n, b] = sum of GT[n, s] over the run of bin b,
+// out[v, n, nbins + l] = GT[n, S + l] (the frame columns, copied): a per-video operator with 128 + L instead of S + L
+// columns whose product with [R ; k] is the same B -- without materialising xm[Bv, S, e] and with half the
+// contraction length.  long_term_attention.py:239-250.
+__global__ void __launch_bounds__(256)
+fold_sample_columns_kernel(const float* __restrict__ GT, long long ldg, const int32_t* __restrict__ b_sorted,
+                           float* __restrict__ out, int N, int S, int L, int nbins, int rows_per_cta) {
+  __shared__ int start[257];
+  const int v = blockIdx.y;
+  const int32_t* bs = b_sorted + (size_t)v * S;
+  for (int b = threadIdx.x; b <= nbins; b += blockDim.x) {     // lower bound of bin b in the sorted draws
+    int lo = 0, hi = S;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (bs[mid] < b) lo = mid + 1; else hi = mid;
+    }
+    start[b] = lo;
+  }
+  __syncthreads();
+  const int W = nbins + L;
+  const int n0 = blockIdx.x * rows_per_cta;
+  for (int i = threadIdx.x; i < rows_per_cta * W; i += blockDim.x) {
+    const int n = n0 + i / W, c = i - (i / W) * W;
+    if (n >= N) break;
+    const float* g = GT + (size_t)n * ldg;
+    float acc;
+    if (c < nbins) {
+      acc = 0.f;
+      for (int s = start[c]; s < start[c + 1]; ++s) acc += g[s];
+    } else {
+      acc = g[S + c - nbins];
+    }
+    out[((size_t)v * N + n) * W + c] = acc;
+  }
+}
+
 // out[v,s,:] = src[v, idx[v,s], :]
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const float4* __restrict__ src, const int32_t* __restrict__ idx, float4* __restrict__ out,
@@ -217,5 +255,18 @@ extern "C" int ltm_gather_rows(const float* src, const int32_t* idx, float* out,
   gather_rows_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4*>(src), idx, reinterpret_cast<float4*>(out), rows_src, S, e4);
   LTM_CHECK_LAUNCH("gather_rows");
+  return 0;
+}
+
+extern "C" int ltm_fold_sample_columns(const float* GT, int64_t ldg, const int32_t* b_sorted, float* out, int Bv, int N,
+                                       int S, int L, int nbins, void* stream) {
+  using namespace ltm;
+  LTM_REQUIRE(GT && b_sorted && out, "fold_sample_columns: null pointer");
+  LTM_REQUIRE(Bv > 0 && Bv <= 65535 && N > 0 && S > 0 && L >= 0 && nbins > 0 && nbins <= 256 && ldg >= S + L,
+              "fold_sample_columns: bad shape Bv=%d N=%d S=%d L=%d nbins=%d", Bv, N, S, L, nbins);
+  const int rows_per_cta = 8;
+  fold_sample_columns_kernel<<<dim3((N + rows_per_cta - 1) / rows_per_cta, Bv), 256, 0, (cudaStream_t)stream>>>(
+      GT, (long long)ldg, b_sorted, out, N, S, L, nbins, rows_per_cta);
+  LTM_CHECK_LAUNCH("fold_sample_columns");
   return 0;
 }

@@ -551,6 +551,20 @@ def gather_rows(src, idx, out=None):
     return out
 
 
+def fold_sample_columns(GT, b_sorted, S, L, nbins=128):
+    """Variant G: per-video update operator with the S sample columns of GT[N, >= S+L] folded per sticky bin
+    (b_sorted[Bv,S] ascending) and the L frame columns copied: [Bv, N, nbins + L]."""
+    require_cuda(GT, b_sorted)
+    if GT.dim() != 2 or GT.stride(1) != 1 or GT.shape[1] < S + L or b_sorted.dtype != torch.int32:
+        raise ValueError("fold_sample_columns: GT must be [N, >= S+L] row-major, b_sorted int32 [Bv,S]")
+    b_sorted = b_sorted.contiguous()
+    Bv, N = b_sorted.shape[0], GT.shape[0]
+    out = torch.empty(Bv, N, nbins + L, device=GT.device, dtype=torch.float32)
+    check(lib().ltm_fold_sample_columns(ptr(GT), GT.stride(0), ptr(b_sorted), ptr(out), Bv, N, S, L, nbins,
+                                        stream_ptr(GT.device)), "fold_sample_columns")
+    return out
+
+
 def _device_guarded(fn):
     """Make the device of the first CUDA tensor argument current for the call (stream handles of one device are
     invalid while another device is current)."""

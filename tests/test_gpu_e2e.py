@@ -351,6 +351,23 @@ def test_gauss_matches_oracle_with_shared_operators(dev, N, L, Bv, C):
                 assert err < 5e-3 and ours <= 1.5 * max(theirs, 1e-4), (c, err, ours, theirs)
 
 
+def test_gauss_folded_operator_equals_gathered_samples(dev):
+    """Variant G sticky update through the per-video folded operator (default) and through the gathered sample rows:
+    same coefficients (two summation orders of one product), same draws, same contexts."""
+    from infinite_video_b200.batched import BatchedGaussLTM
+    key, val = make_proj(43, 768)
+    a = BatchedGaussLTM(256, .75, *proj_tensors(key, val), device=dev, fold_samples=True)
+    b = BatchedGaussLTM(256, .75, *proj_tensors(key, val), device=dev, fold_samples=False)
+    ks, qs, us = make_inputs(44, 3, 2, 64, 768, 32)
+    for c in range(3):
+        x = a.step(ks[c].to(dev), qs[c].to(dev), us[c].to(dev) if c else None, new_doc=(c == 0))
+        y = b.step(ks[c].to(dev), qs[c].to(dev), us[c].to(dev) if c else None, new_doc=(c == 0))
+        assert relerr(a.B_past, b.B_past) < 2e-5, c
+        if c:
+            assert torch.equal(a.last["b"], b.last["b"])
+        assert relerr(x, y) < 5e-4, c
+
+
 def test_gauss_device_ridge_end_to_end(dev):
     """With its own fp64 device-solved operators the module must track an fp64-operator oracle."""
     import math

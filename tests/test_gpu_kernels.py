@@ -77,6 +77,25 @@ def test_pool_bins(dev, Bv, N, L, T, e):
     assert torch.equal(got, want)
 
 
+def test_fold_sample_columns(dev):
+    """Variant G: operator columns summed per drawn sticky bin == the gathered product, G^T [R[b_s] ; k] = A_v [R ; k]."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(12)
+    Bv, N, S, L, e = 3, 64, 512, 8, 96
+    GT = torch.randn(N, S + L + 4, generator=g)[:, :S + L + 4].to(dev)        # row pitch > S + L
+    b = torch.randint(0, 127, (Bv, S), generator=g).sort(dim=1).values.int().to(dev)
+    A = ops.fold_sample_columns(GT, b, S, L)
+    assert A.shape == (Bv, N, 128 + L)
+    R = torch.randn(Bv, 128, e, generator=g).double().to(dev)
+    k = torch.randn(Bv, L, e, generator=g).double().to(dev)
+    xm = torch.gather(R, 1, b.long().unsqueeze(-1).expand(-1, -1, e))
+    want = GT[:, :S + L].double() @ torch.cat([xm, k], 1)
+    got = A.double() @ torch.cat([R, k], 1)
+    assert relerr(got, want) < 1e-6
+    assert torch.equal(A[:, :, 128:], GT[:, S:S + L].unsqueeze(0).expand(Bv, -1, -1))
+    assert float(A[:, :, 127].abs().max()) == 0.0                 # bin 127 is never drawn
+
+
 # ---------------------------------------------------------------------------------------- R7
 @pytest.mark.parametrize("ncat,Bv,zeros,sort", [(127, 1, False, False), (127, 37, True, False),
                                                 (128, 5, False, True), (128, 4, True, True)])
