@@ -368,6 +368,10 @@ int ltm_blend(const float* a, const float* b, float alpha, float* out, int64_t n
 int ltm_softmax_rows_h(float* S, const float* mask, void* P16, int rows, int n, int rows_per_mask, float scale,
                        void* stream);
 int ltm_to_half(const float* src, void* dst, int64_t n, void* stream);
+/* fp32 [rows, K] -> fp16 [rows, 3K], x ~ hi + lo in three K segments per row: side 0 (A operand) [hi | lo | hi], side 1
+ * (B operand) [hi | hi | lo].  A plain fp16 ltm_gemm (ab_fp16) over K' = 3K then computes a_hi b_hi + a_lo b_hi +
+ * a_hi b_lo: the three-term product of the split-TF32 mode at the fp16 tensor rate. */
+int ltm_split_half3(const float* src, void* dst, int64_t rows, int K, int side, void* stream);
 
 /* ---- CUDA-event helpers so a ctypes host can time stages on the launching stream */
 int ltm_event_create(void** ev);

@@ -78,6 +78,7 @@ _SIGS = {
     "ltm_pool_mean": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_pool_mean_convert": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_fold_sample_columns": (C.c_int, [_P, _L, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "ltm_split_half3": (C.c_int, [_P, _P, _L, _I, _I, _P]),
     "ltm_pool_bins": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_pool_mean_16": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_pool_mean_grid": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),

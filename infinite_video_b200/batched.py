@@ -653,7 +653,12 @@ class BatchedGaussLTM(_BatchedBase):
                          precision, device)
         self.sigmas = tuple(float(s) for s in sigmas)
         self.spacing = spacing
-        self.proj_precision = proj_precision or precision
+        # K/V projection (three quarters of the variant's flops): "fp16x2" (default) = operands split into two fp16 terms
+        # each (22 significant bits) and laid out along K so that ONE plain kind::f16 GEMM over 3e computes the
+        # three-term product (ops.split_half3): as accurate as split-TF32 (4e-6 vs 6e-6 against fp64) at the fp16
+        # tensor rate, 370 -> 202 + 39 us per 128-video chunk.  fp16's range applies to the coefficients (|B| <= 65504);
+        # "tf32x3" keeps the fp32 operands.
+        self.proj_precision = proj_precision or ("fp16x2" if precision == "tf32x3" else precision)
         # precision of the value half of the projection: None (default) = split-TF32 like the keys.  Both cheaper
         # options were measured and miss the 1e-3 context tolerance: "tf32" (single pass on the fp32 operands; the
         # tensor core TRUNCATES them, a systematic ~1e-3 shrink of V; 128.7 k -> 161.3 k chunks/s) and "fp16" (operands
@@ -663,6 +668,7 @@ class BatchedGaussLTM(_BatchedBase):
         # sticky update as A_v [R ; k] with the operator's sample columns folded per drawn bin (ltm_fold_sample_columns)
         # instead of G_inf^T [gather(R) ; k]: same B, no [Bv,S,e] intermediate, contraction 128 + L instead of S + L
         self.fold_samples = bool(fold_samples)
+        self._W3 = None
         self.ridge = float(ridge)
         self._ops = {}
         self._B = None
@@ -752,11 +758,17 @@ class BatchedGaussLTM(_BatchedBase):
                              impl=self.gemm_impl)
         self._B = B
         if ops.attn_fast_supported(self.N, self.d):
+            w3 = None
+            if self.proj_precision == "fp16x2":
+                if self._W3 is None or self._W3_src != self.Wkv.data_ptr():
+                    self._W3, self._W3_src = ops.split_half3(self.Wkv, 1), self.Wkv.data_ptr()
+                w3 = self._W3
             Kt, V = ops.project_kv_t(B, self.Wkv, self.bkv, self.N, precision=self.proj_precision,
-                                     impl=self.gemm_impl, precision_v=self.value_precision)
+                                     impl=self.gemm_impl, precision_v=self.value_precision, w_split=w3)
             ctx, scores, mu, sd = ops.cont_attn_gauss_t(q, Kt, V, op["mu"], op["sigma"])
         else:
-            KV = ops.project_kv(B, self.Wkv, self.bkv, precision=self.proj_precision, impl=self.gemm_impl)
+            pp = self.precision if self.proj_precision == "fp16x2" else self.proj_precision      # (generic layout: fp32 operands)
+            KV = ops.project_kv(B, self.Wkv, self.bkv, precision=pp, impl=self.gemm_impl)
             KV = KV.view(Bv, self.N, 2 * self.D)
             ctx, scores, mu, sd = ops.cont_attn_gauss(q, KV, op["mu"], op["sigma"], n_heads=self.H)
         self._mu, self._sd = mu, sd

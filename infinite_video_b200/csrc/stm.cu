@@ -27,6 +27,35 @@ to_half_kernel(const float4* __restrict__ src, uint4* __restrict__ dst, long lon
   }
 }
 
+// fp32 -> two IEEE fp16 terms, x ~ hi + lo (hi = rn(x), lo = rn(x - hi): 22 significant bits while |x| >= 2^-3, an
+// absolute floor of 2^-25 below), laid out along K as three segments per row so that a PLAIN kind::f16 GEMM over
+// K' = 3K computes the three-term product a_hi b_hi + a_lo b_hi + a_hi b_lo -- fp32-grade like the split-TF32 mode, at the
+// fp16 rate:   side 0 (A operand): [hi | lo | hi]     side 1 (B operand): [hi | hi | lo]
+__global__ void __launch_bounds__(256)
+split_half3_kernel(const float4* __restrict__ src, uint4* __restrict__ dst, long long rows, int k8, int side) {
+  const long long total = rows * k8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / k8;
+    const int c = (int)(i - r * k8);
+    const float4 a = src[2 * i], b = src[2 * i + 1];
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half2 h = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(x[2 * j] - hf.x, x[2 * j + 1] - hf.y);
+      hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+      lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    const uint4 H = make_uint4(hi[0], hi[1], hi[2], hi[3]), Lo = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    uint4* row = dst + r * 3 * k8 + c;
+    row[0] = H;
+    row[k8] = side == 0 ? Lo : H;
+    row[2 * k8] = side == 0 ? H : Lo;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 softmax_rows_kernel(float* __restrict__ S, const float* __restrict__ mask, int n, int rows_per_mask, float scale,
                     __half* __restrict__ P16) {
@@ -198,6 +227,19 @@ extern "C" int ltm_to_half(const float* src, void* dst, int64_t n, void* stream)
   to_half_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(src),
                                                            reinterpret_cast<uint4*>(dst), n8);
   LTM_CHECK_LAUNCH("to_half");
+  return 0;
+}
+
+extern "C" int ltm_split_half3(const float* src, void* dst, int64_t rows, int K, int side, void* stream) {
+  using namespace ltm;
+  LTM_REQUIRE(src && dst, "split_half3: null pointer");
+  LTM_REQUIRE(rows > 0 && K > 0 && K % 8 == 0 && (side == 0 || side == 1) && aligned16(src) && aligned16(dst),
+              "split_half3: rows=%lld K=%d (K %% 8 == 0), side 0 / 1, 16-byte alignment", (long long)rows, K);
+  const long long total = rows * (K / 8);
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  split_half3_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(src),
+                                                               reinterpret_cast<uint4*>(dst), rows, K / 8, side);
+  LTM_CHECK_LAUNCH("split_half3");
   return 0;
 }
 

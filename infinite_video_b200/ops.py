@@ -413,7 +413,7 @@ def cont_attn_rect_tc16(q, KV16, X16, W, W_out, c_none, jb=None, tb=None, want_s
     return ctx, scores, hist
 
 
-def project_kv_t(Bcoef, Wkv, bkv, N, precision="tf32", impl="tcgen05", precision_v=None):
+def project_kv_t(Bcoef, Wkv, bkv, N, precision="tf32", impl="tcgen05", precision_v=None, w_split=None):
     """Same projection with the keys stored transposed per head: -> (Kt[Bv,H,64,N], V[Bv,N,D]).
     `precision_v` (None = `precision`): a different precision for the value half -- the Gaussian variant needs
     fp32-grade keys (softmax(20 S) amplifies score errors 20x) but its values only enter the final contraction."""
@@ -424,6 +424,21 @@ def project_kv_t(Bcoef, Wkv, bkv, N, precision="tf32", impl="tcgen05", precision
     Bv = M // N
     Kt = torch.empty(Bv, D // 64, 64, N, device=Bc.device, dtype=torch.float32)
     V = torch.empty(Bv, N, D, device=Bc.device, dtype=torch.float32)
+    if precision == "fp16x2":
+        # both halves as ONE plain fp16 GEMM over K' = 3e on hi/lo-split operands (split_half3): fp32-grade products
+        # at the fp16 tensor rate.  W3: the weights split once by the caller ([2D, 3e], side 1).
+        A3 = split_half3(Bc, 0)
+        W3 = w_split if w_split is not None else split_half3(Wkv, 1)
+        g = GemmArgs()
+        g.A, g.lda, g.a_kmajor = A3.data_ptr(), 3 * e, 1
+        g.B, g.ldb, g.b_kmajor = W3.data_ptr(), 3 * e, 1
+        g.K1, g.bias = 3 * e, bkv.data_ptr()
+        g.C, g.ldc = V.data_ptr(), D
+        g.CT, g.ct_cols, g.ct_group = Kt.data_ptr(), D, N
+        g.M, g.Nc, g.K, g.batch = M, 2 * D, 3 * e, 1
+        g.precision, g.impl, g.ab_fp16 = PRECISION["tf32"], GEMM_IMPL[impl], 1
+        check(lib().ltm_gemm(C.byref(g), stream_ptr(Bc.device)), "project_kv_t(fp16x2)")
+        return Kt, V
     if precision_v is not None and (precision_v == "fp16" or PRECISION[precision_v] != PRECISION[precision]):
         g = GemmArgs()                                   # keys: all D columns through the transposed store
         g.A, g.lda, g.a_kmajor = Bc.data_ptr(), e, 1
@@ -548,6 +563,17 @@ def gather_rows(src, idx, out=None):
     if out is None:
         out = torch.empty(Bv, S, e, device=src.device, dtype=torch.float32)
     check(lib().ltm_gather_rows(ptr(src), ptr(idx), ptr(out), Bv, R, S, e, stream_ptr(src.device)), "gather_rows")
+    return out
+
+
+def split_half3(x, side):
+    """fp32 [rows, K] -> fp16 [rows, 3K]: x ~ hi + lo laid out [hi | lo | hi] (side 0, A operand) or [hi | hi | lo]
+    (side 1, B operand), so that a plain fp16 GEMM over 3K gives the three-term split product."""
+    require_cuda(x)
+    x = _f32c(x)
+    rows, K = x.shape
+    out = torch.empty(rows, 3 * K, device=x.device, dtype=torch.float16)
+    check(lib().ltm_split_half3(ptr(x), ptr(out), rows, K, int(side), stream_ptr(x.device)), "split_half3")
     return out
 
 

@@ -9,7 +9,8 @@ dev = torch.device("cuda:0")
 Bv, L, E, Q, N = int(os.environ.get("BV", 128)), 256, 768, 32, 256
 torch.manual_seed(0)
 key, val = torch.nn.Linear(E, 768), torch.nn.Linear(E, 768)
-eng = BatchedGaussLTM(N, .75, key.weight.detach(), key.bias.detach(), val.weight.detach(), val.bias.detach(), device=dev)
+eng = BatchedGaussLTM(N, .75, key.weight.detach(), key.bias.detach(), val.weight.detach(), val.bias.detach(), device=dev,
+                      proj_precision=os.environ.get("PROJ") or None)
 ks = [torch.randn(Bv, L, E, device=dev) for _ in range(3)]
 qs = [torch.randn(Bv, Q, 768, device=dev) for _ in range(3)]
 us = [torch.rand(Bv, 512, dtype=torch.float64, device=dev) for _ in range(3)]

@@ -77,6 +77,29 @@ def test_pool_bins(dev, Bv, N, L, T, e):
     assert torch.equal(got, want)
 
 
+def test_split_half3_gives_fp32_grade_products_on_fp16_tensor_cores(dev):
+    """x ~ hi + lo in fp16, laid out [hi|lo|hi] x [hi|hi|lo] along K: a plain fp16 GEMM over 3K is the three-term split
+    product -- as accurate as split-TF32 (4e-6 vs 6e-6 here), far beyond a single fp16 / tf32 pass (5e-4)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(13)
+    M, Nc, K = 384, 256, 768
+    A = (torch.randn(M, K, generator=g) * 3).to(dev)
+    W = (torch.randn(Nc, K, generator=g) / 28).to(dev)
+    bias = torch.randn(Nc, generator=g).to(dev)
+    A3, W3 = ops.split_half3(A, 0), ops.split_half3(W, 1)
+    hi = A.half()
+    assert torch.equal(A3[:, :K], hi) and torch.equal(A3[:, 2 * K:], hi) and torch.equal(W3[:, K:2 * K], W.half())
+    assert torch.equal(A3[:, K:2 * K], (A - hi.float()).half())
+    out = torch.zeros(M, Nc, device=dev)
+    ops.gemm_raw(A3, 3 * K, 0, True, W3, 3 * K, 0, True, out, Nc, 0, M, Nc, 3 * K, 1, bias=bias, ab_fp16=True,
+                 precision="tf32")
+    want = A.double() @ W.double().t() + bias.double()
+    x3 = torch.zeros(M, Nc, device=dev)
+    ops.gemm_raw(A, K, 0, True, W, K, 0, True, x3, Nc, 0, M, Nc, K, 1, bias=bias, precision="tf32x3")
+    e16, e32 = relerr(out, want), relerr(x3, want)
+    assert e16 < 1e-5 and e16 < 2 * e32, (e16, e32)
+
+
 def test_fold_sample_columns(dev):
     """Variant G: operator columns summed per drawn sticky bin == the gathered product, G^T [R[b_s] ; k] = A_v [R ; k]."""
     ops = _ops()
