@@ -870,8 +870,11 @@ def run_gauss_arm(dev, Bv, C, Lk, steps=3):
     return {"value": calls / (ms * 1e-3), "unit": "chunks/s", "videos": Bv, "chunks": C, "frames_per_chunk": Lk,
             "ms_per_step": ms, "precision": "tf32x3", "finite": finite, "ridge_setup_s": t_ridge,
             "roofline": {"bound": "tensor", "achieved": tfl, "peak": peak_tf32, "unit": "TFLOP/s",
-                         "frac": tfl / peak_tf32, "note": "algorithmic (single-product) flops; the split-TF32 path "
-                         "issues 3 MMAs per product; peak = 1/2 of the measured bf16 GEMM"}}
+                         "frac": tfl / peak_tf32, "issued_frac_of_tf32_peak": 3.0 * tfl / peak_tf32,
+                         "note": "algorithmic (single-product) flops of the reference's update (reconstruct 128 rows, "
+                         "regress over S + L, project, attend); every product is issued as 3 MMAs for fp32-grade "
+                         "results (split-TF32 state GEMMs, fp16x2 projection at the fp16 rate), the sticky regression "
+                         "runs over 128 + L columns instead of S + L; peak = 1/2 of the measured bf16 GEMM"}}
 
 
 def run_caller_arm(dev, Bv=32, C=3, steps=3):
