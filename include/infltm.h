@@ -173,6 +173,9 @@ typedef struct {
   /* != 0: C points to IEEE fp16 storage (ldc / strideC / c_group_stride in elements; round to nearest even): the
    * product feeds a kind::f16 tensor-core contraction whose operands carry the same 11-bit significand as tf32 */
   int c_fp16;
+  /* with c_fp16: optional second fp16 output of the same layout, C_lo = rn(x - float(rn(x))) -- the result as two fp16
+   * terms (22 significant bits), the operand format of the fp16x2 contractions (ltm_cont_attn_gauss_tc16).  NULL: off */
+  void* C_lo;
 } ltm_gemm_args;
 int ltm_gemm(const ltm_gemm_args* args, void* stream);
 
@@ -269,6 +272,14 @@ int ltm_ridge_solve(const float* positions, int P, int trim, int rows,
 /* ---- gather rows: out[v, s, :] = src[v, idx[v,s], :]  (zero row when idx < 0) */
 int ltm_gather_rows(const float* src, const int32_t* idx, float* out, int Bv, int rows_src, int S, int e,
                     void* stream);
+
+/* ---- G4 on the tensor cores: continuous attention of the Gaussian variant (long_term_attention.py:286-325) with both
+ * contractions as kind::f16 UMMAs over two-term operands (x ~ hi + lo: fp32-grade products).  KV_hi / KV_lo: fp16
+ * [Bv*N, ldkv] from ltm_gemm (c_fp16 + C_lo), keys of head h at columns [h*d, (h+1)*d), values at H*d + the same.
+ * Outputs ctx[Bv,Q,H*d], mu / sd [Bv, H*Q] (either may be NULL).  num_basis 64 / 128 / 256, head size 64. */
+int ltm_cont_attn_gauss_tc16(const float* q, const void* KV_hi, const void* KV_lo, int64_t ldkv, const float* basis_mu,
+                             const float* basis_sigma, float* ctx, float* mu_out, float* sd_out, int Bv, int Q, int N,
+                             int H, int d, void* stream);
 
 /* ---- variant G, sticky update without materialising the re-sampled rows: b_sorted[Bv,S] are the drawn bins in
  * ascending order (ltm_resample sort = 1), GT[N, >= S+L] the update operator G_inf^T (row pitch ldg).

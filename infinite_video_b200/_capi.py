@@ -28,6 +28,7 @@ class GemmArgs(C.Structure):
         ("c_group", C.c_int), ("c_group_stride", C.c_int64), ("bias_stride", C.c_int64),
         ("round_tf32", C.c_int), ("ab_fp16", C.c_int),
         ("a_group", C.c_int), ("a_group_stride", C.c_int64), ("c_fp16", C.c_int),
+        ("C_lo", C.c_void_p),
     ]
 
 
@@ -78,6 +79,7 @@ _SIGS = {
     "ltm_pool_mean": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_pool_mean_convert": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_fold_sample_columns": (C.c_int, [_P, _L, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "ltm_cont_attn_gauss_tc16": (C.c_int, [_P, _P, _P, _L, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_split_half3": (C.c_int, [_P, _P, _L, _I, _I, _P]),
     "ltm_pool_bins": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ltm_pool_mean_16": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _I, _P]),

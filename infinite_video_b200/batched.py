@@ -644,7 +644,7 @@ class BatchedGaussLTM(_BatchedBase):
     def __init__(self, num_basis, tau, w_key, b_key, w_value, b_value, *, sigmas=(0.005, 0.01), n_heads=12,
                  head_size=64, sticky=True, nb_samples=tables.NB_SAMPLES, precision="tf32x3",
                  proj_precision=None, device="cuda", ridge=tables.RIDGE_PENALTY,
-                 spacing="linear", value_precision=None, fold_samples=True):
+                 spacing="linear", value_precision=None, fold_samples=True, tc_attn=True):
         ns = len(sigmas)
         n = int(num_basis)
         if n % ns:
@@ -669,6 +669,9 @@ class BatchedGaussLTM(_BatchedBase):
         # instead of G_inf^T [gather(R) ; k]: same B, no [Bv,S,e] intermediate, contraction 128 + L instead of S + L
         self.fold_samples = bool(fold_samples)
         self._W3 = None
+        # tensor-core attention (csrc/attn_g16.cu): num_basis 64 / 128 / 256, head size 64, with the fp16x2 projection
+        self.tc_attn = (bool(tc_attn) and self.proj_precision == "fp16x2" and ops.attn_tc_supported(self.N, self.d)
+                        and self.value_precision is None and self.e % 8 == 0)
         self.ridge = float(ridge)
         self._ops = {}
         self._B = None
@@ -757,7 +760,14 @@ class BatchedGaussLTM(_BatchedBase):
                 B = ops.gemm(op["GinfT"], xm, B2=k, a_kmajor=True, b_kmajor=False, precision=self.precision,
                              impl=self.gemm_impl)
         self._B = B
-        if ops.attn_fast_supported(self.N, self.d):
+        if self.tc_attn:
+            # tensor-core path: K|V straight out of the fp16x2 projection as two fp16 terms, both attention
+            # contractions as kind::f16 UMMAs over the two-term operands (csrc/attn_g16.cu)
+            if self._W3 is None or self._W3_src != self.Wkv.data_ptr():
+                self._W3, self._W3_src = ops.split_half3(self.Wkv, 1), self.Wkv.data_ptr()
+            KVh, KVl = ops.project_kv_split(B, self.bkv, self.N, self._W3)
+            ctx, mu, sd = ops.cont_attn_gauss_tc16(q, KVh, KVl, op["mu"], op["sigma"], n_heads=self.H)
+        elif ops.attn_fast_supported(self.N, self.d):
             w3 = None
             if self.proj_precision == "fp16x2":
                 if self._W3 is None or self._W3_src != self.Wkv.data_ptr():

@@ -548,7 +548,7 @@ static int launch(const CUtensorMap& mK, const CUtensorMap& mV, const CUtensorMa
 }  // namespace tc16
 
 // fp16 tensor map {inner halves, outer rows}, box {64, box_outer}, SWIZZLE_128B
-static int tma_encode_2d_f16(CUtensorMap* map, const void* base, unsigned long long inner, unsigned long long outer,
+int tma_encode_2d_f16(CUtensorMap* map, const void* base, unsigned long long inner, unsigned long long outer,
                              unsigned long long pitch_elems, unsigned box_outer, const char* what) {
   static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
   if (!enc) {

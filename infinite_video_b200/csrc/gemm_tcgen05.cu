@@ -52,6 +52,7 @@ struct GemmDev {
   int c_vec;                                // row-major stores may be 128-bit (alignment checked on the host)
   int a_group;                              // two-level row mapping of A (0 = off): tile rows span 128 / a_group groups
   int c_half;                               // C is fp16 storage (row-major path only)
+  void* C_lo;                               // fp16 output only: second array for the residual x - float(half(x))
   int dbg;                                  // bring-up builds only (-DLTM_BRINGUP): 1 = no global stores, 2 = no TMA loads
 };
 // The bring-up switches exist only in builds made with -DLTM_BRINGUP (scripts/*_probe.py); the product library
@@ -227,18 +228,34 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& g, uint32_t tmem_ac
                             v1.x + bb[4], v1.y + bb[5], v1.z + bb[6], v1.w + bb[7]};
         if (rok[i]) {
           __half* dst = reinterpret_cast<__half*>(g.C) + (size_t)bz * g.strideC + roff[i] + (col8 - (g.CT != nullptr ? g.ct_cols : 0));
+          __half* dlo = g.C_lo ? reinterpret_cast<__half*>(g.C_lo) + (dst - reinterpret_cast<__half*>(g.C)) : nullptr;
           if (vec8) {
             uint4 pk;
-            __half2 h;
-            h = __floats2half2_rn(f[0], f[1]); pk.x = *reinterpret_cast<const uint32_t*>(&h);
-            h = __floats2half2_rn(f[2], f[3]); pk.y = *reinterpret_cast<const uint32_t*>(&h);
-            h = __floats2half2_rn(f[4], f[5]); pk.z = *reinterpret_cast<const uint32_t*>(&h);
-            h = __floats2half2_rn(f[6], f[7]); pk.w = *reinterpret_cast<const uint32_t*>(&h);
+            __half2 h[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(f[2 * t], f[2 * t + 1]);
+            pk.x = *reinterpret_cast<const uint32_t*>(&h[0]); pk.y = *reinterpret_cast<const uint32_t*>(&h[1]);
+            pk.z = *reinterpret_cast<const uint32_t*>(&h[2]); pk.w = *reinterpret_cast<const uint32_t*>(&h[3]);
             *reinterpret_cast<uint4*>(dst) = pk;
+            if (dlo != nullptr) {                    // residual term: x ~ hi + lo, 22 significant bits
+              __half2 l[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 hf = __half22float2(h[t]);
+                l[t] = __floats2half2_rn(f[2 * t] - hf.x, f[2 * t + 1] - hf.y);
+              }
+              pk.x = *reinterpret_cast<const uint32_t*>(&l[0]); pk.y = *reinterpret_cast<const uint32_t*>(&l[1]);
+              pk.z = *reinterpret_cast<const uint32_t*>(&l[2]); pk.w = *reinterpret_cast<const uint32_t*>(&l[3]);
+              *reinterpret_cast<uint4*>(dlo) = pk;
+            }
           } else {
 #pragma unroll
             for (int t = 0; t < 8; ++t)
-              if (col8 + t < g.Nc) dst[t] = __float2half_rn(f[t]);
+              if (col8 + t < g.Nc) {
+                const __half hh = __float2half_rn(f[t]);
+                dst[t] = hh;
+                if (dlo != nullptr) dlo[t] = __float2half_rn(f[t] - __half2float(hh));
+              }
           }
         }
       }
@@ -1022,6 +1039,8 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
              (a.CT == nullptr || a.ct_cols % 4 == 0)) ? 1 : 0;
   d.a_group = a.a_group;
   d.c_half = a.c_fp16 ? 1 : 0;
+  d.C_lo = a.c_fp16 ? a.C_lo : nullptr;
+  LTM_REQUIRE(a.C_lo == nullptr || (a.c_fp16 && aligned16(a.C_lo)), "gemm: C_lo needs c_fp16 and 16-byte alignment");
   LTM_REQUIRE(!a.c_fp16 || a.CT == nullptr, "gemm: fp16 output has no transposed store");
   d.a_batched = a.strideA != 0; d.b_batched = a.strideB != 0; d.b2_batched = a.strideB2 != 0; d.has_b2 = two ? 1 : 0;
 #ifdef LTM_BRINGUP

@@ -225,7 +225,8 @@ def gemm(A, B, *, a_kmajor=True, b_kmajor=True, B2=None, bias=None, out=None, pr
 
 def gemm_raw(A, lda, strideA, a_kmajor, B, ldb, strideB, b_kmajor, C_, ldc, strideC, M, Nc, K, batch, *, bias=None,
              bias_stride=0, c_group=0, c_group_stride=0, precision="tf32", impl="tcgen05", a_offset=0, b_offset=0,
-             c_offset=0, round_tf32=False, a_group=0, a_group_stride=0, bias_offset=0, c_fp16=False, ab_fp16=False):
+             c_offset=0, round_tf32=False, a_group=0, a_group_stride=0, bias_offset=0, c_fp16=False, ab_fp16=False,
+             C_lo=None):
     """ltm_gemm with every pitch / batch stride spelled out (elements).  A, B, C_ are the base tensors; *_offset
     shifts the start (elements).  Used where operands are strided views that tensor shapes cannot express
     (per-head column blocks, per-head / per-video output layouts)."""
@@ -240,6 +241,7 @@ def gemm_raw(A, lda, strideA, a_kmajor, B, ldb, strideB, b_kmajor, C_, ldc, stri
     g.bias_stride = bias_stride
     g.C, g.ldc, g.strideC = C_.data_ptr() + (2 if c_fp16 else 4) * c_offset, ldc, strideC
     g.c_fp16 = int(bool(c_fp16))
+    g.C_lo = (C_lo.data_ptr() + 2 * c_offset) if C_lo is not None else None      # residual fp16 term (c_fp16 only)
     g.M, g.Nc, g.K, g.batch = M, Nc, K, batch
     g.precision, g.impl = PRECISION[precision], GEMM_IMPL[impl]
     g.CT, g.ct_cols, g.ct_group = None, 0, 0
@@ -493,6 +495,41 @@ def cont_attn_gauss_t(q, Kt, V, basis_mu, basis_sigma, want_scores=False):
                                       ptr(scores), ptr(mu), ptr(sd), Bv, Q, N, H, d, stream_ptr(q.device)),
           "cont_attn_gauss_t")
     return ctx, scores, mu, sd
+
+
+def cont_attn_gauss_tc16(q, KV_hi, KV_lo, basis_mu, basis_sigma, n_heads=12):
+    """Tensor-core Gaussian closed form: q[Bv,Q,D], KV_hi / KV_lo fp16 [Bv,N,2D] (two-term K|V from the projection
+    GEMM) -> (ctx, mu[Bv,H*Q], sd[Bv,H*Q])."""
+    require_cuda(q, KV_hi, KV_lo, basis_mu, basis_sigma)
+    q = _f32c(q)
+    Bv, Q, D = q.shape
+    N = KV_hi.shape[1]
+    if KV_hi.dtype != torch.float16 or KV_lo.dtype != torch.float16 or KV_hi.shape != KV_lo.shape \
+            or not KV_hi.is_contiguous() or not KV_lo.is_contiguous() or KV_hi.shape[2] != 2 * D:
+        raise ValueError("cont_attn_gauss_tc16: KV_hi / KV_lo must be contiguous float16 [Bv,N,2D]")
+    H = n_heads
+    ctx = torch.empty(Bv, Q, D, device=q.device, dtype=torch.float32)
+    mu = torch.empty(Bv, H * Q, device=q.device, dtype=torch.float32)
+    sd = torch.empty(Bv, H * Q, device=q.device, dtype=torch.float32)
+    check(lib().ltm_cont_attn_gauss_tc16(ptr(q), ptr(KV_hi), ptr(KV_lo), 2 * D, ptr(basis_mu), ptr(basis_sigma),
+                                         ptr(ctx), ptr(mu), ptr(sd), Bv, Q, N, H, D // H, stream_ptr(q.device)),
+          "cont_attn_gauss_tc16")
+    return ctx, mu, sd
+
+
+def project_kv_split(Bcoef, bkv, N, w_split):
+    """K|V = B W^T + b as two fp16 terms (hi, lo), [Bv,N,2D] each: one fp16 GEMM over the hi/lo-split operands
+    (split_half3) whose epilogue writes the result and its fp16 residual.  w_split: split_half3(Wkv, 1)."""
+    require_cuda(Bcoef, bkv, w_split)
+    Bc = _f32c(Bcoef).reshape(-1, Bcoef.shape[-1])
+    M, e = Bc.shape
+    D2 = w_split.shape[0]
+    A3 = split_half3(Bc, 0)
+    hi = torch.empty(M // N, N, D2, device=Bc.device, dtype=torch.float16)
+    lo = torch.empty_like(hi)
+    gemm_raw(A3, 3 * e, 0, True, w_split, 3 * e, 0, True, hi, D2, 0, M, D2, 3 * e, 1, bias=bkv, ab_fp16=True,
+             c_fp16=True, C_lo=lo, precision="tf32")
+    return hi, lo
 
 
 def cont_attn_rect(q, KV, W, W_out, jb=None, tb=None, n_heads=12, want_scores=False, want_hist=True):

@@ -100,6 +100,59 @@ def test_split_half3_gives_fp32_grade_products_on_fp16_tensor_cores(dev):
     assert e16 < 1e-5 and e16 < 2 * e32, (e16, e32)
 
 
+def test_gemm_two_term_fp16_output(dev):
+    """ltm_gemm c_fp16 + C_lo: the result as two fp16 terms, hi + lo within 2^-21 of the fp32 result."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(14)
+    M, Nc, K = 300, 192, 256
+    A = torch.randn(M, K, generator=g).to(dev)
+    W = torch.randn(Nc, K, generator=g).to(dev)
+    bias = torch.randn(Nc, generator=g).to(dev)
+    hi = torch.zeros(M, Nc, device=dev, dtype=torch.float16)
+    lo = torch.zeros_like(hi)
+    ops.gemm_raw(A, K, 0, True, W, K, 0, True, hi, Nc, 0, M, Nc, K, 1, bias=bias, precision="tf32x3", c_fp16=True, C_lo=lo)
+    full = torch.zeros(M, Nc, device=dev)
+    ops.gemm_raw(A, K, 0, True, W, K, 0, True, full, Nc, 0, M, Nc, K, 1, bias=bias, precision="tf32x3")
+    assert torch.equal(hi, full.half())
+    assert torch.equal(lo, (full - hi.float()).half())
+    assert relerr(hi.float() + lo.float(), full) < 5e-7
+
+
+@pytest.mark.parametrize("N,Bv,Q", [(256, 3, 32), (64, 2, 32), (128, 2, 40), (256, 1, 96)])
+def test_cont_attn_gauss_on_tensor_cores(dev, N, Bv, Q):
+    """Tensor-core Gaussian attention (two-term fp16 operands, csrc/attn_g16.cu) against the fp32 FMA kernel on the same
+    keys / values, and both against an fp64 evaluation: the density parameters and the context."""
+    ops, T = _ops(), _tables()
+    g = torch.Generator().manual_seed(N + Q)
+    H, d, D = 12, 64, 768
+    t = T.gauss_tables(8, N, .75)
+    bmu, bsig = torch.from_numpy(t.basis_mu).to(dev), torch.from_numpy(t.basis_sigma).to(dev)
+    q = torch.randn(Bv, Q, D, generator=g).to(dev)
+    KV = (torch.randn(Bv, N, 2 * D, generator=g) * 0.5).to(dev)
+    KV[:, :, D:] *= 3.0
+    hi = KV.half()
+    lo = (KV - hi.float()).half()
+    ctx, mu, sd = ops.cont_attn_gauss_tc16(q, hi, lo, bmu, bsig)
+    Kt = KV[:, :, :D].reshape(Bv, N, H, d).permute(0, 2, 3, 1).contiguous()
+    V = KV[:, :, D:].contiguous()
+    ctx_f, _, mu_f, sd_f = ops.cont_attn_gauss_t(q, Kt, V, bmu, bsig)
+    # fp64 reference
+    K64 = KV[:, :, :D].double().view(Bv, N, H, d).transpose(1, 2)
+    V64 = KV[:, :, D:].double().view(Bv, N, H, d).transpose(1, 2)
+    qh = q.double().view(Bv, Q, H, d).transpose(1, 2) / 8.0
+    a = torch.softmax(20 * (qh @ K64.transpose(-1, -2)), -1)
+    bm, bs = bmu.double(), bsig.double()
+    m = a @ bm
+    var = a @ (bm ** 2 + bs ** 2) - m ** 2
+    s = torch.sqrt(bs ** 2 + var.unsqueeze(-1))
+    r = torch.exp(-0.5 * ((m.unsqueeze(-1) - bm) / s) ** 2) / (2 * torch.pi) ** 0.5 / s
+    want = (r @ V64).transpose(1, 2).reshape(Bv, Q, D)
+    e_tc, e_f = relerr(ctx, want), relerr(ctx_f, want)
+    assert relerr(mu.view(Bv, H, Q), m) < 1e-5 and relerr(sd.view(Bv, H, Q), var.sqrt()) < 1e-3
+    assert e_tc < 1e-3 and e_tc < 2 * e_f + 2e-5, (e_tc, e_f)      # (peaky random softmax: both ~3e-4 from fp64)
+    assert relerr(mu, mu_f) < 1e-5
+
+
 def test_fold_sample_columns(dev):
     """Variant G: operator columns summed per drawn sticky bin == the gathered product, G^T [R[b_s] ; k] = A_v [R ; k]."""
     ops = _ops()
