@@ -42,9 +42,12 @@ if which in ("all", "caller"):
     for c in range(2):
         mod(q[c], k[c], new_video=(c == 0), u=u[c] if c else None)
 if which in ("all", "gauss"):
-    eng = BatchedGaussLTM(N, .75, *w, device=dev)
     kg = [x.view(Bv, L, T, E)[:, :, 0].contiguous() for x in k]
-    for c in range(3):
-        eng.step(kg[c], q[c], u[c] if c else None, new_doc=(c == 0))
+    # default: folded sticky operator, fp16x2 projection, tensor-core attention; then the round-1 route (gathered
+    # samples, split-TF32 projection, FMA attention) so that its kernels are captured too
+    for kw in ({}, dict(fold_samples=False, proj_precision="tf32x3", tc_attn=False)):
+        eng = BatchedGaussLTM(N, .75, *w, device=dev, **kw)
+        for c in range(3):
+            eng.step(kg[c], q[c], u[c] if c else None, new_doc=(c == 0))
 torch.cuda.synchronize()
 print("ok")
