@@ -134,35 +134,54 @@ consolidate_rect_kernel(const float4* __restrict__ B_past, const float4* __restr
 // out[v, n, nbins + l] = GT[n, S + l] (the frame columns, copied): a per-video operator with 128 + L instead of S + L
 // columns whose product with [R ; k] is the same B -- without materialising xm[Bv, S, e] and with half the
 // contraction length.  long_term_attention.py:239-250.
+// One warp per operator row: the S sample columns are read 32 at a time (coalesced) next to their (sorted) bins, a
+// segmented warp scan adds the members of a bin that sit in the same 32, and the last lane of each segment adds the
+// partial to the row's per-bin accumulator in shared memory -- a long run (a peaky histogram puts a hundred draws into
+// one bin) costs what a short one does.
+constexpr int FOLD_UNROLL = 8;
 __global__ void __launch_bounds__(256)
 fold_sample_columns_kernel(const float* __restrict__ GT, long long ldg, const int32_t* __restrict__ b_sorted,
                            float* __restrict__ out, int N, int S, int L, int nbins, int rows_per_cta) {
-  __shared__ int start[257];
-  const int v = blockIdx.y;
+  extern __shared__ float facc[];                          // [8 warps][nbins]
+  const int v = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int32_t* bs = b_sorted + (size_t)v * S;
-  for (int b = threadIdx.x; b <= nbins; b += blockDim.x) {     // lower bound of bin b in the sorted draws
-    int lo = 0, hi = S;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (bs[mid] < b) lo = mid + 1; else hi = mid;
-    }
-    start[b] = lo;
-  }
-  __syncthreads();
+  float* acc = facc + warp * nbins;
   const int W = nbins + L;
-  const int n0 = blockIdx.x * rows_per_cta;
-  for (int i = threadIdx.x; i < rows_per_cta * W; i += blockDim.x) {
-    const int n = n0 + i / W, c = i - (i / W) * W;
-    if (n >= N) break;
+  for (int r = warp; r < rows_per_cta; r += 8) {
+    const int n = blockIdx.x * rows_per_cta + r;
+    if (n >= N) break;                                     // warp-uniform
     const float* g = GT + (size_t)n * ldg;
-    float acc;
-    if (c < nbins) {
-      acc = 0.f;
-      for (int s = start[c]; s < start[c + 1]; ++s) acc += g[s];
-    } else {
-      acc = g[S + c - nbins];
+    for (int b = lane; b < nbins; b += 32) acc[b] = 0.f;
+    __syncwarp();
+    for (int s0 = 0; s0 < S; s0 += 32 * FOLD_UNROLL) {
+      // the loads of FOLD_UNROLL chunks go out together (the loop is bound by their latency, not by the arithmetic)
+      int key[FOLD_UNROLL];
+      float val[FOLD_UNROLL];
+#pragma unroll
+      for (int u = 0; u < FOLD_UNROLL; ++u) {
+        const int s = s0 + 32 * u + lane;
+        key[u] = s < S ? __ldg(bs + s) : -1 - lane;        // (padding lanes: unique keys, nothing to add)
+        val[u] = s < S ? __ldg(g + s) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < FOLD_UNROLL; ++u) {
+        const int s = s0 + 32 * u + lane;
+        // segmented inclusive scan over equal (sorted, hence adjacent) keys
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float up = __shfl_up_sync(0xffffffffu, val[u], o);
+          const int ku = __shfl_up_sync(0xffffffffu, key[u], o);
+          if (lane >= o && ku == key[u]) val[u] += up;
+        }
+        const int kn = __shfl_down_sync(0xffffffffu, key[u], 1);
+        if (s < S && (lane == 31 || kn != key[u]) && key[u] >= 0 && key[u] < nbins) acc[key[u]] += val[u];
+        __syncwarp();                                      // segment tails of one chunk hit distinct bins
+      }
     }
-    out[((size_t)v * N + n) * W + c] = acc;
+    float* o = out + ((size_t)v * N + n) * W;
+    for (int b = lane; b < nbins; b += 32) o[b] = acc[b];
+    for (int l = lane; l < L; l += 32) o[nbins + l] = g[S + l];
+    __syncwarp();
   }
 }
 
@@ -264,8 +283,9 @@ extern "C" int ltm_fold_sample_columns(const float* GT, int64_t ldg, const int32
   LTM_REQUIRE(GT && b_sorted && out, "fold_sample_columns: null pointer");
   LTM_REQUIRE(Bv > 0 && Bv <= 65535 && N > 0 && S > 0 && L >= 0 && nbins > 0 && nbins <= 256 && ldg >= S + L,
               "fold_sample_columns: bad shape Bv=%d N=%d S=%d L=%d nbins=%d", Bv, N, S, L, nbins);
-  const int rows_per_cta = 8;
-  fold_sample_columns_kernel<<<dim3((N + rows_per_cta - 1) / rows_per_cta, Bv), 256, 0, (cudaStream_t)stream>>>(
+  const int rows_per_cta = 8;           // one warp per row
+  fold_sample_columns_kernel<<<dim3((N + rows_per_cta - 1) / rows_per_cta, Bv), 256, 8 * nbins * sizeof(float),
+                               (cudaStream_t)stream>>>(
       GT, (long long)ldg, b_sorted, out, N, S, L, nbins, rows_per_cta);
   LTM_CHECK_LAUNCH("fold_sample_columns");
   return 0;
