@@ -326,13 +326,15 @@ def test_gauss_matches_oracle_with_shared_operators(dev, N, L, Bv, C):
     ks, qs, us = make_inputs(42, C, Bv, L, 768, 32)
     with torch.no_grad():
         for c in range(C):
+            # no guard band: the uniforms go in as drawn; the oracle continues with the bins the CUDA path sampled and
+            # its own draws are compared with them -- a difference must be a tie on a CDF edge (helpers.compare_draws)
             u = us[c]
-            if c > 0:
-                u = guard_band(u, orc.sticky_hist(tb))
-            want = orc.forward(ks[c], qs[c], c == 0, u)
             got = eng.step(ks[c].to(dev), qs[c].to(dev), u.to(dev) if c else None, new_doc=(c == 0))
+            b_got = eng.last["b"].cpu().long() if c else None
+            want = orc.forward(ks[c], qs[c], c == 0, u, b_override=b_got)
             if c > 0:
-                assert torch.equal(eng.last["b"].cpu().long(), orc.last["b"]), f"bins differ at chunk {c}"
+                flips, _ = compare_draws(b_got, orc.last["b_own"], u, orc.last["p"], 1e-5)
+                assert flips <= 2, f"{flips} flipped draws at chunk {c}"
                 assert torch.equal(eng.last["ts"].cpu(), orc.last["ts"])
             assert relerr(eng.B_past, orc.B_past) < TOL_B, f"B, chunk {c}"
             # ctx: 1e-3 wherever the reference's own result is well conditioned.  Its variance
