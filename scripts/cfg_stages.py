@@ -9,7 +9,7 @@ dev = torch.device("cuda:0")
 lib = _capi.lib()
 names = ["pool", "resample", "consolidate", "project_kv", "attention"]
 torch.manual_seed(0)
-for name, (Bv, N, L, T, e, Q) in {"cfg1": (1024, 64, 8, 32, 768, 32), "cfg3": (64, 64, 16, 196, 1024, 96),
+for name, (Bv, N, L, T, e, Q) in {"cfg1": (1024, 64, 8, 32, 768, 32), "cfg3": (128, 64, 16, 196, 1024, 96),
                                   "cfg4": (64, 512, 256, 32, 768, 32), "cfg2": (128, 256, 256, 32, 768, 32)}.items():
     key, val = torch.nn.Linear(e, 768), torch.nn.Linear(e, 768)
     eng = BatchedRectLTM(N, .75, key.weight.detach(), key.bias.detach(), val.weight.detach(), val.bias.detach(),
