@@ -90,6 +90,19 @@ __device__ __forceinline__ float4 ldg_nc(const float4* p) {
 __device__ __forceinline__ void f4_add(float4& a, const float4& b) {
   a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
 }
+// the same four IEEE additions as two packed instructions (sm_100 add.rn.f32x2): half the issue slots of the
+// accumulation in the streaming kernels
+__device__ __forceinline__ void f4_add_packed(float4& a, const float4& b) {
+  unsigned long long a0, a1, b0, b1;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a0) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a1) : "f"(a.z), "f"(a.w));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b0) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b1) : "f"(b.z), "f"(b.w));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a0) : "l"(b0));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a1) : "l"(b1));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(a0));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a.z), "=f"(a.w) : "l"(a1));
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

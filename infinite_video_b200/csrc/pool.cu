@@ -32,7 +32,7 @@ __device__ __forceinline__ float4 pool_rows(const float4* __restrict__ base, int
 #pragma unroll
     for (int i = 0; i < POOL_UNROLL; ++i) v[i] = ldg_stream(base + (size_t)(r + i) * e4 + c, pol);
 #pragma unroll
-    for (int i = 0; i < POOL_UNROLL; ++i) f4_add(acc[i % POOL_ACC], v[i]);
+    for (int i = 0; i < POOL_UNROLL; ++i) f4_add_packed(acc[i % POOL_ACC], v[i]);
   }
   for (; r < r1; ++r) f4_add(acc[0], ldg_stream(base + (size_t)r * e4 + c, pol));
 #pragma unroll
