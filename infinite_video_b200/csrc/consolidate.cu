@@ -5,7 +5,8 @@
 // 1/(cnt_j + 0.5), and  B = G^T [xm ; x]  is a segmented mean over the (contiguous) positions that
 // fall into bin j: contracted re-samples of the old memory -- rows of B_past gathered through the
 // sticky sample indices, i.e. the one-hot product B_past^T Psi^T of :208-210 -- followed by the
-// new pooled frames.  One CTA produces one coefficient row; one thread one 128-bit column group.
+// new pooled frames.  One CTA produces one coefficient row (four in a row for large batches); one thread one 128-bit
+// column group.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
