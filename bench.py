@@ -387,6 +387,8 @@ def run_b200(args):
                          proj_precision=args.proj_precision, kv_dtype=args.kv_dtype,
                          bin_pool=False if args.no_bin_pool else None)
     eng.video_block = args.video_block
+    if args.gemm_ctas is not None:
+        eng.gemm_ctas_overlap = args.gemm_ctas
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     # the chunks of all videos stay resident when they fit (128 videos x 8 chunks = 25.8 GB); a large shard (1024
     # videos on one GPU: 25.8 GB per chunk) streams through a ring of 3 chunk buffers instead -- still far more
@@ -724,6 +726,7 @@ def run_b200(args):
                                                 projected_memory_state=bool(eng.kv_state),
                                                 video_block=args.video_block, kv_dtype=args.kv_dtype,
                                                 proj_operands=args.proj_operands, pool_per_bin=bool(binned_pool),
+                                                projection_ctas_beside_pooling=int(eng.gemm_ctas_overlap) if overlap else 0,
                                                 proj_precision=args.proj_precision or args.precision),
             "frame_blocks_per_s": value * L,
             "roofline": {"bound": "hbm",
@@ -1041,6 +1044,9 @@ def main():
                     help="storage of the projected memory K|V on the tensor-core path")
     ap.add_argument("--no-bin-pool", action="store_true",
                     help="pool every frame on its own (round-1 layout) instead of one row per basis bin on update chunks")
+    ap.add_argument("--gemm-ctas", type=int, default=None,
+                    help="grid bound of the K/V projection while the next chunk is pooled beside the step "
+                         "(default: the engine's 7/16 of the SMs; 0 = one CTA per SM)")
     ap.add_argument("--video-block", type=int, default=0,
                     help="consolidate / project / attend in blocks of this many videos (L2 reuse); 0 = all at once")
     ap.add_argument("--no-kv-state", action="store_true",

@@ -176,6 +176,11 @@ typedef struct {
   /* with c_fp16: optional second fp16 output of the same layout, C_lo = rn(x - float(rn(x))) -- the result as two fp16
    * terms (22 significant bits), the operand format of the fp16x2 contractions (ltm_cont_attn_gauss_tc16).  NULL: off */
   void* C_lo;
+  /* bound of the persistent grid (0 = one CTA per SM).  A contraction that runs BESIDE an HBM-bound kernel of another
+   * stream (the K/V projection beside the next chunk's frame pooling) is not on the critical path, and confined to
+   * fewer SMs it takes less of the L2 -> SM bandwidth the streaming kernel lives on at any one time: measured at the
+   * NExT-QA shape, 148 -> 64 CTAs: the overlapped step 194.6 k -> 207.3 k chunks/s (the projection itself 0.09 -> 0.11 ms) */
+  int max_ctas;
 } ltm_gemm_args;
 int ltm_gemm(const ltm_gemm_args* args, void* stream);
 
@@ -344,6 +349,9 @@ typedef struct {
    * seg_ptr1b / seg_mem1b the update tables with the frames of a bin collapsed into one member S + r. */
   int binned, xb_rows;
   const int32_t* fbin_ptr; const int32_t* seg_ptr1b; const int32_t* seg_mem1b;
+  /* grid bound of the K/V projection GEMM (ltm_gemm_args.max_ctas; 0 = one CTA per SM): set when the next chunk's
+   * pooling runs beside this step */
+  int gemm_ctas;
 } ltm_rect_step_args;
 int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const float* q, const double* u,
                   const uint8_t* new_doc, float* ctx, void* stream);

@@ -28,7 +28,7 @@ class GemmArgs(C.Structure):
         ("c_group", C.c_int), ("c_group_stride", C.c_int64), ("bias_stride", C.c_int64),
         ("round_tf32", C.c_int), ("ab_fp16", C.c_int),
         ("a_group", C.c_int), ("a_group_stride", C.c_int64), ("c_fp16", C.c_int),
-        ("C_lo", C.c_void_p),
+        ("C_lo", C.c_void_p), ("max_ctas", C.c_int),
     ]
 
 
@@ -58,6 +58,7 @@ class RectStepArgs(C.Structure):
         ("kv_half", C.c_int), ("X16", C.c_void_p),
         ("binned", C.c_int), ("xb_rows", C.c_int),
         ("fbin_ptr", C.c_void_p), ("seg_ptr1b", C.c_void_p), ("seg_mem1b", C.c_void_p),
+        ("gemm_ctas", C.c_int),
     ]
 
 

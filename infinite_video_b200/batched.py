@@ -113,6 +113,11 @@ class BatchedRectLTM(_BatchedBase):
         # the tables allow it; False: never.  Applies where this engine pools the chunk itself (`step` without
         # `pooled=`, `prefetch(update=True)`, `step_overlapped`).
         self.bin_pool = bin_pool
+        # grid bound of the K/V projection while the next chunk is pooled beside the step (0 = all SMs): the projection
+        # is not on the critical path there, and on 64 of the 148 SMs it takes less of the L2 -> SM bandwidth the
+        # pooling kernel needs at any one time (step 194.6 k -> 207.3 k chunks/s; 32 .. 77 CTAs within 1 % of each other)
+        self.gemm_ctas_overlap = max(32, (self.sm_count * 7) // 16)
+        self.gemm_ctas_min_ratio = 16          # chunk tokens per basis function from which the bound applies
         self.spacing = spacing        # first-chunk frame positions: 'linear' | 'log' (gibbs:101-127)
         self.keep_scores = keep_scores
         # transposed-key attention path (num_basis 64/128/256, head size 64); `fast_attn=False` forces the generic one
@@ -261,7 +266,7 @@ class BatchedRectLTM(_BatchedBase):
         return self._B[self._cur] if (self._B is not None and self.has_state) else None
 
     # ------------------------------------------------------------------ one chunk
-    def _args(self, Bv, L, Q, ws, tab, tdev):
+    def _args(self, Bv, L, Q, ws, tab, tdev, beside_pool=False):
         # the argument block is built once per workspace / table set / weights and only its per-call fields are
         # rewritten afterwards (the ~40 ctypes assignments were a third of the host time of a chunk)
         sig = (id(tdev), self.Wkv.data_ptr(), self.bkv.data_ptr(), self._hist.data_ptr(), self.sticky,
@@ -277,6 +282,10 @@ class BatchedRectLTM(_BatchedBase):
         a.B_new = self._B[1 - self._cur].data_ptr()
         a.xpart = ws["xbufs"][ws["xi"]].data_ptr()
         a.binned = 1 if ws["xtag"][ws["xi"]] else 0
+        # (only where the pooling is the long pole of the step: a chunk of at least 16 tokens per basis function; with
+        # 8 frames x 32 tokens on 64 bins the chain of this stream is, and a narrower projection would lengthen it)
+        bound = beside_pool and L * self.T >= self.gemm_ctas_min_ratio * self.N
+        a.gemm_ctas = int(self.gemm_ctas_overlap) if bound else 0
         if ws["KVs"] is not None and len(ws["KVs"]) == 2:      # K|V ping-pong, in phase with the coefficient buffers
             a.KV = ws["KVs"][1 - self._cur].data_ptr()
             a.KV_past = ws["KVs"][self._cur].data_ptr() if (self.has_state and ws.get("kv_valid")) else None
@@ -540,7 +549,8 @@ class BatchedRectLTM(_BatchedBase):
             if ws["xi"] in held:
                 self._pref[:] = [e for e in self._pref if e["buf"] != ws["xi"]]
             ws["xtag"][ws["xi"]] = update and self._bin_ok(Bv, L, tab)
-        a = self._args(Bv, L, Q, ws, tab, tdev)
+        # (a pending prefetch = the next chunk is being pooled on the side stream while this step runs)
+        a = self._args(Bv, L, Q, ws, tab, tdev, beside_pool=bool(self._pref))
         check(lib().ltm_rect_step(C.byref(a), None if pooled else ptr(k), ptr(q), ptr(u), ptr(flags), ptr(ctx),
                                   C.c_void_p(run.cuda_stream)), "rect_step")
         if pooled:
@@ -595,7 +605,7 @@ class BatchedRectLTM(_BatchedBase):
             self._pref.append(dict(ref=weakref.ref(k_next), ver=k_next._version, buf=b, event=ev["pooled"][b],
                                    captured=capturing, binned=nb))
         ctx = torch.empty(Bv, Q, self.D, device=self.device, dtype=torch.float32)   # main joins the compute stream
-        a = self._args(Bv, L, Q, ws, tab, tdev)
+        a = self._args(Bv, L, Q, ws, tab, tdev, beside_pool=k_next is not None)
         check(lib().ltm_rect_step_overlap(C.byref(a), C.byref(o), ptr(q), ptr(u), ptr(flags), ptr(ctx)),
               "rect_step_overlap")
         self._finish(ws, k=k)

@@ -150,6 +150,7 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
       ga.M = nv * n_new; ga.Nc = 2 * D; ga.K = a->e; ga.batch = 1;
       ga.precision = half_ops ? 1 : pprec; ga.impl = a->gemm_impl; ga.round_tf32 = (tcp && !kvh) ? 1 : 0;
       ga.c_fp16 = kvh ? 1 : 0;
+      ga.max_ctas = a->gemm_ctas;
       rc = ltm_gemm(&ga, stream);
     } else if (half_ops) {
       ltm_gemm_args ga;
@@ -160,6 +161,7 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
       ga.C = KVn; ga.ldc = 2 * D;
       ga.M = nv * a->N; ga.Nc = 2 * D; ga.K = a->e; ga.batch = 1;
       ga.precision = 1; ga.impl = 0; ga.round_tf32 = kvh ? 0 : 1; ga.ab_fp16 = 1; ga.c_fp16 = kvh ? 1 : 0;
+      ga.max_ctas = a->gemm_ctas;
       rc = ltm_gemm(&ga, stream);
     } else if (kvh) {
       ltm_gemm_args ga;
@@ -170,6 +172,7 @@ extern "C" int ltm_rect_step(const ltm_rect_step_args* a, const float* k, const 
       ga.C = KVn; ga.ldc = 2 * D;
       ga.M = nv * a->N; ga.Nc = 2 * D; ga.K = a->e; ga.batch = 1;
       ga.precision = pprec; ga.impl = a->gemm_impl; ga.c_fp16 = 1;
+      ga.max_ctas = a->gemm_ctas;
       rc = ltm_gemm(&ga, stream);
     } else if (tcp)
       rc = ltm_project_kv_r(Bn, a->Wkv, a->bkv, KVn, nv * a->N, a->e, 2 * D, pprec, a->gemm_impl, stream);

@@ -27,6 +27,7 @@ __device__ __forceinline__ float tf32_round(float x) {
   return __uint_as_float(r);
 }
 
+template <int ROWS>
 __global__ void __launch_bounds__(256)
 consolidate_rect_kernel(const float4* __restrict__ B_past, const float4* __restrict__ xpart,
                         const int32_t* __restrict__ idx, const long long idx_stride,
@@ -36,9 +37,13 @@ consolidate_rect_kernel(const float4* __restrict__ B_past, const float4* __restr
                         const int32_t* __restrict__ seg_ptr1, const int32_t* __restrict__ seg_mem1,
                         const float* __restrict__ g1,
                         float4* __restrict__ B_new, uint2* __restrict__ B_half, const KvState kv, int N, int e4, int L,
-                        int splits, int S, int rows_per_cta) {
+                        int splits, int S) {
   const int v = blockIdx.y;
-  for (int j = blockIdx.x * rows_per_cta; j < min(N, (int)(blockIdx.x + 1) * rows_per_cta); ++j) {
+  // ROWS coefficient rows per CTA (1: the loop folds away and the kernel is the one-row kernel, 32 registers)
+#pragma unroll 1
+  for (int jr = 0; jr < ROWS; ++jr) {
+  const int j = blockIdx.x * ROWS + jr;
+  if (ROWS > 1 && j >= N) break;
   const bool first = (B_past == nullptr) || (new_doc != nullptr && new_doc[v] != 0);
   const int32_t* seg_ptr = first ? seg_ptr0 : seg_ptr1;
   const int32_t* seg_mem = first ? seg_mem0 : seg_mem1;
@@ -258,12 +263,19 @@ extern "C" int ltm_consolidate_rect_kv(const float* B_past, const float* xpart, 
   // four coefficient rows per CTA once there are plenty of rows: a row is ~10 dependent loads per thread, and four in
   // a row amortise the CTA's launch and tail (measured at 128 videos x 256 bins: consolidate 0.109 -> 0.101 ms alone,
   // the overlapped step 190.2 k -> 195.1 k chunks/s on the same box; 8 rows: no further gain)
-  const int rows_per_cta = (long long)N * Bv >= 16384 ? 4 : 1;
+  // (num_basis 64 x 1024 videos: 5 % slower with four rows under the overlap -- its rows are longer, 8-10 members each)
+  const int rows_per_cta = (N >= 128 && (long long)N * Bv >= 16384) ? 4 : 1;
   dim3 grid((N + rows_per_cta - 1) / rows_per_cta, Bv);
-  consolidate_rect_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float4*>(B_past), reinterpret_cast<const float4*>(xpart), idx, (long long)idx_stride,
-      new_doc, seg_ptr0, seg_mem0, g0, seg_ptr1, seg_mem1, g1, reinterpret_cast<float4*>(B_new),
-      reinterpret_cast<uint2*>(B_half), kv, N, e4, L, splits, S, rows_per_cta);
+  if (rows_per_cta == 4)
+    consolidate_rect_kernel<4><<<grid, threads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(B_past), reinterpret_cast<const float4*>(xpart), idx, (long long)idx_stride,
+        new_doc, seg_ptr0, seg_mem0, g0, seg_ptr1, seg_mem1, g1, reinterpret_cast<float4*>(B_new),
+        reinterpret_cast<uint2*>(B_half), kv, N, e4, L, splits, S);
+  else
+    consolidate_rect_kernel<1><<<grid, threads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(B_past), reinterpret_cast<const float4*>(xpart), idx, (long long)idx_stride,
+        new_doc, seg_ptr0, seg_mem0, g0, seg_ptr1, seg_mem1, g1, reinterpret_cast<float4*>(B_new),
+        reinterpret_cast<uint2*>(B_half), kv, N, e4, L, splits, S);
   LTM_CHECK_LAUNCH("consolidate_rect");
   return 0;
 }

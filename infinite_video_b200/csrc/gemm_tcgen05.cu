@@ -53,6 +53,7 @@ struct GemmDev {
   int a_group;                              // two-level row mapping of A (0 = off): tile rows span 128 / a_group groups
   int c_half;                               // C is fp16 storage (row-major path only)
   void* C_lo;                               // fp16 output only: second array for the residual x - float(half(x))
+  int max_ctas;                             // bound of the persistent grid (0 = one CTA per SM)
   int dbg;                                  // bring-up builds only (-DLTM_BRINGUP): 1 = no global stores, 2 = no TMA loads
 };
 // The bring-up switches exist only in builds made with -DLTM_BRINGUP (scripts/*_probe.py); the product library
@@ -938,7 +939,8 @@ static int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const CUtens
     LTM_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, STAGES, SPLIT, CLUSTER, HOUT>, mA, mB, mB2, d));
     return 0;
   }
-  const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);     // persistent: one CTA per SM
+  unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);     // persistent: one CTA per SM
+  if (d.max_ctas > 0 && (unsigned)d.max_ctas < grid) grid = (unsigned)d.max_ctas;   // ... or fewer (ltm_gemm_args.max_ctas)
   gemm_tf32_kernel<BN, STAGES, SPLIT, 1, HOUT><<<grid, C_::THREADS, C_::SMEM_BYTES, stream>>>(mA, mB, mB2, d);
   LTM_CHECK_LAUNCH("gemm(tcgen05)");
   return 0;
@@ -1040,6 +1042,7 @@ static int gemm_tcgen05_launch(const ltm_gemm_args& a, cudaStream_t stream) {
   d.a_group = a.a_group;
   d.c_half = a.c_fp16 ? 1 : 0;
   d.C_lo = a.c_fp16 ? a.C_lo : nullptr;
+  d.max_ctas = a.max_ctas;
   LTM_REQUIRE(a.C_lo == nullptr || (a.c_fp16 && aligned16(a.C_lo)), "gemm: C_lo needs c_fp16 and 16-byte alignment");
   LTM_REQUIRE(!a.c_fp16 || a.CT == nullptr, "gemm: fp16 output has no transposed store");
   d.a_batched = a.strideA != 0; d.b_batched = a.strideB != 0; d.b2_batched = a.strideB2 != 0; d.has_b2 = two ? 1 : 0;
