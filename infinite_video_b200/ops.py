@@ -226,7 +226,7 @@ def gemm(A, B, *, a_kmajor=True, b_kmajor=True, B2=None, bias=None, out=None, pr
 def gemm_raw(A, lda, strideA, a_kmajor, B, ldb, strideB, b_kmajor, C_, ldc, strideC, M, Nc, K, batch, *, bias=None,
              bias_stride=0, c_group=0, c_group_stride=0, precision="tf32", impl="tcgen05", a_offset=0, b_offset=0,
              c_offset=0, round_tf32=False, a_group=0, a_group_stride=0, bias_offset=0, c_fp16=False, ab_fp16=False,
-             C_lo=None):
+             C_lo=None, max_ctas=0):
     """ltm_gemm with every pitch / batch stride spelled out (elements).  A, B, C_ are the base tensors; *_offset
     shifts the start (elements).  Used where operands are strided views that tensor shapes cannot express
     (per-head column blocks, per-head / per-video output layouts)."""
@@ -242,6 +242,7 @@ def gemm_raw(A, lda, strideA, a_kmajor, B, ldb, strideB, b_kmajor, C_, ldc, stri
     g.C, g.ldc, g.strideC = C_.data_ptr() + (2 if c_fp16 else 4) * c_offset, ldc, strideC
     g.c_fp16 = int(bool(c_fp16))
     g.C_lo = (C_lo.data_ptr() + 2 * c_offset) if C_lo is not None else None      # residual fp16 term (c_fp16 only)
+    g.max_ctas = int(max_ctas)                    # bound of the persistent grid (0 = one CTA per SM)
     g.M, g.Nc, g.K, g.batch = M, Nc, K, batch
     g.precision, g.impl = PRECISION[precision], GEMM_IMPL[impl]
     g.CT, g.ct_cols, g.ct_group = None, 0, 0

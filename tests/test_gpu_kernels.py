@@ -100,6 +100,23 @@ def test_split_half3_gives_fp32_grade_products_on_fp16_tensor_cores(dev):
     assert e16 < 1e-5 and e16 < 2 * e32, (e16, e32)
 
 
+@pytest.mark.parametrize("ctas", [1, 5, 64])
+def test_gemm_with_a_bounded_grid_is_bit_identical(dev, ctas):
+    """ltm_gemm_args.max_ctas: the persistent kernel walks the same tiles with fewer CTAs -- same bits."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(15)
+    M, Nc, K = 1500, 700, 320
+    A = torch.randn(M, K, generator=g).to(dev)
+    W = torch.randn(Nc, K, generator=g).to(dev)
+    bias = torch.randn(Nc, generator=g).to(dev)
+    full = torch.zeros(M, Nc, device=dev)
+    few = torch.zeros(M, Nc, device=dev)
+    for prec in ("tf32", "tf32x3"):
+        ops.gemm_raw(A, K, 0, True, W, K, 0, True, full, Nc, 0, M, Nc, K, 1, bias=bias, precision=prec)
+        ops.gemm_raw(A, K, 0, True, W, K, 0, True, few, Nc, 0, M, Nc, K, 1, bias=bias, precision=prec, max_ctas=ctas)
+        assert torch.equal(full, few), prec
+
+
 def test_gemm_two_term_fp16_output(dev):
     """ltm_gemm c_fp16 + C_lo: the result as two fp16 terms, hi + lo within 2^-21 of the fp32 result."""
     ops = _ops()
