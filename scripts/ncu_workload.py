@@ -7,7 +7,7 @@ import torch
 from infinite_video_b200.batched import BatchedGaussLTM, BatchedRectLTM
 
 dev = torch.device("cuda:0")
-Bv, L, T, E, Q, N = 32, 256, 32, 768, 32, 256
+Bv, L, T, E, Q, N = int(os.environ.get("BV", 32)), 256, 32, 768, 32, 256
 torch.manual_seed(0)
 key, val = torch.nn.Linear(E, 768), torch.nn.Linear(E, 768)
 w = (key.weight.detach(), key.bias.detach(), val.weight.detach(), val.bias.detach())
