@@ -493,10 +493,11 @@ class BatchedRectLTM(_BatchedBase):
         return ops.pool_mean(k.view(Bv, L, self.T, e), self._splits(Bv * L))
 
     @_on_device
-    def step(self, k, q, u=None, new_doc=False, pooled=None):
+    def step(self, k, q, u=None, new_doc=False, pooled=None, beside_pooling=False):
         """k[Bv, L*T, e], q[Bv,Q,D] fp32 CUDA; u[Bv,S] fp64 uniforms (needed from the second chunk on when
         sticky); new_doc: bool or per-video flags; pooled: result of `pool(k)` (then `k` is only used for its
-        shape).  Returns ctx[Bv,Q,D]."""
+        shape); beside_pooling: the caller pools another chunk on a second stream while this step runs (the K/V
+        projection then keeps to part of the SMs, see `gemm_ctas_overlap`).  Returns ctx[Bv,Q,D]."""
         require_cuda(k, q, u)
         if k.dtype in (torch.float16, torch.bfloat16) and pooled is None:
             pooled = self.pool(k)                  # 16-bit chunk: pooled straight from its 16-bit storage
@@ -513,7 +514,7 @@ class BatchedRectLTM(_BatchedBase):
                     raise ValueError(f"sticky re-sampling needs u: float64 [{Bv},{self.S}]")
                 u = u.contiguous()
             ctx = torch.empty(Bv, Q, self.D, device=self.device, dtype=torch.float32)
-            a = self._args(Bv, L, Q, ws, tab, tdev)
+            a = self._args(Bv, L, Q, ws, tab, tdev, beside_pool=bool(beside_pooling))
             a.xpart, a.splits, a.binned = pooled.data_ptr(), pooled.shape[2], 0
             check(lib().ltm_rect_step(C.byref(a), None, ptr(q), ptr(u), ptr(flags), ptr(ctx),
                                       stream_ptr(self.device)), "rect_step")
@@ -550,7 +551,7 @@ class BatchedRectLTM(_BatchedBase):
                 self._pref[:] = [e for e in self._pref if e["buf"] != ws["xi"]]
             ws["xtag"][ws["xi"]] = update and self._bin_ok(Bv, L, tab)
         # (a pending prefetch = the next chunk is being pooled on the side stream while this step runs)
-        a = self._args(Bv, L, Q, ws, tab, tdev, beside_pool=bool(self._pref))
+        a = self._args(Bv, L, Q, ws, tab, tdev, beside_pool=bool(self._pref) or bool(beside_pooling))
         check(lib().ltm_rect_step(C.byref(a), None if pooled else ptr(k), ptr(q), ptr(u), ptr(flags), ptr(ctx),
                                   C.c_void_p(run.cuda_stream)), "rect_step")
         if pooled:

@@ -62,7 +62,7 @@ def consolidate_video(engines, chunks, queries, uniforms=None, new_doc=True, red
                 q = queries(li, c, prev) if callable(queries) else queries[li][c]
                 u = None if uniforms is None else uniforms[li][c]
                 ctx = eng.step(chunks[c], q, u if c > 0 or not new_doc else None, new_doc=(new_doc and c == 0),
-                               pooled=pooled[c])
+                               pooled=pooled[c], beside_pooling=(c + 1 < C))
                 prev = ctx
                 if reduce == "mean":
                     acc[li] = ctx.clone() if acc[li] is None else acc[li].add_(ctx)
