@@ -99,6 +99,9 @@ pool_mean_convert_kernel(const float4* __restrict__ k, float4* __restrict__ xpar
   const int r1 = (int)(((long long)T * (sp + 1)) / splits);
   const float4* base = k + (size_t)unit * T * e4;
   uint2* base16 = k16 + (size_t)unit * T * e4;
+  // lane pairs (c, c ^ 1) share 16-byte stores when every lane of the warp has a partner inside the row
+  // (whole warps only: the exchange is a full-mask shuffle)
+  const bool paired = (e4 % 32 == 0) && (reinterpret_cast<uintptr_t>(k16) & 15u) == 0;
   for (int c = threadIdx.x; c < e4; c += blockDim.x) {
     float4 acc[POOL_ACC];
 #pragma unroll
@@ -108,14 +111,31 @@ pool_mean_convert_kernel(const float4* __restrict__ k, float4* __restrict__ xpar
       float4 v[POOL_UNROLL];
 #pragma unroll
       for (int i = 0; i < POOL_UNROLL; ++i) v[i] = ldg_stream(base + (size_t)(r + i) * e4 + c, pol);
+      uint2 pk[POOL_UNROLL];
 #pragma unroll
       for (int i = 0; i < POOL_UNROLL; ++i) {
         f4_add(acc[i % POOL_ACC], v[i]);
         const __half2 lo = __floats2half2_rn(v[i].x, v[i].y), hi = __floats2half2_rn(v[i].z, v[i].w);
-        uint2 pk;
-        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-        base16[(size_t)(r + i) * e4 + c] = pk;
+        pk[i].x = *reinterpret_cast<const uint32_t*>(&lo);
+        pk[i].y = *reinterpret_cast<const uint32_t*>(&hi);
+      }
+      if (paired) {
+        // 16-byte stores: neighbouring lanes swap halves of a row pair -- the even lane stores 8 columns of the even
+        // row, the odd lane the same 8 columns of the odd row
+        const bool odd = (c & 1) != 0;
+#pragma unroll
+        for (int i = 0; i < POOL_UNROLL; i += 2) {
+          const uint2 give = odd ? pk[i] : pk[i + 1];
+          uint2 take;
+          take.x = __shfl_xor_sync(0xffffffffu, give.x, 1);
+          take.y = __shfl_xor_sync(0xffffffffu, give.y, 1);
+          const uint2 keep = odd ? pk[i + 1] : pk[i];
+          const uint4 out = odd ? make_uint4(take.x, take.y, keep.x, keep.y) : make_uint4(keep.x, keep.y, take.x, take.y);
+          *reinterpret_cast<uint4*>(base16 + (size_t)(r + i + (odd ? 1 : 0)) * e4 + (c & ~1)) = out;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < POOL_UNROLL; ++i) base16[(size_t)(r + i) * e4 + c] = pk[i];
       }
     }
     for (; r < r1; ++r) {
