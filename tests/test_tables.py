@@ -125,3 +125,41 @@ def test_folded_frame_tables_expand_to_the_per_frame_tables(N, L, spacing):
                 assert r == j - t.xb_row0
                 got.extend(t.S + f for f in range(t.fbin_ptr[r], t.fbin_ptr[r + 1]))
         assert got == want, j
+
+
+def test_folded_frame_tables_over_many_shapes():
+    """Property over a spread of (L, N, tau, spacing): either the frames cannot be folded (xb_rows == 0: the engine keeps
+    the per-frame layout) or the folded tables expand to the per-frame tables exactly and cover every frame that lies
+    inside a basis once."""
+    rng = np.random.default_rng(5)
+    seen = 0
+    for _ in range(60):
+        L = int(rng.integers(2, 300))
+        N = int(rng.choice([16, 32, 64, 100, 128, 256, 512]))
+        tau = float(rng.choice([0.5, 0.6, 0.75, 0.9]))
+        spacing = str(rng.choice(["linear", "log"]))
+        t = T.rect_tables(L, N, tau, 512, spacing=spacing)
+        if t.xb_rows == 0:
+            continue
+        seen += 1
+        assert t.xb_row0 == t.jf and t.xb_rows == N - t.jf
+        covered = np.zeros(L, bool)
+        for r in range(t.xb_rows):
+            assert not covered[t.fbin_ptr[r]:t.fbin_ptr[r + 1]].any()
+            covered[t.fbin_ptr[r]:t.fbin_ptr[r + 1]] = True
+        for j in range(N):
+            want = list(t.seg_mem1[t.seg_ptr1[j]:t.seg_ptr1[j + 1]])
+            got = []
+            for m in t.seg_mem1b[t.seg_ptr1b[j]:t.seg_ptr1b[j + 1]]:
+                if m < t.S:
+                    got.append(int(m))
+                else:
+                    r = int(m) - t.S
+                    got.extend(t.S + f for f in range(t.fbin_ptr[r], t.fbin_ptr[r + 1]))
+            assert got == want, (L, N, tau, spacing, j)
+        frames_in_a_bin = np.zeros(L, bool)
+        for j in range(N):
+            mem = t.seg_mem1[t.seg_ptr1[j]:t.seg_ptr1[j + 1]]
+            frames_in_a_bin[mem[mem >= t.S] - t.S] = True
+        assert np.array_equal(covered, frames_in_a_bin), (L, N, tau, spacing)
+    assert seen >= 30
