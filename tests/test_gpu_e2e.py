@@ -587,6 +587,46 @@ def test_overlapped_step_is_bit_identical(dev):
     torch.cuda.synchronize()
 
 
+def test_headline_batch_overlapped_equals_plain(dev):
+    """The bench configuration at size (128 videos x 256 frames, num_basis 256): `step_overlapped` with its defaults --
+    update chunks pooled per basis bin, four consolidation rows per CTA, the projection confined to part of the SMs
+    beside the pooling -- against plain `step` calls of an engine that pools per frame; and three of the videos against
+    the oracle."""
+    from infinite_video_b200.batched import BatchedRectLTM
+    from infinite_video_b200 import tables as _T
+    key, val = make_proj(91, 768)
+    N, L, Bv, C = 256, 256, 128, 3
+    a = BatchedRectLTM(N, .75, *proj_tensors(key, val), device=dev, bin_pool=False)
+    b = BatchedRectLTM(N, .75, *proj_tensors(key, val), device=dev)
+    assert b._bin_ok(Bv, L, _T.rect_tables(L, N, .75, 512)) and b.gemm_ctas_overlap > 0
+    check = [0, 63, 127]
+    orcs = {v: O.RectLTM(N, .75, *proj_tensors(key, val), rebuild_tables=False, faithful_quadrature=False)
+            for v in check}
+    g = torch.Generator(device=dev).manual_seed(92)
+    ks = [torch.randn(Bv, L * 32, 768, device=dev, generator=g) for _ in range(C)]
+    qs = [torch.randn(Bv, 32, 768, device=dev, generator=g) for _ in range(C)]
+    us = [torch.rand(Bv, 512, dtype=torch.float64, device=dev, generator=g) for _ in range(C)]
+    with torch.no_grad():
+        for c in range(C):
+            x = a.step(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0))
+            y = b.step_overlapped(ks[c], qs[c], us[c] if c else None, new_doc=(c == 0),
+                                  k_next=ks[c + 1] if c + 1 < C else None)
+            assert relerr(b.B_past, a.B_past) < 1e-6, c
+            if c:
+                assert torch.equal(b.last["b"], a.last["b"]), c
+            assert relerr(y, x) < 1e-4, c
+            b_got = b.last["b"].cpu().long() if c else None
+            for v in check:
+                want = orcs[v].forward(ks[c][v:v + 1].cpu(), qs[c][v:v + 1].cpu(), c == 0, us[c][v:v + 1].cpu(),
+                                       b_override=b_got[v:v + 1] if c else None)
+                if c:
+                    compare_draws(b_got[v:v + 1], orcs[v].last["b_own"], us[c][v:v + 1].cpu(), orcs[v].last["p"],
+                                  TIE["tf32"])
+                assert relerr(b.B_past[v:v + 1], orcs[v].B_past) < TOL_B, (c, v)
+                assert relerr(y[v:v + 1], want) < TOL_CTX, (c, v)
+    torch.cuda.synchronize()
+
+
 def test_fp32_projection_operands(dev):
     """`proj_operands="fp32"`: tf32 UMMAs straight from the fp32 coefficients and weights (the default converts both to
     fp16 first).  Same tolerances; the coefficients themselves are fp32 either way."""
