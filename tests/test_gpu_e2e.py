@@ -353,21 +353,32 @@ def test_gauss_matches_oracle_with_shared_operators(dev, N, L, Bv, C):
                 assert err < 5e-3 and ours <= 1.5 * max(theirs, 1e-4), (c, err, ours, theirs)
 
 
-def test_gauss_folded_operator_equals_gathered_samples(dev):
+@pytest.mark.parametrize("Bv,round1", [(2, False), (64, True)])
+def test_gauss_folded_operator_equals_gathered_samples(dev, Bv, round1):
     """Variant G sticky update through the per-video folded operator (default) and through the gathered sample rows:
-    same coefficients (two summation orders of one product), same draws, same contexts."""
+    same coefficients (two summation orders of one product), same draws, same contexts.  `round1`: the whole round-1
+    route on the other side (gathered samples, split-TF32 projection, FMA attention) against today's defaults (folded
+    operator, fp16x2 projection, tensor-core attention) at a batch of 64 videos."""
     from infinite_video_b200.batched import BatchedGaussLTM
     key, val = make_proj(43, 768)
     a = BatchedGaussLTM(256, .75, *proj_tensors(key, val), device=dev, fold_samples=True)
-    b = BatchedGaussLTM(256, .75, *proj_tensors(key, val), device=dev, fold_samples=False)
-    ks, qs, us = make_inputs(44, 3, 2, 64, 768, 32)
+    kw = dict(proj_precision="tf32x3", tc_attn=False) if round1 else {}
+    b = BatchedGaussLTM(256, .75, *proj_tensors(key, val), device=dev, fold_samples=False, **kw)
+    assert a.tc_attn and (not round1 or not b.tc_attn)
+    ks, qs, us = make_inputs(44, 3, Bv, 64, 768, 32)
+    same = torch.ones(Bv, dtype=torch.bool)
     for c in range(3):
         x = a.step(ks[c].to(dev), qs[c].to(dev), us[c].to(dev) if c else None, new_doc=(c == 0))
         y = b.step(ks[c].to(dev), qs[c].to(dev), us[c].to(dev) if c else None, new_doc=(c == 0))
-        assert relerr(a.B_past, b.B_past) < 2e-5, c
         if c:
-            assert torch.equal(a.last["b"], b.last["b"])
-        assert relerr(x, y) < 5e-4, c
+            # the two routes hand slightly different (mu, sd) to the erf histogram: a uniform on a CDF edge may land in
+            # the neighbouring bin -- verified to be a tie, and that video is left out from then on
+            flips, _ = compare_draws(a.last["b"], b.last["b"], us[c], b.last["p"].cpu(), 1e-5)
+            assert flips <= 2, (c, flips)
+            same &= (a.last["b"] == b.last["b"]).all(dim=1).cpu()
+        assert relerr(a.B_past[same], b.B_past[same]) < 2e-5, c
+        assert relerr(x[same], y[same]) < 5e-4, c
+    assert int(same.sum()) >= Bv - 2
 
 
 def test_gauss_device_ridge_end_to_end(dev):
